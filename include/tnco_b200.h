@@ -1,0 +1,138 @@
+/*
+ * tnco_b200 -- C-ABI of the B200-native simulated-annealing engine for contraction trees.
+ *
+ * This is the drop-in boundary for ONE path of google-research/tnco (v0.4.0): what
+ * `tnco.app.Optimizer(method='sa').optimize(tn, betas, n_steps, n_runs)` does below the Python driver,
+ * i.e. the work the reference performs through its pybind module `tnco_core`
+ *   tnco_core.optimize.infinite_memory.Optimizer_float64        (include/tnco/optimize/infinite_memory/main.hpp:33-51)
+ *   tnco_core.optimize.finite_width.greedy.Optimizer_float64_float32 (…/finite_width/greedy/main.hpp:32-46)
+ * one process and one object per run.  Here one engine owns one GPU and steps thousands of independent
+ * chains (runs) per kernel launch.  All entry points are plain C: pointers + sizes, caller-owned host
+ * buffers (C-contiguous), the engine owns all device memory.  Calls are blocking and not re-entrant per
+ * engine.  Return value: 0 on success, negative on error with the text available from tnb_last_error().
+ * There is NO CPU fallback: tnb_create() fails if no sm_100 device is usable.
+ *
+ * Node numbering is the reference's (include/tnco/tree.hpp:73-99): leaves are [0, n_leaves), internal
+ * nodes follow, the root is node 2*n_leaves-2; -1 is "null" (include/tnco/node.hpp:33-43).
+ * Index sets are bitsets of 32-bit words, bit i of the set = bit (i%32) of word (i/32)
+ * (the reference's Bitset position i, include/tnco/bitset.hpp:54-80).  W32 = ceil(n_inds/32).
+ */
+#ifndef TNCO_B200_H
+#define TNCO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tnb_engine tnb_engine;
+
+/* acceptance rule (include/tnco/optimize/prob/{mh,greedy,base}.hpp) */
+#define TNB_PROB_MH 0
+#define TNB_PROB_GREEDY 1
+#define TNB_PROB_ALWAYS 2
+
+/* random-number source */
+#define TNB_RNG_PHILOX 0  /* production: per-chain counter-based Philox4x32-10, generated in-kernel */
+#define TNB_RNG_MT19937 1 /* parity: the reference's std::mt19937 stream per chain (seed = run seed), same
+                             draw order as include/tnco/optimize/infinite_memory/optimizer.hpp:100-162 */
+#define TNB_RNG_REPLAY 2  /* parity: caller-recorded raw 32-bit draw stream per chain (tnb_set_stream) */
+
+/* chain-state layout */
+#define TNB_LAYOUT_AUTO 0
+#define TNB_LAYOUT_GLOBAL 1 /* chain state in HBM / L2, operated on in place */
+#define TNB_LAYOUT_SHARED 2 /* chain state staged into shared memory for the duration of a launch */
+
+#define TNB_TREES_GREEDY 0 /* random tie-broken greedy merges (stand-in for opt_einsum 'greedy', tnco/utils/tn.py:225) */
+#define TNB_TREES_RANDOM 1 /* uniformly random merges of index-sharing pairs */
+
+int tnb_version(void);
+/* last error of `e`, or of the failed tnb_create / host helper when e == NULL */
+const char* tnb_last_error(const tnb_engine* e);
+
+/* ---------------------------------------------------------------- host-side helpers (no GPU needed) */
+
+/* Initial contraction trees, one per seed (replaces tnco/utils/tn.py:109-273 get_random_contraction_path
+ * + tnco/ctree.py:108-226 for a CONNECTED network without hyper-indices).  Every contracted pair shares
+ * an index (check_shared_inds).  Outputs are [n_trees][2*n_leaves-1] each. */
+int tnb_random_trees(int n_leaves, int n_inds, const uint32_t* leaf_bits, int n_trees, const uint64_t* seeds,
+                     int method, int n_threads, int32_t* parent, int32_t* child0, int32_t* child1);
+
+/* Tree -> linear (einsum) contraction path; replaces include/tnco/utils.hpp:54-71 get_contraction +
+ * tnco/ctree.py:350-388 ContractionTree.path() with tensors_pos = identity.  path is [n_trees][n_leaves-1][2]. */
+int tnb_tree_to_path(int n_leaves, int n_trees, const int32_t* child0, const int32_t* child1, int32_t* path);
+
+/* Linear path -> tree in reference numbering (tnco/ctree.py:108-131,208-218).  path is [n_leaves-1][2]. */
+int tnb_path_to_tree(int n_leaves, const int32_t* path, int32_t* parent, int32_t* child0, int32_t* child1);
+
+/* First n outputs of std::mt19937(seed) (include/tnco/optimize/optimizer.hpp:48,75). */
+void tnb_mt19937_stream(uint32_t seed, uint64_t n, uint32_t* out);
+
+/* ---------------------------------------------------------------- engine */
+
+int tnb_create(tnb_engine** e, int device);
+void tnb_destroy(tnb_engine* e);
+
+/* Network = what ContractionTree carries besides the tree (include/tnco/ctree.hpp:32-40): per-leaf index
+ * sets and dims.  leaf_bits [n_leaves][W32].  dims == NULL: every index has dimension `dim`
+ * (ctree.hpp:80-89).  The network must be connected and free of hyper-indices (each index on <= 2 tensors). */
+int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* leaf_bits, uint64_t dim,
+                    const uint64_t* dims);
+
+/* max_width < 0 or +inf: unconstrained (infinite_memory optimizer).  Otherwise the memory-constrained
+ * optimizer with float32 width arithmetic (tnco/app/app.py:757) and the greedy slicer, re-slicing on
+ * sweeps s with s % update_slices_every == 0 (tnco/app/finite_width/sa.py:228). */
+int tnb_set_mode(tnb_engine* e, double max_width, int update_slices_every, int disable_shared_inds,
+                 int prob_kind, int rng_kind, int layout);
+
+/* One chain per tree ([n_chains][2*n_leaves-1] each) and per seed.  Builds every chain's caches on the
+ * device (index sets of internal nodes, contraction / partial costs, initial slices) exactly as the
+ * reference constructors do (infinite_memory/optimizer.hpp:61-88, finite_width/greedy/optimizer.hpp:72-115).
+ * chain_id0 = global id of chain 0 (multi-GPU sharding; enters the Philox counter). */
+int tnb_set_chains(tnb_engine* e, int n_chains, const int32_t* parent, const int32_t* child0,
+                   const int32_t* child1, const uint64_t* seeds, uint64_t chain_id0);
+
+/* TNB_RNG_REPLAY: raw draw stream per chain, words [n_chains][len]; cursors reset to 0. */
+int tnb_set_stream(tnb_engine* e, const uint32_t* words, uint64_t len);
+
+/* Inverse temperatures, one per sweep (tnco/app/infinite_memory/sa.py:147-156,199-205). */
+int tnb_set_betas(tnb_engine* e, const double* betas, int64_t n);
+
+/* Advance every chain to sweep index `until_sweep` (one sweep == one reference Optimizer::update()).
+ * In REPLAY mode a chain stops early when its stream cannot cover another sweep; see tnb_get_progress. */
+int tnb_run(tnb_engine* e, int64_t until_sweep);
+
+/* elapsed device time (ms, CUDA events on the engine's stream) and launch count of the sweep kernel
+ * accumulated since the last call */
+int tnb_get_timing(tnb_engine* e, double* kernel_ms, int64_t* launches);
+
+/* per chain: partial_cost[root] of the current tree and min_total_cost (linear domain, fp64) */
+int tnb_get_costs(tnb_engine* e, double* total, double* min_total);
+/* per chain [n][2*n_leaves-1]; best != 0: the reference's min_ctree */
+int tnb_get_trees(tnb_engine* e, int best, int chain0, int n, int32_t* parent, int32_t* child0, int32_t* child1);
+/* index sets of every node of the CURRENT tree of one chain, [2*n_leaves-1][W32] */
+int tnb_get_bits(tnb_engine* e, int chain, uint32_t* node_bits);
+/* per chain [n][W32]; best != 0: min_slices */
+int tnb_get_slices(tnb_engine* e, int best, int chain0, int n, uint32_t* slices);
+/* per chain: sweeps done, proposals (level-loop iterations), accepted moves, width-gate rejections,
+ * 32-bit draws consumed (stream modes).  Any pointer may be NULL. */
+int tnb_get_progress(tnb_engine* e, int64_t* sweeps, uint64_t* proposals, uint64_t* accepts,
+                     uint64_t* width_rejects, uint64_t* words);
+/* sums over all chains */
+int tnb_get_counters(tnb_engine* e, uint64_t* proposals, uint64_t* accepts, uint64_t* sweeps);
+
+/* Full-tree evaluation of arbitrary trees (does not touch the chains): total cost summed in traversal
+ * order (infinite_memory/utils.hpp:102-116 get_cost), partial_cost[root] (CostCache order, :32-56) and the
+ * maximum log2 width over all nodes after removing `slices` ([n_trees][W32] or NULL). */
+int tnb_eval_cost(tnb_engine* e, int n_trees, const int32_t* parent, const int32_t* child0,
+                  const int32_t* child1, const uint32_t* slices, double* total_seq, double* total_pc,
+                  double* max_width);
+
+/* the layout / tile shape the engine picked: lanes per chain, words per lane, TNB_LAYOUT_* , smem bytes per chain */
+int tnb_get_config(tnb_engine* e, int* tile, int* words_per_lane, int* layout, int* state_bytes_per_chain);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

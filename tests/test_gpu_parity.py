@@ -1,0 +1,179 @@
+"""GPU parity (run on the B200 box: pytest -m gpu): the CUDA engine, through the C-ABI, against
+ (i) golden vectors produced by the unmodified reference C++ core (tests/golden), in TNB_RNG_MT19937 mode
+     (same seeds => bit-identical trees, costs, slices as the reference, checkpoint by checkpoint);
+ (ii) the CPU oracle on a replayed, oracle-recorded draw stream (TNB_RNG_REPLAY);
+ (iii) the CPU oracle's full-tree cost on random trees (tnb_eval_cost), tolerance 1e-12 relative
+      (actual agreement is bit-exact for dim=2).
+Every tile shape the engine can pick is exercised via TNB_TILE."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, random_tree, regular_network
+from oracle import sa_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, '*.npz')) if 'hyper' not in p)
+
+
+def _engine(g, rng, tile=None, every=None):
+    from tnco_b200.engine import Engine
+    if tile:
+        os.environ['TNB_TILE'] = str(tile)
+    else:
+        os.environ.pop('TNB_TILE', None)
+    mw = float(g['max_width'])
+    mw = None if mw < 0 else mw
+    n = (g['parent'].shape[0] + 1) // 2
+    e = Engine()
+    e.set_network(g['bits'][:n], int(g['n_inds']), dim=int(g['dim']))
+    e.set_mode(max_width=mw, update_slices_every=int(g['every']) if every is None else every, rng=rng)
+    e.set_chains(g['parent'][None], g['child0'][None], g['child1'][None], [int(g['seed'])])
+    os.environ.pop('TNB_TILE', None)
+    return e, mw
+
+
+def _check_against_golden(g, e, mw):
+    n_sweeps = int(g['n_sweeps'])
+    e.set_betas([100.0 * s / n_sweeps for s in range(n_sweeps)])
+    t, m = e.costs()
+    assert np.log2(t[0]) == float(g['init_log2_total'])
+    if mw is not None:
+        assert (e.slices()[0] == g['init_slices']).all()
+    for k, s in enumerate(g['checkpoints'].tolist()):
+        e.run(s + 1)
+        p, a, b = e.trees()
+        assert (p[0] == g['cp_parent'][k]).all() and (a[0] == g['cp_child0'][k]).all() and (
+            b[0] == g['cp_child1'][k]).all(), s
+        t, m = e.costs()
+        assert np.log2(t[0]) == g['cp_log2_total'][k], s
+        assert np.log2(m[0]) == g['cp_log2_min'][k], s
+        if mw is not None:
+            assert (e.slices()[0] == g['cp_slices'][k]).all(), s
+            assert (e.slices(True)[0] == g['cp_min_slices'][k]).all(), s
+    e.run(n_sweeps)
+    p, a, b = e.trees(True)
+    assert (p[0] == g['best_parent']).all() and (a[0] == g['best_child0']).all() and (
+        b[0] == g['best_child1']).all()
+    assert (e.bits(0) == g['final_bits']).all()
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_mt19937_mode_matches_reference_golden(name):
+    from tnco_b200.engine import RNG_MT19937
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    e, mw = _engine(g, RNG_MT19937)
+    _check_against_golden(g, e, mw)
+
+
+@pytest.mark.parametrize('tile', [8, 16, 32])
+@pytest.mark.parametrize('name', ['reg64_inf', 'reg64_fw50', 'reg40_d3_inf'])
+def test_every_tile_shape_matches_golden(name, tile):
+    from tnco_b200.engine import RNG_MT19937
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    e, mw = _engine(g, RNG_MT19937, tile=tile)
+    assert e.config()['tile'] == tile
+    _check_against_golden(g, e, mw)
+
+
+@pytest.mark.parametrize('name', ['reg64_inf', 'reg100_fw30', 'reg300_inf'])
+def test_replay_of_recorded_draw_stream_is_bit_exact(name):
+    """north_star: replaying a reference-recorded proposal / uniform-draw sequence yields identical trees.
+    The stream is recorded by the oracle (itself pinned to the reference) while it runs the same sweeps."""
+    from tnco_b200.engine import RNG_REPLAY
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    mw = float(g['max_width'])
+    mw = None if mw < 0 else mw
+    n_sweeps = 400
+    oc = so.Chain(g['parent'], g['child0'], g['child1'], g['bits'], int(g['n_inds']), dim=int(g['dim']),
+                  max_width=mw, seed=int(g['seed']))
+    # the constructor's slicer draws precede the recording; re-create the full stream from the seed instead
+    betas = [100.0 * s / n_sweeps for s in range(n_sweeps)]
+    oc.run(betas, update_slices_every=int(g['every']))
+    words = oc.counters()['words_drawn']
+    stream = so.mt_stream(int(g['seed']), words + 8 * int(g['n_inds']) + 64 + 3 * len(g['parent']))
+    e, _ = _engine(g, RNG_REPLAY)
+    e.set_stream(stream[None])
+    e.set_betas(betas)
+    e.run(n_sweeps)
+    pr = e.progress()
+    assert pr['sweeps'][0] == n_sweeps
+    assert pr['words'][0] == words
+    for x, y in zip(e.trees(), oc.tree()):
+        assert (x[0] == y).all()
+    for x, y in zip(e.trees(True), oc.tree(True)):
+        assert (x[0] == y).all()
+    t, m = e.costs()
+    assert t[0] == oc.total_cost and m[0] == oc.min_total_cost
+    assert (e.bits(0) == oc.bits()).all()
+    c = oc.counters()
+    assert pr['proposals'][0] == c['proposals'] and pr['accepts'][0] == c['accepts']
+    if mw is not None:
+        assert (e.slices()[0] == oc.slices()).all() and (e.slices(True)[0] == oc.slices(True)).all()
+        assert pr['width_rejects'][0] == c['width_rejects']
+
+
+@pytest.mark.parametrize('n,dim', [(8, 2), (64, 2), (180, 2), (64, 3), (1000, 2)])
+def test_eval_cost_matches_oracle(n, dim):
+    from tnco_b200.engine import Engine
+    ts, ni = regular_network(n, 100 + n)
+    trees = [random_tree(ts, ni, s) for s in range(6)]
+    e = Engine()
+    e.set_network(trees[0][3][:n], ni, dim=dim)
+    P, A, B = (np.stack([t[k] for t in trees]) for k in range(3))
+    seq, pc, mw = e.eval_cost(P, A, B)
+    sl = np.zeros((6, (ni + 31) // 32), np.uint32)
+    sl[:, 0] = 0b1011
+    seq_s, pc_s, mw_s = e.eval_cost(P, A, B, slices=sl)
+    for i, t in enumerate(trees):
+        o_seq, o_mw, o_pc = so.tree_cost(t[1], t[2], t[3], ni, dim=dim)
+        assert abs(seq[i] - o_seq) <= 1e-12 * o_seq and abs(pc[i] - o_pc) <= 1e-12 * o_pc
+        assert abs(mw[i] - o_mw) <= 1e-12 * max(o_mw, 1)
+        if dim == 2:
+            assert seq[i] == o_seq and pc[i] == o_pc and mw[i] == o_mw
+        o_seq, o_mw, o_pc = so.tree_cost(t[1], t[2], t[3], ni, dim=dim, slices=sl[i])
+        assert abs(seq_s[i] - o_seq) <= 1e-12 * o_seq and abs(pc_s[i] - o_pc) <= 1e-12 * o_pc
+        assert abs(mw_s[i] - o_mw) <= 1e-12 * max(o_mw, 1)
+
+
+def test_philox_chains_are_valid_and_deterministic():
+    """Production RNG: no reference trajectory exists; check invariants the reference's tests check
+    (tests/test_utils.py:600-748): cached total == independent recomputation, min <= total, leaves fixed,
+    determinism for equal seeds, different seeds differ."""
+    from tnco_b200.engine import Engine, random_trees
+    ts, ni = regular_network(120, 7)
+    lb = so_leaf = None
+    from helpers import leaf_bits
+    lb = leaf_bits(ts, ni)
+    seeds = np.arange(64, dtype=np.uint64) + 11
+    p, a, b = random_trees(lb, ni, seeds)
+    outs = []
+    for rep in range(2):
+        e = Engine()
+        e.set_network(lb, ni)
+        e.set_mode()
+        e.set_chains(p, a, b, seeds)
+        e.set_betas(np.linspace(0, 100, 500, endpoint=False))
+        e.run(250)
+        e.run(500)
+        t, m = e.costs()
+        P, A, B = e.trees()
+        bP, bA, bB = e.trees(True)
+        seq, pc, _ = e.eval_cost(P, A, B)
+        assert (pc == t).all() or np.allclose(np.log2(pc), np.log2(t), atol=1e-9)
+        bseq, bpc, _ = e.eval_cost(bP, bA, bB)
+        assert np.allclose(np.log2(bpc), np.log2(m), atol=1e-9)
+        assert (m <= t).all()
+        for c in (0, 17, 63):
+            nb = e.bits(c)
+            o_seq, _, o_pc = so.tree_cost(A[c], B[c], nb, ni)
+            assert np.isclose(np.log2(o_pc), np.log2(t[c]), atol=1e-9)
+            assert (nb[:120] == lb).all()
+        outs.append((t.copy(), m.copy(), P.copy()))
+        assert e.counters()['sweeps'] == 64 * 500
+    assert (outs[0][0] == outs[1][0]).all() and (outs[0][2] == outs[1][2]).all()
+    assert len(set(outs[0][1].tolist())) > 8
+    assert np.log2(outs[0][1]).mean() < np.log2(seq).mean() + 1e-9

@@ -1,0 +1,734 @@
+// The engine behind the C-ABI of include/tnco_b200.h: device memory, kernel launches, host-side MT19937
+// stream feeding, result read-back.  Compiled by nvcc for sm_100a into libtnco_b200.so.
+//
+// (With -DTNB_EMU and a plain C++ compiler the same file builds tests/emu's logic-emulation harness: the
+// "device" is host memory and a launch is a loop over chains with one lane per chain.  That build is test
+// infrastructure; the tnco_b200 package never loads it.)
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "tnb_internal.h"
+#include "tnb_kernels.h"
+
+namespace tnb {
+
+// ------------------------------------------------------------------------------------------ runtime layer
+#if defined(TNB_EMU)
+struct Rt {
+  std::string err;
+  bool init(int) { return true; }
+  void* alloc(size_t b) { return std::calloc(std::max<size_t>(b, 1), 1); }
+  void free_(void* p) { std::free(p); }
+  bool h2d(void* d, const void* h, size_t b) { std::memcpy(d, h, b); return true; }
+  bool d2h(void* h, const void* d, size_t b) { std::memcpy(h, d, b); return true; }
+  bool zero(void* d, size_t b) { std::memset(d, 0, b); return true; }
+  bool fill_ff(void* d, size_t b) { std::memset(d, 0xff, b); return true; }
+  bool sync() { return true; }
+  void destroy() {}
+};
+#else
+struct Rt {
+  std::string err;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+  }
+  bool init(int dev) {
+    int count = 0;
+    if (!ok(cudaGetDeviceCount(&count), "cudaGetDeviceCount")) return false;
+    if (dev < 0 || dev >= count) { err = "no such CUDA device"; return false; }
+    cudaDeviceProp prop;
+    if (!ok(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties")) return false;
+    if (prop.major != 10) {
+      err = "tnco_b200 needs an sm_100 (Blackwell B200) device; found sm_" + std::to_string(prop.major) +
+            std::to_string(prop.minor) + " (there is no CPU or other-architecture fallback)";
+      return false;
+    }
+    device = dev;
+    if (!ok(cudaSetDevice(dev), "cudaSetDevice")) return false;
+    if (!ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+    if (!ok(cudaEventCreate(&ev0), "cudaEventCreate") || !ok(cudaEventCreate(&ev1), "cudaEventCreate")) return false;
+    return true;
+  }
+  void* alloc(size_t b) {
+    void* p = nullptr;
+    cudaSetDevice(device);
+    if (!ok(cudaMalloc(&p, std::max<size_t>(b, 16)), "cudaMalloc")) return nullptr;
+    cudaMemsetAsync(p, 0, std::max<size_t>(b, 16), stream);
+    return p;
+  }
+  void free_(void* p) { if (p) cudaFree(p); }
+  bool h2d(void* d, const void* h, size_t b) {
+    return b == 0 || ok(cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, stream), "cudaMemcpy H2D");
+  }
+  bool d2h(void* h, const void* d, size_t b) {
+    if (b == 0) return true;
+    return ok(cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, stream), "cudaMemcpy D2H") && sync();
+  }
+  bool zero(void* d, size_t b) { return b == 0 || ok(cudaMemsetAsync(d, 0, b, stream), "cudaMemset"); }
+  bool fill_ff(void* d, size_t b) { return b == 0 || ok(cudaMemsetAsync(d, 0xff, b, stream), "cudaMemset"); }
+  bool sync() { return ok(cudaStreamSynchronize(stream), "cudaStreamSynchronize"); }
+  void destroy() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+#endif
+
+// ------------------------------------------------------------------------------------------ kernels
+constexpr int kBlock = 128;
+
+#if !defined(TNB_EMU)
+template <int TILE, int WPL, bool FINITE, class Rng>
+__global__ void __launch_bounds__(kBlock) sa_init_kernel(const __grid_constant__ Params P) {
+  const int chain = (blockIdx.x * kBlock + threadIdx.x) / TILE;
+  if (chain >= P.n_chains) return;
+  chain_init<TILE, WPL, FINITE, Rng>(P, chain);
+}
+template <int TILE, int WPL, bool FINITE, class Rng>
+__global__ void __launch_bounds__(kBlock) sa_sweep_kernel(const __grid_constant__ Params P) {
+  const int chain = (blockIdx.x * kBlock + threadIdx.x) / TILE;
+  if (chain >= P.n_chains) return;
+  chain_sweeps<TILE, WPL, FINITE, Rng>(P, chain);
+}
+#endif
+
+template <int TILE, int WPL, bool FINITE, class Rng>
+static bool launch_t(Rt& rt, const Params& P, bool init) {
+#if defined(TNB_EMU)
+  (void)rt;
+  for (int c = 0; c < P.n_chains; ++c) {
+    if (init) chain_init<TILE, WPL, FINITE, Rng>(P, c);
+    else chain_sweeps<TILE, WPL, FINITE, Rng>(P, c);
+  }
+  return true;
+#else
+  const long long threads = (long long)P.n_chains * TILE;
+  const int grid = int((threads + kBlock - 1) / kBlock);
+  if (grid == 0) return true;
+  if (init) sa_init_kernel<TILE, WPL, FINITE, Rng><<<grid, kBlock, 0, rt.stream>>>(P);
+  else sa_sweep_kernel<TILE, WPL, FINITE, Rng><<<grid, kBlock, 0, rt.stream>>>(P);
+  return rt.ok(cudaGetLastError(), init ? "sa_init_kernel launch" : "sa_sweep_kernel launch");
+#endif
+}
+
+template <int TILE, int WPL>
+static bool launch_tw(Rt& rt, const Params& P, bool init, bool finite, bool stream_rng) {
+  if (finite) {
+    return stream_rng ? launch_t<TILE, WPL, true, RngStream<TILE>>(rt, P, init)
+                      : launch_t<TILE, WPL, true, RngPhilox<TILE>>(rt, P, init);
+  }
+  return stream_rng ? launch_t<TILE, WPL, false, RngStream<TILE>>(rt, P, init)
+                    : launch_t<TILE, WPL, false, RngPhilox<TILE>>(rt, P, init);
+}
+
+static bool launch(Rt& rt, const Params& P, int tile, int wpl, bool init, bool finite, bool stream_rng) {
+#if defined(TNB_EMU)
+  (void)tile;
+  (void)wpl;
+  if (P.W <= 4) return launch_tw<1, 4>(rt, P, init, finite, stream_rng);
+  if (P.W <= 16) return launch_tw<1, 16>(rt, P, init, finite, stream_rng);
+  if (P.W <= 48) return launch_tw<1, 48>(rt, P, init, finite, stream_rng);
+  return launch_tw<1, 128>(rt, P, init, finite, stream_rng);
+#else
+  switch (tile * 16 + wpl) {
+    case 4 * 16 + 1: return launch_tw<4, 1>(rt, P, init, finite, stream_rng);
+    case 8 * 16 + 1: return launch_tw<8, 1>(rt, P, init, finite, stream_rng);
+    case 16 * 16 + 1: return launch_tw<16, 1>(rt, P, init, finite, stream_rng);
+    case 32 * 16 + 1: return launch_tw<32, 1>(rt, P, init, finite, stream_rng);
+    case 32 * 16 + 2: return launch_tw<32, 2>(rt, P, init, finite, stream_rng);
+    case 32 * 16 + 3: return launch_tw<32, 3>(rt, P, init, finite, stream_rng);
+    case 32 * 16 + 4: return launch_tw<32, 4>(rt, P, init, finite, stream_rng);
+  }
+  rt.err = "unsupported tile shape";
+  return false;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------ chain storage
+struct ChainSet {
+  int n_chains = 0;
+  int16_t *par = nullptr, *bpar = nullptr;
+  uint32_t *ch = nullptr, *bch = nullptr, *bits = nullptr, *slices = nullptr, *bslices = nullptr;
+  dbl2 *cp = nullptr, *cp2 = nullptr;
+  double *total = nullptr, *min_total = nullptr, *out_seq = nullptr, *out_maxw = nullptr;
+  unsigned long long *seeds = nullptr, *rng_ctr = nullptr, *n_prop = nullptr, *n_acc = nullptr, *n_wrej = nullptr,
+                     *cursor = nullptr;
+  long long* sweep_idx = nullptr;
+  int* overrun = nullptr;
+  uint16_t* nbig = nullptr;
+  int16_t* posbuf = nullptr;
+  uint32_t* stream = nullptr;
+  unsigned long long stream_len = 0;
+
+  void release(Rt& rt) {
+    void* ps[] = {par, bpar, ch, bch, bits, slices, bslices, cp, cp2, total, min_total, out_seq, out_maxw, seeds,
+                  rng_ctr, n_prop, n_acc, n_wrej, cursor, sweep_idx, overrun, nbig, posbuf, stream};
+    for (void* p : ps) rt.free_(p);
+    *this = ChainSet();
+  }
+};
+
+}  // namespace tnb
+
+using namespace tnb;
+
+struct tnb_engine {
+  Rt rt;
+  std::string err;
+  // network
+  int n = 0, N = 0, n_int = 0, n_inds = 0, W = 0, Ws = 0, Npad = 0;
+  int tile = 32, wpl = 1;
+  uint64_t dim = 2;
+  double log2d = 1.0;
+  uint32_t* d_leaf_bits = nullptr;
+  double* d_pow_tab = nullptr;
+  std::vector<uint32_t> h_leaf_bits;  // [n][W]
+  // mode
+  bool finite = false;
+  float max_width = 0.f;
+  int every = 0, dsi = 0, prob_kind = TNB_PROB_MH, rng_kind = TNB_RNG_PHILOX, layout = TNB_LAYOUT_GLOBAL;
+  // chains
+  ChainSet cs;
+  bool initialized = false;
+  uint64_t chain_id0 = 0;
+  std::vector<uint64_t> h_seeds;
+  // schedule
+  double* d_betas = nullptr;
+  int64_t n_betas = 0;
+  // MT19937 feeding
+  std::vector<Mt19937> mts;
+  std::vector<uint32_t> h_stream;
+  // timing
+  double kernel_ms = 0.0;
+  int64_t launches = 0;
+
+  bool fail(const std::string& m) { err = m; return false; }
+  bool rtfail() { err = rt.err; return false; }
+};
+
+namespace tnb {
+
+static int pick_tile(int W, int& wpl) {
+  wpl = 1;
+  int tile = 32;
+  if (W <= 4) tile = 4;
+  else if (W <= 8) tile = 8;
+  else if (W <= 16) tile = 16;
+  else if (W <= 32) tile = 32;
+  else { tile = 32; wpl = (W + 31) / 32; }
+  if (const char* f = std::getenv("TNB_TILE")) {
+    const int t = std::atoi(f);
+    if ((t == 4 || t == 8 || t == 16 || t == 32) && t >= tile) tile = t;
+  }
+  return tile;
+}
+
+static unsigned long long sweep_reserve(const tnb_engine* e) {
+  // worst case draws of one sweep: leaf + (coin + 2) per level, depth <= n-1; plus slicer head-room
+  unsigned long long r = 1ull + 3ull * (unsigned long long)(e->n > 1 ? e->n - 1 : 1);
+  if (e->finite) r += 8ull * (unsigned long long)e->n_inds + 64ull;
+  return r;
+}
+
+static void fill_params(const tnb_engine* e, const ChainSet& cs, Params& P) {
+  std::memset(&P, 0, sizeof(P));
+  P.n = e->n; P.N = e->N; P.n_int = e->n_int; P.n_inds = e->n_inds; P.W = e->W; P.Ws = e->Ws;
+  P.leaf_bits = e->d_leaf_bits; P.pow_tab = e->d_pow_tab; P.dim2 = e->dim == 2; P.log2d = e->log2d;
+  P.finite = e->finite; P.every = e->every; P.dsi = e->dsi; P.prob_kind = e->prob_kind; P.max_width = e->max_width;
+  P.n_chains = cs.n_chains; P.Npad = e->Npad;
+  P.par = cs.par; P.ch = cs.ch; P.bits = cs.bits; P.cp = cs.cp; P.bpar = cs.bpar; P.bch = cs.bch;
+  P.slices = cs.slices; P.bslices = cs.bslices; P.total = cs.total; P.min_total = cs.min_total;
+  P.seeds = cs.seeds; P.rng_ctr = cs.rng_ctr; P.chain_id0 = e->chain_id0; P.sweep_idx = cs.sweep_idx;
+  P.n_prop = cs.n_prop; P.n_acc = cs.n_acc; P.n_wrej = cs.n_wrej;
+  P.stream = cs.stream; P.cursor = cs.cursor; P.stream_len = cs.stream_len; P.reserve = sweep_reserve(e);
+  P.overrun = cs.overrun;
+  P.betas = e->d_betas; P.n_betas = e->n_betas; P.until = 0;
+  P.nbig = cs.nbig; P.posbuf = cs.posbuf; P.cp2 = cs.cp2;
+  P.slices_given = 0; P.out_seq = cs.out_seq; P.out_maxw = cs.out_maxw;
+}
+
+template <class T>
+static bool alloc_to(Rt& rt, T*& p, size_t count) {
+  p = static_cast<T*>(rt.alloc(count * sizeof(T)));
+  return p != nullptr;
+}
+
+// allocate a chain set and upload the packed topology
+static bool make_chains(tnb_engine* e, ChainSet& cs, int n_chains, const int32_t* parent, const int32_t* c0,
+                        const int32_t* c1, bool with_best, bool with_slicer) {
+  Rt& rt = e->rt;
+  cs.n_chains = n_chains;
+  const size_t nc = size_t(n_chains), ni = size_t(std::max(e->n_int, 1));
+  bool ok = alloc_to(rt, cs.par, nc * e->Npad) && alloc_to(rt, cs.ch, nc * ni) &&
+            alloc_to(rt, cs.bits, nc * ni * e->Ws) && alloc_to(rt, cs.cp, nc * ni) &&
+            alloc_to(rt, cs.slices, nc * e->Ws) && alloc_to(rt, cs.total, nc) && alloc_to(rt, cs.min_total, nc) &&
+            alloc_to(rt, cs.out_seq, nc) && alloc_to(rt, cs.out_maxw, nc) && alloc_to(rt, cs.seeds, nc) &&
+            alloc_to(rt, cs.rng_ctr, nc) && alloc_to(rt, cs.n_prop, nc) && alloc_to(rt, cs.n_acc, nc) &&
+            alloc_to(rt, cs.n_wrej, nc) && alloc_to(rt, cs.cursor, nc) && alloc_to(rt, cs.sweep_idx, nc) &&
+            alloc_to(rt, cs.overrun, nc);
+  if (ok && with_best)
+    ok = alloc_to(rt, cs.bpar, nc * e->Npad) && alloc_to(rt, cs.bch, nc * ni) && alloc_to(rt, cs.bslices, nc * e->Ws);
+  if (ok && with_slicer)
+    ok = alloc_to(rt, cs.nbig, nc * e->Ws * 32) && alloc_to(rt, cs.posbuf, nc * e->Ws * 32) &&
+         alloc_to(rt, cs.cp2, nc * ni);
+  if (!ok) return e->rtfail();
+  // validate + pack
+  const int N = e->N, n = e->n;
+  std::vector<int16_t> hp(nc * e->Npad, int16_t(-1));
+  std::vector<uint32_t> hc(nc * ni, 0u);
+  std::vector<int> seen(size_t(N), 0);
+  for (int c = 0; c < n_chains; ++c) {
+    const int32_t *p = parent + size_t(c) * N, *a = c0 + size_t(c) * N, *b = c1 + size_t(c) * N;
+    std::fill(seen.begin(), seen.end(), 0);
+    for (int z = 0; z < N; ++z) {
+      const bool leaf = z < n;
+      if (leaf ? (a[z] != -1 || b[z] != -1) : (a[z] < 0 || a[z] >= N || b[z] < 0 || b[z] >= N || a[z] == b[z]))
+        return e->fail("invalid tree: leaves must come first and internal nodes need two children (chain " +
+                       std::to_string(c) + ", node " + std::to_string(z) + ")");
+      if (z == N - 1 ? p[z] != -1 : (p[z] < n || p[z] >= N))
+        return e->fail("invalid tree: bad parent / root must be the last node (chain " + std::to_string(c) + ")");
+      if (!leaf) {
+        if (p[a[z]] != z || p[b[z]] != z) return e->fail("invalid tree: parent/children mismatch");
+        seen[a[z]]++; seen[b[z]]++;
+        hc[size_t(c) * ni + (z - n)] = uint32_t(a[z]) | (uint32_t(b[z]) << 16);
+      }
+      hp[size_t(c) * e->Npad + z] = int16_t(p[z]);
+    }
+    for (int z = 0; z < N - 1; ++z)
+      if (seen[z] != 1) return e->fail("invalid tree: every non-root node must be a child exactly once");
+  }
+  if (!rt.h2d(cs.par, hp.data(), hp.size() * sizeof(int16_t)) || !rt.h2d(cs.ch, hc.data(), hc.size() * sizeof(uint32_t)))
+    return e->rtfail();
+  if (!rt.sync()) return e->rtfail();  // hp/hc go out of scope
+  return true;
+}
+
+static bool check_shared(tnb_engine* e, const int32_t* c0, const int32_t* c1, int n_chains) {
+  // check_shared_inds (include/tnco/ctree.hpp:101-152): children of every contraction must share an index.
+  // inds(z) = xor of leaf sets for hyper-free networks, computed here on the host for validation only.
+  if (e->dsi) return true;
+  const int N = e->N, n = e->n, W = e->W;
+  std::vector<uint32_t> bits(size_t(N) * W);
+  std::vector<int32_t> order;
+  std::vector<int32_t> stack;
+  std::vector<uint8_t> vis(N);
+  for (int c = 0; c < n_chains; ++c) {
+    const int32_t *a = c0 + size_t(c) * N, *b = c1 + size_t(c) * N;
+    std::memcpy(bits.data(), e->h_leaf_bits.data(), sizeof(uint32_t) * size_t(n) * W);
+    std::fill(vis.begin(), vis.end(), 0);
+    stack.assign(1, N - 1);
+    while (!stack.empty()) {
+      const int z = stack.back();
+      if (z < n || vis[z]) {
+        stack.pop_back();
+        if (z >= n) {
+          bool inter = false;
+          for (int w = 0; w < W; ++w) {
+            const uint32_t x = bits[size_t(a[z]) * W + w], y = bits[size_t(b[z]) * W + w];
+            inter |= (x & y) != 0;
+            bits[size_t(z) * W + w] = x ^ y;
+          }
+          if (!inter)
+            return e->fail("invalid tree: contracted tensors share no index (check_shared_inds), chain " +
+                           std::to_string(c) + " node " + std::to_string(z));
+        }
+      } else {
+        vis[z] = 1;
+        stack.push_back(b[z]);
+        stack.push_back(a[z]);
+      }
+    }
+  }
+  return true;
+}
+
+static bool stream_mode(const tnb_engine* e) { return e->rng_kind != TNB_RNG_PHILOX; }
+
+// MT19937: (re)fill every chain's window of the draw stream from the host generators
+static bool mt_refill(tnb_engine* e, bool first) {
+  ChainSet& cs = e->cs;
+  const size_t L = cs.stream_len, nc = size_t(cs.n_chains);
+  std::vector<unsigned long long> cur(nc, 0);
+  if (!first && !e->rt.d2h(cur.data(), cs.cursor, nc * sizeof(unsigned long long))) return e->rtfail();
+  for (size_t c = 0; c < nc; ++c) {
+    uint32_t* w = e->h_stream.data() + c * L;
+    const size_t used = first ? L : size_t(cur[c]);
+    if (!first && used < L) std::memmove(w, w + used, (L - used) * sizeof(uint32_t));
+    e->mts[c].fill(w + (L - used), used);
+  }
+  if (!e->rt.h2d(cs.stream, e->h_stream.data(), nc * L * sizeof(uint32_t))) return e->rtfail();
+  if (!e->rt.zero(cs.cursor, nc * sizeof(unsigned long long))) return e->rtfail();
+  return e->rt.sync() || e->rtfail();
+}
+
+static bool ensure_init(tnb_engine* e) {
+  if (e->initialized) return true;
+  if (e->cs.n_chains == 0) return e->fail("no chains: call tnb_set_chains first");
+  if (e->rng_kind == TNB_RNG_REPLAY && !e->cs.stream) return e->fail("TNB_RNG_REPLAY needs tnb_set_stream");
+  if (e->rng_kind == TNB_RNG_MT19937) {
+    ChainSet& cs = e->cs;
+    const unsigned long long res = sweep_reserve(e);
+    unsigned long long L = (256ull << 20) / 4ull / (unsigned long long)cs.n_chains;
+    L = std::max(L, 4ull * res);
+    L = std::min(L, std::max(1ull << 22, 4ull * res));
+    cs.stream_len = L;
+    e->rt.free_(cs.stream);
+    if (!alloc_to(e->rt, cs.stream, size_t(cs.n_chains) * L)) return e->rtfail();
+    e->h_stream.assign(size_t(cs.n_chains) * L, 0u);
+    e->mts.resize(size_t(cs.n_chains));
+    for (int c = 0; c < cs.n_chains; ++c) e->mts[size_t(c)].seed(uint32_t(e->h_seeds[size_t(c)]));
+    if (!mt_refill(e, true)) return false;
+  }
+  Params P;
+  fill_params(e, e->cs, P);
+  if (!launch(e->rt, P, e->tile, e->wpl, true, e->finite, stream_mode(e))) return e->rtfail();
+  if (!e->rt.sync()) return e->rtfail();
+  // "Precision is too low." (infinite_memory/optimizer.hpp:77-87)
+  std::vector<double> tot(size_t(e->cs.n_chains));
+  if (!e->rt.d2h(tot.data(), e->cs.total, tot.size() * sizeof(double))) return e->rtfail();
+  if (e->n_int > 0)
+    for (double t : tot)
+      if (!(t > 0.0) || std::isinf(t) || std::isnan(t)) return e->fail("Precision is too low.");
+  e->initialized = true;
+  return true;
+}
+
+}  // namespace tnb
+
+// ============================================================================================ C-ABI
+extern "C" {
+
+const char* tnb_last_error(const tnb_engine* e) { return e ? e->err.c_str() : global_error(); }
+
+int tnb_create(tnb_engine** out, int device) {
+  if (!out) { set_global_error("tnb_create: null output pointer"); return -1; }
+  *out = nullptr;
+  tnb_engine* e = new tnb_engine();
+  if (!e->rt.init(device)) {
+    set_global_error("tnb_create: " + e->rt.err);
+    delete e;
+    return -2;
+  }
+  *out = e;
+  return 0;
+}
+
+void tnb_destroy(tnb_engine* e) {
+  if (!e) return;
+  e->cs.release(e->rt);
+  e->rt.free_(e->d_leaf_bits);
+  e->rt.free_(e->d_pow_tab);
+  e->rt.free_(e->d_betas);
+  e->rt.destroy();
+  delete e;
+}
+
+int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* leaf_bits, uint64_t dim,
+                    const uint64_t* dims) {
+  if (!e) return -1;
+  if (n_leaves < 1 || n_inds < 1 || !leaf_bits) return e->fail("tnb_set_network: invalid arguments"), -1;
+  if (dims) {
+    bool uniform = true;
+    for (int i = 1; i < n_inds; ++i) uniform &= dims[i] == dims[0];
+    if (!uniform) return e->fail("tnb_set_network: per-index dims are not supported yet (uniform dim only)"), -2;
+    dim = dims[0];
+  }
+  if (dim < 1) return e->fail("tnb_set_network: dim must be positive"), -1;
+  if (2 * n_leaves - 1 > 32767) return e->fail("tnb_set_network: at most 16384 tensors"), -2;
+  const int W = (n_inds + 31) / 32;
+  if (W > 128) return e->fail("tnb_set_network: at most 4096 indices"), -2;
+  // hyper-index check: every index on at most two tensors
+  std::vector<uint8_t> cnt(size_t(W) * 32, 0);
+  for (int t = 0; t < n_leaves; ++t)
+    for (int w = 0; w < W; ++w) {
+      uint32_t v = leaf_bits[size_t(t) * W + w];
+      while (v) {
+        const int i = w * 32 + __builtin_ctz(v);
+        v &= v - 1;
+        if (i >= n_inds) return e->fail("tnb_set_network: leaf_bits has a bit beyond n_inds"), -1;
+        if (++cnt[size_t(i)] > 2)
+          return e->fail("tnb_set_network: hyper-indices (an index on more than two tensors) are not supported yet"), -2;
+      }
+    }
+  e->cs.release(e->rt);
+  e->initialized = false;
+  e->n = n_leaves; e->N = 2 * n_leaves - 1; e->n_int = n_leaves - 1; e->n_inds = n_inds; e->W = W;
+  e->Ws = (W + 3) / 4 * 4;
+  e->Npad = (e->N + 7) / 8 * 8;
+  e->tile = pick_tile(W, e->wpl);
+  e->dim = dim;
+  e->log2d = std::log2(double(dim));
+  e->h_leaf_bits.assign(leaf_bits, leaf_bits + size_t(n_leaves) * W);
+  std::vector<uint32_t> padded(size_t(n_leaves) * e->Ws, 0u);
+  for (int t = 0; t < n_leaves; ++t)
+    std::memcpy(&padded[size_t(t) * e->Ws], leaf_bits + size_t(t) * W, sizeof(uint32_t) * size_t(W));
+  e->rt.free_(e->d_leaf_bits);
+  e->rt.free_(e->d_pow_tab);
+  e->d_leaf_bits = nullptr; e->d_pow_tab = nullptr;
+  if (!alloc_to(e->rt, e->d_leaf_bits, padded.size())) return e->rtfail(), -3;
+  std::vector<double> tab(size_t(n_inds) + 1);
+  for (int k = 0; k <= n_inds; ++k) tab[size_t(k)] = std::pow(double(dim), double(k));
+  if (!alloc_to(e->rt, e->d_pow_tab, tab.size())) return e->rtfail(), -3;
+  if (!e->rt.h2d(e->d_leaf_bits, padded.data(), padded.size() * sizeof(uint32_t)) ||
+      !e->rt.h2d(e->d_pow_tab, tab.data(), tab.size() * sizeof(double)) || !e->rt.sync())
+    return e->rtfail(), -3;
+  return 0;
+}
+
+int tnb_set_mode(tnb_engine* e, double max_width, int update_slices_every, int disable_shared_inds, int prob_kind,
+                 int rng_kind, int layout) {
+  if (!e) return -1;
+  if (prob_kind < 0 || prob_kind > 2 || rng_kind < 0 || rng_kind > 2 || layout < 0 || layout > 2)
+    return e->fail("tnb_set_mode: invalid arguments"), -1;
+  if (layout == TNB_LAYOUT_SHARED) return e->fail("tnb_set_mode: TNB_LAYOUT_SHARED is not available in this build"), -2;
+  e->finite = !(max_width < 0.0) && !std::isinf(max_width) && !std::isnan(max_width);
+  e->max_width = e->finite ? float(max_width) : 0.f;
+  e->every = update_slices_every > 0 ? update_slices_every : 0;
+  e->dsi = disable_shared_inds != 0;
+  e->prob_kind = prob_kind;
+  e->rng_kind = rng_kind;
+  e->layout = TNB_LAYOUT_GLOBAL;
+  e->cs.release(e->rt);  // chains are (re)built under the new mode: call tnb_set_chains afterwards
+  e->initialized = false;
+  return 0;
+}
+
+int tnb_set_chains(tnb_engine* e, int n_chains, const int32_t* parent, const int32_t* child0, const int32_t* child1,
+                   const uint64_t* seeds, uint64_t chain_id0) {
+  if (!e) return -1;
+  if (e->n == 0) return e->fail("tnb_set_chains: call tnb_set_network first"), -1;
+  if (n_chains < 1 || !parent || !child0 || !child1 || !seeds) return e->fail("tnb_set_chains: invalid arguments"), -1;
+  e->cs.release(e->rt);
+  e->initialized = false;
+  e->chain_id0 = chain_id0;
+  if (!make_chains(e, e->cs, n_chains, parent, child0, child1, true, true)) { e->cs.release(e->rt); return -2; }
+  if (!check_shared(e, child0, child1, n_chains)) { e->cs.release(e->rt); return -2; }
+  e->h_seeds.assign(seeds, seeds + n_chains);
+  if (!e->rt.h2d(e->cs.seeds, seeds, size_t(n_chains) * sizeof(uint64_t)) || !e->rt.sync()) return e->rtfail(), -3;
+  return 0;
+}
+
+int tnb_set_stream(tnb_engine* e, const uint32_t* words, uint64_t len) {
+  if (!e) return -1;
+  if (e->cs.n_chains == 0) return e->fail("tnb_set_stream: call tnb_set_chains first"), -1;
+  if (e->rng_kind != TNB_RNG_REPLAY) return e->fail("tnb_set_stream: engine is not in TNB_RNG_REPLAY mode"), -1;
+  if (!words || len == 0) return e->fail("tnb_set_stream: invalid arguments"), -1;
+  ChainSet& cs = e->cs;
+  e->rt.free_(cs.stream);
+  cs.stream = nullptr;
+  cs.stream_len = len;
+  if (!alloc_to(e->rt, cs.stream, size_t(cs.n_chains) * len)) return e->rtfail(), -3;
+  if (!e->rt.h2d(cs.stream, words, size_t(cs.n_chains) * len * sizeof(uint32_t)) ||
+      !e->rt.zero(cs.cursor, size_t(cs.n_chains) * sizeof(unsigned long long)) ||
+      !e->rt.zero(cs.overrun, size_t(cs.n_chains) * sizeof(int)) || !e->rt.sync())
+    return e->rtfail(), -3;
+  return 0;
+}
+
+int tnb_set_betas(tnb_engine* e, const double* betas, int64_t n) {
+  if (!e) return -1;
+  if (!betas || n < 1) return e->fail("tnb_set_betas: invalid arguments"), -1;
+  e->rt.free_(e->d_betas);
+  e->d_betas = nullptr;
+  if (!alloc_to(e->rt, e->d_betas, size_t(n))) return e->rtfail(), -3;
+  if (!e->rt.h2d(e->d_betas, betas, size_t(n) * sizeof(double)) || !e->rt.sync()) return e->rtfail(), -3;
+  e->n_betas = n;
+  return 0;
+}
+
+int tnb_run(tnb_engine* e, int64_t until_sweep) {
+  if (!e) return -1;
+  if (!e->d_betas) return e->fail("tnb_run: call tnb_set_betas first"), -1;
+  if (!ensure_init(e)) return -2;
+  Params P;
+  for (int guard = 0;; ++guard) {
+    fill_params(e, e->cs, P);
+    P.until = until_sweep;
+#if !defined(TNB_EMU)
+    cudaEventRecord(e->rt.ev0, e->rt.stream);
+#else
+    const auto t0 = std::chrono::steady_clock::now();
+#endif
+    if (!launch(e->rt, P, e->tile, e->wpl, false, e->finite, stream_mode(e))) return e->rtfail(), -3;
+#if !defined(TNB_EMU)
+    cudaEventRecord(e->rt.ev1, e->rt.stream);
+    if (!e->rt.sync()) return e->rtfail(), -3;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->rt.ev0, e->rt.ev1);
+    e->kernel_ms += double(ms);
+#else
+    e->kernel_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+#endif
+    e->launches += 1;
+    if (e->rng_kind == TNB_RNG_PHILOX) break;
+    // stream modes: did everybody get there?
+    const size_t nc = size_t(e->cs.n_chains);
+    std::vector<long long> sw(nc);
+    std::vector<int> ov(nc);
+    if (!e->rt.d2h(sw.data(), e->cs.sweep_idx, nc * sizeof(long long)) ||
+        !e->rt.d2h(ov.data(), e->cs.overrun, nc * sizeof(int)))
+      return e->rtfail(), -3;
+    for (int o : ov)
+      if (o) return e->fail("draw stream exhausted in the middle of a sweep (chain state is no longer valid)"), -4;
+    bool done = true;
+    for (long long s : sw) done &= s >= until_sweep;
+    if (done) break;
+    if (e->rng_kind == TNB_RNG_REPLAY) break;  // caller inspects tnb_get_progress and supplies more words
+    if (!mt_refill(e, false)) return -3;
+    if (guard > (1 << 20)) return e->fail("tnb_run: no progress"), -4;
+  }
+  return 0;
+}
+
+int tnb_get_timing(tnb_engine* e, double* kernel_ms, int64_t* launches) {
+  if (!e) return -1;
+  if (kernel_ms) *kernel_ms = e->kernel_ms;
+  if (launches) *launches = e->launches;
+  e->kernel_ms = 0.0;
+  e->launches = 0;
+  return 0;
+}
+
+int tnb_get_costs(tnb_engine* e, double* total, double* min_total) {
+  if (!e) return -1;
+  if (!ensure_init(e)) return -2;
+  const size_t b = size_t(e->cs.n_chains) * sizeof(double);
+  if ((total && !e->rt.d2h(total, e->cs.total, b)) || (min_total && !e->rt.d2h(min_total, e->cs.min_total, b)))
+    return e->rtfail(), -3;
+  return 0;
+}
+
+int tnb_get_trees(tnb_engine* e, int best, int chain0, int n, int32_t* parent, int32_t* child0, int32_t* child1) {
+  if (!e) return -1;
+  if (!ensure_init(e)) return -2;
+  if (chain0 < 0 || n < 0 || chain0 + n > e->cs.n_chains) return e->fail("tnb_get_trees: chain range"), -1;
+  const size_t ni = size_t(std::max(e->n_int, 1));
+  std::vector<int16_t> hp(size_t(n) * e->Npad);
+  std::vector<uint32_t> hc(size_t(n) * ni);
+  if (!e->rt.d2h(hp.data(), (best ? e->cs.bpar : e->cs.par) + size_t(chain0) * e->Npad, hp.size() * sizeof(int16_t)) ||
+      !e->rt.d2h(hc.data(), (best ? e->cs.bch : e->cs.ch) + size_t(chain0) * ni, hc.size() * sizeof(uint32_t)))
+    return e->rtfail(), -3;
+  const int N = e->N, nl = e->n;
+  for (int c = 0; c < n; ++c)
+    for (int z = 0; z < N; ++z) {
+      parent[size_t(c) * N + z] = hp[size_t(c) * e->Npad + z];
+      if (z < nl) {
+        child0[size_t(c) * N + z] = -1;
+        child1[size_t(c) * N + z] = -1;
+      } else {
+        const uint32_t w = hc[size_t(c) * ni + (z - nl)];
+        child0[size_t(c) * N + z] = int32_t(w & 0xffffu);
+        child1[size_t(c) * N + z] = int32_t(w >> 16);
+      }
+    }
+  return 0;
+}
+
+int tnb_get_bits(tnb_engine* e, int chain, uint32_t* node_bits) {
+  if (!e) return -1;
+  if (!ensure_init(e)) return -2;
+  if (chain < 0 || chain >= e->cs.n_chains) return e->fail("tnb_get_bits: chain range"), -1;
+  const int W = e->W, Ws = e->Ws;
+  std::memcpy(node_bits, e->h_leaf_bits.data(), sizeof(uint32_t) * size_t(e->n) * W);
+  std::vector<uint32_t> hb(size_t(std::max(e->n_int, 1)) * Ws);
+  if (!e->rt.d2h(hb.data(), e->cs.bits + size_t(chain) * std::max(e->n_int, 1) * Ws, hb.size() * sizeof(uint32_t)))
+    return e->rtfail(), -3;
+  for (int z = 0; z < e->n_int; ++z)
+    std::memcpy(node_bits + size_t(e->n + z) * W, &hb[size_t(z) * Ws], sizeof(uint32_t) * size_t(W));
+  return 0;
+}
+
+int tnb_get_slices(tnb_engine* e, int best, int chain0, int n, uint32_t* slices) {
+  if (!e) return -1;
+  if (!ensure_init(e)) return -2;
+  if (chain0 < 0 || n < 0 || chain0 + n > e->cs.n_chains) return e->fail("tnb_get_slices: chain range"), -1;
+  std::vector<uint32_t> hs(size_t(n) * e->Ws);
+  if (!e->rt.d2h(hs.data(), (best ? e->cs.bslices : e->cs.slices) + size_t(chain0) * e->Ws, hs.size() * sizeof(uint32_t)))
+    return e->rtfail(), -3;
+  for (int c = 0; c < n; ++c) std::memcpy(slices + size_t(c) * e->W, &hs[size_t(c) * e->Ws], sizeof(uint32_t) * size_t(e->W));
+  return 0;
+}
+
+int tnb_get_progress(tnb_engine* e, int64_t* sweeps, uint64_t* proposals, uint64_t* accepts, uint64_t* width_rejects,
+                     uint64_t* words) {
+  if (!e) return -1;
+  if (!ensure_init(e)) return -2;
+  const size_t nc = size_t(e->cs.n_chains);
+  if ((sweeps && !e->rt.d2h(sweeps, e->cs.sweep_idx, nc * 8)) || (proposals && !e->rt.d2h(proposals, e->cs.n_prop, nc * 8)) ||
+      (accepts && !e->rt.d2h(accepts, e->cs.n_acc, nc * 8)) ||
+      (width_rejects && !e->rt.d2h(width_rejects, e->cs.n_wrej, nc * 8)) ||
+      (words && !e->rt.d2h(words, e->cs.cursor, nc * 8)))
+    return e->rtfail(), -3;
+  return 0;
+}
+
+int tnb_get_counters(tnb_engine* e, uint64_t* proposals, uint64_t* accepts, uint64_t* sweeps) {
+  if (!e) return -1;
+  if (!ensure_init(e)) return -2;
+  const size_t nc = size_t(e->cs.n_chains);
+  std::vector<uint64_t> a(nc), b(nc);
+  std::vector<int64_t> s(nc);
+  if (tnb_get_progress(e, s.data(), a.data(), b.data(), nullptr, nullptr) != 0) return -3;
+  uint64_t sa = 0, sb = 0, ss = 0;
+  for (size_t i = 0; i < nc; ++i) { sa += a[i]; sb += b[i]; ss += uint64_t(s[i]); }
+  if (proposals) *proposals = sa;
+  if (accepts) *accepts = sb;
+  if (sweeps) *sweeps = ss;
+  return 0;
+}
+
+int tnb_eval_cost(tnb_engine* e, int n_trees, const int32_t* parent, const int32_t* child0, const int32_t* child1,
+                  const uint32_t* slices, double* total_seq, double* total_pc, double* max_width) {
+  if (!e) return -1;
+  if (e->n == 0) return e->fail("tnb_eval_cost: call tnb_set_network first"), -1;
+  if (n_trees < 1 || !parent || !child0 || !child1) return e->fail("tnb_eval_cost: invalid arguments"), -1;
+  ChainSet tmp;
+  int rc = 0;
+  if (!make_chains(e, tmp, n_trees, parent, child0, child1, false, false)) rc = -2;
+  if (rc == 0 && slices) {
+    std::vector<uint32_t> hs(size_t(n_trees) * e->Ws, 0u);
+    for (int c = 0; c < n_trees; ++c)
+      std::memcpy(&hs[size_t(c) * e->Ws], slices + size_t(c) * e->W, sizeof(uint32_t) * size_t(e->W));
+    if (!e->rt.h2d(tmp.slices, hs.data(), hs.size() * sizeof(uint32_t)) || !e->rt.sync()) { e->rtfail(); rc = -3; }
+  }
+  if (rc == 0) {
+    Params P;
+    fill_params(e, tmp, P);
+    P.slices_given = 1;
+    P.finite = slices != nullptr;
+    if (!launch(e->rt, P, e->tile, e->wpl, true, slices != nullptr, false) || !e->rt.sync()) { e->rtfail(); rc = -3; }
+  }
+  const size_t b = size_t(n_trees) * sizeof(double);
+  if (rc == 0 && ((total_seq && !e->rt.d2h(total_seq, tmp.out_seq, b)) || (total_pc && !e->rt.d2h(total_pc, tmp.total, b)) ||
+                  (max_width && !e->rt.d2h(max_width, tmp.out_maxw, b)))) {
+    e->rtfail();
+    rc = -3;
+  }
+  tmp.release(e->rt);
+  return rc;
+}
+
+int tnb_get_config(tnb_engine* e, int* tile, int* words_per_lane, int* layout, int* state_bytes_per_chain) {
+  if (!e) return -1;
+  if (tile) *tile = e->tile;
+  if (words_per_lane) *words_per_lane = e->wpl;
+  if (layout) *layout = e->layout;
+  if (state_bytes_per_chain)
+    *state_bytes_per_chain = int(size_t(e->n_int) * (size_t(e->Ws) * 4 + 16 + 4) + size_t(e->Npad) * 2);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,298 @@
+// Host-side (no GPU) entry points of the C-ABI: initial trees, tree <-> linear path, mt19937 streams.
+// See include/tnco_b200.h for the reference interfaces each one replaces.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <queue>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "tnb_internal.h"
+
+namespace tnb {
+
+static thread_local std::string g_err;
+void set_global_error(const std::string& s) { g_err = s; }
+const char* global_error() { return g_err.c_str(); }
+
+// ----------------------------------------------------------------------------------------- mt19937
+// Bit-compatible with std::mt19937 seeded by prng.seed(s) (include/tnco/optimize/optimizer.hpp:75).
+void Mt19937::seed(uint32_t s) {
+  x[0] = s;
+  for (int i = 1; i < 624; ++i) x[i] = 1812433253u * (x[i - 1] ^ (x[i - 1] >> 30)) + uint32_t(i);
+  p = 624;
+}
+void Mt19937::refill() {
+  auto mix = [](uint32_t a, uint32_t b) {
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+  };
+  int i = 0;
+  for (; i < 624 - 397; ++i) x[i] = x[i + 397] ^ mix(x[i], x[i + 1]);
+  for (; i < 623; ++i) x[i] = x[i + 397 - 624] ^ mix(x[i], x[i + 1]);
+  x[623] = x[396] ^ mix(x[623], x[0]);
+  p = 0;
+}
+void Mt19937::fill(uint32_t* out, uint64_t n) {
+  for (uint64_t i = 0; i < n; ++i) out[i] = next();
+}
+
+// ----------------------------------------------------------------------------------------- small rng
+struct SplitMix {
+  uint64_t s;
+  explicit SplitMix(uint64_t seed) : s(seed) {}
+  uint64_t next() {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  }
+  uint32_t below(uint32_t n) { return uint32_t((uint64_t(uint32_t(next() >> 32)) * n) >> 32); }
+};
+
+// ----------------------------------------------------------------------------------------- trees
+static inline int popc_row(const uint32_t* a, int W) {
+  int k = 0;
+  for (int i = 0; i < W; ++i) k += __builtin_popcount(a[i]);
+  return k;
+}
+
+struct Net {
+  int n, n_inds, W;
+  const uint32_t* leaf_bits;
+  std::vector<int32_t> own0, own1;  // the (<=2) leaves holding each index
+};
+
+static bool build_net(Net& net, std::string& err) {
+  net.own0.assign(net.n_inds, -1);
+  net.own1.assign(net.n_inds, -1);
+  for (int t = 0; t < net.n; ++t)
+    for (int w = 0; w < net.W; ++w) {
+      uint32_t v = net.leaf_bits[size_t(t) * net.W + w];
+      while (v) {
+        const int i = w * 32 + __builtin_ctz(v);
+        v &= v - 1;
+        if (i >= net.n_inds) { err = "leaf_bits has a bit beyond n_inds"; return false; }
+        if (net.own0[i] < 0) net.own0[i] = t;
+        else if (net.own1[i] < 0) net.own1[i] = t;
+        else { err = "hyper-indices (an index on more than two tensors) are not supported"; return false; }
+      }
+    }
+  return true;
+}
+
+// One tree.  method 0: greedy on size(out)-size(a)-size(b) with random tie-breaks; 1: random edge order.
+static bool one_tree(const Net& net, uint64_t seed, int method, int32_t* par, int32_t* c0, int32_t* c1) {
+  const int n = net.n, N = 2 * n - 1, W = net.W;
+  SplitMix rng(seed * 0x9E3779B97F4A7C15ull + 0x1234567ull + uint64_t(method));
+  std::fill(par, par + N, -1);
+  std::fill(c0, c0 + N, -1);
+  std::fill(c1, c1 + N, -1);
+  if (n == 1) return true;
+  std::vector<uint32_t> bits(size_t(N) * W, 0u);
+  std::memcpy(bits.data(), net.leaf_bits, sizeof(uint32_t) * size_t(n) * W);
+  std::vector<int32_t> o0(net.own0), o1(net.own1);  // current cluster holding each index
+  std::vector<uint8_t> alive(N, 0);
+  std::fill(alive.begin(), alive.begin() + n, 1);
+  int nxt = n;
+  auto merge = [&](int a, int b) {
+    const int z = nxt++;
+    uint32_t* bz = &bits[size_t(z) * W];
+    const uint32_t *ba = &bits[size_t(a) * W], *bb = &bits[size_t(b) * W];
+    for (int w = 0; w < W; ++w) bz[w] = ba[w] ^ bb[w];
+    for (int w = 0; w < W; ++w) {
+      uint32_t v = bz[w];
+      while (v) {
+        const int i = w * 32 + __builtin_ctz(v);
+        v &= v - 1;
+        if (o0[i] == a || o0[i] == b) o0[i] = z;
+        if (o1[i] == a || o1[i] == b) o1[i] = z;
+      }
+    }
+    c0[z] = a; c1[z] = b; par[a] = z; par[b] = z;
+    alive[a] = alive[b] = 0; alive[z] = 1;
+    return z;
+  };
+  if (method == TNB_TREES_RANDOM) {
+    std::vector<int32_t> edges;
+    for (int i = 0; i < net.n_inds; ++i)
+      if (net.own1[i] >= 0) edges.push_back(i);
+    for (size_t i = edges.size(); i > 1; --i) std::swap(edges[i - 1], edges[rng.below(uint32_t(i))]);
+    for (int32_t i : edges) {
+      if (nxt == N) break;
+      const int a = o0[i], b = o1[i];
+      if (a == b || a < 0 || b < 0) continue;
+      if (rng.next() & 1) merge(a, b); else merge(b, a);
+    }
+    return nxt == N;
+  }
+  struct Cand {
+    double score;
+    uint32_t tie;
+    int32_t a, b;
+    bool operator<(const Cand& o) const { return score != o.score ? score > o.score : tie > o.tie; }  // min-heap
+  };
+  std::priority_queue<Cand> pq;
+  std::vector<int> kcache(N, 0);
+  for (int t = 0; t < n; ++t) kcache[t] = popc_row(&bits[size_t(t) * W], W);
+  auto sz = [](int k) { return std::ldexp(1.0, std::min(k, 1000)); };
+  auto push = [&](int a, int b) {
+    const uint32_t *ba = &bits[size_t(a) * W], *bb = &bits[size_t(b) * W];
+    int ko = 0;
+    for (int w = 0; w < W; ++w) ko += __builtin_popcount(ba[w] ^ bb[w]);
+    pq.push(Cand{sz(ko) - sz(kcache[a]) - sz(kcache[b]), uint32_t(rng.next() >> 32), a, b});
+  };
+  for (int i = 0; i < net.n_inds; ++i)
+    if (net.own1[i] >= 0 && net.own0[i] != net.own1[i]) push(net.own0[i], net.own1[i]);
+  std::vector<int32_t> seen(N, -1);
+  while (nxt < N && !pq.empty()) {
+    const Cand c = pq.top();
+    pq.pop();
+    if (!alive[c.a] || !alive[c.b]) continue;
+    const int z = (c.tie & 1) ? merge(c.a, c.b) : merge(c.b, c.a);
+    const uint32_t* bz = &bits[size_t(z) * W];
+    kcache[z] = popc_row(bz, W);
+    for (int w = 0; w < W; ++w) {
+      uint32_t v = bz[w];
+      while (v) {
+        const int i = w * 32 + __builtin_ctz(v);
+        v &= v - 1;
+        const int other = (o0[i] == z) ? o1[i] : o0[i];
+        if (other >= 0 && other != z && seen[other] != z) {
+          seen[other] = z;
+          push(z, other);
+        }
+      }
+    }
+  }
+  return nxt == N;
+}
+
+// Fenwick tree over list slots with "live" flags (prefix counts + k-th live slot).
+struct Fenwick {
+  int n;
+  std::vector<int32_t> t;
+  explicit Fenwick(int n_) : n(n_), t(n_ + 1, 0) {}
+  void add(int i, int v) { for (++i; i <= n; i += i & -i) t[i] += v; }
+  int prefix(int i) const { int s = 0; for (; i > 0; i -= i & -i) s += t[i]; return s; }  // live in [0,i)
+  int kth(int k) const {  // slot of the k-th (0-based) live element
+    int pos = 0, lg = 1;
+    while ((lg << 1) <= n) lg <<= 1;
+    for (int pw = lg; pw; pw >>= 1)
+      if (pos + pw <= n && t[pos + pw] <= k) { pos += pw; k -= t[pos]; }
+    return pos;
+  }
+};
+
+}  // namespace tnb
+
+using namespace tnb;
+
+extern "C" {
+
+int tnb_version(void) { return 100; }
+
+void tnb_mt19937_stream(uint32_t seed, uint64_t n, uint32_t* out) {
+  Mt19937 m;
+  m.seed(seed);
+  m.fill(out, n);
+}
+
+int tnb_random_trees(int n_leaves, int n_inds, const uint32_t* leaf_bits, int n_trees, const uint64_t* seeds,
+                     int method, int n_threads, int32_t* parent, int32_t* child0, int32_t* child1) {
+  if (n_leaves < 1 || n_inds < 0 || n_trees < 0 || !leaf_bits || !seeds) {
+    set_global_error("tnb_random_trees: invalid arguments");
+    return -1;
+  }
+  Net net{n_leaves, n_inds, (n_inds + 31) / 32, leaf_bits, {}, {}};
+  std::string err;
+  if (!build_net(net, err)) { set_global_error("tnb_random_trees: " + err); return -2; }
+  const int N = 2 * n_leaves - 1;
+  if (n_threads <= 0) n_threads = int(std::max(1u, std::thread::hardware_concurrency()));
+  n_threads = std::max(1, std::min(n_threads, n_trees));
+  std::vector<int> ok(size_t(n_threads), 1);
+  auto work = [&](int tid) {
+    for (int t = tid; t < n_trees; t += n_threads)
+      if (!one_tree(net, seeds[t], method, parent + size_t(t) * N, child0 + size_t(t) * N, child1 + size_t(t) * N))
+        ok[size_t(tid)] = 0;
+  };
+  if (n_threads == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (int i = 0; i < n_threads; ++i) th.emplace_back(work, i);
+    for (auto& t : th) t.join();
+  }
+  for (int v : ok)
+    if (!v) { set_global_error("tnb_random_trees: the network is not connected"); return -3; }
+  return 0;
+}
+
+int tnb_tree_to_path(int n_leaves, int n_trees, const int32_t* child0, const int32_t* child1, int32_t* path) {
+  const int n = n_leaves, N = 2 * n - 1;
+  std::vector<int32_t> stack, slot(N);
+  std::vector<uint8_t> vis(N);
+  for (int t = 0; t < n_trees; ++t) {
+    const int32_t *a = child0 + size_t(t) * N, *b = child1 + size_t(t) * N;
+    int32_t* out = path + size_t(t) * (n - 1) * 2;
+    Fenwick fw(N);
+    for (int i = 0; i < n; ++i) { fw.add(i, 1); slot[i] = i; }
+    std::fill(vis.begin(), vis.end(), 0);
+    stack.assign(1, N - 1);
+    int step = 0;
+    while (!stack.empty()) {  // post-order, children[0] first (include/tnco/utils.hpp:35-52)
+      const int pos = stack.back();
+      if (pos < 0 || pos >= N) { set_global_error("tnb_tree_to_path: bad node id"); return -1; }
+      if (vis[pos] || a[pos] < 0) {
+        stack.pop_back();
+        if (a[pos] >= 0) {
+          if (step >= n - 1) { set_global_error("tnb_tree_to_path: not a tree"); return -1; }
+          const int sx = slot[a[pos]], sy = slot[b[pos]];
+          out[2 * step] = fw.prefix(sx);
+          out[2 * step + 1] = fw.prefix(sy);
+          fw.add(sx, -1);
+          fw.add(sy, -1);
+          slot[pos] = n + step;
+          fw.add(slot[pos], 1);
+          ++step;
+        }
+      } else {
+        vis[pos] = 1;
+        stack.push_back(b[pos]);
+        stack.push_back(a[pos]);
+      }
+    }
+    if (step != n - 1) { set_global_error("tnb_tree_to_path: not a full binary tree"); return -1; }
+  }
+  return 0;
+}
+
+int tnb_path_to_tree(int n_leaves, const int32_t* path, int32_t* parent, int32_t* child0, int32_t* child1) {
+  const int n = n_leaves, N = 2 * n - 1;
+  std::fill(parent, parent + N, -1);
+  std::fill(child0, child0 + N, -1);
+  std::fill(child1, child1 + N, -1);
+  Fenwick fw(N);
+  std::vector<int32_t> node_of_slot(N);
+  for (int i = 0; i < n; ++i) { fw.add(i, 1); node_of_slot[i] = i; }
+  int live = n;
+  for (int i = 0; i < n - 1; ++i) {
+    int x = path[2 * i], y = path[2 * i + 1];
+    if (x > y) std::swap(x, y);
+    if (x < 0 || y >= live || x == y) { set_global_error("tnb_path_to_tree: invalid path entry"); return -1; }
+    const int sy = fw.kth(y), sx = fw.kth(x);
+    const int py = node_of_slot[sy], px = node_of_slot[sx];
+    fw.add(sy, -1);
+    fw.add(sx, -1);
+    const int z = n + i;
+    node_of_slot[z] = z;
+    fw.add(z, 1);
+    live -= 1;
+    child0[z] = px; child1[z] = py; parent[px] = z; parent[py] = z;
+  }
+  return 0;
+}
+
+}  // extern "C"

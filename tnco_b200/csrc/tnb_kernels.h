@@ -1,0 +1,704 @@
+// Chain kernels of the SA engine: one TILE of lanes owns one chain (one reference Optimizer object).
+//
+//   chain_init    builds a chain's caches from its tree, like the reference constructors
+//                 (infinite_memory/optimizer.hpp:61-88, finite_width/greedy/optimizer.hpp:72-115)
+//   chain_sweeps  runs leaf->root sweeps == Optimizer::update() (infinite_memory/optimizer.hpp:90-201,
+//                 finite_width/greedy/optimizer.hpp:117-390 with max_number_new_slices == 0)
+//
+// Data mapping: lane `tl` of the tile owns words tl, tl+TILE, ... of every index bitset, so all bitset
+// traffic is lane-private (no cross-lane memory hand-off); tile-uniform scalars (topology, costs) are
+// stored redundantly by all lanes with the same value (one coalesced transaction), so a lane only ever
+// reads back its own stores.  Cross-lane reads exist only in the slicer scratch and are fenced by
+// Tile::sync().  Networks must be free of hyper-indices, hence inds(z) = inds(c0) ^ inds(c1).
+#pragma once
+#include "tnb_simt.h"
+
+namespace tnb {
+
+constexpr int kProbMH = 0, kProbGreedy = 1, kProbAlways = 2;
+
+struct Params {
+  // network
+  int n, N, n_int, n_inds, W, Ws;  // leaves, nodes, internal nodes, indices, words per bitset, row stride
+  const uint32_t* leaf_bits;        // [n][Ws]
+  const double* pow_tab;            // [n_inds+1] dim^k (host std::pow), unused when dim2
+  int dim2;
+  double log2d;
+  // mode
+  int finite, every, dsi, prob_kind;
+  float max_width;
+  // chains
+  int n_chains, Npad;
+  int16_t* par;    // [n_chains][Npad]
+  uint32_t* ch;    // [n_chains][n_int]   child0 | child1 << 16
+  uint32_t* bits;  // [n_chains][n_int][Ws]
+  dbl2* cp;        // [n_chains][n_int]   {contraction_cost, partial_cost}
+  int16_t* bpar;   // best tree (reference min_ctree)
+  uint32_t* bch;
+  uint32_t* slices;   // [n_chains][Ws]
+  uint32_t* bslices;  // [n_chains][Ws]
+  double* total;      // [n_chains] partial_cost[root]
+  double* min_total;  // [n_chains]
+  const unsigned long long* seeds;
+  unsigned long long* rng_ctr;
+  unsigned long long chain_id0;
+  long long* sweep_idx;
+  unsigned long long *n_prop, *n_acc, *n_wrej;
+  // draw stream (MT19937 / REPLAY)
+  const uint32_t* stream;       // [n_chains][stream_len]
+  unsigned long long* cursor;   // [n_chains]
+  unsigned long long stream_len, reserve;
+  int* overrun;                 // [n_chains]
+  // schedule
+  const double* betas;
+  long long n_betas, until;
+  // scratch for the slicer
+  uint16_t* nbig;   // [n_chains][Ws*32]
+  int16_t* posbuf;  // [n_chains][Ws*32]
+  dbl2* cp2;        // [n_chains][n_int]
+  // init / eval
+  int slices_given;
+  double* out_seq;   // [n_chains] cost summed in traversal order (get_cost)
+  double* out_maxw;  // [n_chains] max log2 width after slicing
+};
+
+// ------------------------------------------------------------------------------------------ Philox
+TNB_D TNB_INLINE void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                   uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+TNB_D TNB_INLINE double uniform_from(uint32_t lo, uint32_t hi) {
+  // libstdc++ generate_canonical<double,53> over a 32-bit engine: (lo + hi*2^32) / 2^64, kept below 1
+  double u = (double(lo) + double(hi) * 4294967296.0) * 5.42101086242752217003726400434970855712890625e-20;
+  if (u >= 1.0) u = 0.99999999999999988897769753748434595763683319091796875;
+  return u;
+}
+
+// Counter-based production RNG.  Vector index v counts "events" of the chain: one per sweep start (word 0
+// -> leaf) and one per level (word 0 -> D/E coin, words 1,2 -> uniform).  A tile generates TILE vectors at
+// a time, one per lane, and fetches them by shuffle, so the 10-round Philox costs 1/TILE per event.
+template <int TILE>
+struct RngPhilox {
+  uint32_t k0, k1, g0, g1;
+  unsigned long long v, blk;
+  uint32_t r0, r1, r2, r3;
+  uint32_t e0, e1, e2;
+  TNB_D void load(const Params& P, int chain) {
+    const unsigned long long s = P.seeds[chain], g = P.chain_id0 + (unsigned long long)chain;
+    k0 = uint32_t(s); k1 = uint32_t(s >> 32); g0 = uint32_t(g); g1 = uint32_t(g >> 32);
+    v = P.rng_ctr[chain];
+    blk = ~0ull;
+    r0 = r1 = r2 = r3 = e0 = e1 = e2 = 0;
+  }
+  TNB_D void store(const Params& P, int chain) const { P.rng_ctr[chain] = v; }
+  TNB_D bool can_start(const Params&) const { return true; }
+  TNB_D TNB_INLINE void event(const Tile<TILE>& t) {
+    const unsigned long long b = v / TILE;
+    if (b != blk) {
+      blk = b;
+      const unsigned long long idx = b * TILE + (unsigned long long)t.tl;
+      philox4x32_10(uint32_t(idx), uint32_t(idx >> 32), g0, g1, k0, k1, r0, r1, r2, r3);
+    }
+    const int src = int(v % TILE);
+    e0 = t.bcast(r0, src);
+    e1 = t.bcast(r1, src);
+    e2 = t.bcast(r2, src);
+    ++v;
+  }
+  TNB_D TNB_INLINE uint32_t leaf_word(const Tile<TILE>& t) { event(t); return e0; }
+  TNB_D TNB_INLINE void begin_level(const Tile<TILE>& t) { event(t); }
+  TNB_D TNB_INLINE uint32_t coin_word(const Tile<TILE>&) { return e0; }
+  TNB_D TNB_INLINE double uniform(const Tile<TILE>&) { return uniform_from(e1, e2); }
+  // lane-local draw (slicer, executed by lane 0 only); re-synchronise with sync_from0 afterwards
+  TNB_D uint32_t local_next() {
+    uint32_t a, b, c, d;
+    philox4x32_10(uint32_t(v), uint32_t(v >> 32), g0, g1, k0, k1, a, b, c, d);
+    ++v;
+    return a;
+  }
+  TNB_D void sync_from0(const Tile<TILE>& t) { v = t.bcast_u64(v, 0); }
+  TNB_D unsigned long long words() const { return 0; }
+  TNB_D int overrun() const { return 0; }
+};
+
+// Raw 32-bit draw stream consumed in the reference's own order (std::mt19937 words, or a recorded stream).
+template <int TILE>
+struct RngStream {
+  const uint32_t* w;
+  unsigned long long cur, len;
+  int over;
+  TNB_D void load(const Params& P, int chain) {
+    w = P.stream + size_t(chain) * P.stream_len;
+    cur = P.cursor[chain];
+    len = P.stream_len;
+    over = P.overrun[chain];
+  }
+  TNB_D void store(const Params& P, int chain) const {
+    P.cursor[chain] = cur;
+    P.overrun[chain] = over;
+  }
+  TNB_D bool can_start(const Params& P) const { return !over && cur + P.reserve <= len; }
+  TNB_D TNB_INLINE uint32_t next() {
+    if (cur >= len) { over = 1; return 0u; }
+    return w[cur++];
+  }
+  TNB_D TNB_INLINE uint32_t leaf_word(const Tile<TILE>&) { return next(); }
+  TNB_D TNB_INLINE void begin_level(const Tile<TILE>&) {}
+  TNB_D TNB_INLINE uint32_t coin_word(const Tile<TILE>&) { return next(); }
+  TNB_D TNB_INLINE double uniform(const Tile<TILE>&) {
+    const uint32_t lo = next();
+    const uint32_t hi = next();
+    return uniform_from(lo, hi);
+  }
+  TNB_D uint32_t local_next() { return next(); }
+  TNB_D void sync_from0(const Tile<TILE>& t) {
+    cur = t.bcast_u64(cur, 0);
+    over = int(t.bcast(uint32_t(over), 0));
+  }
+  TNB_D unsigned long long words() const { return cur; }
+  TNB_D int overrun() const { return over; }
+};
+
+// ------------------------------------------------------------------------------------------ chain view
+template <int TILE, int WPL>
+struct ChainView {
+  const Params& P;
+  Tile<TILE> t;
+  int chain;
+  int16_t* par;
+  uint32_t* ch;
+  uint32_t* bits;
+  dbl2* cp;
+
+  TNB_D ChainView(const Params& P_, int chain_) : P(P_), chain(chain_) {
+    par = P.par + size_t(chain) * P.Npad;
+    ch = P.ch + size_t(chain) * P.n_int;
+    bits = P.bits + size_t(chain) * P.n_int * P.Ws;
+    cp = P.cp + size_t(chain) * P.n_int;
+  }
+  TNB_D TNB_INLINE void load_bits(int node, uint32_t (&o)[WPL]) const {
+    if (node < P.n) {
+      const uint32_t* src = P.leaf_bits + size_t(node) * P.Ws;
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) {
+        const int w = t.tl + k * TILE;
+        o[k] = w < P.W ? ldg(src + w) : 0u;
+      }
+    } else {
+      const uint32_t* src = bits + size_t(node - P.n) * P.Ws;
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) {
+        const int w = t.tl + k * TILE;
+        o[k] = w < P.W ? src[w] : 0u;
+      }
+    }
+  }
+  TNB_D TNB_INLINE void store_bits(int node, const uint32_t (&v)[WPL]) const {
+    uint32_t* dst = bits + size_t(node - P.n) * P.Ws;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      const int w = t.tl + k * TILE;
+      if (w < P.W) dst[w] = v[k];
+    }
+  }
+  TNB_D TNB_INLINE double pc_of(int node) const { return node < P.n ? 0.0 : cp[node - P.n].y; }
+  TNB_D TNB_INLINE double cost_of(int k) const {
+    // pow(dim, k) (infinite_memory/cost_model/simple.hpp:45); dim == 2: the exact power of two, +inf past 2^1023
+    if (P.dim2) return bits_to_f64((unsigned long long)(1023 + (k > 1024 ? 1024 : k)) << 52);
+    return ldg(P.pow_tab + k);
+  }
+  TNB_D TNB_INLINE float width_of(int k) const { return float(P.log2d * double(k)); }  // fw simple.hpp:47
+  // stackless post-order over the CURRENT topology, children[0] subtree first (utils.hpp:35-52)
+  TNB_D int po_first() const {
+    int x = P.N - 1;
+    while (x >= P.n) x = int(ch[x - P.n] & 0xffffu);
+    return x;
+  }
+  TNB_D int po_next(int x) const {
+    if (x == P.N - 1) return -1;
+    const int p = par[x];
+    const uint32_t c = ch[p - P.n];
+    if (int(c & 0xffffu) == x) {
+      x = int(c >> 16);
+      while (x >= P.n) x = int(ch[x - P.n] & 0xffffu);
+      return x;
+    }
+    return p;
+  }
+};
+
+template <int WPL>
+TNB_D TNB_INLINE uint32_t popc_or3(const uint32_t (&a)[WPL], const uint32_t (&b)[WPL], const uint32_t (&c)[WPL]) {
+  uint32_t k = 0;
+#pragma unroll
+  for (int i = 0; i < WPL; ++i) k += popc32(a[i] | b[i] | c[i]);
+  return k;
+}
+
+// Post-order cost pass (CostCache ctor, infinite_memory/utils.hpp:32-56; with slices finite_width/utils.hpp:36-45).
+// Optionally (re)builds the index sets of internal nodes and tracks get_cost's sequential sum and the widest node.
+template <int TILE, int WPL, bool BUILD>
+TNB_D void cost_pass(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL], dbl2* dst, double& seq,
+                     uint32_t& maxk) {
+  const Params& P = c.P;
+  seq = 0.0;
+  maxk = 0;
+  for (int z = c.po_first(); z >= 0; z = c.po_next(z)) {
+    uint32_t x[WPL];
+    if (z < P.n) {
+      if (BUILD) {
+        c.load_bits(z, x);
+        uint32_t k = 0;
+#pragma unroll
+        for (int i = 0; i < WPL; ++i) k += popc32(x[i] & ~S[i]);
+        k = c.t.sum(k);
+        maxk = k > maxk ? k : maxk;
+      }
+      continue;
+    }
+    const uint32_t cc_ = c.ch[z - P.n];
+    const int a = int(cc_ & 0xffffu), b = int(cc_ >> 16);
+    uint32_t xa[WPL], xb[WPL];
+    c.load_bits(a, xa);
+    c.load_bits(b, xb);
+    uint32_t kk = popc_or3<WPL>(xa, xb, S);
+    if (BUILD) {
+      uint32_t k = 0;
+#pragma unroll
+      for (int i = 0; i < WPL; ++i) {
+        x[i] = xa[i] ^ xb[i];
+        k += popc32(x[i] & ~S[i]);
+      }
+      c.store_bits(z, x);
+      kk |= k << 16;
+    }
+    kk = c.t.sum(kk);
+    if (BUILD) {
+      const uint32_t k = kk >> 16;
+      maxk = k > maxk ? k : maxk;
+      kk &= 0xffffu;
+    }
+    const double cost = c.cost_of(int(kk));
+    const double pa = a < P.n ? 0.0 : dst[a - P.n].y;
+    const double pb = b < P.n ? 0.0 : dst[b - P.n].y;
+    dst[z - P.n] = make_dbl2(cost, cost + pa + pb);
+    seq += cost;
+  }
+}
+
+// Index sets of internal nodes only (needed before the slicer can run at construction time).
+template <int TILE, int WPL>
+TNB_D void build_bits(const ChainView<TILE, WPL>& c) {
+  const Params& P = c.P;
+  for (int z = c.po_first(); z >= 0; z = c.po_next(z)) {
+    if (z < P.n) continue;
+    const uint32_t cc_ = c.ch[z - P.n];
+    uint32_t xa[WPL], xb[WPL];
+    c.load_bits(int(cc_ & 0xffffu), xa);
+    c.load_bits(int(cc_ >> 16), xb);
+#pragma unroll
+    for (int i = 0; i < WPL; ++i) xa[i] ^= xb[i];
+    c.store_bits(z, xa);
+  }
+}
+
+// Greedy slicer (finite_width/greedy/utils.hpp:24-125, skip_slices = nullopt, uniform dims), including
+// libstdc++'s std::shuffle / uniform_int_distribution draw pattern so that stream modes stay bit-exact.
+template <int TILE, int WPL, class Rng>
+TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2)[WPL]) {
+  const Params& P = c.P;
+  const Tile<TILE>& t = c.t;
+  uint16_t* nbig = P.nbig + size_t(c.chain) * P.Ws * 32;
+  int16_t* pos = P.posbuf + size_t(c.chain) * P.Ws * 32;
+#pragma unroll
+  for (int k = 0; k < WPL; ++k) {
+    S2[k] = 0u;
+    const int w = t.tl + k * TILE;
+    if (w < P.W)
+      for (int b = 0; b < 32; ++b) nbig[w * 32 + b] = 0;
+  }
+  // n_big_tensors (:41-47): every node, leaves included
+  for (int z = 0; z < P.N; ++z) {
+    uint32_t x[WPL];
+    c.load_bits(z, x);
+    uint32_t k = 0;
+#pragma unroll
+    for (int i = 0; i < WPL; ++i) k += popc32(x[i]);
+    k = t.sum(k);
+    if (c.width_of(int(k)) > P.max_width) {
+#pragma unroll
+      for (int i = 0; i < WPL; ++i) {
+        const int w = t.tl + i * TILE;
+        uint32_t v = x[i];
+        while (v) {
+          nbig[w * 32 + ctz32(v)]++;
+          v &= v - 1;
+        }
+      }
+    }
+  }
+  t.sync();
+  for (int z = c.po_first(); z >= 0; z = c.po_next(z)) {
+    uint32_t x[WPL];
+    c.load_bits(z, x);
+    uint32_t k = 0, ks = 0;
+#pragma unroll
+    for (int i = 0; i < WPL; ++i) {
+      k += popc32(x[i]);
+      x[i] &= ~S2[i];
+      ks += popc32(x[i]);
+    }
+    k = t.sum(k | (ks << 16));
+    ks = k >> 16;
+    k &= 0xffffu;
+    if (!(c.width_of(int(k)) > P.max_width)) continue;
+    float sw = c.width_of(int(ks));
+    if (!(sw > P.max_width)) continue;
+    // ascending positions of the still unsliced indices of this node
+    uint32_t np = 0;
+#pragma unroll
+    for (int i = 0; i < WPL; ++i) {
+      uint32_t tot;
+      uint32_t off = np + t.excl_scan_sum(uint32_t(popc32(x[i])), tot);
+      const int w = t.tl + i * TILE;
+      uint32_t v = x[i];
+      while (v) {
+        pos[off++] = int16_t(w * 32 + ctz32(v));
+        v &= v - 1;
+      }
+      np += tot;
+    }
+    t.sync();
+    if (t.tl == 0) {
+      auto nd = [&](uint32_t range) -> uint32_t {  // uniform_int_distribution, 32-bit URNG (Lemire)
+        unsigned long long prod = (unsigned long long)rng.local_next() * range;
+        uint32_t low = uint32_t(prod);
+        if (low < range) {
+          const uint32_t thr = (0u - range) % range;
+          while (low < thr) {
+            prod = (unsigned long long)rng.local_next() * range;
+            low = uint32_t(prod);
+            if (rng.overrun()) break;
+          }
+        }
+        return uint32_t(prod >> 32);
+      };
+      auto swp = [&](uint32_t a, uint32_t b) {
+        const int16_t tmp = pos[a];
+        pos[a] = pos[b];
+        pos[b] = tmp;
+      };
+      // std::shuffle (GCC 13 bits/stl_algo.h:3768-3799), two swaps per draw
+      uint32_t i = 1;
+      if ((np % 2u) == 0u) {
+        swp(1, nd(2));
+        i = 2;
+      }
+      while (i != np) {
+        const uint32_t r = i + 1;
+        const uint32_t xx = nd(r * (r + 1));
+        swp(i, xx / (r + 1));
+        ++i;
+        swp(i, xx % (r + 1));
+        ++i;
+      }
+      // std::stable_sort by n_big_tensors, descending (:85); insertion sort is stable
+      for (uint32_t a = 1; a < np; ++a) {
+        const int16_t key = pos[a];
+        const uint16_t kb = nbig[key];
+        int b = int(a) - 1;
+        while (b >= 0 && kb > nbig[pos[b]]) {
+          pos[b + 1] = pos[b];
+          --b;
+        }
+        pos[b + 1] = key;
+      }
+    }
+    rng.sync_from0(t);
+    t.sync();
+    uint32_t m = 0;
+    const float dw = float(-P.log2d);  // get_delta_width for a present index (fw simple.hpp:60-76)
+    while (m < np) {
+      sw += dw;
+      ++m;
+      if (sw <= P.max_width) break;
+    }
+    for (uint32_t j = 0; j < m; ++j) {
+      const int idx = pos[j];
+      const int w = idx >> 5;
+#pragma unroll
+      for (int i = 0; i < WPL; ++i)
+        if (w == t.tl + i * TILE) S2[i] |= 1u << (idx & 31);
+    }
+    t.sync();
+  }
+}
+
+template <int TILE, int WPL>
+TNB_D void snapshot_best(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL], bool finite) {
+  const Params& P = c.P;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(c.par);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(P.bpar + size_t(c.chain) * P.Npad);
+  for (int i = c.t.tl; i < P.Npad / 2; i += TILE) dst[i] = src[i];
+  uint32_t* dch = P.bch + size_t(c.chain) * P.n_int;
+  for (int i = c.t.tl; i < P.n_int; i += TILE) dch[i] = c.ch[i];
+  if (finite) {
+    uint32_t* ds = P.bslices + size_t(c.chain) * P.Ws;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      const int w = c.t.tl + k * TILE;
+      if (w < P.W) ds[w] = S[k];
+    }
+  }
+}
+
+template <int TILE, int WPL>
+TNB_D void load_slices(const ChainView<TILE, WPL>& c, uint32_t (&S)[WPL]) {
+  const uint32_t* s = c.P.slices + size_t(c.chain) * c.P.Ws;
+#pragma unroll
+  for (int k = 0; k < WPL; ++k) {
+    const int w = c.t.tl + k * TILE;
+    S[k] = w < c.P.W ? s[w] : 0u;
+  }
+}
+template <int TILE, int WPL>
+TNB_D void store_slices(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL]) {
+  uint32_t* s = c.P.slices + size_t(c.chain) * c.P.Ws;
+#pragma unroll
+  for (int k = 0; k < WPL; ++k) {
+    const int w = c.t.tl + k * TILE;
+    if (w < c.P.W) s[w] = S[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ construction
+template <int TILE, int WPL, bool FINITE, class Rng>
+TNB_D void chain_init(const Params& P, int chain) {
+  ChainView<TILE, WPL> c(P, chain);
+  uint32_t S[WPL];
+#pragma unroll
+  for (int k = 0; k < WPL; ++k) S[k] = 0u;
+  if (P.n_int == 0) {  // single tensor: nothing to contract
+    P.total[chain] = 0.0;
+    P.min_total[chain] = 0.0;
+    if (P.out_seq) P.out_seq[chain] = 0.0;
+    if (P.out_maxw) P.out_maxw[chain] = 0.0;
+    return;
+  }
+  if (FINITE) {
+    if (P.slices_given) {
+      load_slices(c, S);
+    } else {
+      // reference ctor order: seed PRNG -> WidthCache -> slices (consumes the PRNG) -> CostCache
+      build_bits(c);
+      Rng rng;
+      rng.load(P, chain);
+      get_slices_dev(c, rng, S);
+      rng.store(P, chain);
+      store_slices(c, S);
+    }
+  }
+  double seq;
+  uint32_t maxk;
+  cost_pass<TILE, WPL, true>(c, S, c.cp, seq, maxk);
+  const double rootpc = c.cp[P.n_int - 1].y;
+  P.total[chain] = rootpc;
+  P.min_total[chain] = seq;  // get_cost(min_ctree) sums in traversal order (infinite_memory/utils.hpp:102-116)
+  if (P.out_seq) P.out_seq[chain] = seq;
+  if (P.out_maxw) P.out_maxw[chain] = P.log2d * double(maxk);
+  if (P.bpar) snapshot_best(c, S, FINITE);
+}
+
+// ------------------------------------------------------------------------------------------ sweeps
+template <int TILE, int WPL, bool FINITE, class Rng>
+TNB_D void chain_sweeps(const Params& P, int chain) {
+  ChainView<TILE, WPL> c(P, chain);
+  const Tile<TILE>& t = c.t;
+  const int n = P.n, root = P.N - 1;
+  if (P.n_int == 0) {
+    P.sweep_idx[chain] = P.until;
+    return;
+  }
+  Rng rng;
+  rng.load(P, chain);
+  long long s = P.sweep_idx[chain];
+  double min_total = P.min_total[chain];
+  unsigned long long n_prop = 0, n_acc = 0, n_wrej = 0;
+  uint32_t S[WPL];
+#pragma unroll
+  for (int k = 0; k < WPL; ++k) S[k] = 0u;
+  if (FINITE) load_slices(c, S);
+
+  for (; s < P.until; ++s) {
+    if (!rng.can_start(P)) break;
+    const double beta = P.betas[s < P.n_betas ? s : P.n_betas - 1];
+    const int leaf = int(rng.leaf_word(t) % uint32_t(n));  // optimizer.hpp:103
+    int B = c.par[leaf];
+    double total = c.cp[root - n].y;                       // :112
+    double root_pc = total;
+    {
+      uint32_t cw = c.ch[B - n];
+      int p0 = int(cw & 0xffffu), p1 = int(cw >> 16);
+      uint32_t b0[WPL], b1[WPL];
+      c.load_bits(p0, b0);
+      c.load_bits(p1, b1);
+      double pc0 = c.pc_of(p0), pc1 = c.pc_of(p1);
+      double ccB = c.cp[B - n].x;
+      int A = c.par[B];
+      while (A >= 0) {
+        // get_ctree_nn (optimize/optimizer.hpp:86-172)
+        uint32_t aw = c.ch[A - n];
+        int a0 = int(aw & 0xffffu), a1 = int(aw >> 16);
+        const bool bslot0 = (a0 == B);
+        int C = bslot0 ? a1 : a0;
+        uint32_t bC[WPL];
+        c.load_bits(C, bC);
+        double pcC = c.pc_of(C);
+        double ccA = c.cp[A - n].x;
+        bool l0 = false, l1 = false;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) {
+          l0 |= (b0[k] & bC[k]) != 0u;
+          l1 |= (b1[k] & bC[k]) != 0u;
+        }
+        const bool i0 = t.any(l0), i1 = t.any(l1);
+        rng.begin_level(t);
+        bool pick0;
+        if (P.dsi || (i0 && i1)) pick0 = (rng.coin_word(t) & 1u) != 0u;
+        else pick0 = i0;
+        int E = pick0 ? p1 : p0;  // D = the other child
+        uint32_t bD[WPL], bE[WPL], nb[WPL];
+        uint32_t kpack = 0, ks = 0;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) {
+          bD[k] = pick0 ? b0[k] : b1[k];
+          bE[k] = pick0 ? b1[k] : b0[k];
+          nb[k] = bD[k] ^ bC[k];  // new inds of B (infinite_memory/optimizer.hpp:147; no hyper-indices)
+          kpack += uint32_t(popc32(nb[k] | bE[k] | S[k])) | (uint32_t(popc32(bD[k] | bC[k] | S[k])) << 16);
+          if (FINITE) ks += uint32_t(popc32(nb[k] & ~S[k]));
+        }
+        const double pcD = pick0 ? pc0 : pc1;
+        double pcE = pick0 ? pc1 : pc0;
+        ++n_prop;
+        bool gate = true;
+        if (FINITE) {  // finite_width/greedy/optimizer.hpp:176-188
+          ks = t.sum(ks);
+          gate = c.width_of(int(ks)) <= P.max_width;
+          if (!gate) ++n_wrej;
+        }
+        bool acc = false;
+        double nA = 0.0, nB = 0.0, delta = 0.0;
+        if (gate) {
+          kpack = t.sum(kpack);
+          nA = c.cost_of(int(kpack & 0xffffu));  // cost(new_B | E [| slices])
+          nB = c.cost_of(int(kpack >> 16));      // cost(D | C [| slices])
+          delta = (nB - ccB) + (nA - ccA);       // :158, this association order
+          const double u = rng.uniform(t);       // always drawn (:162)
+          double p;
+          if (P.prob_kind == kProbMH) {          // prob/mh.hpp:45-59
+            if (delta <= 0.0) p = 1.0;
+            else if (total == 0.0) p = 0.0;
+            else p = pow(1.0 + delta / total, -beta);
+          } else if (P.prob_kind == kProbGreedy) {
+            p = delta <= 0.0 ? 1.0 : 0.0;
+          } else {
+            p = 1.0;
+          }
+          acc = u <= p;
+        }
+        uint32_t bB[WPL];
+        if (acc) {
+          // Tree::swap_with_nn(E): E <-> C, child slots preserved (tree.hpp:141-192)
+          if (bslot0) a1 = E; else a0 = E;
+          if (pick0) p1 = C; else p0 = C;
+          c.ch[A - n] = uint32_t(a0) | (uint32_t(a1) << 16);
+          c.ch[B - n] = uint32_t(p0) | (uint32_t(p1) << 16);
+          c.par[C] = int16_t(B);
+          c.par[E] = int16_t(A);
+          c.store_bits(B, nb);
+          ccB = nB;
+          ccA = nA;
+          total += delta;
+          ++n_acc;
+          {
+            const int ti = C; C = E; E = ti;
+            const double td = pcC; pcC = pcE; pcE = td;
+          }
+#pragma unroll
+          for (int k = 0; k < WPL; ++k) {
+            bB[k] = nb[k];
+            bC[k] = bE[k];  // the node now called C is the old E
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < WPL; ++k) bB[k] = bD[k] ^ bE[k];
+        }
+        // propagate partial costs (:185-188), post-swap names
+        const double pcB = pcD + pcE + ccB;
+        const double pcA = pcB + pcC + ccA;
+        c.cp[B - n] = make_dbl2(ccB, pcB);
+        c.cp[A - n] = make_dbl2(ccA, pcA);
+        root_pc = pcA;
+        // next level: B <- A, whose children are (a0, a1) = {B, C} in slot order
+        p0 = a0;
+        p1 = a1;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) {
+          b0[k] = bslot0 ? bB[k] : bC[k];
+          b1[k] = bslot0 ? bC[k] : bB[k];
+        }
+        pc0 = bslot0 ? pcB : pcC;
+        pc1 = bslot0 ? pcC : pcB;
+        ccB = ccA;
+        B = A;
+        A = c.par[B];
+      }
+    }
+    if (FINITE && P.every > 0 && (s % P.every) == 0) {  // finite_width/greedy/optimizer.hpp:360-376
+      bool anyS = false;
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) anyS |= S[k] != 0u;
+      if (t.any(anyS)) {
+        uint32_t S2[WPL];
+        get_slices_dev(c, rng, S2);
+        dbl2* cp2 = P.cp2 + size_t(chain) * P.n_int;
+        double seq;
+        uint32_t maxk;
+        cost_pass<TILE, WPL, false>(c, S2, cp2, seq, maxk);
+        const double r2 = cp2[P.n_int - 1].y;
+        if (r2 < root_pc) {
+          t.sync();
+          for (int i = t.tl; i < P.n_int; i += TILE) c.cp[i] = cp2[i];
+          t.sync();
+#pragma unroll
+          for (int k = 0; k < WPL; ++k) S[k] = S2[k];
+          store_slices(c, S);
+          root_pc = r2;
+        }
+      }
+    }
+    if (root_pc < min_total) {  // :197-201
+      min_total = root_pc;
+      snapshot_best(c, S, FINITE);
+    }
+    if (rng.overrun()) { ++s; break; }
+  }
+  rng.store(P, chain);
+  P.sweep_idx[chain] = s;
+  P.min_total[chain] = min_total;
+  P.total[chain] = c.cp[root - n].y;
+  P.n_prop[chain] += n_prop;
+  P.n_acc[chain] += n_acc;
+  P.n_wrej[chain] += n_wrej;
+}
+
+}  // namespace tnb

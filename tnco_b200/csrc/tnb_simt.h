@@ -1,0 +1,127 @@
+// SIMT portability layer for the chain kernels.
+//
+// Product build (nvcc, sm_100a): a chain is owned by a TILE of 4/8/16/32 lanes of one warp; tile
+// collectives map to VOTE / REDUX / SHFL with the tile's member mask.
+// TNB_EMU build (plain g++, used ONLY by tests/emu to exercise the kernel logic on machines without a GPU;
+// it is never loaded by the tnco_b200 package): TILE == 1, the collectives are identities.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#if defined(TNB_EMU)
+#define TNB_HD
+#define TNB_D
+#define TNB_INLINE inline
+struct tnb_double2 {
+  double x, y;
+};
+typedef tnb_double2 dbl2;
+static inline dbl2 make_dbl2(double x, double y) { return dbl2{x, y}; }
+#else
+#include <cuda_runtime.h>
+#define TNB_HD __host__ __device__
+#define TNB_D __device__
+#define TNB_INLINE __forceinline__
+typedef double2 dbl2;
+static __device__ __forceinline__ dbl2 make_dbl2(double x, double y) { return make_double2(x, y); }
+#endif
+
+namespace tnb {
+
+template <int TILE>
+struct Tile {
+#if defined(TNB_EMU)
+  static_assert(TILE == 1, "the emulation build runs one lane per chain");
+  int tl = 0;
+  TNB_D bool any(bool p) const { return p; }
+  TNB_D uint32_t sum(uint32_t v) const { return v; }
+  TNB_D uint32_t bcast(uint32_t v, int) const { return v; }
+  TNB_D void sync() const {}
+#else
+  unsigned mask;
+  int tl;  // lane within the tile
+  TNB_D Tile() {
+    const int lane = threadIdx.x & 31;
+    tl = lane & (TILE - 1);
+    mask = TILE == 32 ? 0xffffffffu : (((1u << TILE) - 1u) << (lane & ~(TILE - 1)));
+  }
+  TNB_D TNB_INLINE bool any(bool p) const { return __ballot_sync(mask, p) != 0u; }
+  TNB_D TNB_INLINE uint32_t sum(uint32_t v) const { return __reduce_add_sync(mask, v); }
+  TNB_D TNB_INLINE uint32_t bcast(uint32_t v, int src) const { return __shfl_sync(mask, v, src, TILE); }
+  TNB_D TNB_INLINE void sync() const { __syncwarp(mask); }
+#endif
+  // exclusive prefix sum over the tile's lanes (lane order); returns this lane's offset
+  TNB_D TNB_INLINE uint32_t excl_scan_sum(uint32_t v, uint32_t& total) const {
+#if defined(TNB_EMU)
+    total = v;
+    return 0;
+#else
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < TILE; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(mask, x, d, TILE);
+      if (tl >= d) x += y;
+    }
+    total = __shfl_sync(mask, x, TILE - 1, TILE);
+    return x - v;
+#endif
+  }
+  TNB_D TNB_INLINE double bcast_f64(double v, int src) const {
+#if defined(TNB_EMU)
+    (void)src;
+    return v;
+#else
+    return __shfl_sync(mask, v, src, TILE);
+#endif
+  }
+  TNB_D TNB_INLINE unsigned long long bcast_u64(unsigned long long v, int src) const {
+#if defined(TNB_EMU)
+    (void)src;
+    return v;
+#else
+    return __shfl_sync(mask, v, src, TILE);
+#endif
+  }
+};
+
+TNB_D TNB_INLINE int popc32(uint32_t x) {
+#if defined(TNB_EMU)
+  return __builtin_popcount(x);
+#else
+  return __popc(x);
+#endif
+}
+TNB_D TNB_INLINE int ctz32(uint32_t x) {
+#if defined(TNB_EMU)
+  return __builtin_ctz(x);
+#else
+  return __ffs(int(x)) - 1;
+#endif
+}
+template <class T>
+TNB_D TNB_INLINE T ldg(const T* p) {
+#if defined(TNB_EMU)
+  return *p;
+#else
+  return __ldg(p);
+#endif
+}
+TNB_D TNB_INLINE double bits_to_f64(unsigned long long v) {
+#if defined(TNB_EMU)
+  double d;
+  std::memcpy(&d, &v, 8);
+  return d;
+#else
+  return __longlong_as_double((long long)v);
+#endif
+}
+TNB_D TNB_INLINE uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(TNB_EMU)
+  return uint32_t((uint64_t(a) * uint64_t(b)) >> 32);
+#else
+  return __umulhi(a, b);
+#endif
+}
+
+}  // namespace tnb

@@ -1,0 +1,228 @@
+"""Thin numpy-facing wrapper over the C-ABI (include/tnco_b200.h).  One Engine == one GPU.
+
+Host code only marshals buffers; all optimisation work happens in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import (LAYOUT_AUTO, PROB_MH, RNG_MT19937, RNG_PHILOX, RNG_REPLAY, TREES_GREEDY,  # noqa: F401
+                   TREES_RANDOM)
+
+
+def _ptr(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def pack_leaf_bits(ts_inds, n_inds):
+    """Per-tensor lists of index positions -> [n][W32] uint32 bitsets (bit i -> word i//32, bit i%32)."""
+    W = (int(n_inds) + 31) // 32
+    out = np.zeros((len(ts_inds), W), np.uint32)
+    for t, xs in enumerate(ts_inds):
+        for x in xs:
+            out[t, x >> 5] |= np.uint32(1 << (x & 31))
+    return out
+
+
+def unpack_bits(row):
+    """uint32 bitset row -> sorted list of positions."""
+    return [w * 32 + b for w, v in enumerate(np.asarray(row).tolist()) for b in range(32) if (v >> b) & 1]
+
+
+# ------------------------------------------------------------------------------------------ host helpers
+def random_trees(leaf_bits, n_inds, seeds, method=TREES_GREEDY, n_threads=0):
+    """Initial contraction trees, one per seed: (parent, child0, child1), each [n_trees][2n-1] int32."""
+    L = _lib.lib()
+    lb = _c(leaf_bits, np.uint32)
+    n = lb.shape[0]
+    seeds = _c(seeds, np.uint64)
+    T, N = len(seeds), 2 * n - 1
+    p, a, b = (np.empty((T, N), np.int32) for _ in range(3))
+    rc = L.tnb_random_trees(n, int(n_inds), _ptr(lb, C.c_uint32), T, _ptr(seeds, C.c_uint64), int(method),
+                            int(n_threads), _ptr(p, C.c_int32), _ptr(a, C.c_int32), _ptr(b, C.c_int32))
+    if rc:
+        raise ValueError(L.tnb_last_error(None).decode())
+    return p, a, b
+
+
+def tree_to_path(child0, child1):
+    """Tree(s) -> linear (einsum) path(s), [n_trees][n-1][2] (ContractionTree.path(), tnco/ctree.py:350-388)."""
+    L = _lib.lib()
+    a, b = _c(child0, np.int32), _c(child1, np.int32)
+    single = a.ndim == 1
+    a2, b2 = np.atleast_2d(a), np.atleast_2d(b)
+    T, N = a2.shape
+    n = (N + 1) // 2
+    out = np.empty((T, max(n - 1, 0), 2), np.int32)
+    rc = L.tnb_tree_to_path(n, T, _ptr(a2, C.c_int32), _ptr(b2, C.c_int32), _ptr(out, C.c_int32))
+    if rc:
+        raise ValueError(L.tnb_last_error(None).decode())
+    return out[0] if single else out
+
+
+def path_to_tree(path, n_leaves):
+    """Linear path -> (parent, child0, child1) in reference numbering (tnco/ctree.py:108-131,208-218)."""
+    L = _lib.lib()
+    pth = _c(path, np.int32).reshape(-1, 2)
+    n = int(n_leaves)
+    if len(pth) != n - 1:
+        raise ValueError('a full path needs n_leaves-1 contractions')
+    p, a, b = (np.empty(2 * n - 1, np.int32) for _ in range(3))
+    rc = L.tnb_path_to_tree(n, _ptr(pth, C.c_int32), _ptr(p, C.c_int32), _ptr(a, C.c_int32), _ptr(b, C.c_int32))
+    if rc:
+        raise ValueError(L.tnb_last_error(None).decode())
+    return p, a, b
+
+
+def mt19937_stream(seed, n):
+    out = np.empty(int(n), np.uint32)
+    _lib.lib().tnb_mt19937_stream(int(seed) & 0xFFFFFFFF, int(n), _ptr(out, C.c_uint32))
+    return out
+
+
+# ------------------------------------------------------------------------------------------ engine
+class Engine:
+    """Batched SA chains on one B200."""
+
+    def __init__(self, device=0):
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        rc = self._L.tnb_create(C.byref(h), int(device))
+        if rc:
+            raise EngineError(self._L.tnb_last_error(None).decode())
+        self._h = h
+        self.n = self.N = self.W = self.n_chains = 0
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._L.tnb_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, rc):
+        if rc:
+            msg = self._L.tnb_last_error(self._h).decode()
+            if 'Precision is too low' in msg or 'invalid' in msg or 'not supported' in msg:
+                raise ValueError(msg)
+            raise EngineError(msg)
+
+    def set_network(self, leaf_bits, n_inds, dim=2, dims=None):
+        lb = _c(leaf_bits, np.uint32)
+        self.n, self.n_inds = lb.shape[0], int(n_inds)
+        self.N, self.W = 2 * self.n - 1, (self.n_inds + 31) // 32
+        if lb.shape != (self.n, self.W):
+            raise ValueError('leaf_bits must be [n_leaves][ceil(n_inds/32)]')
+        d = None if dims is None else _c(dims, np.uint64)
+        self._chk(self._L.tnb_set_network(self._h, self.n, self.n_inds, _ptr(lb, C.c_uint32), int(dim),
+                                          _ptr(d, C.c_uint64)))
+        return self
+
+    def set_mode(self, max_width=None, update_slices_every=10, disable_shared_inds=False, prob=PROB_MH,
+                 rng=RNG_PHILOX, layout=LAYOUT_AUTO):
+        mw = -1.0 if (max_width is None or math.isinf(max_width)) else float(max_width)
+        self.finite = mw >= 0
+        self._chk(self._L.tnb_set_mode(self._h, mw, int(update_slices_every), int(bool(disable_shared_inds)),
+                                       int(prob), int(rng), int(layout)))
+        return self
+
+    def set_chains(self, parent, child0, child1, seeds, chain_id0=0):
+        p, a, b = (np.atleast_2d(_c(x, np.int32)) for x in (parent, child0, child1))
+        s = _c(seeds, np.uint64).reshape(-1)
+        if p.shape != (len(s), self.N) or a.shape != p.shape or b.shape != p.shape:
+            raise ValueError('trees must be [n_chains][2*n_leaves-1] with one seed per chain')
+        self.n_chains = len(s)
+        self._chk(self._L.tnb_set_chains(self._h, self.n_chains, _ptr(p, C.c_int32), _ptr(a, C.c_int32),
+                                         _ptr(b, C.c_int32), _ptr(s, C.c_uint64), int(chain_id0)))
+        return self
+
+    def set_stream(self, words):
+        w = np.atleast_2d(_c(words, np.uint32))
+        if w.shape[0] != self.n_chains:
+            raise ValueError('one stream per chain')
+        self._chk(self._L.tnb_set_stream(self._h, _ptr(w, C.c_uint32), w.shape[1]))
+        return self
+
+    def set_betas(self, betas):
+        b = _c(betas, np.float64).reshape(-1)
+        self._chk(self._L.tnb_set_betas(self._h, _ptr(b, C.c_double), len(b)))
+        return self
+
+    def run(self, until_sweep):
+        self._chk(self._L.tnb_run(self._h, int(until_sweep)))
+        return self
+
+    def timing(self):
+        ms, n = C.c_double(0), C.c_int64(0)
+        self._chk(self._L.tnb_get_timing(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def costs(self):
+        t, m = np.empty(self.n_chains), np.empty(self.n_chains)
+        self._chk(self._L.tnb_get_costs(self._h, _ptr(t, C.c_double), _ptr(m, C.c_double)))
+        return t, m
+
+    def trees(self, best=False, chain0=0, n=None):
+        n = self.n_chains - chain0 if n is None else n
+        p, a, b = (np.empty((n, self.N), np.int32) for _ in range(3))
+        self._chk(self._L.tnb_get_trees(self._h, int(best), int(chain0), int(n), _ptr(p, C.c_int32),
+                                        _ptr(a, C.c_int32), _ptr(b, C.c_int32)))
+        return p, a, b
+
+    def bits(self, chain):
+        o = np.empty((self.N, self.W), np.uint32)
+        self._chk(self._L.tnb_get_bits(self._h, int(chain), _ptr(o, C.c_uint32)))
+        return o
+
+    def slices(self, best=False, chain0=0, n=None):
+        n = self.n_chains - chain0 if n is None else n
+        o = np.empty((n, self.W), np.uint32)
+        self._chk(self._L.tnb_get_slices(self._h, int(best), int(chain0), int(n), _ptr(o, C.c_uint32)))
+        return o
+
+    def progress(self):
+        s = np.empty(self.n_chains, np.int64)
+        p, a, w, d = (np.empty(self.n_chains, np.uint64) for _ in range(4))
+        self._chk(self._L.tnb_get_progress(self._h, _ptr(s, C.c_int64), _ptr(p, C.c_uint64), _ptr(a, C.c_uint64),
+                                           _ptr(w, C.c_uint64), _ptr(d, C.c_uint64)))
+        return dict(sweeps=s, proposals=p, accepts=a, width_rejects=w, words=d)
+
+    def counters(self):
+        p, a, s = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._chk(self._L.tnb_get_counters(self._h, C.byref(p), C.byref(a), C.byref(s)))
+        return dict(proposals=p.value, accepts=a.value, sweeps=s.value)
+
+    def eval_cost(self, parent, child0, child1, slices=None):
+        """(total cost summed in traversal order, partial_cost[root], max log2 width after slicing) per tree."""
+        p, a, b = (np.atleast_2d(_c(x, np.int32)) for x in (parent, child0, child1))
+        T = p.shape[0]
+        sl = None if slices is None else np.atleast_2d(_c(slices, np.uint32))
+        ts, tp, mw = np.empty(T), np.empty(T), np.empty(T)
+        self._chk(self._L.tnb_eval_cost(self._h, T, _ptr(p, C.c_int32), _ptr(a, C.c_int32), _ptr(b, C.c_int32),
+                                        _ptr(sl, C.c_uint32), _ptr(ts, C.c_double), _ptr(tp, C.c_double),
+                                        _ptr(mw, C.c_double)))
+        return ts, tp, mw
+
+    def config(self):
+        v = [C.c_int(0) for _ in range(4)]
+        self._chk(self._L.tnb_get_config(self._h, *[C.byref(x) for x in v]))
+        return dict(tile=v[0].value, words_per_lane=v[1].value, layout=v[2].value,
+                    state_bytes_per_chain=v[3].value)
