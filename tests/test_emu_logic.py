@@ -1,0 +1,48 @@
+"""Kernel LOGIC on CPU: tests/emu builds the very same kernel sources (tnb_kernels.h) with one lane per chain
+and host memory as the "device", so the sweep / slicer / init logic can be checked against the reference's
+golden vectors on machines without a GPU.  This is test infrastructure -- the tnco_b200 package never loads
+the emulation library; the real parity tests are tests/test_gpu_parity.py (-m gpu)."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+import test_gpu_parity as G
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope='module')
+def emu_lib():
+    subprocess.check_call(['make', '-C', os.path.join(HERE, 'emu')], stdout=subprocess.DEVNULL,
+                          stderr=subprocess.DEVNULL)
+    from tnco_b200 import _lib
+    return _lib.bind(ctypes.CDLL(os.path.join(HERE, 'emu', 'libtnb_emu.so')))
+
+
+@pytest.fixture()
+def emu(emu_lib, monkeypatch):
+    from tnco_b200 import _lib
+    monkeypatch.setattr(_lib, '_LIB', emu_lib)
+    yield
+
+
+@pytest.mark.parametrize('name', G.CASES)
+def test_emu_mt19937_matches_reference_golden(emu, name):
+    G.test_mt19937_mode_matches_reference_golden.__wrapped__(name) if hasattr(
+        G.test_mt19937_mode_matches_reference_golden, '__wrapped__') else G.test_mt19937_mode_matches_reference_golden(name)
+
+
+@pytest.mark.parametrize('name', ['reg64_inf', 'reg100_fw30', 'reg300_inf'])
+def test_emu_replay(emu, name):
+    G.test_replay_of_recorded_draw_stream_is_bit_exact(name)
+
+
+@pytest.mark.parametrize('n,dim', [(8, 2), (64, 2), (64, 3), (300, 2)])
+def test_emu_eval_cost(emu, n, dim):
+    G.test_eval_cost_matches_oracle(n, dim)
+
+
+def test_emu_philox(emu):
+    G.test_philox_chains_are_valid_and_deterministic()
