@@ -60,14 +60,20 @@ int tnb_random_trees(int n_leaves, int n_inds, const uint32_t* leaf_bits, int n_
                      int method, int n_threads, int32_t* parent, int32_t* child0, int32_t* child1);
 
 /* Tree -> linear (einsum) contraction path; replaces include/tnco/utils.hpp:54-71 get_contraction +
- * tnco/ctree.py:350-388 ContractionTree.path() with tensors_pos = identity.  path is [n_trees][n_leaves-1][2]. */
-int tnb_tree_to_path(int n_leaves, int n_trees, const int32_t* child0, const int32_t* child1, int32_t* path);
+ * tnco/ctree.py:350-388 ContractionTree.path().  The tree's leaf k is tensor tensors_pos[k] of a network of
+ * n_tensors tensors (tensors_pos == NULL: identity, n_tensors = n_leaves); positions in the path count all
+ * n_tensors tensors, as the reference's per-component paths do.  path is [n_trees][n_leaves-1][2]. */
+int tnb_tree_to_path(int n_leaves, int n_trees, const int32_t* child0, const int32_t* child1, int n_tensors,
+                     const int32_t* tensors_pos, int32_t* path);
 
 /* Linear path -> tree in reference numbering (tnco/ctree.py:108-131,208-218).  path is [n_leaves-1][2]. */
 int tnb_path_to_tree(int n_leaves, const int32_t* path, int32_t* parent, int32_t* child0, int32_t* child1);
 
 /* First n outputs of std::mt19937(seed) (include/tnco/optimize/optimizer.hpp:48,75). */
 void tnb_mt19937_stream(uint32_t seed, uint64_t n, uint32_t* out);
+/* Internal state of std::mt19937(seed) after n_draws outputs: the 624 words and the position that
+ * libstdc++'s operator<< prints (reference Optimizer.prng_state, optimize/optimizer.hpp:191-195). */
+void tnb_mt19937_state(uint32_t seed, uint64_t n_draws, uint32_t* state624, int32_t* pos);
 
 /* ---------------------------------------------------------------- engine */
 
@@ -128,6 +134,9 @@ int tnb_get_counters(tnb_engine* e, uint64_t* proposals, uint64_t* accepts, uint
 int tnb_eval_cost(tnb_engine* e, int n_trees, const int32_t* parent, const int32_t* child0,
                   const int32_t* child1, const uint32_t* slices, double* total_seq, double* total_pc,
                   double* max_width);
+
+/* Evict the L2 cache (writes a buffer larger than L2); benchmarking aid. */
+int tnb_flush_l2(tnb_engine* e);
 
 /* the layout / tile shape the engine picked: lanes per chain, words per lane, TNB_LAYOUT_* , smem bytes per chain */
 int tnb_get_config(tnb_engine* e, int* tile, int* words_per_lane, int* layout, int* state_bytes_per_chain);

@@ -25,9 +25,10 @@ SIGNATURES = {
     'tnb_version': (C.c_int, []),
     'tnb_last_error': (C.c_char_p, [C.c_void_p]),
     'tnb_random_trees': (C.c_int, [C.c_int, C.c_int, u32p, C.c_int, u64p, C.c_int, C.c_int, i32p, i32p, i32p]),
-    'tnb_tree_to_path': (C.c_int, [C.c_int, C.c_int, i32p, i32p, i32p]),
+    'tnb_tree_to_path': (C.c_int, [C.c_int, C.c_int, i32p, i32p, C.c_int, i32p, i32p]),
     'tnb_path_to_tree': (C.c_int, [C.c_int, i32p, i32p, i32p, i32p]),
     'tnb_mt19937_stream': (None, [C.c_uint32, C.c_uint64, u32p]),
+    'tnb_mt19937_state': (None, [C.c_uint32, C.c_uint64, u32p, i32p]),
     'tnb_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     'tnb_destroy': (None, [C.c_void_p]),
     'tnb_set_network': (C.c_int, [C.c_void_p, C.c_int, C.c_int, u32p, C.c_uint64, u64p]),
@@ -44,6 +45,7 @@ SIGNATURES = {
     'tnb_get_progress': (C.c_int, [C.c_void_p, i64p, u64p, u64p, u64p, u64p]),
     'tnb_get_counters': (C.c_int, [C.c_void_p, u64p, u64p, u64p]),
     'tnb_eval_cost': (C.c_int, [C.c_void_p, C.c_int, i32p, i32p, i32p, u32p, f64p, f64p, f64p]),
+    'tnb_flush_l2': (C.c_int, [C.c_void_p]),
     'tnb_get_config': (C.c_int, [C.c_void_p, intp, intp, intp, intp]),
 }
 

@@ -1,0 +1,151 @@
+"""Shared driver of ``Optimizer.optimize`` for both SA plugins (tnco/app/infinite_memory/sa.py:100-257 and
+tnco/app/finite_width/sa.py:116-289): argument checks, beta ramp, seeds, per-component runs, result assembly.
+The per-run loop of the reference (one process per run, one pybind call per sweep) is replaced by ONE batched
+engine run over all ``n_runs`` chains on the GPU."""
+from __future__ import annotations
+
+import functools as fts
+import operator as op
+import time
+from sys import stderr
+
+import numpy as np
+
+from .. import dist
+from ..engine import (Engine, RNG_MT19937, RNG_PHILOX, TREES_GREEDY, TREES_RANDOM, pack_leaf_bits, random_trees,
+                      tree_to_path, unpack_bits)
+from ..tn import get_connected_components, merge_contraction_paths
+from .app import cost_to_decimal
+
+
+def expand_betas(betas, n_steps):
+    """tnco/app/infinite_memory/sa.py:139-156."""
+    if n_steps is not None:
+        if int(n_steps) != n_steps or n_steps <= 0:
+            raise ValueError("'n_steps' must be a positive number.")
+        n_steps = int(n_steps)
+    if isinstance(betas, tuple) and len(betas) == 2:
+        if n_steps is None:
+            raise ValueError("'n_steps' must be provided if 'betas' has the format '(beta_min, beta_max)'.")
+        if betas[0] == betas[1]:
+            raise ValueError("'betas' must use the format '(beta_ini, beta_end)', with 'beta_ini != beta_end'.")
+        step = (betas[1] - betas[0]) / n_steps  # more_itertools.numeric_range: start + n*step
+        return np.array([betas[0] + n * step for n in range(n_steps)], np.float64)
+    b = np.array(list(betas), np.float64)
+    if n_steps is not None:
+        b = b[:n_steps]
+    if len(b) == 0:
+        raise ValueError("'betas' is empty.")
+    return b
+
+
+def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, deadline, stats):
+    """All runs of one connected component.  Returns per run: min cost (float), best tree -> path over all
+    tensors of tn, slices (index names)."""
+    ts = [tn.ts_inds[t] for t in comp]
+    inds = list(dict.fromkeys(x for xs in ts for x in xs))
+    pos = {x: k for k, x in enumerate(inds)}
+    dims = [tn.dims[x] for x in inds]
+    if any(d != dims[0] for d in dims):
+        raise NotImplementedError('tnco_b200: per-index dimensions are not supported yet (uniform dims only).')
+    if any(x in tn.output_inds for x in inds if sum(x in xs for xs in ts) > 1):
+        raise NotImplementedError('tnco_b200: hyper-indices are not supported yet.')
+    lb = pack_leaf_bits([[pos[x] for x in xs] for xs in ts], len(inds))
+    n_runs = len(seeds)
+    lo, hi = dist.shard(n_runs) if opt.distributed else (0, n_runs)
+    my_seeds = np.asarray(seeds[lo:hi], np.uint64)
+    n_local = hi - lo
+    t0 = time.perf_counter()
+    P, A, B = random_trees(lb, len(inds), my_seeds,
+                           method=TREES_GREEDY if opt.init_trees == 'greedy' else TREES_RANDOM)
+    stats['tree_gen_s'] += time.perf_counter() - t0
+    eng = Engine(dist.local_device(opt.device))
+    try:
+        eng.set_network(lb, len(inds), dim=dims[0])
+        eng.set_mode(max_width=opt.max_width if finite else None, update_slices_every=update_slices,
+                     rng=RNG_MT19937 if opt.rng == 'mt19937' else RNG_PHILOX)
+        eng.set_chains(P, A, B, my_seeds, chain_id0=lo)
+        eng.set_betas(betas)
+        n_steps = len(betas)
+        if deadline is None:
+            eng.run(n_steps)
+        else:  # timeout: the reference polls a stop flag every sweep (sa.py:201); here between launches
+            done, chunk = 0, 16
+            while done < n_steps and time.perf_counter() < deadline:
+                t1 = time.perf_counter()
+                done = min(n_steps, done + chunk)
+                eng.run(done)
+                if time.perf_counter() - t1 < 0.05:
+                    chunk *= 2
+        ms, nl = eng.timing()
+        stats['kernel_ms'] += ms
+        stats['launches'] += nl
+        c = eng.counters()
+        for k in ('proposals', 'accepts', 'sweeps'):
+            stats[k] += c[k]
+        _, mins = eng.costs()
+        bp, ba, bb = eng.trees(best=True)
+        sl = eng.slices(best=True) if finite else np.zeros((n_local, eng.W), np.uint32)
+        stats['config'] = eng.config()
+    finally:
+        eng.close()
+    # the one exchange step: global min + broadcast of the winning tree (reporting only)
+    if opt.distributed and dist.world()[1] > 1:
+        k = int(np.argmin(mins))
+        payload = np.concatenate([bp[k], ba[k], bb[k], sl[k].view(np.int32)])
+        stats['global_best'] = dist.global_best(float(mins[k]), payload)[0]
+        mins = dist.all_gather_rows(mins, n_runs)
+        ba, bb = dist.all_gather_rows(ba, n_runs), dist.all_gather_rows(bb, n_runs)
+        sl = dist.all_gather_rows(sl, n_runs)
+    paths = tree_to_path(ba, bb, n_tensors=len(tn), tensors_pos=np.asarray(comp, np.int32))
+    slices = [frozenset(inds[i] for i in unpack_bits(row)) for row in sl] if finite else None
+    return mins, paths, slices
+
+
+def optimize(opt, results_cls, tn, betas, n_steps, n_runs, n_projs, update_slices, timeout, finite,
+             load_tn_options):
+    load_tn_options.setdefault('fuse', False)
+    load_tn_options.setdefault('decompose_hyper_inds', False)
+    tn = opt._load_tn(tn, **load_tn_options)
+    if tn.sparse_inds or n_projs is not None:
+        raise NotImplementedError('tnco_b200: sparse indices / n_projs are not supported yet.')
+    betas = expand_betas(betas, n_steps)
+    if int(n_runs) != n_runs or n_runs < 1:
+        raise ValueError("'n_runs' must be a positive number.")
+    seeds = opt._rng.choices(range(2**32), k=int(n_runs))  # sa.py:237
+    if opt.verbose == 1:
+        print('# Optimizing ...', file=stderr, flush=True, end='')
+    t_start = time.perf_counter()
+    deadline = None if timeout is None else t_start + float(timeout)
+    stats = dict(tree_gen_s=0.0, kernel_ms=0.0, launches=0, proposals=0, accepts=0, sweeps=0)
+    comps = get_connected_components(tn.ts_inds)
+    per_comp = []
+    for comp in comps:
+        if len(comp) < 2:  # trivial path (sa.py:179-183)
+            per_comp.append(None)
+            continue
+        per_comp.append(run_component(opt, comp, tn, None, seeds, betas, finite=finite,
+                                      update_slices=update_slices, deadline=deadline, stats=stats))
+    runtime = time.perf_counter() - t_start
+    results = []
+    for r in range(int(n_runs)):
+        d_costs, d_paths, d_slices = [], [], []
+        for pc in per_comp:
+            if pc is None:
+                d_costs.append(0)
+                d_paths.append([])
+                d_slices.append(frozenset())
+            else:
+                d_costs.append(cost_to_decimal(pc[0][r]))
+                d_paths.append([(int(x), int(y)) for x, y in pc[1][r]])
+                d_slices.append(pc[2][r] if finite else frozenset())
+        kw = dict(cost=sum(d_costs), runtime_s=runtime, disconnected_costs=d_costs, disconnected_paths=d_paths,
+                  path=merge_contraction_paths(len(tn), d_paths))
+        if finite:
+            kw.update(disconnected_slices=d_slices, slices=fts.reduce(op.or_, d_slices))
+        results.append(results_cls(**kw))
+    if opt.verbose == 1:
+        print(' Done!', file=stderr, flush=True)
+    stats['runtime_s'] = runtime
+    object.__setattr__(opt, 'last_stats', stats)
+    return opt._dump_results(tn, sorted(results))

@@ -211,6 +211,8 @@ struct tnb_engine {
   // MT19937 feeding
   std::vector<Mt19937> mts;
   std::vector<uint32_t> h_stream;
+  std::vector<uint64_t> words_base;  // draws consumed before the current stream window, per chain
+  void* d_flush = nullptr;
   // timing
   double kernel_ms = 0.0;
   int64_t launches = 0;
@@ -366,6 +368,7 @@ static bool mt_refill(tnb_engine* e, bool first) {
   for (size_t c = 0; c < nc; ++c) {
     uint32_t* w = e->h_stream.data() + c * L;
     const size_t used = first ? L : size_t(cur[c]);
+    if (!first) e->words_base[c] += used;
     if (!first && used < L) std::memmove(w, w + used, (L - used) * sizeof(uint32_t));
     e->mts[c].fill(w + (L - used), used);
   }
@@ -389,6 +392,7 @@ static bool ensure_init(tnb_engine* e) {
     if (!alloc_to(e->rt, cs.stream, size_t(cs.n_chains) * L)) return e->rtfail();
     e->h_stream.assign(size_t(cs.n_chains) * L, 0u);
     e->mts.resize(size_t(cs.n_chains));
+    e->words_base.assign(size_t(cs.n_chains), 0);
     for (int c = 0; c < cs.n_chains; ++c) e->mts[size_t(c)].seed(uint32_t(e->h_seeds[size_t(c)]));
     if (!mt_refill(e, true)) return false;
   }
@@ -432,6 +436,7 @@ void tnb_destroy(tnb_engine* e) {
   e->rt.free_(e->d_leaf_bits);
   e->rt.free_(e->d_pow_tab);
   e->rt.free_(e->d_betas);
+  e->rt.free_(e->d_flush);
   e->rt.destroy();
   delete e;
 }
@@ -672,6 +677,8 @@ int tnb_get_progress(tnb_engine* e, int64_t* sweeps, uint64_t* proposals, uint64
       (width_rejects && !e->rt.d2h(width_rejects, e->cs.n_wrej, nc * 8)) ||
       (words && !e->rt.d2h(words, e->cs.cursor, nc * 8)))
     return e->rtfail(), -3;
+  if (words && e->rng_kind == TNB_RNG_MT19937 && e->words_base.size() == nc)
+    for (size_t c = 0; c < nc; ++c) words[c] += e->words_base[c];
   return 0;
 }
 
@@ -719,6 +726,14 @@ int tnb_eval_cost(tnb_engine* e, int n_trees, const int32_t* parent, const int32
   }
   tmp.release(e->rt);
   return rc;
+}
+
+int tnb_flush_l2(tnb_engine* e) {
+  if (!e) return -1;
+  const size_t bytes = size_t(256) << 20;  // 2 x the 126 MB L2
+  if (!e->d_flush && !(e->d_flush = e->rt.alloc(bytes))) return e->rtfail(), -3;
+  if (!e->rt.fill_ff(e->d_flush, bytes) || !e->rt.sync()) return e->rtfail(), -3;
+  return 0;
 }
 
 int tnb_get_config(tnb_engine* e, int* tile, int* words_per_lane, int* layout, int* state_bytes_per_chain) {

@@ -201,6 +201,14 @@ void tnb_mt19937_stream(uint32_t seed, uint64_t n, uint32_t* out) {
   m.fill(out, n);
 }
 
+void tnb_mt19937_state(uint32_t seed, uint64_t n_draws, uint32_t* state624, int32_t* pos) {
+  Mt19937 m;
+  m.seed(seed);
+  for (uint64_t i = 0; i < n_draws; ++i) (void)m.next();
+  std::memcpy(state624, m.x, sizeof(m.x));
+  *pos = m.p;
+}
+
 int tnb_random_trees(int n_leaves, int n_inds, const uint32_t* leaf_bits, int n_trees, const uint64_t* seeds,
                      int method, int n_threads, int32_t* parent, int32_t* child0, int32_t* child1) {
   if (n_leaves < 1 || n_inds < 0 || n_trees < 0 || !leaf_bits || !seeds) {
@@ -230,15 +238,22 @@ int tnb_random_trees(int n_leaves, int n_inds, const uint32_t* leaf_bits, int n_
   return 0;
 }
 
-int tnb_tree_to_path(int n_leaves, int n_trees, const int32_t* child0, const int32_t* child1, int32_t* path) {
+int tnb_tree_to_path(int n_leaves, int n_trees, const int32_t* child0, const int32_t* child1, int n_tensors,
+                     const int32_t* tensors_pos, int32_t* path) {
   const int n = n_leaves, N = 2 * n - 1;
+  if (!tensors_pos) n_tensors = n;
+  if (n_tensors < n) { set_global_error("tnb_tree_to_path: n_tensors < n_leaves"); return -1; }
   std::vector<int32_t> stack, slot(N);
   std::vector<uint8_t> vis(N);
   for (int t = 0; t < n_trees; ++t) {
     const int32_t *a = child0 + size_t(t) * N, *b = child1 + size_t(t) * N;
     int32_t* out = path + size_t(t) * (n - 1) * 2;
-    Fenwick fw(N);
-    for (int i = 0; i < n; ++i) { fw.add(i, 1); slot[i] = i; }
+    Fenwick fw(n_tensors + n - 1);
+    for (int i = 0; i < n_tensors; ++i) fw.add(i, 1);
+    for (int i = 0; i < n; ++i) {
+      slot[i] = tensors_pos ? tensors_pos[i] : i;
+      if (slot[i] < 0 || slot[i] >= n_tensors) { set_global_error("tnb_tree_to_path: bad tensors_pos"); return -1; }
+    }
     std::fill(vis.begin(), vis.end(), 0);
     stack.assign(1, N - 1);
     int step = 0;
@@ -254,7 +269,7 @@ int tnb_tree_to_path(int n_leaves, int n_trees, const int32_t* child0, const int
           out[2 * step + 1] = fw.prefix(sy);
           fw.add(sx, -1);
           fw.add(sy, -1);
-          slot[pos] = n + step;
+          slot[pos] = n_tensors + step;
           fw.add(slot[pos], 1);
           ++step;
         }

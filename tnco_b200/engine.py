@@ -57,16 +57,19 @@ def random_trees(leaf_bits, n_inds, seeds, method=TREES_GREEDY, n_threads=0):
     return p, a, b
 
 
-def tree_to_path(child0, child1):
-    """Tree(s) -> linear (einsum) path(s), [n_trees][n-1][2] (ContractionTree.path(), tnco/ctree.py:350-388)."""
+def tree_to_path(child0, child1, n_tensors=None, tensors_pos=None):
+    """Tree(s) -> linear (einsum) path(s), [n_trees][n-1][2] (ContractionTree.path(), tnco/ctree.py:350-388).
+    Leaf k is tensor ``tensors_pos[k]`` of a network of ``n_tensors`` tensors (default: identity)."""
     L = _lib.lib()
+    tp = None if tensors_pos is None else _c(tensors_pos, np.int32)
     a, b = _c(child0, np.int32), _c(child1, np.int32)
     single = a.ndim == 1
     a2, b2 = np.atleast_2d(a), np.atleast_2d(b)
     T, N = a2.shape
     n = (N + 1) // 2
     out = np.empty((T, max(n - 1, 0), 2), np.int32)
-    rc = L.tnb_tree_to_path(n, T, _ptr(a2, C.c_int32), _ptr(b2, C.c_int32), _ptr(out, C.c_int32))
+    rc = L.tnb_tree_to_path(n, T, _ptr(a2, C.c_int32), _ptr(b2, C.c_int32), int(n_tensors or n),
+                            _ptr(tp, C.c_int32), _ptr(out, C.c_int32))
     if rc:
         raise ValueError(L.tnb_last_error(None).decode())
     return out[0] if single else out
@@ -90,6 +93,14 @@ def mt19937_stream(seed, n):
     out = np.empty(int(n), np.uint32)
     _lib.lib().tnb_mt19937_stream(int(seed) & 0xFFFFFFFF, int(n), _ptr(out, C.c_uint32))
     return out
+
+
+def mt19937_state_str(seed, n_draws):
+    """libstdc++ text form of std::mt19937(seed) after n_draws outputs == reference ``Optimizer.prng_state``."""
+    st = np.empty(624, np.uint32)
+    pos = C.c_int32(0)
+    _lib.lib().tnb_mt19937_state(int(seed) & 0xFFFFFFFF, int(n_draws), _ptr(st, C.c_uint32), C.byref(pos))
+    return ' '.join(map(str, st.tolist())) + ' ' + str(pos.value)
 
 
 # ------------------------------------------------------------------------------------------ engine
@@ -220,6 +231,9 @@ class Engine:
                                         _ptr(sl, C.c_uint32), _ptr(ts, C.c_double), _ptr(tp, C.c_double),
                                         _ptr(mw, C.c_double)))
         return ts, tp, mw
+
+    def flush_l2(self):
+        self._chk(self._L.tnb_flush_l2(self._h))
 
     def config(self):
         v = [C.c_int(0) for _ in range(4)]

@@ -1,0 +1,209 @@
+"""Minimal tensor-network containers and path utilities on the host side of the SA path.
+
+Mirrors the parts of the reference that ``Optimizer.optimize`` touches:
+  Tensor / TensorNetwork          tnco/app/tn.py:77-362   (structure only: inds, dims, tags; no arrays)
+  read_inds                       tnco/utils/tn.py:520-569
+  get_hyper_count                 tnco/utils/tn.py:572-595
+  get_connected_components        tnco/utils/tn.py:61-106
+  merge_contraction_paths         tnco/utils/tn.py:334-401
+Numeric pre-processing (fuse, hyper-index decomposition, circuit loading) is out of scope.
+"""
+from __future__ import annotations
+
+import json
+from collections import Counter, defaultdict
+from dataclasses import dataclass
+from types import MappingProxyType
+from typing import Any, Iterable
+
+
+class JSONEncoder(json.JSONEncoder):
+
+    def default(self, obj):
+        if isinstance(obj, frozenset):
+            return tuple(obj)
+        if isinstance(obj, Tensor):
+            return dict(inds=obj.inds, dims=obj.dims, array=None, tags=obj.tags)
+        if isinstance(obj, TensorNetwork):
+            return dict(tensors=obj.tensors, output_inds=obj.output_inds, sparse_inds=obj.sparse_inds)
+        if hasattr(obj, 'to_json'):
+            return obj.to_json()
+        return super().default(obj)
+
+
+@dataclass(frozen=True, repr=False, eq=False)
+class Tensor:
+    """A tensor of the network: its indices and their dimensions (tnco/app/tn.py:77-175, without arrays)."""
+    inds: tuple
+    dims: Any = None
+    array: Any = None
+    tags: dict | None = None
+
+    def __post_init__(self):
+        if self.array is not None:
+            raise ValueError('tnco_b200 handles network structure only: pass dims, not arrays.')
+        if self.dims is None:
+            raise ValueError("One of 'dims' or 'array' must be provided.")
+        object.__setattr__(self, 'inds', tuple(self.inds))
+        try:
+            d = int(self.dims)
+        except (TypeError, ValueError):
+            object.__setattr__(self, 'dims', tuple(self.dims))
+        else:
+            if d != self.dims or d < 1:
+                raise ValueError("'dims' must be a positive integer.")
+            object.__setattr__(self, 'dims', (d,) * len(self.inds))
+        object.__setattr__(self, 'tags', {} if self.tags is None else dict(self.tags))
+        if any(int(d) != d or d < 1 for d in self.dims):
+            raise ValueError('Every dimension must be a positive integers.')
+        if len(self.dims) != len(self.inds):
+            raise ValueError("Wrong number of 'inds'.")
+
+    def __eq__(self, other):
+        return isinstance(other, Tensor) and self.inds == other.inds and self.dims == other.dims
+
+    def __hash__(self):
+        return hash((self.inds, self.dims))
+
+    def __repr__(self):
+        return 'Tensor(ndim={}, array=None{})'.format(self.ndim, ', tags={}'.format(self.tags) if self.tags else '')
+
+    @property
+    def ndim(self):
+        return len(self.dims)
+
+    def to_json(self):
+        return json.dumps(self, cls=JSONEncoder)
+
+
+def get_hyper_count(ts_inds: Iterable[Iterable], output_inds: Iterable | None = None) -> dict:
+    """#tensors an index appears in minus one, plus one if it is an output index (tnco/utils/tn.py:572-595)."""
+    hc = {x: n - 1 for x, n in Counter(x for xs in ts_inds for x in xs).items()}
+    if output_inds is not None:
+        for x in output_inds:
+            hc[x] = hc.get(x, 0) + 1
+    return hc
+
+
+@dataclass(frozen=True, repr=False)
+class TensorNetwork:
+    """tnco/app/tn.py:178-362 (structure only)."""
+    tensors: tuple
+    output_inds: frozenset | None = None
+    sparse_inds: frozenset | None = None
+    tags: dict | None = None
+
+    def __post_init__(self):
+        object.__setattr__(self, 'tensors', tuple(self.tensors))
+        if any(not isinstance(t, Tensor) for t in self.tensors):
+            raise ValueError("'tensors' must be a list of valid 'Tensor'.")
+        object.__setattr__(self, 'sparse_inds', frozenset(() if self.sparse_inds is None else self.sparse_inds))
+        object.__setattr__(self, '_inds', frozenset(x for t in self.tensors for x in t.inds))
+        dims = {}
+        for t in self.tensors:
+            for x, d in zip(t.inds, t.dims):
+                if dims.setdefault(x, d) != d:
+                    raise ValueError("Dimensions of 'tensors' are not consistent.")
+        object.__setattr__(self, '_dims', dims)
+        hc = get_hyper_count(self.ts_inds)
+        if self.output_inds is None:
+            if any(v > 1 for v in hc.values()):
+                raise ValueError("'output_inds' must be provided if 'ts_inds' has hyper-indices.")
+            object.__setattr__(self, 'output_inds', frozenset(x for x, v in hc.items() if v == 0))
+        object.__setattr__(self, 'output_inds', frozenset(self.output_inds))
+        if not self.output_inds.issubset(self._inds):
+            raise ValueError("'output_inds' contains indices not in 'tensors'.")
+        if not self.sparse_inds.issubset(self._inds):
+            raise ValueError("'sparse_inds' contains indices not in 'tensors'.")
+        object.__setattr__(self, 'tags', dict(() if self.tags is None else self.tags))
+
+    def __repr__(self):
+        return 'TensorNetwork(n_tensors={}, n_inds={})'.format(self.n_tensors, self.n_inds)
+
+    n_tensors = property(lambda s: len(s.tensors))
+    n_inds = property(lambda s: len(s._inds))
+    ts_inds = property(lambda s: tuple(t.inds for t in s.tensors))
+    arrays = property(lambda s: tuple(None for _ in s.tensors))
+    ts_tags = property(lambda s: tuple(t.tags for t in s.tensors))
+    inds = property(lambda s: s._inds)
+    dims = property(lambda s: MappingProxyType(s._dims))
+
+    def __len__(self):
+        return self.n_tensors
+
+    def __getitem__(self, k):
+        return self.tensors[k]
+
+    def __iter__(self):
+        return iter(self.tensors)
+
+    def to_json(self):
+        return json.dumps(self, cls=JSONEncoder)
+
+
+def read_inds(inds_map: dict, *, output_index_token='*', sparse_index_token='/'):
+    """index -> (dimension, tensor names...)  =>  (tensor_map, dims, output_inds, sparse_inds)."""
+    if output_index_token == sparse_index_token:
+        raise ValueError("'output_index_token' and 'sparse_index_token' must differ.")
+    tensor_map, dims = defaultdict(list), {}
+    for i, (d, *ts) in inds_map.items():
+        dims[i] = int(d)
+        for t in ts:
+            tensor_map[t].append(i)
+    output_inds = frozenset(tensor_map.pop(output_index_token, ()))
+    sparse_inds = frozenset(tensor_map.pop(sparse_index_token, ()))
+    return {k: tuple(v) for k, v in tensor_map.items()}, dims, output_inds, sparse_inds
+
+
+def get_connected_components(ts_inds: Iterable[Iterable]) -> list[tuple[int, ...]]:
+    """Union-find over shared indices; components in order of their smallest tensor, sorted inside."""
+    ts = list(ts_inds)
+    parent = list(range(len(ts)))
+
+    def find(i):
+        while parent[i] != i:
+            parent[i] = parent[parent[i]]
+            i = parent[i]
+        return i
+
+    owner = {}
+    for t, xs in enumerate(ts):
+        for x in xs:
+            if x in owner:
+                a, b = find(t), find(owner[x])
+                if a != b:
+                    parent[max(a, b)] = min(a, b)
+            else:
+                owner[x] = t
+    comps = {}
+    for t in range(len(ts)):
+        comps.setdefault(find(t), []).append(t)
+    return [tuple(sorted(v)) for v in comps.values()]
+
+
+def merge_contraction_paths(n_tensors: int, paths, *, autocomplete: bool = True):
+    """Merge per-component linear paths (each expressed over all n_tensors tensors) into one path.
+
+    >>> merge_contraction_paths(4, [[(0, 1)], [(2, 3)]])
+    [(0, 1), (0, 1), (0, 1)]
+    """
+    merged_pos = list(range(n_tensors))
+    merged = []
+    for i, path in enumerate(paths):
+        pos = list(range(n_tensors))
+        for x, y in path:
+            x, y = sorted((x, y))
+            y = pos.pop(y)
+            x = pos.pop(x)
+            pos.append((i, len(pos)))
+            try:
+                mx, my = sorted((merged_pos.index(x), merged_pos.index(y)))
+            except ValueError as e:
+                raise ValueError("'paths' are not valid or not disconnected.") from e
+            merged.append((mx, my))
+            merged_pos.pop(my)
+            merged_pos.pop(mx)
+            merged_pos.append(pos[-1])
+    if autocomplete:
+        merged += [(0, 1)] * (len(merged_pos) - 1)
+    return merged
