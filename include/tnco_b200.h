@@ -66,6 +66,13 @@ int tnb_random_trees(int n_leaves, int n_inds, const uint32_t* leaf_bits, int n_
 int tnb_tree_to_path(int n_leaves, int n_trees, const int32_t* child0, const int32_t* child1, int n_tensors,
                      const int32_t* tensors_pos, int32_t* path);
 
+/* Merge per-component linear paths (each expressed over all n_tensors tensors) into one path and connect the
+ * components with trailing (0,1) steps; replaces tnco/utils/tn.py:334-401 merge_contraction_paths
+ * (autocomplete=True), batched over runs.  lens[n_paths] = contractions per component path (same for every
+ * run); paths is [n_runs][sum(lens)][2]; merged is [n_runs][n_tensors-1][2]. */
+int tnb_merge_paths(int n_tensors, int n_runs, int n_paths, const int32_t* lens, const int32_t* paths,
+                    int32_t* merged);
+
 /* Linear path -> tree in reference numbering (tnco/ctree.py:108-131,208-218).  path is [n_leaves-1][2]. */
 int tnb_path_to_tree(int n_leaves, const int32_t* path, int32_t* parent, int32_t* child0, int32_t* child1);
 

@@ -26,6 +26,7 @@ SIGNATURES = {
     'tnb_last_error': (C.c_char_p, [C.c_void_p]),
     'tnb_random_trees': (C.c_int, [C.c_int, C.c_int, u32p, C.c_int, u64p, C.c_int, C.c_int, i32p, i32p, i32p]),
     'tnb_tree_to_path': (C.c_int, [C.c_int, C.c_int, i32p, i32p, C.c_int, i32p, i32p]),
+    'tnb_merge_paths': (C.c_int, [C.c_int, C.c_int, C.c_int, i32p, i32p, i32p]),
     'tnb_path_to_tree': (C.c_int, [C.c_int, i32p, i32p, i32p, i32p]),
     'tnb_mt19937_stream': (None, [C.c_uint32, C.c_uint64, u32p]),
     'tnb_mt19937_state': (None, [C.c_uint32, C.c_uint64, u32p, i32p]),

@@ -12,9 +12,9 @@ from sys import stderr
 import numpy as np
 
 from .. import dist
-from ..engine import (Engine, RNG_MT19937, RNG_PHILOX, TREES_GREEDY, TREES_RANDOM, pack_leaf_bits, random_trees,
-                      tree_to_path, unpack_bits)
-from ..tn import get_connected_components, merge_contraction_paths
+from ..engine import (Engine, RNG_MT19937, RNG_PHILOX, TREES_GREEDY, TREES_RANDOM, merge_paths, pack_leaf_bits,
+                      random_trees, tree_to_path, unpack_bits)
+from ..tn import get_connected_components
 from .app import cost_to_decimal
 
 
@@ -127,20 +127,40 @@ def optimize(opt, results_cls, tn, betas, n_steps, n_runs, n_projs, update_slice
         per_comp.append(run_component(opt, comp, tn, None, seeds, betas, finite=finite,
                                       update_slices=update_slices, deadline=deadline, stats=stats))
     runtime = time.perf_counter() - t_start
+    R = int(n_runs)
+    live = [pc for pc in per_comp if pc is not None]
+    lens = [pc[1].shape[1] for pc in live]
+    cat = np.concatenate([pc[1] for pc in live], axis=1) if live else np.zeros((R, 0, 2), np.int32)
+    # tn_utils.merge_contraction_paths (sa.py:230), batched in C++; one component spanning the whole network
+    # merges to itself with each pair sorted
+    if len(live) == 1 and lens[0] == len(tn) - 1:
+        merged = np.sort(cat, axis=2)
+    else:
+        merged = merge_paths(len(tn), lens, cat)
+
+    pair_t = np.dtype([('x', '<i4'), ('y', '<i4')])
+
+    def pairs(a):  # [R][k][2] int32 -> R lists of k 2-tuples, one C-level conversion
+        a = np.ascontiguousarray(a, np.int32)
+        return a.view(pair_t).reshape(a.shape[0], a.shape[1]).tolist()
+
+    merged_l = pairs(merged)
+    comp_l = [None if pc is None else pairs(pc[1]) for pc in per_comp]
+
     results = []
-    for r in range(int(n_runs)):
+    for r in range(R):
         d_costs, d_paths, d_slices = [], [], []
-        for pc in per_comp:
+        for pc, pl in zip(per_comp, comp_l):
             if pc is None:
                 d_costs.append(0)
                 d_paths.append([])
                 d_slices.append(frozenset())
             else:
                 d_costs.append(cost_to_decimal(pc[0][r]))
-                d_paths.append([(int(x), int(y)) for x, y in pc[1][r]])
+                d_paths.append(pl[r])
                 d_slices.append(pc[2][r] if finite else frozenset())
         kw = dict(cost=sum(d_costs), runtime_s=runtime, disconnected_costs=d_costs, disconnected_paths=d_paths,
-                  path=merge_contraction_paths(len(tn), d_paths))
+                  path=merged_l[r])
         if finite:
             kw.update(disconnected_slices=d_slices, slices=fts.reduce(op.or_, d_slices))
         results.append(results_cls(**kw))

@@ -97,9 +97,12 @@ __global__ void __launch_bounds__(kBlock) sa_init_kernel(const __grid_constant__
   if (chain >= P.n_chains) return;
   chain_init<TILE, WPL, FINITE, Rng>(P, chain);
 }
+// One warp per block: the hardware block scheduler then balances chains over the 148 SMs at warp granularity
+// (4096 chains of 16 lanes = 2048 blocks = 13.8 per SM, all resident in a single wave at <= 128 registers).
+constexpr int kSweepBlock = 32;
 template <int TILE, int WPL, bool FINITE, class Rng>
-__global__ void __launch_bounds__(kBlock) sa_sweep_kernel(const __grid_constant__ Params P) {
-  const int chain = (blockIdx.x * kBlock + threadIdx.x) / TILE;
+__global__ void __launch_bounds__(kSweepBlock, 16) sa_sweep_kernel(const __grid_constant__ Params P) {
+  const int chain = (blockIdx.x * kSweepBlock + threadIdx.x) / TILE;
   if (chain >= P.n_chains) return;
   chain_sweeps<TILE, WPL, FINITE, Rng>(P, chain);
 }
@@ -116,10 +119,11 @@ static bool launch_t(Rt& rt, const Params& P, bool init) {
   return true;
 #else
   const long long threads = (long long)P.n_chains * TILE;
-  const int grid = int((threads + kBlock - 1) / kBlock);
+  const int blk = init ? kBlock : kSweepBlock;
+  const int grid = int((threads + blk - 1) / blk);
   if (grid == 0) return true;
   if (init) sa_init_kernel<TILE, WPL, FINITE, Rng><<<grid, kBlock, 0, rt.stream>>>(P);
-  else sa_sweep_kernel<TILE, WPL, FINITE, Rng><<<grid, kBlock, 0, rt.stream>>>(P);
+  else sa_sweep_kernel<TILE, WPL, FINITE, Rng><<<grid, kSweepBlock, 0, rt.stream>>>(P);
   return rt.ok(cudaGetLastError(), init ? "sa_init_kernel launch" : "sa_sweep_kernel launch");
 #endif
 }

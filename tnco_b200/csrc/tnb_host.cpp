@@ -284,6 +284,58 @@ int tnb_tree_to_path(int n_leaves, int n_trees, const int32_t* child0, const int
   return 0;
 }
 
+int tnb_merge_paths(int n_tensors, int n_runs, int n_paths, const int32_t* lens, const int32_t* paths,
+                    int32_t* merged) {
+  if (n_tensors < 1 || n_runs < 0 || n_paths < 0 || (n_paths > 0 && (!lens || !paths)) || !merged) {
+    set_global_error("tnb_merge_paths: invalid arguments");
+    return -1;
+  }
+  int total = 0;
+  for (int i = 0; i < n_paths; ++i) total += lens[i];
+  if (total > n_tensors - 1) { set_global_error("tnb_merge_paths: too many contractions"); return -1; }
+  std::vector<int32_t> l2m(size_t(n_tensors) + size_t(total));
+  for (int r = 0; r < n_runs; ++r) {
+    const int32_t* in = paths + size_t(r) * total * 2;
+    int32_t* out = merged + size_t(r) * (n_tensors - 1) * 2;
+    Fenwick mf(n_tensors + total);
+    for (int i = 0; i < n_tensors; ++i) mf.add(i, 1);
+    std::vector<uint8_t> mlive(size_t(n_tensors) + size_t(total), 0);
+    std::fill(mlive.begin(), mlive.begin() + n_tensors, 1);
+    int gstep = 0;
+    for (int i = 0; i < n_paths; ++i) {
+      Fenwick lf(n_tensors + lens[i]);
+      for (int k = 0; k < n_tensors; ++k) { lf.add(k, 1); l2m[size_t(k)] = k; }
+      int live = n_tensors;
+      for (int k = 0; k < lens[i]; ++k, ++gstep) {
+        int x = in[2 * gstep], y = in[2 * gstep + 1];
+        if (x > y) std::swap(x, y);
+        if (x < 0 || y >= live || x == y) { set_global_error("tnb_merge_paths: invalid path entry"); return -2; }
+        const int sx = lf.kth(x), sy = lf.kth(y);
+        const int mx = l2m[size_t(sx)], my = l2m[size_t(sy)];
+        if (!mlive[size_t(mx)] || !mlive[size_t(my)]) {
+          set_global_error("'paths' are not valid or not disconnected.");
+          return -2;
+        }
+        int px = mf.prefix(mx), py = mf.prefix(my);
+        if (px > py) std::swap(px, py);
+        out[2 * gstep] = px;
+        out[2 * gstep + 1] = py;
+        mf.add(mx, -1); mf.add(my, -1);
+        mlive[size_t(mx)] = mlive[size_t(my)] = 0;
+        lf.add(sx, -1); lf.add(sy, -1);
+        const int ls = n_tensors + k, ms = n_tensors + gstep;
+        lf.add(ls, 1);
+        mf.add(ms, 1);
+        mlive[size_t(ms)] = 1;
+        l2m[size_t(ls)] = ms;
+        live -= 1;
+      }
+    }
+    for (int k = gstep; k < n_tensors - 1; ++k) { out[2 * k] = 0; out[2 * k + 1] = 1; }  // autocomplete
+  }
+  return 0;
+}
+
 int tnb_path_to_tree(int n_leaves, const int32_t* path, int32_t* parent, int32_t* child0, int32_t* child1) {
   const int n = n_leaves, N = 2 * n - 1;
   std::fill(parent, parent + N, -1);

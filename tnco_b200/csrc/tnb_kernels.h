@@ -88,16 +88,19 @@ TNB_D TNB_INLINE double uniform_from(uint32_t lo, uint32_t hi) {
 // a time, one per lane, and fetches them by shuffle, so the 10-round Philox costs 1/TILE per event.
 template <int TILE>
 struct RngPhilox {
+  static constexpr bool kFast = true;  // log-domain fp32 acceptance test (see chain_sweeps)
   uint32_t k0, k1, g0, g1;
   unsigned long long v, blk;
   uint32_t r0, r1, r2, r3;
   uint32_t e0, e1, e2;
+  float rf, ef;  // -log2(u) of this lane's vector / of the current event
   TNB_D void load(const Params& P, int chain) {
     const unsigned long long s = P.seeds[chain], g = P.chain_id0 + (unsigned long long)chain;
     k0 = uint32_t(s); k1 = uint32_t(s >> 32); g0 = uint32_t(g); g1 = uint32_t(g >> 32);
     v = P.rng_ctr[chain];
     blk = ~0ull;
     r0 = r1 = r2 = r3 = e0 = e1 = e2 = 0;
+    rf = ef = 0.f;
   }
   TNB_D void store(const Params& P, int chain) const { P.rng_ctr[chain] = v; }
   TNB_D bool can_start(const Params&) const { return true; }
@@ -107,17 +110,30 @@ struct RngPhilox {
       blk = b;
       const unsigned long long idx = b * TILE + (unsigned long long)t.tl;
       philox4x32_10(uint32_t(idx), uint32_t(idx >> 32), g0, g1, k0, k1, r0, r1, r2, r3);
+      // u = (r1 + 0.5) / 2^32 in (0,1);  -log2(u) = 32 - log2(r1 + 0.5), computed once per vector
+#if defined(TNB_EMU)
+      rf = 32.f - log2f(float(r1) + 0.5f);
+#else
+      rf = 32.f - __log2f(float(r1) + 0.5f);
+#endif
     }
     const int src = int(v % TILE);
     e0 = t.bcast(r0, src);
-    e1 = t.bcast(r1, src);
-    e2 = t.bcast(r2, src);
+#if defined(TNB_EMU)
+    ef = rf;
+#else
+    ef = __uint_as_float(t.bcast(__float_as_uint(rf), src));
+#endif
     ++v;
   }
+  TNB_D TNB_INLINE float neg_log2_u() const { return ef; }
   TNB_D TNB_INLINE uint32_t leaf_word(const Tile<TILE>& t) { event(t); return e0; }
   TNB_D TNB_INLINE void begin_level(const Tile<TILE>& t) { event(t); }
   TNB_D TNB_INLINE uint32_t coin_word(const Tile<TILE>&) { return e0; }
-  TNB_D TNB_INLINE double uniform(const Tile<TILE>&) { return uniform_from(e1, e2); }
+  TNB_D TNB_INLINE double uniform(const Tile<TILE>& t) {  // exact path (greedy / always rules)
+    const int src = int((v - 1) % TILE);
+    return uniform_from(t.bcast(r1, src), t.bcast(r2, src));
+  }
   // lane-local draw (slicer, executed by lane 0 only); re-synchronise with sync_from0 afterwards
   TNB_D uint32_t local_next() {
     uint32_t a, b, c, d;
@@ -133,6 +149,8 @@ struct RngPhilox {
 // Raw 32-bit draw stream consumed in the reference's own order (std::mt19937 words, or a recorded stream).
 template <int TILE>
 struct RngStream {
+  static constexpr bool kFast = false;  // parity modes keep the reference's pow() acceptance in fp64
+  TNB_D TNB_INLINE float neg_log2_u() const { return 0.f; }
   const uint32_t* w;
   unsigned long long cur, len;
   int over;
@@ -519,6 +537,50 @@ TNB_D void chain_init(const Params& P, int chain) {
 }
 
 // ------------------------------------------------------------------------------------------ sweeps
+// log2(1 + delta/total) for delta > 0, total > 0 in float with ~2e-6 relative error, without a double division:
+// mantissas (23 bits) divided in fp32, exponents subtracted as integers.  Production (Philox) acceptance only.
+TNB_HD TNB_INLINE float log2_1p_ratio(double delta, double total) {
+  unsigned long long ud, ut;
+#if defined(TNB_EMU) || !defined(__CUDA_ARCH__)
+  std::memcpy(&ud, &delta, 8);
+  std::memcpy(&ut, &total, 8);
+#else
+  ud = (unsigned long long)__double_as_longlong(delta);
+  ut = (unsigned long long)__double_as_longlong(total);
+#endif
+  const int diff = int((ud >> 52) & 0x7ffu) - int((ut >> 52) & 0x7ffu);
+  const uint32_t id = 0x3f800000u | uint32_t((ud >> 29) & 0x7fffffu);
+  const uint32_t it = 0x3f800000u | uint32_t((ut >> 29) & 0x7fffffu);
+  float md, mt;
+#if defined(TNB_EMU) || !defined(__CUDA_ARCH__)
+  std::memcpy(&md, &id, 4);
+  std::memcpy(&mt, &it, 4);
+  const float q = md / mt;
+  if (diff > 64) return float(diff) + log2f(q);
+  if (diff < -64) return 0.f;
+  const uint32_t ie = uint32_t(127 + diff) << 23;
+  float sc;
+  std::memcpy(&sc, &ie, 4);
+  const float x = q * sc;
+  if (x < 0.03125f) return x * 1.44269504f * (1.f - x * (0.5f - x * (0.33333334f - 0.25f * x)));
+  return log2f(1.f + x);
+#else
+  md = __uint_as_float(id);
+  mt = __uint_as_float(it);
+  const float q = __fdividef(md, mt);
+  if (diff > 64) return float(diff) + __log2f(q);
+  if (diff < -64) return 0.f;
+  const float x = q * __uint_as_float(uint32_t(127 + diff) << 23);
+  if (x < 0.03125f) return x * 1.44269504f * (1.f - x * (0.5f - x * (0.33333334f - 0.25f * x)));
+  return __log2f(1.f + x);
+#endif
+}
+
+// One flat loop per tile: every iteration is either a sweep boundary (finish sweep s, start sweep s+1) or one
+// level of the leaf->root walk, so the tiles sharing a warp stay converged instead of waiting for each other's
+// walks.  The inputs of level k+1 (parent A', its children word and contraction cost, the sibling's index set
+// and partial cost) do not depend on the move at level k, so they are loaded during level k in three stages and
+// are in registers when level k+1 starts.
 template <int TILE, int WPL, bool FINITE, class Rng>
 TNB_D void chain_sweeps(const Params& P, int chain) {
   ChainView<TILE, WPL> c(P, chain);
@@ -538,159 +600,198 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   for (int k = 0; k < WPL; ++k) S[k] = 0u;
   if (FINITE) load_slices(c, S);
 
-  for (; s < P.until; ++s) {
-    if (!rng.can_start(P)) break;
-    const double beta = P.betas[s < P.n_betas ? s : P.n_betas - 1];
-    const int leaf = int(rng.leaf_word(t) % uint32_t(n));  // optimizer.hpp:103
-    int B = c.par[leaf];
-    double total = c.cp[root - n].y;                       // :112
-    double root_pc = total;
-    {
-      uint32_t cw = c.ch[B - n];
-      int p0 = int(cw & 0xffffu), p1 = int(cw >> 16);
-      uint32_t b0[WPL], b1[WPL];
+  bool in_sweep = false;
+  int B = 0, A = -1, C = 0, p0 = 0, p1 = 0, a0 = 0, a1 = 0;
+  uint32_t b0[WPL], b1[WPL], bC[WPL];
+#pragma unroll
+  for (int k = 0; k < WPL; ++k) b0[k] = b1[k] = bC[k] = 0u;
+  double pc0 = 0.0, pc1 = 0.0, pcC = 0.0, ccA = 0.0, ccB = 0.0, total = 0.0, root_pc = 0.0, beta = 0.0;
+  float beta_f = 0.f;
+
+  while (true) {
+    if (A < 0) {
+      // ------------------------------------------------------------------ sweep boundary
+      if (in_sweep) {
+        if (FINITE && P.every > 0 && (s % P.every) == 0) {  // finite_width/greedy/optimizer.hpp:360-376
+          bool anyS = false;
+#pragma unroll
+          for (int k = 0; k < WPL; ++k) anyS |= S[k] != 0u;
+          if (t.any(anyS)) {
+            uint32_t S2[WPL];
+            get_slices_dev(c, rng, S2);
+            dbl2* cp2 = P.cp2 + size_t(chain) * P.n_int;
+            double seq;
+            uint32_t maxk;
+            cost_pass<TILE, WPL, false>(c, S2, cp2, seq, maxk);
+            const double r2 = cp2[P.n_int - 1].y;
+            if (r2 < root_pc) {
+              t.sync();
+              for (int i = t.tl; i < P.n_int; i += TILE) c.cp[i] = cp2[i];
+              t.sync();
+#pragma unroll
+              for (int k = 0; k < WPL; ++k) S[k] = S2[k];
+              store_slices(c, S);
+              root_pc = r2;
+            }
+          }
+        }
+        if (root_pc < min_total) {  // infinite_memory/optimizer.hpp:197-201
+          min_total = root_pc;
+          snapshot_best(c, S, FINITE);
+        }
+        ++s;
+        in_sweep = false;
+        if (rng.overrun()) break;
+      }
+      if (s >= P.until || !rng.can_start(P)) break;
+      beta = P.betas[s < P.n_betas ? s : P.n_betas - 1];
+      beta_f = float(beta);
+      const int leaf = int(rng.leaf_word(t) % uint32_t(n));  // optimizer.hpp:103
+      B = c.par[leaf];
+      total = c.cp[root - n].y;                              // :112
+      root_pc = total;
+      const uint32_t cw = c.ch[B - n];
+      p0 = int(cw & 0xffffu);
+      p1 = int(cw >> 16);
       c.load_bits(p0, b0);
       c.load_bits(p1, b1);
-      double pc0 = c.pc_of(p0), pc1 = c.pc_of(p1);
-      double ccB = c.cp[B - n].x;
-      int A = c.par[B];
-      while (A >= 0) {
-        // get_ctree_nn (optimize/optimizer.hpp:86-172)
-        uint32_t aw = c.ch[A - n];
-        int a0 = int(aw & 0xffffu), a1 = int(aw >> 16);
-        const bool bslot0 = (a0 == B);
-        int C = bslot0 ? a1 : a0;
-        uint32_t bC[WPL];
+      pc0 = c.pc_of(p0);
+      pc1 = c.pc_of(p1);
+      ccB = c.cp[B - n].x;
+      A = c.par[B];
+      in_sweep = true;
+      if (A >= 0) {
+        const uint32_t aw = c.ch[A - n];
+        a0 = int(aw & 0xffffu);
+        a1 = int(aw >> 16);
+        C = (a0 == B) ? a1 : a0;
         c.load_bits(C, bC);
-        double pcC = c.pc_of(C);
-        double ccA = c.cp[A - n].x;
-        bool l0 = false, l1 = false;
+        pcC = c.pc_of(C);
+        ccA = c.cp[A - n].x;
+      }
+      continue;
+    }
+    // -------------------------------------------------------------------- one level (A >= 0)
+    // get_ctree_nn (optimize/optimizer.hpp:86-172): A = parent(B), C = sibling(B), D/E = children of B
+    const int An = c.par[A];  // stage 1 of the next level's inputs
+    const bool bslot0 = (a0 == B);
+    bool l0 = false, l1 = false;
 #pragma unroll
-        for (int k = 0; k < WPL; ++k) {
-          l0 |= (b0[k] & bC[k]) != 0u;
-          l1 |= (b1[k] & bC[k]) != 0u;
-        }
-        const bool i0 = t.any(l0), i1 = t.any(l1);
-        rng.begin_level(t);
-        bool pick0;
-        if (P.dsi || (i0 && i1)) pick0 = (rng.coin_word(t) & 1u) != 0u;
-        else pick0 = i0;
-        int E = pick0 ? p1 : p0;  // D = the other child
-        uint32_t bD[WPL], bE[WPL], nb[WPL];
-        uint32_t kpack = 0, ks = 0;
+    for (int k = 0; k < WPL; ++k) {
+      l0 |= (b0[k] & bC[k]) != 0u;
+      l1 |= (b1[k] & bC[k]) != 0u;
+    }
+    const bool i0 = t.any(l0), i1 = t.any(l1);
+    rng.begin_level(t);
+    bool pick0;
+    if (P.dsi || (i0 && i1)) pick0 = (rng.coin_word(t) & 1u) != 0u;
+    else pick0 = i0;
+    int E = pick0 ? p1 : p0;  // D = the other child
+    uint32_t bD[WPL], bE[WPL], nb[WPL];
+    uint32_t kpack = 0, ks = 0;
 #pragma unroll
-        for (int k = 0; k < WPL; ++k) {
-          bD[k] = pick0 ? b0[k] : b1[k];
-          bE[k] = pick0 ? b1[k] : b0[k];
-          nb[k] = bD[k] ^ bC[k];  // new inds of B (infinite_memory/optimizer.hpp:147; no hyper-indices)
-          kpack += uint32_t(popc32(nb[k] | bE[k] | S[k])) | (uint32_t(popc32(bD[k] | bC[k] | S[k])) << 16);
-          if (FINITE) ks += uint32_t(popc32(nb[k] & ~S[k]));
-        }
-        const double pcD = pick0 ? pc0 : pc1;
-        double pcE = pick0 ? pc1 : pc0;
-        ++n_prop;
-        bool gate = true;
-        if (FINITE) {  // finite_width/greedy/optimizer.hpp:176-188
-          ks = t.sum(ks);
-          gate = c.width_of(int(ks)) <= P.max_width;
-          if (!gate) ++n_wrej;
-        }
-        bool acc = false;
-        double nA = 0.0, nB = 0.0, delta = 0.0;
-        if (gate) {
-          kpack = t.sum(kpack);
-          nA = c.cost_of(int(kpack & 0xffffu));  // cost(new_B | E [| slices])
-          nB = c.cost_of(int(kpack >> 16));      // cost(D | C [| slices])
-          delta = (nB - ccB) + (nA - ccA);       // :158, this association order
-          const double u = rng.uniform(t);       // always drawn (:162)
-          double p;
-          if (P.prob_kind == kProbMH) {          // prob/mh.hpp:45-59
-            if (delta <= 0.0) p = 1.0;
-            else if (total == 0.0) p = 0.0;
-            else p = pow(1.0 + delta / total, -beta);
-          } else if (P.prob_kind == kProbGreedy) {
-            p = delta <= 0.0 ? 1.0 : 0.0;
-          } else {
-            p = 1.0;
-          }
-          acc = u <= p;
-        }
-        uint32_t bB[WPL];
-        if (acc) {
-          // Tree::swap_with_nn(E): E <-> C, child slots preserved (tree.hpp:141-192)
-          if (bslot0) a1 = E; else a0 = E;
-          if (pick0) p1 = C; else p0 = C;
-          c.ch[A - n] = uint32_t(a0) | (uint32_t(a1) << 16);
-          c.ch[B - n] = uint32_t(p0) | (uint32_t(p1) << 16);
-          c.par[C] = int16_t(B);
-          c.par[E] = int16_t(A);
-          c.store_bits(B, nb);
-          ccB = nB;
-          ccA = nA;
-          total += delta;
-          ++n_acc;
-          {
-            const int ti = C; C = E; E = ti;
-            const double td = pcC; pcC = pcE; pcE = td;
-          }
-#pragma unroll
-          for (int k = 0; k < WPL; ++k) {
-            bB[k] = nb[k];
-            bC[k] = bE[k];  // the node now called C is the old E
-          }
+    for (int k = 0; k < WPL; ++k) {
+      bD[k] = pick0 ? b0[k] : b1[k];
+      bE[k] = pick0 ? b1[k] : b0[k];
+      nb[k] = bD[k] ^ bC[k];  // new inds of B (infinite_memory/optimizer.hpp:147; no hyper-indices)
+      kpack += uint32_t(popc32(nb[k] | bE[k] | S[k])) | (uint32_t(popc32(bD[k] | bC[k] | S[k])) << 16);
+      if (FINITE) ks += uint32_t(popc32(nb[k] & ~S[k]));
+    }
+    const double pcD = pick0 ? pc0 : pc1;
+    double pcE = pick0 ? pc1 : pc0;
+    ++n_prop;
+    bool gate = true;
+    if (FINITE) {  // finite_width/greedy/optimizer.hpp:176-188
+      ks = t.sum(ks);
+      gate = c.width_of(int(ks)) <= P.max_width;
+      if (!gate) ++n_wrej;
+    }
+    // stage 2: children word and contraction cost of the next parent
+    uint32_t awn = 0u;
+    double ccAn = 0.0;
+    if (An >= 0) {
+      awn = c.ch[An - n];
+      ccAn = c.cp[An - n].x;
+    }
+    bool acc = false;
+    double nA = 0.0, nB = 0.0, delta = 0.0;
+    if (gate) {
+      kpack = t.sum(kpack);
+      nA = c.cost_of(int(kpack & 0xffffu));  // cost(new_B | E [| slices])
+      nB = c.cost_of(int(kpack >> 16));      // cost(D | C [| slices])
+      delta = (nB - ccB) + (nA - ccA);       // :158, this association order
+      if (Rng::kFast && P.prob_kind == kProbMH) {
+        // same rule as prob/mh.hpp:45-59 in the log domain: u <= (1+x)^-beta  <=>  beta*log2(1+x) <= -log2(u)
+        acc = delta <= 0.0 || beta_f * log2_1p_ratio(delta, total) <= rng.neg_log2_u();
+      } else {
+        const double u = rng.uniform(t);  // always drawn (:162)
+        double p;
+        if (P.prob_kind == kProbMH) {     // prob/mh.hpp:45-59
+          if (delta <= 0.0) p = 1.0;
+          else if (total == 0.0) p = 0.0;
+          else p = pow(1.0 + delta / total, -beta);
+        } else if (P.prob_kind == kProbGreedy) {
+          p = delta <= 0.0 ? 1.0 : 0.0;
         } else {
-#pragma unroll
-          for (int k = 0; k < WPL; ++k) bB[k] = bD[k] ^ bE[k];
+          p = 1.0;
         }
-        // propagate partial costs (:185-188), post-swap names
-        const double pcB = pcD + pcE + ccB;
-        const double pcA = pcB + pcC + ccA;
-        c.cp[B - n] = make_dbl2(ccB, pcB);
-        c.cp[A - n] = make_dbl2(ccA, pcA);
-        root_pc = pcA;
-        // next level: B <- A, whose children are (a0, a1) = {B, C} in slot order
-        p0 = a0;
-        p1 = a1;
-#pragma unroll
-        for (int k = 0; k < WPL; ++k) {
-          b0[k] = bslot0 ? bB[k] : bC[k];
-          b1[k] = bslot0 ? bC[k] : bB[k];
-        }
-        pc0 = bslot0 ? pcB : pcC;
-        pc1 = bslot0 ? pcC : pcB;
-        ccB = ccA;
-        B = A;
-        A = c.par[B];
+        acc = u <= p;
       }
     }
-    if (FINITE && P.every > 0 && (s % P.every) == 0) {  // finite_width/greedy/optimizer.hpp:360-376
-      bool anyS = false;
-#pragma unroll
-      for (int k = 0; k < WPL; ++k) anyS |= S[k] != 0u;
-      if (t.any(anyS)) {
-        uint32_t S2[WPL];
-        get_slices_dev(c, rng, S2);
-        dbl2* cp2 = P.cp2 + size_t(chain) * P.n_int;
-        double seq;
-        uint32_t maxk;
-        cost_pass<TILE, WPL, false>(c, S2, cp2, seq, maxk);
-        const double r2 = cp2[P.n_int - 1].y;
-        if (r2 < root_pc) {
-          t.sync();
-          for (int i = t.tl; i < P.n_int; i += TILE) c.cp[i] = cp2[i];
-          t.sync();
-#pragma unroll
-          for (int k = 0; k < WPL; ++k) S[k] = S2[k];
-          store_slices(c, S);
-          root_pc = r2;
-        }
+    uint32_t bB[WPL];
+    if (acc) {
+      // Tree::swap_with_nn(E): E <-> C, child slots preserved (tree.hpp:141-192)
+      if (bslot0) a1 = E; else a0 = E;
+      if (pick0) p1 = C; else p0 = C;
+      c.ch[A - n] = uint32_t(a0) | (uint32_t(a1) << 16);
+      c.ch[B - n] = uint32_t(p0) | (uint32_t(p1) << 16);
+      c.par[C] = int16_t(B);
+      c.par[E] = int16_t(A);
+      c.store_bits(B, nb);
+      ccB = nB;
+      ccA = nA;
+      total += delta;
+      ++n_acc;
+      {
+        const int ti = C; C = E; E = ti;
+        const double td = pcC; pcC = pcE; pcE = td;
       }
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) {
+        bB[k] = nb[k];
+        bC[k] = bE[k];  // the node now called C is the old E
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) bB[k] = bD[k] ^ bE[k];
     }
-    if (root_pc < min_total) {  // :197-201
-      min_total = root_pc;
-      snapshot_best(c, S, FINITE);
+    // propagate partial costs (:185-188), post-swap names
+    const double pcB = pcD + pcE + ccB;
+    const double pcA = pcB + pcC + ccA;
+    c.cp[B - n] = make_dbl2(ccB, pcB);
+    c.cp[A - n] = make_dbl2(ccA, pcA);
+    root_pc = pcA;
+    // next level: B <- A, whose children are (a0, a1) = {B, C} in slot order
+    p0 = a0;
+    p1 = a1;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      b0[k] = bslot0 ? bB[k] : bC[k];
+      b1[k] = bslot0 ? bC[k] : bB[k];
     }
-    if (rng.overrun()) { ++s; break; }
+    pc0 = bslot0 ? pcB : pcC;
+    pc1 = bslot0 ? pcC : pcB;
+    ccB = ccA;
+    B = A;
+    A = An;
+    if (An >= 0) {  // stage 3: the next sibling's index set and partial cost
+      a0 = int(awn & 0xffffu);
+      a1 = int(awn >> 16);
+      C = (a0 == B) ? a1 : a0;
+      c.load_bits(C, bC);
+      pcC = c.pc_of(C);
+      ccA = ccAn;
+    }
   }
   rng.store(P, chain);
   P.sweep_idx[chain] = s;

@@ -75,6 +75,20 @@ def tree_to_path(child0, child1, n_tensors=None, tensors_pos=None):
     return out[0] if single else out
 
 
+def merge_paths(n_tensors, lens, paths):
+    """Batched merge_contraction_paths (tnco/utils/tn.py:334-401): ``paths`` is [n_runs][sum(lens)][2] with the
+    per-component paths of a run concatenated; returns [n_runs][n_tensors-1][2]."""
+    L = _lib.lib()
+    lens = _c(lens, np.int32).reshape(-1)
+    pth = _c(paths, np.int32).reshape(-1, int(lens.sum()), 2) if len(lens) else np.zeros((len(paths), 0, 2), np.int32)
+    out = np.empty((pth.shape[0], max(int(n_tensors) - 1, 0), 2), np.int32)
+    rc = L.tnb_merge_paths(int(n_tensors), pth.shape[0], len(lens), _ptr(lens, C.c_int32), _ptr(pth, C.c_int32),
+                           _ptr(out, C.c_int32))
+    if rc:
+        raise ValueError(L.tnb_last_error(None).decode())
+    return out
+
+
 def path_to_tree(path, n_leaves):
     """Linear path -> (parent, child0, child1) in reference numbering (tnco/ctree.py:108-131,208-218)."""
     L = _lib.lib()
