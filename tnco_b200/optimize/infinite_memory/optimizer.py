@@ -1,0 +1,107 @@
+"""``Optimizer(ctree, cmodel, seed=...)`` / ``update(prob)`` -- the reference's core object
+(tnco/optimize/infinite_memory/optimizer.py:47-245 over infinite_memory/optimizer.hpp:61-310) as ONE chain of the
+GPU engine in TNB_RNG_MT19937 mode: for an integer seed every update() consumes the same std::mt19937 draws in
+the same order as the reference, so trees, costs and ``prng_state`` are identical to the reference's."""
+from __future__ import annotations
+
+import math
+import secrets
+from decimal import Decimal
+
+import numpy as np
+
+from ..._lib import RNG_MT19937
+from ...ctree import ContractionTree
+from ...engine import Engine, mt19937_state_str, unpack_bits
+from ..prob import BaseProbability
+
+
+def _dec(x):
+    return Decimal('%.6g' % float(x))
+
+
+class Optimizer:
+    _finite = False
+
+    def __init__(self, ctree: ContractionTree, cmodel, *, seed=None, disable_shared_inds: bool = False,
+                 atol: float = 1e-5, device: int = 0, **kwargs):
+        if kwargs.pop('max_number_new_slices', 0):
+            raise NotImplementedError("tnco_b200: 'max_number_new_slices' > 0 is not supported (the app never "
+                                      "enables it, tnco/optimize/finite_width/optimizer.py:59).")
+        if kwargs.pop('skip_slices', None):
+            raise NotImplementedError("tnco_b200: 'skip_slices' is not supported yet.")
+        kwargs.pop('slice_update', None)
+        if kwargs:
+            raise TypeError('Got unexpected keyword arguments.')
+        if isinstance(seed, str):
+            raise NotImplementedError('tnco_b200: resuming from a PRNG state string is not supported; pass the seed.')
+        self._seed = secrets.randbits(32) if seed is None else int(seed) % 2**32
+        self._ctree0, self._cmodel = ctree, cmodel
+        self._dsi, self._atol = bool(disable_shared_inds), atol
+        dims = set(ctree.dims.values())
+        if len(dims) != 1:
+            raise NotImplementedError('tnco_b200: per-index dimensions are not supported yet.')
+        lb, ni = ctree.leaf_bits()
+        self._e = Engine(device)
+        self._e.set_network(lb, ni, dim=dims.pop())
+        self._e.set_mode(max_width=getattr(cmodel, 'max_width', None) if self._finite else None,
+                         update_slices_every=1, disable_shared_inds=self._dsi, rng=RNG_MT19937)
+        p, a, b = ctree.arrays()
+        self._e.set_chains(p[None], a[None], b[None], [self._seed])
+        self._n_updates = 0
+        self._e.costs()  # construct caches now: invalid input / "Precision is too low." raise here (ValueError)
+
+    # ---- stepping
+    def update(self, prob: BaseProbability, update_slices: bool = True):
+        self._e.set_prob(prob.kind)
+        # the engine re-slices on sweeps s with s % every == 0: park the sweep index on / off that grid
+        self._e.set_betas([getattr(prob, 'beta', 0.0)])
+        if self._finite:
+            self._set_every(1 if update_slices else 0)
+        self._n_updates += 1
+        self._e.run(self._n_updates)
+
+    def _set_every(self, every):
+        pass
+
+    # ---- state
+    def _tree(self, best):
+        p, a, b = self._e.trees(best=best, chain0=0, n=1)
+        c = self._ctree0
+        return ContractionTree.from_arrays(p[0], a[0], b[0], [c.inds[t] for t in range(c.n_leaves)], c.dims,
+                                           output_inds=c.output_inds())
+
+    ctree = property(lambda s: s._tree(False))
+    min_ctree = property(lambda s: s._tree(True))
+    cmodel = property(lambda s: s._cmodel)
+    disable_shared_inds = property(lambda s: s._dsi)
+    total_cost = property(lambda s: _dec(s._e.costs()[0][0]))
+    min_total_cost = property(lambda s: _dec(s._e.costs()[1][0]))
+    log2_total_cost = property(lambda s: math.log2(s._e.costs()[0][0]))
+    log2_min_total_cost = property(lambda s: math.log2(s._e.costs()[1][0]))
+
+    @property
+    def prng_state(self) -> str:
+        return mt19937_state_str(self._seed, int(self._e.progress()['words'][0]))
+
+    def is_valid(self, *, atol: float = 1e-5, return_message: bool = False):
+        """Re-derive the cached totals from the trees (infinite_memory/optimizer.hpp:223-252)."""
+        t, m = self._e.costs()
+        p, a, b = self._e.trees()
+        bp, ba, bb = self._e.trees(best=True)
+        sl = self._e.slices() if self._finite else None
+        bsl = self._e.slices(best=True) if self._finite else None
+        _, pc, mw = self._e.eval_cost(p, a, b, slices=sl)
+        bseq, _, bmw = self._e.eval_cost(bp, ba, bb, slices=bsl)
+        ok, msg = True, ''
+        if abs(math.log(pc[0]) - math.log(t[0])) > atol:
+            ok, msg = False, 'CostCache is not properly cached.'
+        elif abs(math.log(bseq[0]) - math.log(m[0])) > atol:
+            ok, msg = False, 'Cost for min ctree is not correct.'
+        elif self._finite and (mw[0] > self._cmodel.max_width + atol or bmw[0] > self._cmodel.max_width + atol):
+            ok, msg = False, 'Width larger than allowed width after slicing.'
+        return (ok, msg) if return_message else ok
+
+    def _slice_names(self, best):
+        order = self._ctree0._inds_order
+        return frozenset(order[i] for i in unpack_bits(self._e.slices(best=best)[0]))
