@@ -23,6 +23,7 @@ namespace tnb {
 #if defined(TNB_EMU)
 struct Rt {
   std::string err;
+  int minb = 20;
   bool init(int) { return true; }
   void* alloc(size_t b) { return std::calloc(std::max<size_t>(b, 1), 1); }
   void free_(void* p) { std::free(p); }
@@ -36,6 +37,7 @@ struct Rt {
 #else
 struct Rt {
   std::string err;
+  int minb = 20;  // resident single-warp blocks per SM requested from the sweep kernel (20 or 28)
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -100,21 +102,24 @@ __global__ void __launch_bounds__(kBlock) sa_init_kernel(const __grid_constant__
 // One warp per block: the hardware block scheduler then balances chains over the 148 SMs at warp granularity
 // (4096 chains of 16 lanes = 2048 blocks = 13.8 per SM, all resident in a single wave at <= 128 registers).
 constexpr int kSweepBlock = 32;
-template <int TILE, int WPL, bool FINITE, class Rng>
-__global__ void __launch_bounds__(kSweepBlock, 16) sa_sweep_kernel(const __grid_constant__ Params P) {
+// Production (Philox) kernels are held to 72 registers (no spills) so that 28 single-warp blocks fit on an SM:
+// 148 x 28 = 4144 resident chains at TILE = 32.  Parity kernels (fp64 pow, stream bookkeeping) keep 128.
+// MINB = single-warp blocks resident per SM the register allocation must allow (28 -> 72 registers).
+template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2, int MINB>
+__global__ void __launch_bounds__(kSweepBlock, MINB) sa_sweep_kernel(const __grid_constant__ Params P) {
   const int chain = (blockIdx.x * kSweepBlock + threadIdx.x) / TILE;
   if (chain >= P.n_chains) return;
-  chain_sweeps<TILE, WPL, FINITE, Rng>(P, chain);
+  chain_sweeps<TILE, WPL, FINITE, Rng, DIM2>(P, chain);
 }
 #endif
 
-template <int TILE, int WPL, bool FINITE, class Rng>
+template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2>
 static bool launch_t(Rt& rt, const Params& P, bool init) {
 #if defined(TNB_EMU)
   (void)rt;
   for (int c = 0; c < P.n_chains; ++c) {
     if (init) chain_init<TILE, WPL, FINITE, Rng>(P, c);
-    else chain_sweeps<TILE, WPL, FINITE, Rng>(P, c);
+    else chain_sweeps<TILE, WPL, FINITE, Rng, DIM2>(P, c);
   }
   return true;
 #else
@@ -123,19 +128,25 @@ static bool launch_t(Rt& rt, const Params& P, bool init) {
   const int grid = int((threads + blk - 1) / blk);
   if (grid == 0) return true;
   if (init) sa_init_kernel<TILE, WPL, FINITE, Rng><<<grid, kBlock, 0, rt.stream>>>(P);
-  else sa_sweep_kernel<TILE, WPL, FINITE, Rng><<<grid, kSweepBlock, 0, rt.stream>>>(P);
+  else if (!Rng::kFast) sa_sweep_kernel<TILE, WPL, FINITE, Rng, DIM2, 16><<<grid, kSweepBlock, 0, rt.stream>>>(P);
+  else if (rt.minb >= 28) sa_sweep_kernel<TILE, WPL, FINITE, Rng, DIM2, 28><<<grid, kSweepBlock, 0, rt.stream>>>(P);
+  else sa_sweep_kernel<TILE, WPL, FINITE, Rng, DIM2, 20><<<grid, kSweepBlock, 0, rt.stream>>>(P);
   return rt.ok(cudaGetLastError(), init ? "sa_init_kernel launch" : "sa_sweep_kernel launch");
 #endif
 }
 
 template <int TILE, int WPL>
 static bool launch_tw(Rt& rt, const Params& P, bool init, bool finite, bool stream_rng) {
+  // parity (stream) modes always take costs from the std::pow table; the production kernel builds 2^k directly
+  const bool d2 = P.dim2 != 0;
   if (finite) {
-    return stream_rng ? launch_t<TILE, WPL, true, RngStream<TILE>>(rt, P, init)
-                      : launch_t<TILE, WPL, true, RngPhilox<TILE>>(rt, P, init);
+    if (stream_rng) return launch_t<TILE, WPL, true, RngStream<TILE>, false>(rt, P, init);
+    return d2 ? launch_t<TILE, WPL, true, RngPhilox<TILE>, true>(rt, P, init)
+              : launch_t<TILE, WPL, true, RngPhilox<TILE>, false>(rt, P, init);
   }
-  return stream_rng ? launch_t<TILE, WPL, false, RngStream<TILE>>(rt, P, init)
-                    : launch_t<TILE, WPL, false, RngPhilox<TILE>>(rt, P, init);
+  if (stream_rng) return launch_t<TILE, WPL, false, RngStream<TILE>, false>(rt, P, init);
+  return d2 ? launch_t<TILE, WPL, false, RngPhilox<TILE>, true>(rt, P, init)
+            : launch_t<TILE, WPL, false, RngPhilox<TILE>, false>(rt, P, init);
 }
 
 static bool launch(Rt& rt, const Params& P, int tile, int wpl, bool init, bool finite, bool stream_rng) {
@@ -232,12 +243,11 @@ static int pick_tile(int W, int& wpl) {
   int tile = 32;
   if (W <= 4) tile = 4;
   else if (W <= 8) tile = 8;
-  else if (W <= 16) tile = 16;
-  else if (W <= 32) tile = 32;
+  else if (W <= 32) tile = 32;  // measured: 16-lane tiles lose more to intra-warp divergence than they gain
   else { tile = 32; wpl = (W + 31) / 32; }
   if (const char* f = std::getenv("TNB_TILE")) {
     const int t = std::atoi(f);
-    if ((t == 4 || t == 8 || t == 16 || t == 32) && t >= tile) tile = t;
+    if ((t == 4 || t == 8 || t == 16 || t == 32) && t * 1 >= (W <= 32 ? W : 32)) tile = t;
   }
   return tile;
 }
@@ -478,6 +488,14 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* lea
   e->Ws = (W + 3) / 4 * 4;
   e->Npad = (e->N + 7) / 8 * 8;
   e->tile = pick_tile(W, e->wpl);
+  {
+    // Occupancy of the production kernel.  Chain states of ~8..64 KB live in L1 between visits: more resident
+    // chains thrash it (measured on C2/C3), so they get 20 blocks/SM (96 registers).  Tiny states (all in L1)
+    // and huge ones (HBM/L2 resident, latency hidden by parallelism) take 28 blocks/SM (72 registers).
+    const size_t state = size_t(e->n_int) * (size_t(e->Ws) * 4 + 16 + 4) + size_t(e->Npad) * 2;
+    e->rt.minb = (state <= (8u << 10) || state >= (64u << 10)) ? 28 : 20;
+    if (const char* f = std::getenv("TNB_MINB")) e->rt.minb = std::atoi(f) >= 28 ? 28 : 20;
+  }
   e->dim = dim;
   e->log2d = std::log2(double(dim));
   e->h_leaf_bits.assign(leaf_bits, leaf_bits + size_t(n_leaves) * W);

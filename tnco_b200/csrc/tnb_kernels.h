@@ -90,58 +90,71 @@ template <int TILE>
 struct RngPhilox {
   static constexpr bool kFast = true;  // log-domain fp32 acceptance test (see chain_sweeps)
   uint32_t k0, k1, g0, g1;
-  unsigned long long v, blk;
-  uint32_t r0, r1, r2, r3;
-  uint32_t e0, e1, e2;
+  unsigned long long blk;  // index of the block of TILE vectors held in registers
+  uint32_t pos;            // next vector within the block; == TILE: block exhausted
+  bool fresh;              // registers hold block `blk`
+  uint32_t r0, r1, r2;
+  uint32_t e0, esrc;
   float rf, ef;  // -log2(u) of this lane's vector / of the current event
+  TNB_D void set_counter(unsigned long long v) {
+    blk = v / TILE;
+    pos = uint32_t(v % TILE);
+    fresh = false;
+  }
+  TNB_D unsigned long long counter() const { return blk * TILE + pos; }
   TNB_D void load(const Params& P, int chain) {
     const unsigned long long s = P.seeds[chain], g = P.chain_id0 + (unsigned long long)chain;
     k0 = uint32_t(s); k1 = uint32_t(s >> 32); g0 = uint32_t(g); g1 = uint32_t(g >> 32);
-    v = P.rng_ctr[chain];
-    blk = ~0ull;
-    r0 = r1 = r2 = r3 = e0 = e1 = e2 = 0;
+    r0 = r1 = r2 = e0 = esrc = 0;
     rf = ef = 0.f;
+    set_counter(P.rng_ctr[chain]);
   }
-  TNB_D void store(const Params& P, int chain) const { P.rng_ctr[chain] = v; }
+  TNB_D void store(const Params& P, int chain) const { P.rng_ctr[chain] = counter(); }
   TNB_D bool can_start(const Params&) const { return true; }
-  TNB_D TNB_INLINE void event(const Tile<TILE>& t) {
-    const unsigned long long b = v / TILE;
-    if (b != blk) {
-      blk = b;
-      const unsigned long long idx = b * TILE + (unsigned long long)t.tl;
-      philox4x32_10(uint32_t(idx), uint32_t(idx >> 32), g0, g1, k0, k1, r0, r1, r2, r3);
-      // u = (r1 + 0.5) / 2^32 in (0,1);  -log2(u) = 32 - log2(r1 + 0.5), computed once per vector
+  TNB_D void generate(const Tile<TILE>& t) {
+    const unsigned long long idx = blk * TILE + (unsigned long long)t.tl;
+    uint32_t r3;
+    philox4x32_10(uint32_t(idx), uint32_t(idx >> 32), g0, g1, k0, k1, r0, r1, r2, r3);
+    // u = (r1 + 0.5) / 2^32 in (0,1);  -log2(u) = 32 - log2(r1 + 0.5), computed once per vector
 #if defined(TNB_EMU)
-      rf = 32.f - log2f(float(r1) + 0.5f);
+    rf = 32.f - log2f(float(r1) + 0.5f);
 #else
-      rf = 32.f - __log2f(float(r1) + 0.5f);
+    rf = 32.f - __log2f(float(r1) + 0.5f);
 #endif
+    fresh = true;
+  }
+  TNB_D TNB_INLINE void event(const Tile<TILE>& t) {
+    if (pos == TILE) {
+      ++blk;
+      pos = 0;
+      fresh = false;
     }
-    const int src = int(v % TILE);
-    e0 = t.bcast(r0, src);
+    if (!fresh) generate(t);
+    esrc = pos;
+    e0 = t.bcast(r0, int(pos));
 #if defined(TNB_EMU)
     ef = rf;
 #else
-    ef = __uint_as_float(t.bcast(__float_as_uint(rf), src));
+    ef = __uint_as_float(t.bcast(__float_as_uint(rf), int(pos)));
 #endif
-    ++v;
+    ++pos;
   }
   TNB_D TNB_INLINE float neg_log2_u() const { return ef; }
   TNB_D TNB_INLINE uint32_t leaf_word(const Tile<TILE>& t) { event(t); return e0; }
   TNB_D TNB_INLINE void begin_level(const Tile<TILE>& t) { event(t); }
   TNB_D TNB_INLINE uint32_t coin_word(const Tile<TILE>&) { return e0; }
   TNB_D TNB_INLINE double uniform(const Tile<TILE>& t) {  // exact path (greedy / always rules)
-    const int src = int((v - 1) % TILE);
-    return uniform_from(t.bcast(r1, src), t.bcast(r2, src));
+    return uniform_from(t.bcast(r1, int(esrc)), t.bcast(r2, int(esrc)));
   }
   // lane-local draw (slicer, executed by lane 0 only); re-synchronise with sync_from0 afterwards
   TNB_D uint32_t local_next() {
+    const unsigned long long v = counter();
     uint32_t a, b, c, d;
     philox4x32_10(uint32_t(v), uint32_t(v >> 32), g0, g1, k0, k1, a, b, c, d);
-    ++v;
+    set_counter(v + 1);
     return a;
   }
-  TNB_D void sync_from0(const Tile<TILE>& t) { v = t.bcast_u64(v, 0); }
+  TNB_D void sync_from0(const Tile<TILE>& t) { set_counter(t.bcast_u64(counter(), 0)); }
   TNB_D unsigned long long words() const { return 0; }
   TNB_D int overrun() const { return 0; }
 };
@@ -192,62 +205,59 @@ struct ChainView {
   const Params& P;
   Tile<TILE> t;
   int chain;
+  int n;        // leaves: node < n is a leaf
+  unsigned Ws;  // words between consecutive bitset rows
   int16_t* par;
-  uint32_t* ch;
-  uint32_t* bits;
-  dbl2* cp;
+  // bases resolved for this lane and pre-offset by -n so that every array is indexed by the node id itself
+  // (signed element offsets; the virtual bases are only dereferenced at indices >= n)
+  const uint32_t* leaf_lane;  // leaf_bits + tl
+  uint32_t* bits_lane;        // bits of internal node z at bits_lane + z*Ws (+ k*TILE)
+  uint32_t* ch;               // ch[z]  = child0 | child1 << 16 of internal node z
+  dbl2* cp;                   // cp[z]  = {contraction_cost, partial_cost} of internal node z
+  bool lane_ok[WPL];
 
   TNB_D ChainView(const Params& P_, int chain_) : P(P_), chain(chain_) {
+    n = P.n;
+    Ws = unsigned(P.Ws);
     par = P.par + size_t(chain) * P.Npad;
-    ch = P.ch + size_t(chain) * P.n_int;
-    bits = P.bits + size_t(chain) * P.n_int * P.Ws;
-    cp = P.cp + size_t(chain) * P.n_int;
+    const long long row0 = (long long)chain * P.n_int - n;
+    bits_lane = P.bits + (row0 * (long long)P.Ws + t.tl);
+    leaf_lane = P.leaf_bits + t.tl;
+    ch = P.ch + row0;
+    cp = P.cp + row0;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) lane_ok[k] = (t.tl + k * TILE) < P.W;
   }
   TNB_D TNB_INLINE void load_bits(int node, uint32_t (&o)[WPL]) const {
-    if (node < P.n) {
-      const uint32_t* src = P.leaf_bits + size_t(node) * P.Ws;
+    const uint32_t* src = (node < n ? leaf_lane : const_cast<const uint32_t*>(bits_lane)) + unsigned(node) * Ws;
 #pragma unroll
-      for (int k = 0; k < WPL; ++k) {
-        const int w = t.tl + k * TILE;
-        o[k] = w < P.W ? ldg(src + w) : 0u;
-      }
-    } else {
-      const uint32_t* src = bits + size_t(node - P.n) * P.Ws;
-#pragma unroll
-      for (int k = 0; k < WPL; ++k) {
-        const int w = t.tl + k * TILE;
-        o[k] = w < P.W ? src[w] : 0u;
-      }
-    }
+    for (int k = 0; k < WPL; ++k) o[k] = lane_ok[k] ? src[k * TILE] : 0u;
   }
   TNB_D TNB_INLINE void store_bits(int node, const uint32_t (&v)[WPL]) const {
-    uint32_t* dst = bits + size_t(node - P.n) * P.Ws;
+    uint32_t* dst = bits_lane + unsigned(node) * Ws;
 #pragma unroll
-    for (int k = 0; k < WPL; ++k) {
-      const int w = t.tl + k * TILE;
-      if (w < P.W) dst[w] = v[k];
-    }
+    for (int k = 0; k < WPL; ++k)
+      if (lane_ok[k]) dst[k * TILE] = v[k];
   }
-  TNB_D TNB_INLINE double pc_of(int node) const { return node < P.n ? 0.0 : cp[node - P.n].y; }
+  TNB_D TNB_INLINE double pc_of(int node) const { return node < n ? 0.0 : cp[node].y; }
   TNB_D TNB_INLINE double cost_of(int k) const {
-    // pow(dim, k) (infinite_memory/cost_model/simple.hpp:45); dim == 2: the exact power of two, +inf past 2^1023
-    if (P.dim2) return bits_to_f64((unsigned long long)(1023 + (k > 1024 ? 1024 : k)) << 52);
+    // pow(dim, k) (infinite_memory/cost_model/simple.hpp:45) from the host-computed table (std::pow)
     return ldg(P.pow_tab + k);
   }
   TNB_D TNB_INLINE float width_of(int k) const { return float(P.log2d * double(k)); }  // fw simple.hpp:47
   // stackless post-order over the CURRENT topology, children[0] subtree first (utils.hpp:35-52)
   TNB_D int po_first() const {
     int x = P.N - 1;
-    while (x >= P.n) x = int(ch[x - P.n] & 0xffffu);
+    while (x >= n) x = int(ch[x] & 0xffffu);
     return x;
   }
   TNB_D int po_next(int x) const {
     if (x == P.N - 1) return -1;
     const int p = par[x];
-    const uint32_t c = ch[p - P.n];
+    const uint32_t c = ch[p];
     if (int(c & 0xffffu) == x) {
       x = int(c >> 16);
-      while (x >= P.n) x = int(ch[x - P.n] & 0xffffu);
+      while (x >= n) x = int(ch[x] & 0xffffu);
       return x;
     }
     return p;
@@ -283,7 +293,7 @@ TNB_D void cost_pass(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL], db
       }
       continue;
     }
-    const uint32_t cc_ = c.ch[z - P.n];
+    const uint32_t cc_ = c.ch[z];
     const int a = int(cc_ & 0xffffu), b = int(cc_ >> 16);
     uint32_t xa[WPL], xb[WPL];
     c.load_bits(a, xa);
@@ -319,7 +329,7 @@ TNB_D void build_bits(const ChainView<TILE, WPL>& c) {
   const Params& P = c.P;
   for (int z = c.po_first(); z >= 0; z = c.po_next(z)) {
     if (z < P.n) continue;
-    const uint32_t cc_ = c.ch[z - P.n];
+    const uint32_t cc_ = c.ch[z];
     uint32_t xa[WPL], xb[WPL];
     c.load_bits(int(cc_ & 0xffffu), xa);
     c.load_bits(int(cc_ >> 16), xb);
@@ -468,7 +478,7 @@ TNB_D void snapshot_best(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL]
   uint32_t* dst = reinterpret_cast<uint32_t*>(P.bpar + size_t(c.chain) * P.Npad);
   for (int i = c.t.tl; i < P.Npad / 2; i += TILE) dst[i] = src[i];
   uint32_t* dch = P.bch + size_t(c.chain) * P.n_int;
-  for (int i = c.t.tl; i < P.n_int; i += TILE) dch[i] = c.ch[i];
+  for (int i = c.t.tl; i < P.n_int; i += TILE) dch[i] = c.ch[P.n + i];
   if (finite) {
     uint32_t* ds = P.bslices + size_t(c.chain) * P.Ws;
 #pragma unroll
@@ -527,8 +537,8 @@ TNB_D void chain_init(const Params& P, int chain) {
   }
   double seq;
   uint32_t maxk;
-  cost_pass<TILE, WPL, true>(c, S, c.cp, seq, maxk);
-  const double rootpc = c.cp[P.n_int - 1].y;
+  cost_pass<TILE, WPL, true>(c, S, c.cp + c.n, seq, maxk);
+  const double rootpc = c.cp[P.N - 1].y;
   P.total[chain] = rootpc;
   P.min_total[chain] = seq;  // get_cost(min_ctree) sums in traversal order (infinite_memory/utils.hpp:102-116)
   if (P.out_seq) P.out_seq[chain] = seq;
@@ -581,7 +591,7 @@ TNB_HD TNB_INLINE float log2_1p_ratio(double delta, double total) {
 // walks.  The inputs of level k+1 (parent A', its children word and contraction cost, the sibling's index set
 // and partial cost) do not depend on the move at level k, so they are loaded during level k in three stages and
 // are in registers when level k+1 starts.
-template <int TILE, int WPL, bool FINITE, class Rng>
+template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2>
 TNB_D void chain_sweeps(const Params& P, int chain) {
   ChainView<TILE, WPL> c(P, chain);
   const Tile<TILE>& t = c.t;
@@ -594,7 +604,8 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   rng.load(P, chain);
   long long s = P.sweep_idx[chain];
   double min_total = P.min_total[chain];
-  unsigned long long n_prop = 0, n_acc = 0, n_wrej = 0;
+  unsigned long long n_prop = 0, n_acc = 0, n_wrej = 0;  // folded from the 32-bit per-sweep counters below
+  uint32_t q_prop = 0, q_acc = 0, q_wrej = 0;
   uint32_t S[WPL];
 #pragma unroll
   for (int k = 0; k < WPL; ++k) S[k] = 0u;
@@ -626,7 +637,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
             const double r2 = cp2[P.n_int - 1].y;
             if (r2 < root_pc) {
               t.sync();
-              for (int i = t.tl; i < P.n_int; i += TILE) c.cp[i] = cp2[i];
+              for (int i = t.tl; i < P.n_int; i += TILE) c.cp[n + i] = cp2[i];
               t.sync();
 #pragma unroll
               for (int k = 0; k < WPL; ++k) S[k] = S2[k];
@@ -641,6 +652,8 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         }
         ++s;
         in_sweep = false;
+        n_prop += q_prop; n_acc += q_acc; n_wrej += q_wrej;
+        q_prop = q_acc = q_wrej = 0;
         if (rng.overrun()) break;
       }
       if (s >= P.until || !rng.can_start(P)) break;
@@ -648,30 +661,30 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       beta_f = float(beta);
       const int leaf = int(rng.leaf_word(t) % uint32_t(n));  // optimizer.hpp:103
       B = c.par[leaf];
-      total = c.cp[root - n].y;                              // :112
+      total = c.cp[root].y;                              // :112
       root_pc = total;
-      const uint32_t cw = c.ch[B - n];
+      const uint32_t cw = c.ch[B];
       p0 = int(cw & 0xffffu);
       p1 = int(cw >> 16);
       c.load_bits(p0, b0);
       c.load_bits(p1, b1);
       pc0 = c.pc_of(p0);
       pc1 = c.pc_of(p1);
-      ccB = c.cp[B - n].x;
+      ccB = c.cp[B].x;
       A = c.par[B];
       in_sweep = true;
       if (A >= 0) {
-        const uint32_t aw = c.ch[A - n];
+        const uint32_t aw = c.ch[A];
         a0 = int(aw & 0xffffu);
         a1 = int(aw >> 16);
         C = (a0 == B) ? a1 : a0;
         c.load_bits(C, bC);
         pcC = c.pc_of(C);
-        ccA = c.cp[A - n].x;
+        ccA = c.cp[A].x;
       }
-      continue;
-    }
+    } else {
     // -------------------------------------------------------------------- one level (A >= 0)
+    // (if/else, not `continue`: both kinds of iteration join again here so the tiles of a warp re-converge)
     // get_ctree_nn (optimize/optimizer.hpp:86-172): A = parent(B), C = sibling(B), D/E = children of B
     const int An = c.par[A];  // stage 1 of the next level's inputs
     const bool bslot0 = (a0 == B);
@@ -699,26 +712,32 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     }
     const double pcD = pick0 ? pc0 : pc1;
     double pcE = pick0 ? pc1 : pc0;
-    ++n_prop;
+    ++q_prop;
     bool gate = true;
     if (FINITE) {  // finite_width/greedy/optimizer.hpp:176-188
       ks = t.sum(ks);
       gate = c.width_of(int(ks)) <= P.max_width;
-      if (!gate) ++n_wrej;
+      if (!gate) ++q_wrej;
     }
     // stage 2: children word and contraction cost of the next parent
     uint32_t awn = 0u;
     double ccAn = 0.0;
     if (An >= 0) {
-      awn = c.ch[An - n];
-      ccAn = c.cp[An - n].x;
+      awn = c.ch[An];
+      ccAn = c.cp[An].x;
     }
     bool acc = false;
     double nA = 0.0, nB = 0.0, delta = 0.0;
     if (gate) {
       kpack = t.sum(kpack);
-      nA = c.cost_of(int(kpack & 0xffffu));  // cost(new_B | E [| slices])
-      nB = c.cost_of(int(kpack >> 16));      // cost(D | C [| slices])
+      if (DIM2) {  // dim == 2: the exact power of two built from its exponent (+inf past 2^1023, like pow)
+        const uint32_t ka = kpack & 0xffffu, kb = kpack >> 16;
+        nA = bits_to_f64((unsigned long long)(1023u + (ka > 1024u ? 1024u : ka)) << 52);
+        nB = bits_to_f64((unsigned long long)(1023u + (kb > 1024u ? 1024u : kb)) << 52);
+      } else {
+        nA = c.cost_of(int(kpack & 0xffffu));  // cost(new_B | E [| slices])
+        nB = c.cost_of(int(kpack >> 16));      // cost(D | C [| slices])
+      }
       delta = (nB - ccB) + (nA - ccA);       // :158, this association order
       if (Rng::kFast && P.prob_kind == kProbMH) {
         // same rule as prob/mh.hpp:45-59 in the log domain: u <= (1+x)^-beta  <=>  beta*log2(1+x) <= -log2(u)
@@ -743,15 +762,15 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       // Tree::swap_with_nn(E): E <-> C, child slots preserved (tree.hpp:141-192)
       if (bslot0) a1 = E; else a0 = E;
       if (pick0) p1 = C; else p0 = C;
-      c.ch[A - n] = uint32_t(a0) | (uint32_t(a1) << 16);
-      c.ch[B - n] = uint32_t(p0) | (uint32_t(p1) << 16);
+      c.ch[A] = uint32_t(a0) | (uint32_t(a1) << 16);
+      c.ch[B] = uint32_t(p0) | (uint32_t(p1) << 16);
       c.par[C] = int16_t(B);
       c.par[E] = int16_t(A);
       c.store_bits(B, nb);
       ccB = nB;
       ccA = nA;
       total += delta;
-      ++n_acc;
+      ++q_acc;
       {
         const int ti = C; C = E; E = ti;
         const double td = pcC; pcC = pcE; pcE = td;
@@ -768,8 +787,8 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     // propagate partial costs (:185-188), post-swap names
     const double pcB = pcD + pcE + ccB;
     const double pcA = pcB + pcC + ccA;
-    c.cp[B - n] = make_dbl2(ccB, pcB);
-    c.cp[A - n] = make_dbl2(ccA, pcA);
+    c.cp[B] = make_dbl2(ccB, pcB);
+    c.cp[A] = make_dbl2(ccA, pcA);
     root_pc = pcA;
     // next level: B <- A, whose children are (a0, a1) = {B, C} in slot order
     p0 = a0;
@@ -792,11 +811,12 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       pcC = c.pc_of(C);
       ccA = ccAn;
     }
+    }  // level
   }
   rng.store(P, chain);
   P.sweep_idx[chain] = s;
   P.min_total[chain] = min_total;
-  P.total[chain] = c.cp[root - n].y;
+  P.total[chain] = c.cp[root].y;
   P.n_prop[chain] += n_prop;
   P.n_acc[chain] += n_acc;
   P.n_wrej[chain] += n_wrej;

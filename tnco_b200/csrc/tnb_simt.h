@@ -46,10 +46,28 @@ struct Tile {
     tl = lane & (TILE - 1);
     mask = TILE == 32 ? 0xffffffffu : (((1u << TILE) - 1u) << (lane & ~(TILE - 1)));
   }
-  TNB_D TNB_INLINE bool any(bool p) const { return __ballot_sync(mask, p) != 0u; }
-  TNB_D TNB_INLINE uint32_t sum(uint32_t v) const { return __reduce_add_sync(mask, v); }
-  TNB_D TNB_INLINE uint32_t bcast(uint32_t v, int src) const { return __shfl_sync(mask, v, src, TILE); }
-  TNB_D TNB_INLINE void sync() const { __syncwarp(mask); }
+  // (TILE == 32 uses the literal full mask: with a run-time mask the compiler brackets every vote / shuffle
+  // with a divergence check and a WARPSYNC)
+  TNB_D TNB_INLINE bool any(bool p) const {
+    if (TILE == 32) return __any_sync(0xffffffffu, p) != 0;
+    return (__ballot_sync(mask, p) & mask) != 0u;
+  }
+  // Full warp: one REDUX.  Sub-warp tiles: a shuffle butterfly -- REDUX with a partial member mask makes the
+  // compiler run every tile of the warp exclusively (WARPSYNC.EXCLUSIVE), which serialises the tiles.
+  TNB_D TNB_INLINE uint32_t sum(uint32_t v) const {
+    if (TILE == 32) return __reduce_add_sync(0xffffffffu, v);
+#pragma unroll
+    for (int d = TILE / 2; d > 0; d >>= 1) v += __shfl_xor_sync(mask, v, d, TILE);
+    return v;
+  }
+  TNB_D TNB_INLINE uint32_t bcast(uint32_t v, int src) const {
+    if (TILE == 32) return __shfl_sync(0xffffffffu, v, src, 32);
+    return __shfl_sync(mask, v, src, TILE);
+  }
+  TNB_D TNB_INLINE void sync() const {
+    if (TILE == 32) __syncwarp(0xffffffffu);
+    else __syncwarp(mask);
+  }
 #endif
   // exclusive prefix sum over the tile's lanes (lane order); returns this lane's offset
   TNB_D TNB_INLINE uint32_t excl_scan_sum(uint32_t v, uint32_t& total) const {
@@ -60,10 +78,10 @@ struct Tile {
     uint32_t x = v;
 #pragma unroll
     for (int d = 1; d < TILE; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(mask, x, d, TILE);
+      const uint32_t y = TILE == 32 ? __shfl_up_sync(0xffffffffu, x, d, 32) : __shfl_up_sync(mask, x, d, TILE);
       if (tl >= d) x += y;
     }
-    total = __shfl_sync(mask, x, TILE - 1, TILE);
+    total = bcast(x, TILE - 1);
     return x - v;
 #endif
   }
@@ -72,7 +90,7 @@ struct Tile {
     (void)src;
     return v;
 #else
-    return __shfl_sync(mask, v, src, TILE);
+    return TILE == 32 ? __shfl_sync(0xffffffffu, v, src, 32) : __shfl_sync(mask, v, src, TILE);
 #endif
   }
   TNB_D TNB_INLINE unsigned long long bcast_u64(unsigned long long v, int src) const {
