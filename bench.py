@@ -340,7 +340,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--chains', type=int, default=4096, help='chains per GPU')
-    ap.add_argument('--sweeps', type=int, default=2000, help='sweeps per chain per step (n_steps of the anneal)')
+    ap.add_argument('--sweeps', type=int, default=10000, help='sweeps per chain per step (n_steps of the anneal)')
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--e2e-warmup', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -97,9 +97,23 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
         mins = dist.all_gather_rows(mins, n_runs)
         ba, bb = dist.all_gather_rows(ba, n_runs), dist.all_gather_rows(bb, n_runs)
         sl = dist.all_gather_rows(sl, n_runs)
-    paths = tree_to_path(ba, bb, n_tensors=len(tn), tensors_pos=np.asarray(comp, np.int32))
-    slices = [frozenset(inds[i] for i in unpack_bits(row)) for row in sl] if finite else None
-    return mins, paths, slices
+    return dict(mins=mins, c0=ba, c1=bb, slices=sl, inds=inds, comp=np.asarray(comp, np.int32), n_tensors=len(tn),
+                whole=(len(comp) == len(tn)))
+
+
+def _pairs(a):
+    """[k][2] int32 -> list of k 2-tuples (one C-level conversion)."""
+    a = np.ascontiguousarray(a, np.int32)
+    return a.view(np.dtype([('x', '<i4'), ('y', '<i4')])).reshape(a.shape[0]).tolist()
+
+
+def _comp_path(pc, r):
+    """Linear path of run r of one component over all tensors (ContractionTree.path(), ctree.py:350-388)."""
+    return tree_to_path(pc['c0'][r], pc['c1'][r], n_tensors=pc['n_tensors'], tensors_pos=pc['comp'])
+
+
+def _comp_slices(pc, r):
+    return frozenset(pc['inds'][i] for i in unpack_bits(pc['slices'][r]))
 
 
 def optimize(opt, results_cls, tn, betas, n_steps, n_runs, n_projs, update_slices, timeout, finite,
@@ -129,43 +143,40 @@ def optimize(opt, results_cls, tn, betas, n_steps, n_runs, n_projs, update_slice
     runtime = time.perf_counter() - t_start
     R = int(n_runs)
     live = [pc for pc in per_comp if pc is not None]
-    lens = [pc[1].shape[1] for pc in live]
-    cat = np.concatenate([pc[1] for pc in live], axis=1) if live else np.zeros((R, 0, 2), np.int32)
-    # tn_utils.merge_contraction_paths (sa.py:230), batched in C++; one component spanning the whole network
-    # merges to itself with each pair sorted
-    if len(live) == 1 and lens[0] == len(tn) - 1:
-        merged = np.sort(cat, axis=2)
+    # total cost per run = sum of the 6-significant-digit Decimals the reference prints (sa.py:215-220)
+    if len(live) == 1:
+        keys = np.array([float('%.6g' % v) for v in live[0]['mins']])
     else:
-        merged = merge_paths(len(tn), lens, cat)
+        keys = np.array([float(sum(cost_to_decimal(pc['mins'][r]) for pc in live)) for r in range(R)]) if live \
+            else np.zeros(R)
+    order = np.argsort(keys, kind='stable')  # == sorted(results) on cost (app.py:83-87, sa.py:257)
 
-    pair_t = np.dtype([('x', '<i4'), ('y', '<i4')])
+    def make(r):
+        def d_costs():
+            return [0 if pc is None else cost_to_decimal(pc['mins'][r]) for pc in per_comp]
 
-    def pairs(a):  # [R][k][2] int32 -> R lists of k 2-tuples, one C-level conversion
-        a = np.ascontiguousarray(a, np.int32)
-        return a.view(pair_t).reshape(a.shape[0], a.shape[1]).tolist()
+        def d_paths():
+            return [[] if pc is None else _pairs(_comp_path(pc, r)) for pc in per_comp]
 
-    merged_l = pairs(merged)
-    comp_l = [None if pc is None else pairs(pc[1]) for pc in per_comp]
+        def path():
+            if len(live) == 1 and live[0]['whole']:  # one component spanning the network: its path, pairs sorted
+                return _pairs(np.sort(_comp_path(live[0], r), axis=1))
+            cat = np.concatenate([_comp_path(pc, r) for pc in live], axis=0)[None] if live else \
+                np.zeros((1, 0, 2), np.int32)
+            # tn_utils.merge_contraction_paths (sa.py:230), in C++
+            return _pairs(merge_paths(len(tn), [len(pc['comp']) - 1 for pc in live], cat)[0])
 
-    results = []
-    for r in range(R):
-        d_costs, d_paths, d_slices = [], [], []
-        for pc, pl in zip(per_comp, comp_l):
-            if pc is None:
-                d_costs.append(0)
-                d_paths.append([])
-                d_slices.append(frozenset())
-            else:
-                d_costs.append(cost_to_decimal(pc[0][r]))
-                d_paths.append(pl[r])
-                d_slices.append(pc[2][r] if finite else frozenset())
-        kw = dict(cost=sum(d_costs), runtime_s=runtime, disconnected_costs=d_costs, disconnected_paths=d_paths,
-                  path=merged_l[r])
+        kw = dict(cost=lambda: sum(d_costs()), runtime_s=runtime, disconnected_costs=d_costs,
+                  disconnected_paths=d_paths, path=path)
         if finite:
-            kw.update(disconnected_slices=d_slices, slices=fts.reduce(op.or_, d_slices))
-        results.append(results_cls(**kw))
+            def d_slices():
+                return [frozenset() if pc is None else _comp_slices(pc, r) for pc in per_comp]
+            kw.update(disconnected_slices=d_slices, slices=lambda: fts.reduce(op.or_, d_slices(), frozenset()))
+        return results_cls(**kw)
+
+    results = [make(int(r)) for r in order]
     if opt.verbose == 1:
         print(' Done!', file=stderr, flush=True)
     stats['runtime_s'] = runtime
     object.__setattr__(opt, 'last_stats', stats)
-    return opt._dump_results(tn, sorted(results))
+    return opt._dump_results(tn, results)

@@ -38,11 +38,53 @@ class JSONEncoder(json.JSONEncoder):
         return super().default(obj)
 
 
-@dataclass(repr=False, frozen=True, eq=False)
-class BaseContractionResults:
-    cost: Any
-    runtime_s: float
-    path: list
+class _LazyFields:
+    """Result records keep the reference's attribute names (tnco/app/app.py:64-94, sa.py:63-90) but a field may
+    be given as a zero-argument callable: it is evaluated and cached on first access.  optimize() hands out
+    tens of thousands of results whose paths live in numpy arrays until somebody looks at them."""
+    _fields = ()
+
+    def __init__(self, *args, **kwargs):
+        names = self._fields
+        if len(args) > len(names):
+            raise TypeError('too many positional arguments')
+        vals = dict(zip(names, args))
+        for k, v in kwargs.items():
+            if k not in names or k in vals:
+                raise TypeError(f'unexpected or duplicate argument {k!r}')
+            vals[k] = v
+        missing = [k for k in names if k not in vals]
+        if missing:
+            raise TypeError(f'missing arguments: {missing}')
+        for k in names:
+            object.__setattr__(self, '_' + k, vals[k])
+
+    def __setattr__(self, k, v):
+        raise AttributeError('results are read-only')
+
+    def _get(self, k):
+        v = object.__getattribute__(self, '_' + k)
+        if callable(v):
+            v = v()
+            object.__setattr__(self, '_' + k, v)
+        return v
+
+    def __getattr__(self, k):
+        if k in type(self)._fields:
+            return self._get(k)
+        raise AttributeError(k)
+
+    def __getstate__(self):
+        return {k: self._get(k) for k in self._fields}
+
+    def __setstate__(self, state):
+        for k, v in state.items():
+            object.__setattr__(self, '_' + k, v)
+
+
+class BaseContractionResults(_LazyFields):
+    """cost, runtime_s, path (linear einsum format) -- tnco/app/app.py:64-94."""
+    _fields = ('cost', 'runtime_s', 'path')
 
     def __lt__(self, other):
         if not isinstance(other, BaseContractionResults):

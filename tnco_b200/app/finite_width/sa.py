@@ -3,7 +3,6 @@
 from __future__ import annotations
 
 import json
-from dataclasses import dataclass
 from typing import Any, Iterable
 
 from .. import _sa
@@ -20,12 +19,9 @@ class JSONEncoder(BaseJSONEncoder):
         return super().default(obj)
 
 
-@dataclass(repr=False, frozen=True, eq=False)
 class ContractionResults(BaseContractionResults):
-    disconnected_costs: list
-    disconnected_paths: list
-    disconnected_slices: list
-    slices: frozenset
+    """Fields as in tnco/app/finite_width/sa.py (dataclass there; lazily materialised record here)."""
+    _fields = BaseContractionResults._fields + ('disconnected_costs', 'disconnected_paths', 'disconnected_slices', 'slices')
 
     def to_json(self):
         return json.dumps(self, cls=JSONEncoder)

@@ -3,7 +3,6 @@
 from __future__ import annotations
 
 import json
-from dataclasses import dataclass
 from typing import Any, Iterable
 
 from .. import _sa
@@ -19,10 +18,9 @@ class JSONEncoder(BaseJSONEncoder):
         return super().default(obj)
 
 
-@dataclass(repr=False, frozen=True, eq=False)
 class ContractionResults(BaseContractionResults):
-    disconnected_costs: list
-    disconnected_paths: list
+    """Fields as in tnco/app/infinite_memory/sa.py (dataclass there; lazily materialised record here)."""
+    _fields = BaseContractionResults._fields + ('disconnected_costs', 'disconnected_paths')
 
     def to_json(self):
         return json.dumps(self, cls=JSONEncoder)
