@@ -23,7 +23,7 @@ namespace tnb {
 #if defined(TNB_EMU)
 struct Rt {
   std::string err;
-  int minb = 20;
+  int minb = 16;
   bool init(int) { return true; }
   void* alloc(size_t b) { return std::calloc(std::max<size_t>(b, 1), 1); }
   void free_(void* p) { std::free(p); }
@@ -37,7 +37,7 @@ struct Rt {
 #else
 struct Rt {
   std::string err;
-  int minb = 20;  // resident single-warp blocks per SM requested from the sweep kernel (20 or 28)
+  int minb = 16;  // occupancy class of the sweep kernel: 16 (<= 128 registers, ~20 warps/SM) or 28 (72 registers)
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -130,7 +130,7 @@ static bool launch_t(Rt& rt, const Params& P, bool init) {
   if (init) sa_init_kernel<TILE, WPL, FINITE, Rng><<<grid, kBlock, 0, rt.stream>>>(P);
   else if (!Rng::kFast) sa_sweep_kernel<TILE, WPL, FINITE, Rng, DIM2, 16><<<grid, kSweepBlock, 0, rt.stream>>>(P);
   else if (rt.minb >= 28) sa_sweep_kernel<TILE, WPL, FINITE, Rng, DIM2, 28><<<grid, kSweepBlock, 0, rt.stream>>>(P);
-  else sa_sweep_kernel<TILE, WPL, FINITE, Rng, DIM2, 20><<<grid, kSweepBlock, 0, rt.stream>>>(P);
+  else sa_sweep_kernel<TILE, WPL, FINITE, Rng, DIM2, 16><<<grid, kSweepBlock, 0, rt.stream>>>(P);
   return rt.ok(cudaGetLastError(), init ? "sa_init_kernel launch" : "sa_sweep_kernel launch");
 #endif
 }
@@ -490,11 +490,11 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* lea
   e->tile = pick_tile(W, e->wpl);
   {
     // Occupancy of the production kernel.  Chain states of ~8..64 KB live in L1 between visits: more resident
-    // chains thrash it (measured on C2/C3), so they get 20 blocks/SM (96 registers).  Tiny states (all in L1)
+    // chains thrash it (measured on C2/C3), so they keep ~96 registers (20 warps/SM).  Tiny states (all in L1)
     // and huge ones (HBM/L2 resident, latency hidden by parallelism) take 28 blocks/SM (72 registers).
     const size_t state = size_t(e->n_int) * (size_t(e->Ws) * 4 + 16 + 4) + size_t(e->Npad) * 2;
-    e->rt.minb = (state <= (8u << 10) || state >= (64u << 10)) ? 28 : 20;
-    if (const char* f = std::getenv("TNB_MINB")) e->rt.minb = std::atoi(f) >= 28 ? 28 : 20;
+    e->rt.minb = (state <= (8u << 10) || state >= (64u << 10)) ? 28 : 16;
+    if (const char* f = std::getenv("TNB_MINB")) e->rt.minb = std::atoi(f) >= 28 ? 28 : 16;
   }
   e->dim = dim;
   e->log2d = std::log2(double(dim));

@@ -611,6 +611,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   for (int k = 0; k < WPL; ++k) S[k] = 0u;
   if (FINITE) load_slices(c, S);
 
+  const int f_dsi = P.dsi, f_prob = P.prob_kind;
   bool in_sweep = false;
   int B = 0, A = -1, C = 0, p0 = 0, p1 = 0, a0 = 0, a1 = 0;
   uint32_t b0[WPL], b1[WPL], bC[WPL];
@@ -697,7 +698,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     const bool i0 = t.any(l0), i1 = t.any(l1);
     rng.begin_level(t);
     bool pick0;
-    if (P.dsi || (i0 && i1)) pick0 = (rng.coin_word(t) & 1u) != 0u;
+    if (f_dsi || (i0 && i1)) pick0 = (rng.coin_word(t) & 1u) != 0u;
     else pick0 = i0;
     int E = pick0 ? p1 : p0;  // D = the other child
     uint32_t bD[WPL], bE[WPL], nb[WPL];
@@ -739,17 +740,17 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         nB = c.cost_of(int(kpack >> 16));      // cost(D | C [| slices])
       }
       delta = (nB - ccB) + (nA - ccA);       // :158, this association order
-      if (Rng::kFast && P.prob_kind == kProbMH) {
+      if (Rng::kFast && f_prob == kProbMH) {
         // same rule as prob/mh.hpp:45-59 in the log domain: u <= (1+x)^-beta  <=>  beta*log2(1+x) <= -log2(u)
         acc = delta <= 0.0 || beta_f * log2_1p_ratio(delta, total) <= rng.neg_log2_u();
       } else {
         const double u = rng.uniform(t);  // always drawn (:162)
         double p;
-        if (P.prob_kind == kProbMH) {     // prob/mh.hpp:45-59
+        if (f_prob == kProbMH) {          // prob/mh.hpp:45-59
           if (delta <= 0.0) p = 1.0;
           else if (total == 0.0) p = 0.0;
           else p = pow(1.0 + delta / total, -beta);
-        } else if (P.prob_kind == kProbGreedy) {
+        } else if (f_prob == kProbGreedy) {
           p = delta <= 0.0 ? 1.0 : 0.0;
         } else {
           p = 1.0;

@@ -29,6 +29,29 @@ static __device__ __forceinline__ dbl2 make_dbl2(double x, double y) { return ma
 
 namespace tnb {
 
+// Make a value opaque to the optimiser (it then stays in its register instead of being re-derived from kernel
+// parameters at every use; the per-chain base pointers of the sweep loop are kept this way).
+template <class T>
+TNB_D TNB_INLINE void keep_in_register(T*& p) {
+#if !defined(TNB_EMU)
+  asm volatile("" : "+l"(p));
+#else
+  (void)p;
+#endif
+}
+TNB_D TNB_INLINE void keep_in_register(int& v) {
+#if !defined(TNB_EMU)
+  asm volatile("" : "+r"(v));
+#else
+  (void)v;
+#endif
+}
+#if defined(TNB_EMU)
+#define TNB_NOINLINE
+#else
+#define TNB_NOINLINE __noinline__
+#endif
+
 template <int TILE>
 struct Tile {
 #if defined(TNB_EMU)
