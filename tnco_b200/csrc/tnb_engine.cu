@@ -23,7 +23,7 @@ namespace tnb {
 #if defined(TNB_EMU)
 struct Rt {
   std::string err;
-  int minb = 16;
+  int minb = 28;
   bool init(int) { return true; }
   void* alloc(size_t b) { return std::calloc(std::max<size_t>(b, 1), 1); }
   void free_(void* p) { std::free(p); }
@@ -37,7 +37,7 @@ struct Rt {
 #else
 struct Rt {
   std::string err;
-  int minb = 16;  // occupancy class of the sweep kernel: 16 (<= 128 registers, ~20 warps/SM) or 28 (72 registers)
+  int minb = 28;  // occupancy class of the sweep kernel: 28 (72 registers) or 16 (<= 128 registers)
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -489,11 +489,11 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* lea
   e->Npad = (e->N + 7) / 8 * 8;
   e->tile = pick_tile(W, e->wpl);
   {
-    // Occupancy of the production kernel.  Chain states of ~8..64 KB live in L1 between visits: more resident
-    // chains thrash it (measured on C2/C3), so they keep ~96 registers (20 warps/SM).  Tiny states (all in L1)
-    // and huge ones (HBM/L2 resident, latency hidden by parallelism) take 28 blocks/SM (72 registers).
-    const size_t state = size_t(e->n_int) * (size_t(e->Ws) * 4 + 16 + 4) + size_t(e->Npad) * 2;
-    e->rt.minb = (state <= (8u << 10) || state >= (64u << 10)) ? 28 : 16;
+    // Occupancy class of the production kernel: 28 single-warp blocks per SM (72 registers, no spills) -- all
+    // 4096 chains of the benchmark configuration are then resident in one wave (27.7 per SM).  The 16-block
+    // class (<= 128 registers) is kept for experiments (TNB_MINB=16); it was faster only while the kernel still
+    // carried the partial-cost cache (profiles/README.md).
+    e->rt.minb = 28;
     if (const char* f = std::getenv("TNB_MINB")) e->rt.minb = std::atoi(f) >= 28 ? 28 : 16;
   }
   e->dim = dim;

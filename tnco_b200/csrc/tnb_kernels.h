@@ -586,6 +586,21 @@ TNB_HD TNB_INLINE float log2_1p_ratio(double delta, double total) {
 #endif
 }
 
+// Sum of all contraction costs of a chain (production mode keeps no partial-cost cache: the running total is
+// re-based on this exact-as-possible sum every few sweeps, like the reference re-reads partial_cost.back()
+// at the start of every update()).  Same association order on every lane -> tile-uniform result.
+template <int TILE, int WPL>
+TNB_D double sum_ccost(const ChainView<TILE, WPL>& c) {
+  double acc = 0.0;
+  for (int z = c.n + c.t.tl; z < c.P.N; z += TILE) acc += c.cp[z].x;
+#if !defined(TNB_EMU)
+#pragma unroll
+  for (int d = TILE / 2; d > 0; d >>= 1)
+    acc += TILE == 32 ? __shfl_xor_sync(0xffffffffu, acc, d, 32) : __shfl_xor_sync(c.t.mask, acc, d, TILE);
+#endif
+  return acc;
+}
+
 // One flat loop per tile: every iteration is either a sweep boundary (finish sweep s, start sweep s+1) or one
 // level of the leaf->root walk, so the tiles sharing a warp stay converged instead of waiting for each other's
 // walks.  The inputs of level k+1 (parent A', its children word and contraction cost, the sibling's index set
@@ -600,10 +615,15 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     P.sweep_idx[chain] = P.until;
     return;
   }
+  // PC: keep the reference's partial-cost cache (parity modes).  The production kernel drops it: the walk then
+  // needs no partial costs of D/E/C, no two 16-byte stores per level and half the fp64 adds; its total is a
+  // running sum re-based on sum_ccost() every 16 sweeps.
+  constexpr bool PC = !Rng::kFast;
   Rng rng;
   rng.load(P, chain);
   long long s = P.sweep_idx[chain];
   double min_total = P.min_total[chain];
+  bool rebase = true;
   unsigned long long n_prop = 0, n_acc = 0, n_wrej = 0;  // folded from the 32-bit per-sweep counters below
   uint32_t q_prop = 0, q_acc = 0, q_wrej = 0;
   uint32_t S[WPL];
@@ -636,7 +656,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
             uint32_t maxk;
             cost_pass<TILE, WPL, false>(c, S2, cp2, seq, maxk);
             const double r2 = cp2[P.n_int - 1].y;
-            if (r2 < root_pc) {
+            if (r2 < (PC ? root_pc : total)) {
               t.sync();
               for (int i = t.tl; i < P.n_int; i += TILE) c.cp[n + i] = cp2[i];
               t.sync();
@@ -644,9 +664,11 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
               for (int k = 0; k < WPL; ++k) S[k] = S2[k];
               store_slices(c, S);
               root_pc = r2;
+              total = r2;
             }
           }
         }
+        if (!PC) root_pc = total;
         if (root_pc < min_total) {  // infinite_memory/optimizer.hpp:197-201
           min_total = root_pc;
           snapshot_best(c, S, FINITE);
@@ -662,15 +684,22 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       beta_f = float(beta);
       const int leaf = int(rng.leaf_word(t) % uint32_t(n));  // optimizer.hpp:103
       B = c.par[leaf];
-      total = c.cp[root].y;                              // :112
+      if (PC) {
+        total = c.cp[root].y;                            // :112
+      } else if (rebase || (s & 15) == 0) {
+        total = sum_ccost(c);
+        rebase = false;
+      }
       root_pc = total;
       const uint32_t cw = c.ch[B];
       p0 = int(cw & 0xffffu);
       p1 = int(cw >> 16);
       c.load_bits(p0, b0);
       c.load_bits(p1, b1);
-      pc0 = c.pc_of(p0);
-      pc1 = c.pc_of(p1);
+      if (PC) {
+        pc0 = c.pc_of(p0);
+        pc1 = c.pc_of(p1);
+      }
       ccB = c.cp[B].x;
       A = c.par[B];
       in_sweep = true;
@@ -680,7 +709,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         a1 = int(aw >> 16);
         C = (a0 == B) ? a1 : a0;
         c.load_bits(C, bC);
-        pcC = c.pc_of(C);
+        if (PC) pcC = c.pc_of(C);
         ccA = c.cp[A].x;
       }
     } else {
@@ -786,11 +815,17 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       for (int k = 0; k < WPL; ++k) bB[k] = bD[k] ^ bE[k];
     }
     // propagate partial costs (:185-188), post-swap names
-    const double pcB = pcD + pcE + ccB;
-    const double pcA = pcB + pcC + ccA;
-    c.cp[B] = make_dbl2(ccB, pcB);
-    c.cp[A] = make_dbl2(ccA, pcA);
-    root_pc = pcA;
+    double pcB = 0.0;
+    if (PC) {
+      pcB = pcD + pcE + ccB;
+      const double pcA = pcB + pcC + ccA;
+      c.cp[B] = make_dbl2(ccB, pcB);
+      c.cp[A] = make_dbl2(ccA, pcA);
+      root_pc = pcA;
+    } else if (acc) {
+      c.cp[B].x = ccB;
+      c.cp[A].x = ccA;
+    }
     // next level: B <- A, whose children are (a0, a1) = {B, C} in slot order
     p0 = a0;
     p1 = a1;
@@ -799,8 +834,10 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       b0[k] = bslot0 ? bB[k] : bC[k];
       b1[k] = bslot0 ? bC[k] : bB[k];
     }
-    pc0 = bslot0 ? pcB : pcC;
-    pc1 = bslot0 ? pcC : pcB;
+    if (PC) {
+      pc0 = bslot0 ? pcB : pcC;
+      pc1 = bslot0 ? pcC : pcB;
+    }
     ccB = ccA;
     B = A;
     A = An;
@@ -809,7 +846,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       a1 = int(awn >> 16);
       C = (a0 == B) ? a1 : a0;
       c.load_bits(C, bC);
-      pcC = c.pc_of(C);
+      if (PC) pcC = c.pc_of(C);
       ccA = ccAn;
     }
     }  // level
@@ -817,7 +854,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   rng.store(P, chain);
   P.sweep_idx[chain] = s;
   P.min_total[chain] = min_total;
-  P.total[chain] = c.cp[root].y;
+  P.total[chain] = PC ? c.cp[root].y : (rebase ? P.total[chain] : total);
   P.n_prop[chain] += n_prop;
   P.n_acc[chain] += n_acc;
   P.n_wrej[chain] += n_wrej;
