@@ -112,6 +112,12 @@ int tnb_set_update_slices(tnb_engine* e, int update_slices_every);
 int tnb_set_chains(tnb_engine* e, int n_chains, const int32_t* parent, const int32_t* child0,
                    const int32_t* child1, const uint64_t* seeds, uint64_t chain_id0);
 
+/* Same as tnb_set_chains, but the initial tree of every chain is built ON THE DEVICE by the chain's own lanes
+ * (replaces tnco/utils/tn.py:109-273 get_random_contraction_path + tnco/ctree.py:108-226 for a connected,
+ * hyper-index-free network; seed -> tree is deterministic).  method: TNB_TREES_GREEDY / TNB_TREES_RANDOM.
+ * Fails with "not connected" if some chain runs out of index-sharing pairs. */
+int tnb_generate_chains(tnb_engine* e, int n_chains, const uint64_t* seeds, uint64_t chain_id0, int method);
+
 /* TNB_RNG_REPLAY: raw draw stream per chain, words [n_chains][len]; cursors reset to 0. */
 int tnb_set_stream(tnb_engine* e, const uint32_t* words, uint64_t len);
 

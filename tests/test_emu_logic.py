@@ -46,3 +46,17 @@ def test_emu_eval_cost(emu, n, dim):
 
 def test_emu_philox(emu):
     G.test_philox_chains_are_valid_and_deterministic()
+
+
+@pytest.mark.parametrize('n,max_width', [(64, 10), (150, 22)])
+def test_emu_philox_finite(emu, n, max_width):
+    G.test_philox_finite_width_chains_are_valid(n, max_width, None)
+
+
+@pytest.mark.parametrize('n,method', [(2, 0), (3, 1), (64, 0), (64, 1), (180, 0)])
+def test_emu_generated_trees(emu, n, method):
+    G.test_device_generated_trees_are_valid(n, method)
+
+
+def test_emu_generated_trees_disconnected(emu):
+    G.test_device_generated_trees_reject_disconnected_network()

@@ -177,3 +177,125 @@ def test_philox_chains_are_valid_and_deterministic():
     assert (outs[0][0] == outs[1][0]).all() and (outs[0][2] == outs[1][2]).all()
     assert len(set(outs[0][1].tolist())) > 8
     assert np.log2(outs[0][1]).mean() < np.log2(seq).mean() + 1e-9
+
+
+def _check_tree_valid(P, A, B, n):
+    """Reference tree invariants (include/tnco/tree.hpp:57-139): leaves first, root last, consistent links."""
+    N = 2 * n - 1
+    assert P[N - 1] == -1 and (P[:N - 1] >= n).all()
+    assert (A[:n] == -1).all() and (B[:n] == -1).all()
+    seen = np.zeros(N, int)
+    for z in range(n, N):
+        assert P[A[z]] == z and P[B[z]] == z and A[z] != B[z]
+        seen[A[z]] += 1
+        seen[B[z]] += 1
+    assert (seen[:N - 1] == 1).all()
+
+
+@pytest.mark.parametrize('n,max_width,tile', [(64, 10, None), (150, 22, None), (150, 22, 16), (300, 30, None)])
+def test_philox_finite_width_chains_are_valid(n, max_width, tile):
+    """Production finite-width path (fast re-slicer): what the reference's is_valid() checks
+    (finite_width/greedy/optimizer.hpp:406-423) -- every sliced width <= max_width for the current and the
+    best tree, cached totals equal an independent evaluation with the slices -- plus determinism."""
+    from helpers import leaf_bits
+    from tnco_b200.engine import Engine, random_trees
+    ts, ni = regular_network(n, 3 + n)
+    lb = leaf_bits(ts, ni)
+    seeds = np.arange(48, dtype=np.uint64) + 5
+    p, a, b = random_trees(lb, ni, seeds)
+    outs = []
+    for rep in range(2):
+        if tile:
+            os.environ['TNB_TILE'] = str(tile)
+        e = Engine()
+        e.set_network(lb, ni)
+        os.environ.pop('TNB_TILE', None)
+        e.set_mode(max_width=max_width, update_slices_every=10)
+        e.set_chains(p, a, b, seeds)
+        e.set_betas(np.linspace(0, 100, 400, endpoint=False))
+        t0, _ = e.costs()
+        e.run(200)
+        e.run(400)
+        t, m = e.costs()
+        P, A, B = e.trees()
+        S = e.slices()
+        seq, pc, mw = e.eval_cost(P, A, B, slices=S)
+        assert np.allclose(np.log2(seq), np.log2(t), atol=1e-9)
+        assert (mw <= max_width).all()
+        bP, bA, bB = e.trees(True)
+        bS = e.slices(True)
+        bseq, bpc, bmw = e.eval_cost(bP, bA, bB, slices=bS)
+        assert np.allclose(np.log2(bseq), np.log2(m), atol=1e-9)
+        assert (bmw <= max_width).all()
+        assert (m <= t * (1 + 1e-12)).all()
+        for c in (0, 13, 47):
+            _check_tree_valid(P[c], A[c], B[c], n)
+            nb = e.bits(c)
+            assert (nb[:n] == lb).all()
+            o_seq, o_mw, o_pc = so.tree_cost(A[c], B[c], nb, ni, slices=S[c])
+            assert np.isclose(np.log2(o_seq), np.log2(t[c]), atol=1e-9) and o_mw <= max_width
+        pr = e.progress()
+        assert (pr['sweeps'] == 400).all() and pr['width_rejects'].sum() > 0
+        outs.append((t.copy(), m.copy(), P.copy(), S.copy()))
+        e.close()
+    assert all((x == y).all() for x, y in zip(outs[0], outs[1]))
+    assert np.log2(outs[0][1]).mean() < np.log2(t0).mean()
+
+
+@pytest.mark.parametrize('n,method', [(2, 0), (3, 1), (64, 0), (64, 1), (180, 0), (1000, 0)])
+def test_device_generated_trees_are_valid(n, method):
+    """tnb_generate_chains: every chain gets a valid tree whose contractions all share an index
+    (check_shared_inds, include/tnco/ctree.hpp:101-152), deterministic per seed, different across seeds."""
+    from helpers import leaf_bits
+    from tnco_b200.engine import Engine
+    if n <= 3:
+        ts, ni = [[k for k in range(n - 1) if k in (t - 1, t)] for t in range(n)], n - 1   # a path graph
+    else:
+        ts, ni = regular_network(n, 50 + n)
+    lb = leaf_bits(ts, ni)
+    seeds = np.arange(24, dtype=np.uint64) * 7 + 3
+    trees = []
+    for rep in range(2):
+        e = Engine()
+        e.set_network(lb, ni).set_mode()
+        e.generate_chains(seeds, method=method)
+        P, A, B = e.trees()
+        t, m = e.costs()
+        seq, pc, _ = e.eval_cost(P, A, B)
+        assert (pc == t).all()
+        for c in range(len(seeds)):
+            _check_tree_valid(P[c], A[c], B[c], n)
+        nb = e.bits(5)
+        for z in range(n, 2 * n - 1):
+            assert (nb[A[5][z]] & nb[B[5][z]]).any(), 'contracted pair shares no index'
+        # the same trees through the validating entry point
+        e2 = Engine()
+        e2.set_network(lb, ni).set_mode()
+        e2.set_chains(P, A, B, seeds)
+        assert (e2.costs()[0] == t).all()
+        e2.close()
+        trees.append((P.copy(), t.copy()))
+        e.set_betas(np.linspace(0, 100, 50, endpoint=False))
+        e.run(50)
+        assert (e.costs()[1] <= t).all()
+        e.close()
+    assert (trees[0][0] == trees[1][0]).all()
+    if n >= 64:
+        assert len({tuple(r) for r in trees[0][0].tolist()}) > 12
+    if method == 0 and n >= 64:  # greedy is much better than random merges
+        e = Engine()
+        e.set_network(lb, ni).set_mode()
+        e.generate_chains(seeds, method=1)
+        assert np.log2(trees[0][1]).mean() < np.log2(e.costs()[0]).mean()
+        e.close()
+
+
+def test_device_generated_trees_reject_disconnected_network():
+    from helpers import leaf_bits
+    from tnco_b200.engine import Engine
+    lb = leaf_bits([[0], [0], [1], [1]], 2)
+    e = Engine()
+    e.set_network(lb, 2).set_mode()
+    with pytest.raises(ValueError, match='not connected'):
+        e.generate_chains([1, 2, 3])
+    e.close()

@@ -37,6 +37,7 @@ SIGNATURES = {
     'tnb_set_prob': (C.c_int, [C.c_void_p, C.c_int]),
     'tnb_set_update_slices': (C.c_int, [C.c_void_p, C.c_int]),
     'tnb_set_chains': (C.c_int, [C.c_void_p, C.c_int, i32p, i32p, i32p, u64p, C.c_uint64]),
+    'tnb_generate_chains': (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_uint64, C.c_int]),
     'tnb_set_stream': (C.c_int, [C.c_void_p, u32p, C.c_uint64]),
     'tnb_set_betas': (C.c_int, [C.c_void_p, f64p, C.c_int64]),
     'tnb_run': (C.c_int, [C.c_void_p, C.c_int64]),

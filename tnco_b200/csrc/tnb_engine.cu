@@ -111,7 +111,29 @@ __global__ void __launch_bounds__(kSweepBlock, MINB) sa_sweep_kernel(const __gri
   if (chain >= P.n_chains) return;
   chain_sweeps<TILE, WPL, FINITE, Rng, DIM2>(P, chain);
 }
+
+template <int TILE, int WPL>
+__global__ void __launch_bounds__(kBlock) sa_treegen_kernel(const __grid_constant__ Params P) {
+  const int chain = (blockIdx.x * kBlock + threadIdx.x) / TILE;
+  if (chain >= P.n_chains) return;
+  chain_treegen<TILE, WPL>(P, chain);
+}
 #endif
+
+template <int TILE, int WPL>
+static bool launch_treegen_t(Rt& rt, const Params& P) {
+#if defined(TNB_EMU)
+  (void)rt;
+  for (int c = 0; c < P.n_chains; ++c) chain_treegen<TILE, WPL>(P, c);
+  return true;
+#else
+  const long long threads = (long long)P.n_chains * TILE;
+  const int grid = int((threads + kBlock - 1) / kBlock);
+  if (grid == 0) return true;
+  sa_treegen_kernel<TILE, WPL><<<grid, kBlock, 0, rt.stream>>>(P);
+  return rt.ok(cudaGetLastError(), "sa_treegen_kernel launch");
+#endif
+}
 
 template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2>
 static bool launch_t(Rt& rt, const Params& P, bool init) {
@@ -172,6 +194,29 @@ static bool launch(Rt& rt, const Params& P, int tile, int wpl, bool init, bool f
 #endif
 }
 
+static bool launch_treegen(Rt& rt, const Params& P, int tile, int wpl) {
+#if defined(TNB_EMU)
+  (void)tile;
+  (void)wpl;
+  if (P.W <= 4) return launch_treegen_t<1, 4>(rt, P);
+  if (P.W <= 16) return launch_treegen_t<1, 16>(rt, P);
+  if (P.W <= 48) return launch_treegen_t<1, 48>(rt, P);
+  return launch_treegen_t<1, 128>(rt, P);
+#else
+  switch (tile * 16 + wpl) {
+    case 4 * 16 + 1: return launch_treegen_t<4, 1>(rt, P);
+    case 8 * 16 + 1: return launch_treegen_t<8, 1>(rt, P);
+    case 16 * 16 + 1: return launch_treegen_t<16, 1>(rt, P);
+    case 32 * 16 + 1: return launch_treegen_t<32, 1>(rt, P);
+    case 32 * 16 + 2: return launch_treegen_t<32, 2>(rt, P);
+    case 32 * 16 + 3: return launch_treegen_t<32, 3>(rt, P);
+    case 32 * 16 + 4: return launch_treegen_t<32, 4>(rt, P);
+  }
+  rt.err = "unsupported tile shape";
+  return false;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------ chain storage
 struct ChainSet {
   int n_chains = 0;
@@ -184,13 +229,15 @@ struct ChainSet {
   long long* sweep_idx = nullptr;
   int* overrun = nullptr;
   uint16_t* nbig = nullptr;
-  int16_t* posbuf = nullptr;
+  int16_t *posbuf = nullptr, *kpop = nullptr, *kw = nullptr, *sz = nullptr, *word = nullptr;
+  uint32_t* wkey = nullptr;
+  int* tree_fail = nullptr;
   uint32_t* stream = nullptr;
   unsigned long long stream_len = 0;
 
   void release(Rt& rt) {
     void* ps[] = {par, bpar, ch, bch, bits, slices, bslices, cp, cp2, total, min_total, out_seq, out_maxw, seeds,
-                  rng_ctr, n_prop, n_acc, n_wrej, cursor, sweep_idx, overrun, nbig, posbuf, stream};
+                  rng_ctr, n_prop, n_acc, n_wrej, cursor, sweep_idx, overrun, nbig, posbuf, kpop, tree_fail, stream, kw, sz, word, wkey};
     for (void* p : ps) rt.free_(p);
     *this = ChainSet();
   }
@@ -210,6 +257,7 @@ struct tnb_engine {
   double log2d = 1.0;
   uint32_t* d_leaf_bits = nullptr;
   double* d_pow_tab = nullptr;
+  int16_t* d_net_own = nullptr;  // [2][n_inds] the leaves holding each index (device tree construction)
   std::vector<uint32_t> h_leaf_bits;  // [n][W]
   // mode
   bool finite = false;
@@ -274,6 +322,12 @@ static void fill_params(const tnb_engine* e, const ChainSet& cs, Params& P) {
   P.betas = e->d_betas; P.n_betas = e->n_betas; P.until = 0;
   P.nbig = cs.nbig; P.posbuf = cs.posbuf; P.cp2 = cs.cp2;
   P.slices_given = 0; P.out_seq = cs.out_seq; P.out_maxw = cs.out_maxw;
+  P.kw = cs.kw; P.sz = cs.sz; P.word = cs.word; P.wkey = cs.wkey;
+  P.kthr = 0;
+  if (e->finite)
+    for (int k = 0; k <= e->n_inds; ++k)
+      if (float(e->log2d * double(k)) <= e->max_width) P.kthr = k;
+  P.net_own = e->d_net_own; P.kpop = cs.kpop; P.tree_fail = cs.tree_fail; P.tree_method = TNB_TREES_GREEDY;
 }
 
 template <class T>
@@ -282,9 +336,7 @@ static bool alloc_to(Rt& rt, T*& p, size_t count) {
   return p != nullptr;
 }
 
-// allocate a chain set and upload the packed topology
-static bool make_chains(tnb_engine* e, ChainSet& cs, int n_chains, const int32_t* parent, const int32_t* c0,
-                        const int32_t* c1, bool with_best, bool with_slicer) {
+static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_best, bool with_slicer) {
   Rt& rt = e->rt;
   cs.n_chains = n_chains;
   const size_t nc = size_t(n_chains), ni = size_t(std::max(e->n_int, 1));
@@ -300,7 +352,19 @@ static bool make_chains(tnb_engine* e, ChainSet& cs, int n_chains, const int32_t
   if (ok && with_slicer)
     ok = alloc_to(rt, cs.nbig, nc * e->Ws * 32) && alloc_to(rt, cs.posbuf, nc * e->Ws * 32) &&
          alloc_to(rt, cs.cp2, nc * ni);
+  if (ok && with_slicer && e->finite)
+    ok = alloc_to(rt, cs.kw, nc * e->Npad) && alloc_to(rt, cs.sz, nc * e->Npad) &&
+         alloc_to(rt, cs.word, nc * e->Npad) && alloc_to(rt, cs.wkey, nc * e->Npad);
   if (!ok) return e->rtfail();
+  return true;
+}
+
+// allocate a chain set and upload the packed topology
+static bool make_chains(tnb_engine* e, ChainSet& cs, int n_chains, const int32_t* parent, const int32_t* c0,
+                        const int32_t* c1, bool with_best, bool with_slicer) {
+  if (!alloc_chains(e, cs, n_chains, with_best, with_slicer)) return false;
+  Rt& rt = e->rt;
+  const size_t nc = size_t(n_chains), ni = size_t(std::max(e->n_int, 1));
   // validate + pack
   const int N = e->N, n = e->n;
   std::vector<int16_t> hp(nc * e->Npad, int16_t(-1));
@@ -449,6 +513,7 @@ void tnb_destroy(tnb_engine* e) {
   e->cs.release(e->rt);
   e->rt.free_(e->d_leaf_bits);
   e->rt.free_(e->d_pow_tab);
+  e->rt.free_(e->d_net_own);
   e->rt.free_(e->d_betas);
   e->rt.free_(e->d_flush);
   e->rt.destroy();
@@ -471,6 +536,7 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* lea
   if (W > 128) return e->fail("tnb_set_network: at most 4096 indices"), -2;
   // hyper-index check: every index on at most two tensors
   std::vector<uint8_t> cnt(size_t(W) * 32, 0);
+  std::vector<int16_t> own(size_t(2) * n_inds, int16_t(-1));
   for (int t = 0; t < n_leaves; ++t)
     for (int w = 0; w < W; ++w) {
       uint32_t v = leaf_bits[size_t(t) * W + w];
@@ -480,6 +546,7 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* lea
         if (i >= n_inds) return e->fail("tnb_set_network: leaf_bits has a bit beyond n_inds"), -1;
         if (++cnt[size_t(i)] > 2)
           return e->fail("tnb_set_network: hyper-indices (an index on more than two tensors) are not supported yet"), -2;
+        own[size_t(cnt[size_t(i)] - 1) * n_inds + i] = int16_t(t);
       }
     }
   e->cs.release(e->rt);
@@ -504,7 +571,10 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* lea
     std::memcpy(&padded[size_t(t) * e->Ws], leaf_bits + size_t(t) * W, sizeof(uint32_t) * size_t(W));
   e->rt.free_(e->d_leaf_bits);
   e->rt.free_(e->d_pow_tab);
-  e->d_leaf_bits = nullptr; e->d_pow_tab = nullptr;
+  e->rt.free_(e->d_net_own);
+  e->d_leaf_bits = nullptr; e->d_pow_tab = nullptr; e->d_net_own = nullptr;
+  if (!alloc_to(e->rt, e->d_net_own, own.size()) || !e->rt.h2d(e->d_net_own, own.data(), own.size() * sizeof(int16_t)))
+    return e->rtfail(), -3;
   if (!alloc_to(e->rt, e->d_leaf_bits, padded.size())) return e->rtfail(), -3;
   std::vector<double> tab(size_t(n_inds) + 1);
   for (int k = 0; k <= n_inds; ++k) tab[size_t(k)] = std::pow(double(dim), double(k));
@@ -558,6 +628,43 @@ int tnb_set_chains(tnb_engine* e, int n_chains, const int32_t* parent, const int
   if (!check_shared(e, child0, child1, n_chains)) { e->cs.release(e->rt); return -2; }
   e->h_seeds.assign(seeds, seeds + n_chains);
   if (!e->rt.h2d(e->cs.seeds, seeds, size_t(n_chains) * sizeof(uint64_t)) || !e->rt.sync()) return e->rtfail(), -3;
+  return 0;
+}
+
+int tnb_generate_chains(tnb_engine* e, int n_chains, const uint64_t* seeds, uint64_t chain_id0, int method) {
+  if (!e) return -1;
+  if (e->n == 0) return e->fail("tnb_generate_chains: call tnb_set_network first"), -1;
+  if (n_chains < 1 || !seeds || (method != TNB_TREES_GREEDY && method != TNB_TREES_RANDOM))
+    return e->fail("tnb_generate_chains: invalid arguments"), -1;
+  ChainSet& cs = e->cs;
+  cs.release(e->rt);
+  e->initialized = false;
+  e->chain_id0 = chain_id0;
+  if (!alloc_chains(e, cs, n_chains, true, true) || !alloc_to(e->rt, cs.kpop, size_t(n_chains) * e->Npad) ||
+      !alloc_to(e->rt, cs.tree_fail, size_t(n_chains))) {
+    e->rtfail();
+    cs.release(e->rt);
+    return -3;
+  }
+  e->h_seeds.assign(seeds, seeds + n_chains);
+  if (!e->rt.h2d(cs.seeds, seeds, size_t(n_chains) * sizeof(uint64_t)) ||
+      !e->rt.fill_ff(cs.par, size_t(n_chains) * e->Npad * sizeof(int16_t)))
+    return e->rtfail(), -3;
+  if (e->n_int > 0) {
+    Params P;
+    fill_params(e, cs, P);
+    P.tree_method = method;
+    if (!launch_treegen(e->rt, P, e->tile, e->wpl)) return e->rtfail(), -3;
+    std::vector<int> failed(size_t(n_chains), 0);
+    if (!e->rt.d2h(failed.data(), cs.tree_fail, failed.size() * sizeof(int))) return e->rtfail(), -3;
+    for (int f : failed)
+      if (f) {
+        cs.release(e->rt);
+        return e->fail("tnb_generate_chains: the network is not connected"), -2;
+      }
+  } else if (!e->rt.sync()) {
+    return e->rtfail(), -3;
+  }
   return 0;
 }
 

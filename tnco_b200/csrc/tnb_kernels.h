@@ -56,6 +56,17 @@ struct Params {
   uint16_t* nbig;   // [n_chains][Ws*32]
   int16_t* posbuf;  // [n_chains][Ws*32]
   dbl2* cp2;        // [n_chains][n_int]
+  // production re-slicer (finite width, Philox): per-node popcount / leaf count kept in step with the tree
+  int16_t* kw;      // [n_chains][Npad] popcount of every node's index set (unsliced width / log2 d)
+  int16_t* sz;      // [n_chains][Npad] leaves below every node
+  uint32_t* wkey;   // [n_chains][Npad] scratch: (post-order rank << 16 | node) of the wide nodes
+  int16_t* word;    // [n_chains][Npad] scratch: wide nodes, then wide nodes in post-order
+  int kthr;         // largest popcount whose width still fits max_width
+  // initial-tree construction on the device
+  const int16_t* net_own;  // [2][n_inds] the (<= 2) leaves holding each index, -1 if none
+  int16_t* kpop;           // [n_chains][Npad] popcount of every cluster's index set
+  int tree_method;         // TNB_TREES_GREEDY / TNB_TREES_RANDOM
+  int* tree_fail;          // [n_chains] set when the network turned out to be disconnected
   // init / eval
   int slices_given;
   double* out_seq;   // [n_chains] cost summed in traversal order (get_cost)
@@ -471,6 +482,180 @@ TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2
   }
 }
 
+// Production re-slicer: the same greedy rule as get_slices_dev / finite_width/greedy/utils.hpp:24-125 (walk the
+// wide nodes in post-order; while a node is still too wide, slice the index that sits on the most wide nodes,
+// ties broken uniformly at random -- which is what std::shuffle followed by a stable sort yields), restructured
+// so that nothing walks the whole tree:
+//   * wide nodes come from a scan of the per-node popcounts kw[], which the sweep keeps up to date;
+//   * their post-order ranks come from the subtree leaf counts sz[] (also kept by the sweep): the nodes visited
+//     before z are z's own subtree plus the left-sibling subtree of every right turn on the way to the root;
+//   * the per-index counters are NB bit planes in registers (lane-private: a lane counts the 32 indices of its
+//     own word), added with a ripple carry and saturating, so "largest count among the candidates" is NB votes.
+template <int TILE, int WPL, class Rng>
+TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2)[WPL]) {
+  const Params& P = c.P;
+  const Tile<TILE>& t = c.t;
+  constexpr int NB = 8;
+  const int16_t* kw = P.kw + size_t(c.chain) * P.Npad;
+  const int16_t* sz = P.sz + size_t(c.chain) * P.Npad;
+  uint32_t* wkey = P.wkey + size_t(c.chain) * P.Npad;
+  int16_t* word = P.word + size_t(c.chain) * P.Npad;
+  uint32_t cnt[WPL][NB];
+#pragma unroll
+  for (int k = 0; k < WPL; ++k) {
+    S2[k] = 0u;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) cnt[k][b] = 0u;
+  }
+  // (1) wide nodes (leaves included, :41-47): list them and count, per index, how many contain it
+  int nw = 0;
+  for (int base = 0; base < P.N; base += TILE) {
+    const int z = base + t.tl;
+    const bool wide = z < P.N && int(kw[z]) > P.kthr;
+    uint32_t m = t.ballot(wide);
+    if (wide) word[nw + popc32(m & ((1u << t.tl) - 1u))] = int16_t(z);
+    nw += popc32(m);
+    while (m) {
+      const int zz = base + ctz32(m);
+      m &= m - 1;
+      uint32_t x[WPL];
+      c.load_bits(zz, x);
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) {
+        uint32_t carry = x[k];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const uint32_t nc = cnt[k][b] & carry;
+          cnt[k][b] ^= carry;
+          carry = nc;
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) cnt[k][b] |= carry;  // saturate at 2^NB - 1
+      }
+    }
+  }
+  if (nw == 0) return;
+  t.sync();
+  // (2) post-order rank of every wide node, one node per lane
+  for (int j = t.tl; j < nw; j += TILE) {
+    const int z = word[j];
+    uint32_t post = 2u * uint32_t(sz[z]) - 2u;
+    int y = z;
+    while (true) {
+      const int p = c.par[y];
+      if (p < 0) break;
+      const int l = int(c.ch[p] & 0xffffu);
+      if (l != y) post += 2u * uint32_t(sz[l]) - 1u;
+      y = p;
+    }
+    wkey[j] = (post << 16) | uint32_t(z);
+  }
+  t.sync();
+  // rank sort (keys are distinct): word[] <- wide nodes in post-order
+  for (int j = t.tl; j < nw; j += TILE) {
+    const uint32_t key = wkey[j];
+    int rank = 0;
+    for (int k = 0; k < nw; ++k) rank += wkey[k] < key ? 1 : 0;
+    word[rank] = int16_t(key & 0xffffu);
+  }
+  t.sync();
+  // (3) greedy selection (:60-104)
+  for (int j = 0; j < nw; ++j) {
+    const int z = word[j];
+    uint32_t x[WPL];
+    c.load_bits(z, x);
+    uint32_t ks = 0;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      x[k] &= ~S2[k];
+      ks += uint32_t(popc32(x[k]));
+    }
+    ks = t.sum(ks);
+    for (int m = int(ks) - P.kthr; m > 0; --m) {
+      uint32_t cand[WPL];
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) cand[k] = x[k];
+#pragma unroll
+      for (int b = NB - 1; b >= 0; --b) {
+        bool hit = false;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) hit |= (cand[k] & cnt[k][b]) != 0u;
+        if (t.any(hit)) {
+#pragma unroll
+          for (int k = 0; k < WPL; ++k) cand[k] &= cnt[k][b];
+        }
+      }
+      uint32_t mine = 0;
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) mine += uint32_t(popc32(cand[k]));
+      uint32_t tot;
+      const uint32_t off = t.excl_scan_sum(mine, tot);
+      uint32_t r = mulhi32(rng.local_next(), tot);  // every lane draws the same word
+      bool done = !(r >= off && r < off + mine);
+      r -= off;
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) {
+        const uint32_t pk = uint32_t(popc32(cand[k]));
+        if (!done && r < pk) {
+          const uint32_t bit = 1u << nth_set_bit(cand[k], r);
+          S2[k] |= bit;
+          x[k] &= ~bit;
+          done = true;
+        }
+        r -= pk;
+      }
+    }
+  }
+}
+
+// Contraction costs of every internal node under the slices S2, into dst[].x; returns their sum.  No traversal
+// order is needed when only the total matters (production mode keeps no partial-cost cache).
+template <int TILE, int WPL, bool DIM2>
+TNB_D TNB_NOINLINE double recost_all(const ChainView<TILE, WPL>& c, const uint32_t (&S2)[WPL], dbl2* dst) {
+  const Params& P = c.P;
+  const Tile<TILE>& t = c.t;
+  double acc = 0.0;
+  for (int base = P.n; base < P.N; base += TILE) {
+    const int zz = base + t.tl;
+    const uint32_t mych = zz < P.N ? c.ch[zz] : 0u;
+    const int cnt = P.N - base < TILE ? P.N - base : TILE;
+    for (int q = 0; q < cnt; ++q) {
+      const uint32_t w = t.bcast(mych, q);
+      uint32_t xa[WPL], xb[WPL];
+      c.load_bits(int(w & 0xffffu), xa);
+      c.load_bits(int(w >> 16), xb);
+      const uint32_t k = t.sum(popc_or3<WPL>(xa, xb, S2));
+      const double cost = DIM2 ? bits_to_f64((unsigned long long)(1023u + (k > 1024u ? 1024u : k)) << 52)
+                               : c.cost_of(int(k));
+      dst[base - P.n + q].x = cost;
+      acc += cost;
+    }
+  }
+  return acc;
+}
+
+// kw[] / sz[] of every node from scratch (construction time).
+template <int TILE, int WPL>
+TNB_D void build_kw_sz(const ChainView<TILE, WPL>& c) {
+  const Params& P = c.P;
+  int16_t* kw = P.kw + size_t(c.chain) * P.Npad;
+  int16_t* sz = P.sz + size_t(c.chain) * P.Npad;
+  for (int z = c.po_first(); z >= 0; z = c.po_next(z)) {
+    uint32_t x[WPL];
+    c.load_bits(z, x);
+    uint32_t k = 0;
+#pragma unroll
+    for (int i = 0; i < WPL; ++i) k += uint32_t(popc32(x[i]));
+    kw[z] = int16_t(c.t.sum(k));
+    if (z < P.n) {
+      sz[z] = 1;
+    } else {
+      const uint32_t w = c.ch[z];
+      sz[z] = int16_t(sz[w & 0xffffu] + sz[w >> 16]);
+    }
+  }
+}
+
 template <int TILE, int WPL>
 TNB_D void snapshot_best(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL], bool finite) {
   const Params& P = c.P;
@@ -505,6 +690,131 @@ TNB_D void store_slices(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL])
   for (int k = 0; k < WPL; ++k) {
     const int w = c.t.tl + k * TILE;
     if (w < c.P.W) s[w] = S[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ initial trees
+TNB_D TNB_INLINE uint32_t mix32(uint32_t x) {  // murmur3 finaliser
+  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+
+// One initial contraction tree per chain, built by the chain's own tile (replaces the host-side
+// get_random_contraction_path + ContractionTree construction, tnco/utils/tn.py:109-273, tnco/ctree.py:108-226, for
+// hyper-free connected networks).  n-1 merge steps; at every step each lane scores a strided share of the live
+// edges (an index whose two owning clusters differ), the tile takes the arg-min, merges the two clusters
+// (index set = XOR), and re-points the owners of the surviving indices.  GREEDY scores an edge like opt_einsum's
+// greedy, size(out) - size(a) - size(b), ties broken by a per-(seed, step, edge) hash; RANDOM uses the hash only.
+// Every merge is along a shared index, so check_shared_inds holds by construction.
+template <int TILE, int WPL>
+TNB_D void chain_treegen(const Params& P, int chain) {
+  ChainView<TILE, WPL> c(P, chain);
+  const Tile<TILE>& t = c.t;
+  const int n = P.n, N = P.N, W = P.W;
+  int16_t* own0 = reinterpret_cast<int16_t*>(P.nbig + size_t(chain) * P.Ws * 32);
+  int16_t* own1 = P.posbuf + size_t(chain) * P.Ws * 32;
+  int16_t* kpop = P.kpop + size_t(chain) * P.Npad;
+  const unsigned long long seed = P.seeds[chain];
+  const uint32_t s0 = mix32(uint32_t(seed) ^ 0x9e3779b9u), s1 = mix32(uint32_t(seed >> 32) + 0x7f4a7c15u);
+  for (int i = t.tl; i < P.n_inds; i += TILE) {
+    own0[i] = P.net_own[i];
+    own1[i] = P.net_own[P.n_inds + i];
+  }
+  for (int x = t.tl; x < N; x += TILE) {
+    int k = 0;
+    if (x < n)
+      for (int w = 0; w < W; ++w) k += popc32(P.leaf_bits[size_t(x) * P.Ws + w]);
+    kpop[x] = int16_t(k);
+    c.par[x] = int16_t(-1);
+  }
+  t.sync();
+  auto row = [&](int x) -> const uint32_t* {
+    return x < n ? P.leaf_bits + size_t(x) * P.Ws : P.bits + (size_t(chain) * P.n_int + size_t(x - n)) * P.Ws;
+  };
+  // big networks: score a strided sample of ~1024 edges per step instead of all of them
+  const int stride_edges = P.n_inds > 1024 ? (P.n_inds + 1023) / 1024 : 1;
+  for (int step = 0; step < n - 1; ++step) {
+    const int z = n + step;
+    double best = 1.0e308;
+    uint32_t best_tie = 0xffffffffu;
+    int best_i = -1;
+    const uint32_t hs = mix32(s0 + uint32_t(step) * 0x632be5abu);
+    for (int pass = 0; pass < 2 && best_i < 0; ++pass) {  // pass 1 (full scan) only if the sample found nothing
+      const int st = pass == 0 ? stride_edges : 1;
+      const int off = pass == 0 && st > 1 ? int(hs % uint32_t(st)) : 0;
+      for (int i = off + t.tl * st; i < P.n_inds; i += TILE * st) {
+        const int a = own0[i], b = own1[i];
+        if (a < 0 || b < 0 || a == b) continue;
+        const uint32_t tie = mix32(hs ^ (uint32_t(i) * 0x9e3779b1u) ^ s1);
+        double score = 0.0;
+        if (P.tree_method == 0) {
+          const uint32_t *ra = row(a), *rb = row(b);
+          int ko = 0;
+          for (int w = 0; w < W; ++w) ko += popc32(ra[w] ^ rb[w]);
+          const int ka = kpop[a], kb = kpop[b];
+          score = bits_to_f64((unsigned long long)(1023 + (ko > 1000 ? 1000 : ko)) << 52) -
+                  bits_to_f64((unsigned long long)(1023 + (ka > 1000 ? 1000 : ka)) << 52) -
+                  bits_to_f64((unsigned long long)(1023 + (kb > 1000 ? 1000 : kb)) << 52);
+        }
+        if (score < best || (score == best && tie < best_tie)) {
+          best = score;
+          best_tie = tie;
+          best_i = i;
+        }
+      }
+      // tile arg-min over (score, tie); lanes without a candidate carry best_i = -1
+#if !defined(TNB_EMU)
+#pragma unroll
+      for (int d = TILE / 2; d > 0; d >>= 1) {
+        const unsigned m = TILE == 32 ? 0xffffffffu : t.mask;
+        const double os = __shfl_xor_sync(m, best, d, TILE);
+        const uint32_t ot = __shfl_xor_sync(m, best_tie, d, TILE);
+        const int oi = __shfl_xor_sync(m, best_i, d, TILE);
+        const bool take = oi >= 0 && (best_i < 0 || os < best || (os == best && (ot < best_tie || (ot == best_tie && oi < best_i))));
+        if (take) { best = os; best_tie = ot; best_i = oi; }
+      }
+#endif
+    }
+    if (best_i < 0) {  // no live edge left: the network is disconnected
+      P.tree_fail[chain] = 1;
+      return;
+    }
+    int a = own0[best_i], b = own1[best_i];
+    if (best_tie & 1u) { const int tmp = a; a = b; b = tmp; }
+    // merge: index set of z, popcount, topology
+    uint32_t xa[WPL], xb[WPL];
+    c.load_bits(a, xa);
+    c.load_bits(b, xb);
+    uint32_t k = 0;
+#pragma unroll
+    for (int q = 0; q < WPL; ++q) {
+      const uint32_t x = xa[q] ^ xb[q];
+      k += uint32_t(popc32(x));
+      // owners: surviving indices now belong to z, contracted ones (in both) die
+      const int w = t.tl + q * TILE;
+      uint32_t v = x;
+      while (v) {
+        const int idx = w * 32 + ctz32(v);
+        v &= v - 1;
+        if (own0[idx] == a || own0[idx] == b) own0[idx] = int16_t(z);
+        if (own1[idx] == a || own1[idx] == b) own1[idx] = int16_t(z);
+      }
+      v = xa[q] & xb[q];
+      while (v) {
+        const int idx = w * 32 + ctz32(v);
+        v &= v - 1;
+        own0[idx] = int16_t(-1);
+        own1[idx] = int16_t(-1);
+      }
+      xa[q] = x;
+    }
+    c.store_bits(z, xa);
+    k = t.sum(k);
+    kpop[z] = int16_t(k);
+    c.par[a] = int16_t(z);
+    c.par[b] = int16_t(z);
+    c.ch[z] = uint32_t(a) | (uint32_t(b) << 16);
+    t.sync();  // owners / rows written by other lanes are read by everybody in the next step
   }
 }
 
@@ -543,6 +853,7 @@ TNB_D void chain_init(const Params& P, int chain) {
   P.min_total[chain] = seq;  // get_cost(min_ctree) sums in traversal order (infinite_memory/utils.hpp:102-116)
   if (P.out_seq) P.out_seq[chain] = seq;
   if (P.out_maxw) P.out_maxw[chain] = P.log2d * double(maxk);
+  if (FINITE && P.kw) build_kw_sz(c);
   if (P.bpar) snapshot_best(c, S, FINITE);
 }
 
@@ -619,6 +930,11 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   // needs no partial costs of D/E/C, no two 16-byte stores per level and half the fp64 adds; its total is a
   // running sum re-based on sum_ccost() every 16 sweeps.
   constexpr bool PC = !Rng::kFast;
+  // FS: production re-slicer (get_slices_fast); the walk then also maintains kw[] and sz[]
+  constexpr bool FS = FINITE && Rng::kFast;
+  int16_t* const kwp = FS ? P.kw + size_t(chain) * P.Npad : nullptr;
+  int16_t* const szp = FS ? P.sz + size_t(chain) * P.Npad : nullptr;
+  int sz0 = 0, sz1 = 0, szC = 0;
   Rng rng;
   rng.load(P, chain);
   long long s = P.sweep_idx[chain];
@@ -650,21 +966,40 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
           for (int k = 0; k < WPL; ++k) anyS |= S[k] != 0u;
           if (t.any(anyS)) {
             uint32_t S2[WPL];
-            get_slices_dev(c, rng, S2);
             dbl2* cp2 = P.cp2 + size_t(chain) * P.n_int;
-            double seq;
-            uint32_t maxk;
-            cost_pass<TILE, WPL, false>(c, S2, cp2, seq, maxk);
-            const double r2 = cp2[P.n_int - 1].y;
-            if (r2 < (PC ? root_pc : total)) {
-              t.sync();
-              for (int i = t.tl; i < P.n_int; i += TILE) c.cp[n + i] = cp2[i];
-              t.sync();
+            if constexpr (FS) {
+              get_slices_fast(c, rng, S2);
+              bool diff = false;
 #pragma unroll
-              for (int k = 0; k < WPL; ++k) S[k] = S2[k];
-              store_slices(c, S);
-              root_pc = r2;
-              total = r2;
+              for (int k = 0; k < WPL; ++k) diff |= S2[k] != S[k];
+              if (t.any(diff)) {  // same slices -> same costs: nothing to decide
+                const double r2 = recost_all<TILE, WPL, DIM2>(c, S2, cp2);
+                if (r2 < total) {
+                  t.sync();
+                  for (int i = t.tl; i < P.n_int; i += TILE) c.cp[n + i].x = cp2[i].x;
+                  t.sync();
+#pragma unroll
+                  for (int k = 0; k < WPL; ++k) S[k] = S2[k];
+                  store_slices(c, S);
+                  total = r2;
+                }
+              }
+            } else {
+              get_slices_dev(c, rng, S2);
+              double seq;
+              uint32_t maxk;
+              cost_pass<TILE, WPL, false>(c, S2, cp2, seq, maxk);
+              const double r2 = cp2[P.n_int - 1].y;
+              if (r2 < (PC ? root_pc : total)) {
+                t.sync();
+                for (int i = t.tl; i < P.n_int; i += TILE) c.cp[n + i] = cp2[i];
+                t.sync();
+#pragma unroll
+                for (int k = 0; k < WPL; ++k) S[k] = S2[k];
+                store_slices(c, S);
+                root_pc = r2;
+                total = r2;
+              }
             }
           }
         }
@@ -700,6 +1035,10 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         pc0 = c.pc_of(p0);
         pc1 = c.pc_of(p1);
       }
+      if (FS) {
+        sz0 = szp[p0];
+        sz1 = szp[p1];
+      }
       ccB = c.cp[B].x;
       A = c.par[B];
       in_sweep = true;
@@ -710,6 +1049,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         C = (a0 == B) ? a1 : a0;
         c.load_bits(C, bC);
         if (PC) pcC = c.pc_of(C);
+        if (FS) szC = szp[C];
         ccA = c.cp[A].x;
       }
     } else {
@@ -731,7 +1071,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     else pick0 = i0;
     int E = pick0 ? p1 : p0;  // D = the other child
     uint32_t bD[WPL], bE[WPL], nb[WPL];
-    uint32_t kpack = 0, ks = 0;
+    uint32_t kpack = 0, ks = 0, ku = 0;
 #pragma unroll
     for (int k = 0; k < WPL; ++k) {
       bD[k] = pick0 ? b0[k] : b1[k];
@@ -739,13 +1079,20 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       nb[k] = bD[k] ^ bC[k];  // new inds of B (infinite_memory/optimizer.hpp:147; no hyper-indices)
       kpack += uint32_t(popc32(nb[k] | bE[k] | S[k])) | (uint32_t(popc32(bD[k] | bC[k] | S[k])) << 16);
       if (FINITE) ks += uint32_t(popc32(nb[k] & ~S[k]));
+      if (FS) ks += uint32_t(popc32(nb[k])) << 16;  // unsliced popcount of the new B rides in the same reduction
     }
     const double pcD = pick0 ? pc0 : pc1;
     double pcE = pick0 ? pc1 : pc0;
+    const int szD = pick0 ? sz0 : sz1;
+    int szE = pick0 ? sz1 : sz0;
     ++q_prop;
     bool gate = true;
     if (FINITE) {  // finite_width/greedy/optimizer.hpp:176-188
       ks = t.sum(ks);
+      if (FS) {
+        ku = ks >> 16;
+        ks &= 0xffffu;
+      }
       gate = c.width_of(int(ks)) <= P.max_width;
       if (!gate) ++q_wrej;
     }
@@ -801,9 +1148,14 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       ccA = nA;
       total += delta;
       ++q_acc;
+      if (FS) {
+        kwp[B] = int16_t(ku);
+        szp[B] = int16_t(szD + szC);
+      }
       {
         const int ti = C; C = E; E = ti;
         const double td = pcC; pcC = pcE; pcE = td;
+        const int ts = szC; szC = szE; szE = ts;
       }
 #pragma unroll
       for (int k = 0; k < WPL; ++k) {
@@ -838,6 +1190,11 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       pc0 = bslot0 ? pcB : pcC;
       pc1 = bslot0 ? pcC : pcB;
     }
+    if (FS) {
+      const int szB = szD + szE;  // post-swap names
+      sz0 = bslot0 ? szB : szC;
+      sz1 = bslot0 ? szC : szB;
+    }
     ccB = ccA;
     B = A;
     A = An;
@@ -847,6 +1204,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       C = (a0 == B) ? a1 : a0;
       c.load_bits(C, bC);
       if (PC) pcC = c.pc_of(C);
+      if (FS) szC = szp[C];
       ccA = ccAn;
     }
     }  // level

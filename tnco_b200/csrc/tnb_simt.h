@@ -58,6 +58,8 @@ struct Tile {
   static_assert(TILE == 1, "the emulation build runs one lane per chain");
   int tl = 0;
   TNB_D bool any(bool p) const { return p; }
+  TNB_D uint32_t ballot(bool p) const { return p ? 1u : 0u; }
+  TNB_D uint32_t max_u32(uint32_t v) const { return v; }
   TNB_D uint32_t sum(uint32_t v) const { return v; }
   TNB_D uint32_t bcast(uint32_t v, int) const { return v; }
   TNB_D void sync() const {}
@@ -74,6 +76,20 @@ struct Tile {
   TNB_D TNB_INLINE bool any(bool p) const {
     if (TILE == 32) return __any_sync(0xffffffffu, p) != 0;
     return (__ballot_sync(mask, p) & mask) != 0u;
+  }
+  // tile-relative lane mask of the lanes whose predicate holds (bit k = lane k of the tile)
+  TNB_D TNB_INLINE uint32_t ballot(bool p) const {
+    if (TILE == 32) return __ballot_sync(0xffffffffu, p);
+    return (__ballot_sync(mask, p) & mask) >> ((threadIdx.x & 31) & ~(TILE - 1));
+  }
+  TNB_D TNB_INLINE uint32_t max_u32(uint32_t v) const {
+    if (TILE == 32) return __reduce_max_sync(0xffffffffu, v);
+#pragma unroll
+    for (int d = TILE / 2; d > 0; d >>= 1) {
+      const uint32_t o = __shfl_xor_sync(mask, v, d, TILE);
+      v = o > v ? o : v;
+    }
+    return v;
   }
   // Full warp: one REDUX.  Sub-warp tiles: a shuffle butterfly -- REDUX with a partial member mask makes the
   // compiler run every tile of the warp exclusively (WARPSYNC.EXCLUSIVE), which serialises the tiles.
@@ -138,6 +154,15 @@ TNB_D TNB_INLINE int ctz32(uint32_t x) {
   return __builtin_ctz(x);
 #else
   return __ffs(int(x)) - 1;
+#endif
+}
+// position of the r-th (0-based) set bit of x; x must have more than r bits set
+TNB_D TNB_INLINE int nth_set_bit(uint32_t x, uint32_t r) {
+#if defined(TNB_EMU)
+  for (; r > 0; --r) x &= x - 1;
+  return __builtin_ctz(x);
+#else
+  return int(__fns(x, 0u, int(r) + 1));
 #endif
 }
 template <class T>

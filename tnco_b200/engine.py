@@ -146,7 +146,7 @@ class Engine:
     def _chk(self, rc):
         if rc:
             msg = self._L.tnb_last_error(self._h).decode()
-            if 'Precision is too low' in msg or 'invalid' in msg or 'not supported' in msg:
+            if 'Precision is too low' in msg or 'invalid' in msg or 'not supported' in msg or 'not connected' in msg:
                 raise ValueError(msg)
             raise EngineError(msg)
 
@@ -181,6 +181,14 @@ class Engine:
         self.n_chains = len(s)
         self._chk(self._L.tnb_set_chains(self._h, self.n_chains, _ptr(p, C.c_int32), _ptr(a, C.c_int32),
                                          _ptr(b, C.c_int32), _ptr(s, C.c_uint64), int(chain_id0)))
+        return self
+
+    def generate_chains(self, seeds, chain_id0=0, method=TREES_GREEDY):
+        """One chain per seed; the initial trees are built on the device (tnb_generate_chains)."""
+        s = _c(seeds, np.uint64).reshape(-1)
+        self.n_chains = len(s)
+        self._chk(self._L.tnb_generate_chains(self._h, self.n_chains, _ptr(s, C.c_uint64), int(chain_id0),
+                                              int(method)))
         return self
 
     def set_stream(self, words):
