@@ -39,10 +39,10 @@ typedef struct tnb_engine tnb_engine;
                              draw order as include/tnco/optimize/infinite_memory/optimizer.hpp:100-162 */
 #define TNB_RNG_REPLAY 2  /* parity: caller-recorded raw 32-bit draw stream per chain (tnb_set_stream) */
 
-/* chain-state layout */
-#define TNB_LAYOUT_AUTO 0
-#define TNB_LAYOUT_GLOBAL 1 /* chain state in HBM / L2, operated on in place */
-#define TNB_LAYOUT_SHARED 2 /* chain state staged into shared memory for the duration of a launch */
+/* chain-state layout in HBM (both are operated on in place) */
+#define TNB_LAYOUT_AUTO 0        /* INTERLEAVED while the whole batch fits L2 (<= 96 MiB), SPLIT beyond */
+#define TNB_LAYOUT_INTERLEAVED 1 /* one record {children, cost, index set} per tree node */
+#define TNB_LAYOUT_SPLIT 2       /* node headers and index sets in separate arrays (headers stay L2-resident) */
 
 #define TNB_TREES_GREEDY 0 /* random tie-broken greedy merges (stand-in for opt_einsum 'greedy', tnco/utils/tn.py:225) */
 #define TNB_TREES_RANDOM 1 /* uniformly random merges of index-sharing pairs */
@@ -157,7 +157,7 @@ int tnb_eval_cost(tnb_engine* e, int n_trees, const int32_t* parent, const int32
 /* Evict the L2 cache (writes a buffer larger than L2); benchmarking aid. */
 int tnb_flush_l2(tnb_engine* e);
 
-/* the layout / tile shape the engine picked: lanes per chain, words per lane, TNB_LAYOUT_* , smem bytes per chain */
+/* the layout / tile shape the engine picked: lanes per chain, words per lane, TNB_LAYOUT_* , state bytes per chain */
 int tnb_get_config(tnb_engine* e, int* tile, int* words_per_lane, int* layout, int* state_bytes_per_chain);
 
 #ifdef __cplusplus

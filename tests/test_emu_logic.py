@@ -60,3 +60,8 @@ def test_emu_generated_trees(emu, n, method):
 
 def test_emu_generated_trees_disconnected(emu):
     G.test_device_generated_trees_reject_disconnected_network()
+
+
+@pytest.mark.parametrize('max_width', [None, 20])
+def test_emu_split_layout(emu, max_width):
+    G.test_split_layout_gives_identical_results(max_width)

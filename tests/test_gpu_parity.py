@@ -299,3 +299,30 @@ def test_device_generated_trees_reject_disconnected_network():
     with pytest.raises(ValueError, match='not connected'):
         e.generate_chains([1, 2, 3])
     e.close()
+
+
+@pytest.mark.parametrize('max_width', [None, 20])
+def test_split_layout_gives_identical_results(max_width):
+    """TNB_LAYOUT_SPLIT (headers and index sets apart, picked automatically for HBM-sized batches) and
+    TNB_LAYOUT_INTERLEAVED are two placements of the same state: same seeds -> identical chains."""
+    from helpers import leaf_bits
+    from tnco_b200._lib import LAYOUT_INTERLEAVED, LAYOUT_SPLIT
+    from tnco_b200.engine import Engine
+    ts, ni = regular_network(140, 77)
+    lb = leaf_bits(ts, ni)
+    seeds = np.arange(40, dtype=np.uint64) + 9
+    outs = []
+    for layout in (LAYOUT_INTERLEAVED, LAYOUT_SPLIT):
+        e = Engine()
+        e.set_network(lb, ni).set_mode(max_width=max_width, layout=layout)
+        e.generate_chains(seeds)
+        assert e.config()['layout'] == layout
+        e.set_betas(np.linspace(0, 100, 300, endpoint=False))
+        e.run(300)
+        outs.append((e.costs(), e.trees(), e.trees(True), e.slices(True), e.bits(7), e.progress()['proposals']))
+        e.close()
+    a, b = outs
+    assert (a[0][0] == b[0][0]).all() and (a[0][1] == b[0][1]).all()
+    for k in (1, 2):
+        assert all((x == y).all() for x, y in zip(a[k], b[k]))
+    assert (a[3] == b[3]).all() and (a[4] == b[4]).all() and (a[5] == b[5]).all()

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libtnco_b200.so')
 
 PROB_MH, PROB_GREEDY, PROB_ALWAYS = 0, 1, 2
 RNG_PHILOX, RNG_MT19937, RNG_REPLAY = 0, 1, 2
-LAYOUT_AUTO, LAYOUT_GLOBAL, LAYOUT_SHARED = 0, 1, 2
+LAYOUT_AUTO, LAYOUT_INTERLEAVED, LAYOUT_SPLIT = 0, 1, 2
 TREES_GREEDY, TREES_RANDOM = 0, 1
 
 i32p, u32p, u64p, i64p, f64p = (C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),

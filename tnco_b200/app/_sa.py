@@ -55,16 +55,19 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
     lo, hi = dist.shard(n_runs) if opt.distributed else (0, n_runs)
     my_seeds = np.asarray(seeds[lo:hi], np.uint64)
     n_local = hi - lo
-    t0 = time.perf_counter()
-    P, A, B = random_trees(lb, len(inds), my_seeds,
-                           method=TREES_GREEDY if opt.init_trees == 'greedy' else TREES_RANDOM)
-    stats['tree_gen_s'] += time.perf_counter() - t0
+    method = TREES_GREEDY if opt.init_trees == 'greedy' else TREES_RANDOM
     eng = Engine(dist.local_device(opt.device))
     try:
         eng.set_network(lb, len(inds), dim=dims[0])
         eng.set_mode(max_width=opt.max_width if finite else None, update_slices_every=update_slices,
                      rng=RNG_MT19937 if opt.rng == 'mt19937' else RNG_PHILOX)
-        eng.set_chains(P, A, B, my_seeds, chain_id0=lo)
+        t0 = time.perf_counter()
+        if opt.tree_builder == 'device':
+            eng.generate_chains(my_seeds, chain_id0=lo, method=method)
+        else:
+            P, A, B = random_trees(lb, len(inds), my_seeds, method=method)
+            eng.set_chains(P, A, B, my_seeds, chain_id0=lo)
+        stats['tree_gen_s'] += time.perf_counter() - t0
         eng.set_betas(betas)
         n_steps = len(betas)
         if deadline is None:

@@ -208,6 +208,7 @@ class BaseOptimizer:
     # --- tnco_b200 extras
     rng: str = 'philox'        # 'philox' (production) | 'mt19937' (bit-identical to the reference per seed)
     init_trees: str = 'greedy'  # 'greedy' | 'random' initial contraction trees
+    tree_builder: str = 'device'  # 'device' (built by each chain's own lanes) | 'host' (C++ threads)
     device: int | None = None  # CUDA device; default LOCAL_RANK or 0
     distributed: bool = True   # shard runs over torch.distributed ranks when a process group exists
 
@@ -232,6 +233,8 @@ class BaseOptimizer:
             raise ValueError("'rng' must be 'philox' or 'mt19937'.")
         if self.init_trees not in ('greedy', 'random'):
             raise ValueError("'init_trees' must be 'greedy' or 'random'.")
+        if self.tree_builder not in ('device', 'host'):
+            raise ValueError("'tree_builder' must be 'device' or 'host'.")
         self._dump_results(None, None, check_only=True)
 
     def __getstate__(self):

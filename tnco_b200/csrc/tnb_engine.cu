@@ -112,6 +112,16 @@ __global__ void __launch_bounds__(kSweepBlock, MINB) sa_sweep_kernel(const __gri
   chain_sweeps<TILE, WPL, FINITE, Rng, DIM2>(P, chain);
 }
 
+// children words between the compact [n_chains][n_int] array (upload / read-back form) and the node records
+__global__ void __launch_bounds__(256) ch_scatter_kernel(const uint32_t* src, char* rec, int stride, size_t count) {
+  const size_t i = size_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i < count) *reinterpret_cast<uint32_t*>(rec + i * size_t(stride)) = src[i];
+}
+__global__ void __launch_bounds__(256) ch_gather_kernel(uint32_t* dst, const char* rec, int stride, size_t count) {
+  const size_t i = size_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i < count) dst[i] = *reinterpret_cast<const uint32_t*>(rec + i * size_t(stride));
+}
+
 template <int TILE, int WPL>
 __global__ void __launch_bounds__(kBlock) sa_treegen_kernel(const __grid_constant__ Params P) {
   const int chain = (blockIdx.x * kBlock + threadIdx.x) / TILE;
@@ -194,6 +204,23 @@ static bool launch(Rt& rt, const Params& P, int tile, int wpl, bool init, bool f
 #endif
 }
 
+static bool ch_copy(Rt& rt, uint32_t* compact, char* rec, int stride, size_t count, bool to_records) {
+#if defined(TNB_EMU)
+  (void)rt;
+  for (size_t i = 0; i < count; ++i) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(rec + i * size_t(stride));
+    if (to_records) *r = compact[i]; else compact[i] = *r;
+  }
+  return true;
+#else
+  if (count == 0) return true;
+  const unsigned grid = unsigned((count + 255) / 256);
+  if (to_records) ch_scatter_kernel<<<grid, 256, 0, rt.stream>>>(compact, rec, stride, count);
+  else ch_gather_kernel<<<grid, 256, 0, rt.stream>>>(compact, rec, stride, count);
+  return rt.ok(cudaGetLastError(), "ch_copy launch");
+#endif
+}
+
 static bool launch_treegen(Rt& rt, const Params& P, int tile, int wpl) {
 #if defined(TNB_EMU)
   (void)tile;
@@ -221,8 +248,12 @@ static bool launch_treegen(Rt& rt, const Params& P, int tile, int wpl) {
 struct ChainSet {
   int n_chains = 0;
   int16_t *par = nullptr, *bpar = nullptr;
-  uint32_t *ch = nullptr, *bch = nullptr, *bits = nullptr, *slices = nullptr, *bslices = nullptr;
-  dbl2 *cp = nullptr, *cp2 = nullptr;
+  uint32_t *bch = nullptr, *slices = nullptr, *bslices = nullptr;
+  char *rec = nullptr, *bitsb = nullptr;  // node headers / index sets, see Params::hdr (bitsb == rec + 16 when interleaved)
+  char* bits_alloc = nullptr;             // SPLIT layout only: the separate index-set array
+  int hstride = 0, bstride = 0;
+  double* pc = nullptr;
+  dbl2* cp2 = nullptr;
   double *total = nullptr, *min_total = nullptr, *out_seq = nullptr, *out_maxw = nullptr;
   unsigned long long *seeds = nullptr, *rng_ctr = nullptr, *n_prop = nullptr, *n_acc = nullptr, *n_wrej = nullptr,
                      *cursor = nullptr;
@@ -236,7 +267,7 @@ struct ChainSet {
   unsigned long long stream_len = 0;
 
   void release(Rt& rt) {
-    void* ps[] = {par, bpar, ch, bch, bits, slices, bslices, cp, cp2, total, min_total, out_seq, out_maxw, seeds,
+    void* ps[] = {par, bpar, rec, bits_alloc, bch, pc, slices, bslices, cp2, total, min_total, out_seq, out_maxw, seeds,
                   rng_ctr, n_prop, n_acc, n_wrej, cursor, sweep_idx, overrun, nbig, posbuf, kpop, tree_fail, stream, kw, sz, word, wkey};
     for (void* p : ps) rt.free_(p);
     *this = ChainSet();
@@ -251,7 +282,7 @@ struct tnb_engine {
   Rt rt;
   std::string err;
   // network
-  int n = 0, N = 0, n_int = 0, n_inds = 0, W = 0, Ws = 0, Npad = 0;
+  int n = 0, N = 0, n_int = 0, n_inds = 0, W = 0, Ws = 0, Npad = 0, stride = 0;
   int tile = 32, wpl = 1;
   uint64_t dim = 2;
   double log2d = 1.0;
@@ -262,7 +293,7 @@ struct tnb_engine {
   // mode
   bool finite = false;
   float max_width = 0.f;
-  int every = 0, dsi = 0, prob_kind = TNB_PROB_MH, rng_kind = TNB_RNG_PHILOX, layout = TNB_LAYOUT_GLOBAL;
+  int every = 0, dsi = 0, prob_kind = TNB_PROB_MH, rng_kind = TNB_RNG_PHILOX, layout = TNB_LAYOUT_AUTO;
   // chains
   ChainSet cs;
   bool initialized = false;
@@ -313,7 +344,7 @@ static void fill_params(const tnb_engine* e, const ChainSet& cs, Params& P) {
   P.leaf_bits = e->d_leaf_bits; P.pow_tab = e->d_pow_tab; P.dim2 = e->dim == 2; P.log2d = e->log2d;
   P.finite = e->finite; P.every = e->every; P.dsi = e->dsi; P.prob_kind = e->prob_kind; P.max_width = e->max_width;
   P.n_chains = cs.n_chains; P.Npad = e->Npad;
-  P.par = cs.par; P.ch = cs.ch; P.bits = cs.bits; P.cp = cs.cp; P.bpar = cs.bpar; P.bch = cs.bch;
+  P.par = cs.par; P.hdr = cs.rec; P.bitsb = cs.bitsb; P.hstride = cs.hstride; P.bstride = cs.bstride; P.pc = cs.pc; P.bpar = cs.bpar; P.bch = cs.bch;
   P.slices = cs.slices; P.bslices = cs.bslices; P.total = cs.total; P.min_total = cs.min_total;
   P.seeds = cs.seeds; P.rng_ctr = cs.rng_ctr; P.chain_id0 = e->chain_id0; P.sweep_idx = cs.sweep_idx;
   P.n_prop = cs.n_prop; P.n_acc = cs.n_acc; P.n_wrej = cs.n_wrej;
@@ -340,15 +371,23 @@ static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_be
   Rt& rt = e->rt;
   cs.n_chains = n_chains;
   const size_t nc = size_t(n_chains), ni = size_t(std::max(e->n_int, 1));
-  bool ok = alloc_to(rt, cs.par, nc * e->Npad) && alloc_to(rt, cs.ch, nc * ni) &&
-            alloc_to(rt, cs.bits, nc * ni * e->Ws) && alloc_to(rt, cs.cp, nc * ni) &&
+  // layout: interleaved node records while the whole batch fits L2, split beyond
+  const size_t state = nc * ni * size_t(e->stride);
+  bool split = state > (size_t(96) << 20);
+  if (e->layout == TNB_LAYOUT_INTERLEAVED) split = false;
+  if (e->layout == TNB_LAYOUT_SPLIT) split = true;
+  cs.hstride = split ? 16 : e->stride;
+  cs.bstride = split ? 4 * e->Ws : e->stride;
+  bool ok = alloc_to(rt, cs.par, nc * e->Npad) && alloc_to(rt, cs.rec, nc * ni * size_t(cs.hstride)) &&
+            (!split || alloc_to(rt, cs.bits_alloc, nc * ni * size_t(cs.bstride))) &&
+            alloc_to(rt, cs.pc, nc * ni) && alloc_to(rt, cs.bch, nc * ni) &&
             alloc_to(rt, cs.slices, nc * e->Ws) && alloc_to(rt, cs.total, nc) && alloc_to(rt, cs.min_total, nc) &&
             alloc_to(rt, cs.out_seq, nc) && alloc_to(rt, cs.out_maxw, nc) && alloc_to(rt, cs.seeds, nc) &&
             alloc_to(rt, cs.rng_ctr, nc) && alloc_to(rt, cs.n_prop, nc) && alloc_to(rt, cs.n_acc, nc) &&
             alloc_to(rt, cs.n_wrej, nc) && alloc_to(rt, cs.cursor, nc) && alloc_to(rt, cs.sweep_idx, nc) &&
             alloc_to(rt, cs.overrun, nc);
-  if (ok && with_best)
-    ok = alloc_to(rt, cs.bpar, nc * e->Npad) && alloc_to(rt, cs.bch, nc * ni) && alloc_to(rt, cs.bslices, nc * e->Ws);
+  cs.bitsb = split ? cs.bits_alloc : cs.rec + 16;
+  if (ok && with_best) ok = alloc_to(rt, cs.bpar, nc * e->Npad) && alloc_to(rt, cs.bslices, nc * e->Ws);
   if (ok && with_slicer)
     ok = alloc_to(rt, cs.nbig, nc * e->Ws * 32) && alloc_to(rt, cs.posbuf, nc * e->Ws * 32) &&
          alloc_to(rt, cs.cp2, nc * ni);
@@ -390,7 +429,9 @@ static bool make_chains(tnb_engine* e, ChainSet& cs, int n_chains, const int32_t
     for (int z = 0; z < N - 1; ++z)
       if (seen[z] != 1) return e->fail("invalid tree: every non-root node must be a child exactly once");
   }
-  if (!rt.h2d(cs.par, hp.data(), hp.size() * sizeof(int16_t)) || !rt.h2d(cs.ch, hc.data(), hc.size() * sizeof(uint32_t)))
+  // the compact children words travel through bch (the init kernel overwrites it with the first snapshot)
+  if (!rt.h2d(cs.par, hp.data(), hp.size() * sizeof(int16_t)) || !rt.h2d(cs.bch, hc.data(), hc.size() * sizeof(uint32_t)) ||
+      !ch_copy(rt, cs.bch, cs.rec, cs.hstride, nc * size_t(e->n_int), true))
     return e->rtfail();
   if (!rt.sync()) return e->rtfail();  // hp/hc go out of scope
   return true;
@@ -553,6 +594,7 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* lea
   e->initialized = false;
   e->n = n_leaves; e->N = 2 * n_leaves - 1; e->n_int = n_leaves - 1; e->n_inds = n_inds; e->W = W;
   e->Ws = (W + 3) / 4 * 4;
+  e->stride = 16 + 4 * e->Ws;
   e->Npad = (e->N + 7) / 8 * 8;
   e->tile = pick_tile(W, e->wpl);
   {
@@ -590,14 +632,13 @@ int tnb_set_mode(tnb_engine* e, double max_width, int update_slices_every, int d
   if (!e) return -1;
   if (prob_kind < 0 || prob_kind > 2 || rng_kind < 0 || rng_kind > 2 || layout < 0 || layout > 2)
     return e->fail("tnb_set_mode: invalid arguments"), -1;
-  if (layout == TNB_LAYOUT_SHARED) return e->fail("tnb_set_mode: TNB_LAYOUT_SHARED is not available in this build"), -2;
   e->finite = !(max_width < 0.0) && !std::isinf(max_width) && !std::isnan(max_width);
   e->max_width = e->finite ? float(max_width) : 0.f;
   e->every = update_slices_every > 0 ? update_slices_every : 0;
   e->dsi = disable_shared_inds != 0;
   e->prob_kind = prob_kind;
   e->rng_kind = rng_kind;
-  e->layout = TNB_LAYOUT_GLOBAL;
+  e->layout = layout;
   e->cs.release(e->rt);  // chains are (re)built under the new mode: call tnb_set_chains afterwards
   e->initialized = false;
   return 0;
@@ -765,9 +806,21 @@ int tnb_get_trees(tnb_engine* e, int best, int chain0, int n, int32_t* parent, i
   const size_t ni = size_t(std::max(e->n_int, 1));
   std::vector<int16_t> hp(size_t(n) * e->Npad);
   std::vector<uint32_t> hc(size_t(n) * ni);
-  if (!e->rt.d2h(hp.data(), (best ? e->cs.bpar : e->cs.par) + size_t(chain0) * e->Npad, hp.size() * sizeof(int16_t)) ||
-      !e->rt.d2h(hc.data(), (best ? e->cs.bch : e->cs.ch) + size_t(chain0) * ni, hc.size() * sizeof(uint32_t)))
-    return e->rtfail(), -3;
+  uint32_t* d_ch = e->cs.bch + size_t(chain0) * ni;
+  uint32_t* tmp = nullptr;
+  if (!best && e->n_int > 0) {  // current trees: gather the children words out of the node records
+    if (!alloc_to(e->rt, tmp, hc.size())) return e->rtfail(), -3;
+    if (!ch_copy(e->rt, tmp, e->cs.rec + size_t(chain0) * ni * size_t(e->cs.hstride), e->cs.hstride, hc.size(), false)) {
+      e->rt.free_(tmp);
+      return e->rtfail(), -3;
+    }
+    d_ch = tmp;
+  }
+  const bool got = e->rt.d2h(hp.data(), (best ? e->cs.bpar : e->cs.par) + size_t(chain0) * e->Npad,
+                             hp.size() * sizeof(int16_t)) &&
+                   e->rt.d2h(hc.data(), d_ch, hc.size() * sizeof(uint32_t));
+  e->rt.free_(tmp);
+  if (!got) return e->rtfail(), -3;
   const int N = e->N, nl = e->n;
   for (int c = 0; c < n; ++c)
     for (int z = 0; z < N; ++z) {
@@ -790,11 +843,14 @@ int tnb_get_bits(tnb_engine* e, int chain, uint32_t* node_bits) {
   if (chain < 0 || chain >= e->cs.n_chains) return e->fail("tnb_get_bits: chain range"), -1;
   const int W = e->W, Ws = e->Ws;
   std::memcpy(node_bits, e->h_leaf_bits.data(), sizeof(uint32_t) * size_t(e->n) * W);
-  std::vector<uint32_t> hb(size_t(std::max(e->n_int, 1)) * Ws);
-  if (!e->rt.d2h(hb.data(), e->cs.bits + size_t(chain) * std::max(e->n_int, 1) * Ws, hb.size() * sizeof(uint32_t)))
+  (void)Ws;
+  const size_t ni = size_t(std::max(e->n_int, 1));
+  const size_t bs = size_t(e->cs.bstride);
+  std::vector<char> hb(ni * bs);
+  if (!e->rt.d2h(hb.data(), e->cs.bitsb + size_t(chain) * ni * bs, hb.size() - (e->cs.bits_alloc ? 0 : 16)))
     return e->rtfail(), -3;
   for (int z = 0; z < e->n_int; ++z)
-    std::memcpy(node_bits + size_t(e->n + z) * W, &hb[size_t(z) * Ws], sizeof(uint32_t) * size_t(W));
+    std::memcpy(node_bits + size_t(e->n + z) * W, &hb[size_t(z) * bs], sizeof(uint32_t) * size_t(W));
   return 0;
 }
 
@@ -882,9 +938,9 @@ int tnb_get_config(tnb_engine* e, int* tile, int* words_per_lane, int* layout, i
   if (!e) return -1;
   if (tile) *tile = e->tile;
   if (words_per_lane) *words_per_lane = e->wpl;
-  if (layout) *layout = e->layout;
+  if (layout) *layout = e->cs.n_chains ? (e->cs.bits_alloc ? TNB_LAYOUT_SPLIT : TNB_LAYOUT_INTERLEAVED) : e->layout;
   if (state_bytes_per_chain)
-    *state_bytes_per_chain = int(size_t(e->n_int) * (size_t(e->Ws) * 4 + 16 + 4) + size_t(e->Npad) * 2);
+    *state_bytes_per_chain = int(size_t(e->n_int) * size_t(e->stride) + size_t(e->Npad) * 2);
   return 0;
 }
 

@@ -30,9 +30,15 @@ struct Params {
   // chains
   int n_chains, Npad;
   int16_t* par;    // [n_chains][Npad]
-  uint32_t* ch;    // [n_chains][n_int]   child0 | child1 << 16
-  uint32_t* bits;  // [n_chains][n_int][Ws]
-  dbl2* cp;        // [n_chains][n_int]   {contraction_cost, partial_cost}
+  // Per internal node a 16-byte header {+0 u32 child0 | child1 << 16, +4 unused, +8 f64 contraction cost} and
+  // an index set u32[Ws].  INTERLEAVED layout (state fits L2): one record {header, index set} of
+  // stride = 16 + 4*Ws bytes per node, so everything the walk needs of a node sits in 1-2 adjacent sectors.
+  // SPLIT layout (HBM-resident state): headers [n_int] x 16 B and index sets [n_int] x 4*Ws B apart, so the
+  // small, hot headers of all chains stay L2-resident while the index sets stream from HBM.
+  char* hdr;       // header of node i of chain c at hdr + (c*n_int + i) * hstride
+  char* bitsb;     // index set                 at bitsb + (c*n_int + i) * bstride
+  int hstride, bstride;
+  double* pc;      // [n_chains][n_int]   partial costs (kept by the parity modes only)
   int16_t* bpar;   // best tree (reference min_ctree)
   uint32_t* bch;
   uint32_t* slices;   // [n_chains][Ws]
@@ -222,9 +228,10 @@ struct ChainView {
   // bases resolved for this lane and pre-offset by -n so that every array is indexed by the node id itself
   // (signed element offsets; the virtual bases are only dereferenced at indices >= n)
   const uint32_t* leaf_lane;  // leaf_bits + tl
-  uint32_t* bits_lane;        // bits of internal node z at bits_lane + z*Ws (+ k*TILE)
-  uint32_t* ch;               // ch[z]  = child0 | child1 << 16 of internal node z
-  dbl2* cp;                   // cp[z]  = {contraction_cost, partial_cost} of internal node z
+  unsigned hstride, bstride;  // bytes between the headers / index sets of consecutive internal nodes
+  char* rec;                  // header of internal node z at rec + z*hstride
+  char* rec_lane;             // this lane's first word of z's index set at rec_lane + z*bstride (+ 4*k*TILE)
+  double* pcv;                // pcv[z] = partial cost of internal node z (parity modes)
   bool lane_ok[WPL];
 
   TNB_D ChainView(const Params& P_, int chain_) : P(P_), chain(chain_) {
@@ -232,25 +239,37 @@ struct ChainView {
     Ws = unsigned(P.Ws);
     par = P.par + size_t(chain) * P.Npad;
     const long long row0 = (long long)chain * P.n_int - n;
-    bits_lane = P.bits + (row0 * (long long)P.Ws + t.tl);
+    hstride = unsigned(P.hstride);
+    bstride = unsigned(P.bstride);
+    rec = P.hdr + row0 * (long long)P.hstride;
+    rec_lane = P.bitsb + row0 * (long long)P.bstride + 4 * t.tl;
     leaf_lane = P.leaf_bits + t.tl;
-    ch = P.ch + row0;
-    cp = P.cp + row0;
+    pcv = P.pc + row0;
 #pragma unroll
     for (int k = 0; k < WPL; ++k) lane_ok[k] = (t.tl + k * TILE) < P.W;
   }
   TNB_D TNB_INLINE void load_bits(int node, uint32_t (&o)[WPL]) const {
-    const uint32_t* src = (node < n ? leaf_lane : const_cast<const uint32_t*>(bits_lane)) + unsigned(node) * Ws;
+    // two loads rather than one load through a selected pointer: each keeps its address space (LDG) and base
+    if (node < n) {
+      const uint32_t* src = leaf_lane + unsigned(node) * Ws;
 #pragma unroll
-    for (int k = 0; k < WPL; ++k) o[k] = lane_ok[k] ? src[k * TILE] : 0u;
+      for (int k = 0; k < WPL; ++k) o[k] = lane_ok[k] ? ldg(src + k * TILE) : 0u;
+    } else {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(rec_lane + unsigned(node) * bstride);
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) o[k] = lane_ok[k] ? src[k * TILE] : 0u;
+    }
   }
   TNB_D TNB_INLINE void store_bits(int node, const uint32_t (&v)[WPL]) const {
-    uint32_t* dst = bits_lane + unsigned(node) * Ws;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(rec_lane + unsigned(node) * bstride);
 #pragma unroll
     for (int k = 0; k < WPL; ++k)
       if (lane_ok[k]) dst[k * TILE] = v[k];
   }
-  TNB_D TNB_INLINE double pc_of(int node) const { return node < n ? 0.0 : cp[node].y; }
+  // header fields of internal node z
+  TNB_D TNB_INLINE uint32_t& ch(int z) const { return *reinterpret_cast<uint32_t*>(rec + unsigned(z) * hstride); }
+  TNB_D TNB_INLINE double& cc(int z) const { return *reinterpret_cast<double*>(rec + unsigned(z) * hstride + 8); }
+  TNB_D TNB_INLINE double pc_of(int node) const { return node < n ? 0.0 : pcv[node]; }
   TNB_D TNB_INLINE double cost_of(int k) const {
     // pow(dim, k) (infinite_memory/cost_model/simple.hpp:45) from the host-computed table (std::pow)
     return ldg(P.pow_tab + k);
@@ -259,16 +278,16 @@ struct ChainView {
   // stackless post-order over the CURRENT topology, children[0] subtree first (utils.hpp:35-52)
   TNB_D int po_first() const {
     int x = P.N - 1;
-    while (x >= n) x = int(ch[x] & 0xffffu);
+    while (x >= n) x = int(ch(x) & 0xffffu);
     return x;
   }
   TNB_D int po_next(int x) const {
     if (x == P.N - 1) return -1;
     const int p = par[x];
-    const uint32_t c = ch[p];
+    const uint32_t c = ch(p);
     if (int(c & 0xffffu) == x) {
       x = int(c >> 16);
-      while (x >= n) x = int(ch[x] & 0xffffu);
+      while (x >= n) x = int(ch(x) & 0xffffu);
       return x;
     }
     return p;
@@ -285,8 +304,25 @@ TNB_D TNB_INLINE uint32_t popc_or3(const uint32_t (&a)[WPL], const uint32_t (&b)
 
 // Post-order cost pass (CostCache ctor, infinite_memory/utils.hpp:32-56; with slices finite_width/utils.hpp:36-45).
 // Optionally (re)builds the index sets of internal nodes and tracks get_cost's sequential sum and the widest node.
-template <int TILE, int WPL, bool BUILD>
-TNB_D void cost_pass(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL], dbl2* dst, double& seq,
+// where cost_pass puts its results: the chain's own caches, or a scratch array of {contraction, partial} pairs
+template <int TILE, int WPL>
+struct CacheSink {
+  const ChainView<TILE, WPL>& c;
+  TNB_D TNB_INLINE double pc(int node) const { return c.pc_of(node); }
+  TNB_D TNB_INLINE void put(int z, double cost, double pcost) const {
+    c.cc(z) = cost;
+    c.pcv[z] = pcost;
+  }
+};
+struct ScratchSink {
+  dbl2* dst;
+  int n;
+  TNB_D TNB_INLINE double pc(int node) const { return node < n ? 0.0 : dst[node - n].y; }
+  TNB_D TNB_INLINE void put(int z, double cost, double pcost) const { dst[z - n] = make_dbl2(cost, pcost); }
+};
+
+template <int TILE, int WPL, bool BUILD, class Sink>
+TNB_D void cost_pass(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL], const Sink& dst, double& seq,
                      uint32_t& maxk) {
   const Params& P = c.P;
   seq = 0.0;
@@ -304,7 +340,7 @@ TNB_D void cost_pass(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL], db
       }
       continue;
     }
-    const uint32_t cc_ = c.ch[z];
+    const uint32_t cc_ = c.ch(z);
     const int a = int(cc_ & 0xffffu), b = int(cc_ >> 16);
     uint32_t xa[WPL], xb[WPL];
     c.load_bits(a, xa);
@@ -327,9 +363,9 @@ TNB_D void cost_pass(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL], db
       kk &= 0xffffu;
     }
     const double cost = c.cost_of(int(kk));
-    const double pa = a < P.n ? 0.0 : dst[a - P.n].y;
-    const double pb = b < P.n ? 0.0 : dst[b - P.n].y;
-    dst[z - P.n] = make_dbl2(cost, cost + pa + pb);
+    const double pa = dst.pc(a);
+    const double pb = dst.pc(b);
+    dst.put(z, cost, cost + pa + pb);
     seq += cost;
   }
 }
@@ -340,7 +376,7 @@ TNB_D void build_bits(const ChainView<TILE, WPL>& c) {
   const Params& P = c.P;
   for (int z = c.po_first(); z >= 0; z = c.po_next(z)) {
     if (z < P.n) continue;
-    const uint32_t cc_ = c.ch[z];
+    const uint32_t cc_ = c.ch(z);
     uint32_t xa[WPL], xb[WPL];
     c.load_bits(int(cc_ & 0xffffu), xa);
     c.load_bits(int(cc_ >> 16), xb);
@@ -544,7 +580,7 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, Rng& rng,
     while (true) {
       const int p = c.par[y];
       if (p < 0) break;
-      const int l = int(c.ch[p] & 0xffffu);
+      const int l = int(c.ch(p) & 0xffffu);
       if (l != y) post += 2u * uint32_t(sz[l]) - 1u;
       y = p;
     }
@@ -617,7 +653,7 @@ TNB_D TNB_NOINLINE double recost_all(const ChainView<TILE, WPL>& c, const uint32
   double acc = 0.0;
   for (int base = P.n; base < P.N; base += TILE) {
     const int zz = base + t.tl;
-    const uint32_t mych = zz < P.N ? c.ch[zz] : 0u;
+    const uint32_t mych = zz < P.N ? c.ch(zz) : 0u;
     const int cnt = P.N - base < TILE ? P.N - base : TILE;
     for (int q = 0; q < cnt; ++q) {
       const uint32_t w = t.bcast(mych, q);
@@ -650,7 +686,7 @@ TNB_D void build_kw_sz(const ChainView<TILE, WPL>& c) {
     if (z < P.n) {
       sz[z] = 1;
     } else {
-      const uint32_t w = c.ch[z];
+      const uint32_t w = c.ch(z);
       sz[z] = int16_t(sz[w & 0xffffu] + sz[w >> 16]);
     }
   }
@@ -663,7 +699,7 @@ TNB_D void snapshot_best(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL]
   uint32_t* dst = reinterpret_cast<uint32_t*>(P.bpar + size_t(c.chain) * P.Npad);
   for (int i = c.t.tl; i < P.Npad / 2; i += TILE) dst[i] = src[i];
   uint32_t* dch = P.bch + size_t(c.chain) * P.n_int;
-  for (int i = c.t.tl; i < P.n_int; i += TILE) dch[i] = c.ch[P.n + i];
+  for (int i = c.t.tl; i < P.n_int; i += TILE) dch[i] = c.ch(P.n + i);
   if (finite) {
     uint32_t* ds = P.bslices + size_t(c.chain) * P.Ws;
 #pragma unroll
@@ -729,7 +765,8 @@ TNB_D void chain_treegen(const Params& P, int chain) {
   }
   t.sync();
   auto row = [&](int x) -> const uint32_t* {
-    return x < n ? P.leaf_bits + size_t(x) * P.Ws : P.bits + (size_t(chain) * P.n_int + size_t(x - n)) * P.Ws;
+    return x < n ? P.leaf_bits + size_t(x) * P.Ws
+                 : reinterpret_cast<const uint32_t*>(c.rec_lane - 4 * t.tl + unsigned(x) * c.bstride);
   };
   // big networks: score a strided sample of ~1024 edges per step instead of all of them
   const int stride_edges = P.n_inds > 1024 ? (P.n_inds + 1023) / 1024 : 1;
@@ -813,7 +850,7 @@ TNB_D void chain_treegen(const Params& P, int chain) {
     kpop[z] = int16_t(k);
     c.par[a] = int16_t(z);
     c.par[b] = int16_t(z);
-    c.ch[z] = uint32_t(a) | (uint32_t(b) << 16);
+    c.ch(z) = uint32_t(a) | (uint32_t(b) << 16);
     t.sync();  // owners / rows written by other lanes are read by everybody in the next step
   }
 }
@@ -847,8 +884,8 @@ TNB_D void chain_init(const Params& P, int chain) {
   }
   double seq;
   uint32_t maxk;
-  cost_pass<TILE, WPL, true>(c, S, c.cp + c.n, seq, maxk);
-  const double rootpc = c.cp[P.N - 1].y;
+  cost_pass<TILE, WPL, true>(c, S, CacheSink<TILE, WPL>{c}, seq, maxk);
+  const double rootpc = c.pcv[P.N - 1];
   P.total[chain] = rootpc;
   P.min_total[chain] = seq;  // get_cost(min_ctree) sums in traversal order (infinite_memory/utils.hpp:102-116)
   if (P.out_seq) P.out_seq[chain] = seq;
@@ -858,42 +895,11 @@ TNB_D void chain_init(const Params& P, int chain) {
 }
 
 // ------------------------------------------------------------------------------------------ sweeps
-// log2(1 + delta/total) for delta > 0, total > 0 in float with ~2e-6 relative error, without a double division:
-// mantissas (23 bits) divided in fp32, exponents subtracted as integers.  Production (Philox) acceptance only.
-TNB_HD TNB_INLINE float log2_1p_ratio(double delta, double total) {
-  unsigned long long ud, ut;
-#if defined(TNB_EMU) || !defined(__CUDA_ARCH__)
-  std::memcpy(&ud, &delta, 8);
-  std::memcpy(&ut, &total, 8);
+TNB_D TNB_INLINE float exp2_fast(float x) {
+#if defined(TNB_EMU)
+  return exp2f(x);
 #else
-  ud = (unsigned long long)__double_as_longlong(delta);
-  ut = (unsigned long long)__double_as_longlong(total);
-#endif
-  const int diff = int((ud >> 52) & 0x7ffu) - int((ut >> 52) & 0x7ffu);
-  const uint32_t id = 0x3f800000u | uint32_t((ud >> 29) & 0x7fffffu);
-  const uint32_t it = 0x3f800000u | uint32_t((ut >> 29) & 0x7fffffu);
-  float md, mt;
-#if defined(TNB_EMU) || !defined(__CUDA_ARCH__)
-  std::memcpy(&md, &id, 4);
-  std::memcpy(&mt, &it, 4);
-  const float q = md / mt;
-  if (diff > 64) return float(diff) + log2f(q);
-  if (diff < -64) return 0.f;
-  const uint32_t ie = uint32_t(127 + diff) << 23;
-  float sc;
-  std::memcpy(&sc, &ie, 4);
-  const float x = q * sc;
-  if (x < 0.03125f) return x * 1.44269504f * (1.f - x * (0.5f - x * (0.33333334f - 0.25f * x)));
-  return log2f(1.f + x);
-#else
-  md = __uint_as_float(id);
-  mt = __uint_as_float(it);
-  const float q = __fdividef(md, mt);
-  if (diff > 64) return float(diff) + __log2f(q);
-  if (diff < -64) return 0.f;
-  const float x = q * __uint_as_float(uint32_t(127 + diff) << 23);
-  if (x < 0.03125f) return x * 1.44269504f * (1.f - x * (0.5f - x * (0.33333334f - 0.25f * x)));
-  return __log2f(1.f + x);
+  return exp2f(x);  // -use_fast_math is off: exp2f on the device is MUFU.EX2 plus range handling
 #endif
 }
 
@@ -903,7 +909,7 @@ TNB_HD TNB_INLINE float log2_1p_ratio(double delta, double total) {
 template <int TILE, int WPL>
 TNB_D double sum_ccost(const ChainView<TILE, WPL>& c) {
   double acc = 0.0;
-  for (int z = c.n + c.t.tl; z < c.P.N; z += TILE) acc += c.cp[z].x;
+  for (int z = c.n + c.t.tl; z < c.P.N; z += TILE) acc += c.cc(z);
 #if !defined(TNB_EMU)
 #pragma unroll
   for (int d = TILE / 2; d > 0; d >>= 1)
@@ -926,6 +932,10 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     P.sweep_idx[chain] = P.until;
     return;
   }
+  // the per-chain bases stay in registers (otherwise they are re-derived from the kernel parameters at every use)
+  keep_in_register(c.rec);
+  keep_in_register(c.rec_lane);
+  keep_in_register(c.par);
   // PC: keep the reference's partial-cost cache (parity modes).  The production kernel drops it: the walk then
   // needs no partial costs of D/E/C, no two 16-byte stores per level and half the fp64 adds; its total is a
   // running sum re-based on sum_ccost() every 16 sweeps.
@@ -954,7 +964,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
 #pragma unroll
   for (int k = 0; k < WPL; ++k) b0[k] = b1[k] = bC[k] = 0u;
   double pc0 = 0.0, pc1 = 0.0, pcC = 0.0, ccA = 0.0, ccB = 0.0, total = 0.0, root_pc = 0.0, beta = 0.0;
-  float beta_f = 0.f;
+  float inv_beta_f = 0.f;
 
   while (true) {
     if (A < 0) {
@@ -976,7 +986,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
                 const double r2 = recost_all<TILE, WPL, DIM2>(c, S2, cp2);
                 if (r2 < total) {
                   t.sync();
-                  for (int i = t.tl; i < P.n_int; i += TILE) c.cp[n + i].x = cp2[i].x;
+                  for (int i = t.tl; i < P.n_int; i += TILE) c.cc(n + i) = cp2[i].x;
                   t.sync();
 #pragma unroll
                   for (int k = 0; k < WPL; ++k) S[k] = S2[k];
@@ -988,11 +998,14 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
               get_slices_dev(c, rng, S2);
               double seq;
               uint32_t maxk;
-              cost_pass<TILE, WPL, false>(c, S2, cp2, seq, maxk);
+              cost_pass<TILE, WPL, false>(c, S2, ScratchSink{cp2, n}, seq, maxk);
               const double r2 = cp2[P.n_int - 1].y;
               if (r2 < (PC ? root_pc : total)) {
                 t.sync();
-                for (int i = t.tl; i < P.n_int; i += TILE) c.cp[n + i] = cp2[i];
+                for (int i = t.tl; i < P.n_int; i += TILE) {
+                  c.cc(n + i) = cp2[i].x;
+                  c.pcv[n + i] = cp2[i].y;
+                }
                 t.sync();
 #pragma unroll
                 for (int k = 0; k < WPL; ++k) S[k] = S2[k];
@@ -1016,17 +1029,18 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       }
       if (s >= P.until || !rng.can_start(P)) break;
       beta = P.betas[s < P.n_betas ? s : P.n_betas - 1];
-      beta_f = float(beta);
+      // 1/beta for the threshold form of the acceptance test; beta <= 0 accepts everything ((1+x)^-beta >= 1)
+      inv_beta_f = beta > 0.0 ? 1.f / float(beta) : 3.0e38f;
       const int leaf = int(rng.leaf_word(t) % uint32_t(n));  // optimizer.hpp:103
       B = c.par[leaf];
       if (PC) {
-        total = c.cp[root].y;                            // :112
+        total = c.pcv[root];                             // :112
       } else if (rebase || (s & 15) == 0) {
         total = sum_ccost(c);
         rebase = false;
       }
       root_pc = total;
-      const uint32_t cw = c.ch[B];
+      const uint32_t cw = c.ch(B);
       p0 = int(cw & 0xffffu);
       p1 = int(cw >> 16);
       c.load_bits(p0, b0);
@@ -1039,18 +1053,18 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         sz0 = szp[p0];
         sz1 = szp[p1];
       }
-      ccB = c.cp[B].x;
+      ccB = c.cc(B);
       A = c.par[B];
       in_sweep = true;
       if (A >= 0) {
-        const uint32_t aw = c.ch[A];
+        const uint32_t aw = c.ch(A);
         a0 = int(aw & 0xffffu);
         a1 = int(aw >> 16);
         C = (a0 == B) ? a1 : a0;
         c.load_bits(C, bC);
         if (PC) pcC = c.pc_of(C);
         if (FS) szC = szp[C];
-        ccA = c.cp[A].x;
+        ccA = c.cc(A);
       }
     } else {
     // -------------------------------------------------------------------- one level (A >= 0)
@@ -1100,8 +1114,8 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     uint32_t awn = 0u;
     double ccAn = 0.0;
     if (An >= 0) {
-      awn = c.ch[An];
-      ccAn = c.cp[An].x;
+      awn = c.ch(An);
+      ccAn = c.cc(An);
     }
     bool acc = false;
     double nA = 0.0, nB = 0.0, delta = 0.0;
@@ -1117,8 +1131,13 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       }
       delta = (nB - ccB) + (nA - ccA);       // :158, this association order
       if (Rng::kFast && f_prob == kProbMH) {
-        // same rule as prob/mh.hpp:45-59 in the log domain: u <= (1+x)^-beta  <=>  beta*log2(1+x) <= -log2(u)
-        acc = delta <= 0.0 || beta_f * log2_1p_ratio(delta, total) <= rng.neg_log2_u();
+        // same rule as prob/mh.hpp:45-59, solved for the move: u <= (1 + delta/total)^-beta
+        //   <=>  delta <= (2^(-log2(u)/beta) - 1) * total.
+        // The threshold depends only on the event's uniform and beta, so it is ready before delta is; what is
+        // left on the dependent path is one fp64 multiply and one compare (fp32 exp2: ~3e-6 relative error of
+        // the threshold; an overflowing exponent gives +inf = accept, which is the limit of the rule).
+        const float thr = exp2_fast(rng.neg_log2_u() * inv_beta_f) - 1.f;
+        acc = delta <= double(thr) * total;
       } else {
         const double u = rng.uniform(t);  // always drawn (:162)
         double p;
@@ -1139,8 +1158,8 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       // Tree::swap_with_nn(E): E <-> C, child slots preserved (tree.hpp:141-192)
       if (bslot0) a1 = E; else a0 = E;
       if (pick0) p1 = C; else p0 = C;
-      c.ch[A] = uint32_t(a0) | (uint32_t(a1) << 16);
-      c.ch[B] = uint32_t(p0) | (uint32_t(p1) << 16);
+      c.ch(A) = uint32_t(a0) | (uint32_t(a1) << 16);
+      c.ch(B) = uint32_t(p0) | (uint32_t(p1) << 16);
       c.par[C] = int16_t(B);
       c.par[E] = int16_t(A);
       c.store_bits(B, nb);
@@ -1171,12 +1190,14 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     if (PC) {
       pcB = pcD + pcE + ccB;
       const double pcA = pcB + pcC + ccA;
-      c.cp[B] = make_dbl2(ccB, pcB);
-      c.cp[A] = make_dbl2(ccA, pcA);
+      c.cc(B) = ccB;
+      c.pcv[B] = pcB;
+      c.cc(A) = ccA;
+      c.pcv[A] = pcA;
       root_pc = pcA;
     } else if (acc) {
-      c.cp[B].x = ccB;
-      c.cp[A].x = ccA;
+      c.cc(B) = ccB;
+      c.cc(A) = ccA;
     }
     // next level: B <- A, whose children are (a0, a1) = {B, C} in slot order
     p0 = a0;
@@ -1212,7 +1233,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   rng.store(P, chain);
   P.sweep_idx[chain] = s;
   P.min_total[chain] = min_total;
-  P.total[chain] = PC ? c.cp[root].y : (rebase ? P.total[chain] : total);
+  P.total[chain] = PC ? c.pcv[root] : (rebase ? P.total[chain] : total);
   P.n_prop[chain] += n_prop;
   P.n_acc[chain] += n_acc;
   P.n_wrej[chain] += n_wrej;

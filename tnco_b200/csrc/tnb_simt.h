@@ -35,6 +35,7 @@ template <class T>
 TNB_D TNB_INLINE void keep_in_register(T*& p) {
 #if !defined(TNB_EMU)
   asm volatile("" : "+l"(p));
+  __builtin_assume(__isGlobal(p));  // the asm hides the address space: keep LDG/STG instead of generic LD/ST
 #else
   (void)p;
 #endif
