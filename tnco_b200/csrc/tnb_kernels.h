@@ -548,14 +548,20 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, Rng& rng,
   for (int base = 0; base < P.N; base += TILE) {
     const int z = base + t.tl;
     const bool wide = z < P.N && int(kw[z]) > P.kthr;
-    uint32_t m = t.ballot(wide);
+    const uint32_t m = t.ballot(wide);
     if (wide) word[nw + popc32(m & ((1u << t.tl) - 1u))] = int16_t(z);
     nw += popc32(m);
-    while (m) {
-      const int zz = base + ctz32(m);
-      m &= m - 1;
+  }
+  if (nw == 0) return;
+  t.sync();
+  {
+    uint32_t xn[WPL];
+    c.load_bits(word[0], xn);
+    for (int j = 0; j < nw; ++j) {
       uint32_t x[WPL];
-      c.load_bits(zz, x);
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) x[k] = xn[k];
+      if (j + 1 < nw) c.load_bits(word[j + 1], xn);  // the next row is in flight while this one is counted
 #pragma unroll
       for (int k = 0; k < WPL; ++k) {
         uint32_t carry = x[k];
@@ -570,8 +576,6 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, Rng& rng,
       }
     }
   }
-  if (nw == 0) return;
-  t.sync();
   // (2) post-order rank of every wide node, one node per lane
   for (int j = t.tl; j < nw; j += TILE) {
     const int z = word[j];
@@ -596,10 +600,13 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, Rng& rng,
   }
   t.sync();
   // (3) greedy selection (:60-104)
+  uint32_t xnext[WPL];
+  c.load_bits(word[0], xnext);
   for (int j = 0; j < nw; ++j) {
-    const int z = word[j];
     uint32_t x[WPL];
-    c.load_bits(z, x);
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) x[k] = xnext[k];
+    if (j + 1 < nw) c.load_bits(word[j + 1], xnext);
     uint32_t ks = 0;
 #pragma unroll
     for (int k = 0; k < WPL; ++k) {
@@ -667,6 +674,103 @@ TNB_D TNB_NOINLINE double recost_all(const ChainView<TILE, WPL>& c, const uint32
       acc += cost;
     }
   }
+  return acc;
+}
+
+// Re-cost under new slices WITHOUT touching the index sets (dim == 2, where a contraction cost is the exact power
+// 2^popc(U_z | S), U_z = union of the children's index sets).  Going from S to S2 multiplies the cost of node z by
+//   2^(|S2 \ S| - |S \ S2| + #{i in S \ S2 : i in U_z} - #{i in S2 \ S : i in U_z}),
+// and i lies in U_z exactly for the nodes on the two paths from the leaves holding i up to the node where i is
+// contracted.  mark_slice_diff walks those paths for every index of the symmetric difference (one index per lane)
+// and leaves the per-node exponent correction in dz[]; returns the common shift |S2 \ S| - |S \ S2|.
+template <int TILE, int WPL>
+TNB_D TNB_NOINLINE int mark_slice_diff(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL],
+                                       const uint32_t (&S2)[WPL], int* dz, int16_t* list) {
+  const Params& P = c.P;
+  const Tile<TILE>& t = c.t;
+  for (int i = t.tl; i < P.n_int; i += TILE) dz[i] = 0;
+  uint32_t mine = 0, n_add = 0;
+#pragma unroll
+  for (int k = 0; k < WPL; ++k) {
+    mine += uint32_t(popc32(S[k] ^ S2[k]));
+    n_add += uint32_t(popc32(S2[k] & ~S[k]));
+  }
+  uint32_t nd;
+  uint32_t off = t.excl_scan_sum(mine, nd);
+  n_add = t.sum(n_add);
+#pragma unroll
+  for (int k = 0; k < WPL; ++k) {
+    uint32_t v = S[k] ^ S2[k];
+    const int w = t.tl + k * TILE;
+    while (v) {
+      const int b = ctz32(v);
+      v &= v - 1;
+      // bit 15: the index leaves the slice set (its nodes get +1), otherwise it joins (-1)
+      list[off++] = int16_t((w * 32 + b) | (((S[k] >> b) & 1u) ? 0x8000 : 0));
+    }
+  }
+  t.sync();
+  const char* bits0 = c.rec_lane - 4 * t.tl;
+  for (int j = t.tl; j < int(nd); j += TILE) {
+    const int e = uint16_t(list[j]);
+    const int idx = e & 0x7fff, sgn = (e & 0x8000) ? 1 : -1;
+    const unsigned wofs = unsigned(idx) >> 5;
+    const uint32_t bit = 1u << (idx & 31);
+    const int u = P.net_own[idx], v = P.net_own[P.n_inds + idx];
+    int y = u;
+    while (true) {
+      const int p = c.par[y];
+      if (p < 0) break;
+#if defined(TNB_EMU)
+      dz[p - c.n] += sgn;
+#else
+      atomicAdd(dz + (p - c.n), sgn);
+#endif
+      y = p;
+      if (!(*reinterpret_cast<const uint32_t*>(bits0 + unsigned(y) * c.bstride + 4 * wofs) & bit)) break;
+    }
+    const int top = y;  // the node that contracts idx (or the root for an open index)
+    if (v >= 0) {
+      y = v;
+      while (true) {
+        const int p = c.par[y];
+        if (p < 0 || p == top) break;
+#if defined(TNB_EMU)
+        dz[p - c.n] += sgn;
+#else
+        atomicAdd(dz + (p - c.n), sgn);
+#endif
+        y = p;
+      }
+    }
+  }
+  t.sync();
+  return 2 * int(n_add) - int(nd);  // |S2 \ S| - |S \ S2|
+}
+
+// cost * 2^e for a cost that is an exact power of two
+TNB_D TNB_INLINE double scale_pow2(double cost, int e) {
+#if defined(TNB_EMU)
+  return std::ldexp(cost, e);
+#else
+  return __longlong_as_double(__double_as_longlong(cost) + ((long long)e << 52));
+#endif
+}
+
+// Sum of the shifted costs; with STORE the shifted costs also replace the cached ones.
+template <int TILE, int WPL, bool STORE>
+TNB_D double sum_shifted(const ChainView<TILE, WPL>& c, const int* dz, int shift0) {
+  double acc = 0.0;
+  for (int z = c.n + c.t.tl; z < c.P.N; z += TILE) {
+    const double v = scale_pow2(c.cc(z), shift0 + dz[z - c.n]);
+    if (STORE) c.cc(z) = v;
+    acc += v;
+  }
+#if !defined(TNB_EMU)
+#pragma unroll
+  for (int d = TILE / 2; d > 0; d >>= 1)
+    acc += TILE == 32 ? __shfl_xor_sync(0xffffffffu, acc, d, 32) : __shfl_xor_sync(c.t.mask, acc, d, TILE);
+#endif
   return acc;
 }
 
@@ -983,15 +1087,28 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
 #pragma unroll
               for (int k = 0; k < WPL; ++k) diff |= S2[k] != S[k];
               if (t.any(diff)) {  // same slices -> same costs: nothing to decide
-                const double r2 = recost_all<TILE, WPL, DIM2>(c, S2, cp2);
-                if (r2 < total) {
-                  t.sync();
-                  for (int i = t.tl; i < P.n_int; i += TILE) c.cc(n + i) = cp2[i].x;
-                  t.sync();
+                if (DIM2 && P.n_inds <= 1000) {
+                  int* dz = reinterpret_cast<int*>(P.wkey + size_t(chain) * P.Npad);
+                  const int shift0 = mark_slice_diff(c, S, S2, dz, P.word + size_t(chain) * P.Npad);
+                  const double r2 = sum_shifted<TILE, WPL, false>(c, dz, shift0);
+                  if (r2 < total) {
+                    total = sum_shifted<TILE, WPL, true>(c, dz, shift0);
+                    t.sync();
 #pragma unroll
-                  for (int k = 0; k < WPL; ++k) S[k] = S2[k];
-                  store_slices(c, S);
-                  total = r2;
+                    for (int k = 0; k < WPL; ++k) S[k] = S2[k];
+                    store_slices(c, S);
+                  }
+                } else {
+                  const double r2 = recost_all<TILE, WPL, DIM2>(c, S2, cp2);
+                  if (r2 < total) {
+                    t.sync();
+                    for (int i = t.tl; i < P.n_int; i += TILE) c.cc(n + i) = cp2[i].x;
+                    t.sync();
+#pragma unroll
+                    for (int k = 0; k < WPL; ++k) S[k] = S2[k];
+                    store_slices(c, S);
+                    total = r2;
+                  }
                 }
               }
             } else {
