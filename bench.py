@@ -7,10 +7,10 @@
 Workload (config.workload): BASELINE.json configs[1] -- 2D-grid 6x6 random circuit depth 12 tensor network
 (180 tensors, 324 indices, bond dim 2), unconstrained SA, betas 0 -> 100, 4096 chains per GPU.
 One STEP = one full anneal of the whole batch: `--sweeps` leaf->root sweeps of every chain from fresh initial
-trees.  `value` = proposals/s with chain state resident in HBM, timed with CUDA events on the engine's stream
+trees (built on the device, outside the timed region).  `value` = proposals/s with chain state resident in HBM, timed with CUDA events on the engine's stream
 around the sweep kernel (L2 flushed before every step), max over ranks.  `e2e` = the same metric through the
-public API `Optimizer(method='sa').optimize(...)` with host buffers: initial trees built on the host, H2D,
-cache construction, sweeps, D2H of the best trees, path extraction and result objects, wall clock.
+public API `Optimizer(method='sa').optimize(...)` with host buffers: H2D of network / seeds / schedule, initial
+trees and cache construction on the device, sweeps, D2H of the best costs and trees, result objects, wall clock.
 """
 from __future__ import annotations
 
@@ -221,7 +221,7 @@ def run_ours(args):
 
     from tnco_b200 import dist as tdist
     from tnco_b200.app import Optimizer
-    from tnco_b200.engine import Engine, random_trees
+    from tnco_b200.engine import Engine
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -234,7 +234,6 @@ def run_ours(args):
     C, S = args.chains, args.sweeps
     betas = np.array([n_ * (100.0 / S) for n_ in range(S)])
     seeds = (np.arange(C, dtype=np.uint64) + 1) + np.uint64(rank * C)
-    P, A, B = random_trees(lb, ni, seeds)
 
     eng = Engine(local)
     eng.set_network(lb, ni).set_mode()
@@ -242,7 +241,7 @@ def run_ours(args):
     cfg = eng.config()
 
     def step():
-        eng.set_chains(P, A, B, seeds, chain_id0=rank * C)
+        eng.generate_chains(seeds, chain_id0=rank * C)   # fresh initial trees, built on the device
         eng.costs()          # forces cache construction (init kernel) before the timed region
         eng.flush_l2()
         eng.timing()
@@ -289,7 +288,7 @@ def run_ours(args):
             e2e_s += dt
     N = 2 * n - 1
     npad, ws = (N + 7) // 8 * 8, (W + 3) // 4 * 4
-    h2d = C * (npad * 2 + (n - 1) * 4 + 8) + S * 8 + n * ws * 4 + (ni + 1) * 8
+    h2d = C * 8 + S * 8 + n * ws * 4 + (ni + 1) * 8 + 2 * ni * 2   # seeds, betas, network (trees are built on the device)
     d2h = C * (npad * 2 + (n - 1) * 4 + 2 * 8 + 3 * 8)
 
     L = props / max(sweeps, 1)
@@ -298,11 +297,15 @@ def run_ours(args):
     per_rank_rate = props / (tot_ms * 1e-3)
     peak, peak_src = measured_peak_gbs()
     achieved = per_rank_rate * bpp / 1e9
-    traffic = None
+    traffic, issue = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'sweep_kernel_traffic.json')))['dram_bytes_per_launch']
+        prof = json.load(open(os.path.join(ROOT, 'profiles', 'sweep_kernel_traffic.json')))
+        traffic = prof['dram_bytes_per_launch']
+        # the roof that actually binds this L2-resident workload: warp-instruction issue (4 schedulers x 148 SMs,
+        # one instruction per cycle each); instructions per proposal from the committed ncu capture
+        ipp = prof['warp_instructions_per_proposal']
     except Exception:
-        pass
+        ipp = None
     line = dict(metric='SA proposals/sec', value=props_all / (ms_max * 1e-3), unit='proposals/s', n_gpus=world,
                 steps=args.steps, warmup=args.warmup, ms_per_step=ms_max / args.steps, higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
@@ -317,8 +320,16 @@ def run_ours(args):
                 roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
                               traffic=traffic, kernel='sa_sweep_kernel', peak_source=peak_src,
                               bytes_per_proposal=bpp, levels_per_sweep=L, accept_ratio=pacc,
-                              note='chain state (53 MB) is L2-resident; the kernel is latency/issue bound, see DESIGN.md'),
+                              note='chain state (50 MB) is L2-resident; the kernel is latency/issue bound, see DESIGN.md'),
                 best_log2_flops=gbest and float(np.log2(gbest)), proposals_per_step=props / args.steps)
+    if ipp:
+        mhz = line['clocks'].get('sm_mhz') or line['clocks'].get('sm_max_mhz') or 1965.0
+        peak_issue = 148 * 4 * mhz * 1e6
+        line['roofline']['issue'] = dict(bound='warp-instruction issue', warp_instr_per_proposal=ipp,
+                                         achieved=per_rank_rate * ipp / 1e9, peak=peak_issue / 1e9, unit='Ginstr/s',
+                                         frac=per_rank_rate * ipp / peak_issue,
+                                         source='instructions/proposal: ncu smsp__inst_executed.sum of the same kernel '
+                                                '(profiles/sweep_kernel_traffic.json); rate and clock: this run')
     if world == 1 and not args.no_cpu_baseline:
         n_sw = calibrate_ref_sweeps(12.0)
         kind, cores, n_runs, out = cpu_reference_rate(n_sw, repeats=1)

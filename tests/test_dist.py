@@ -34,12 +34,12 @@ rows = [[2] for _ in range(ni)]
 for t, xs in enumerate(ts):
     for x in xs:
         rows[x].append('t%d' % t)
-opt = Optimizer(seed=9, max_width={mw})
+opt = Optimizer(seed=9, max_width={mw}, sync_every=20)
 tn, res = opt.optimize(rows, betas=(0, 100), n_steps=60, n_runs=6)
 out = dict(rank=rank, world=world, best=best, payload=payload.tolist(), owner=owner, gathered=rows_all.ravel().tolist(),
            costs=[str(r.cost) for r in res], paths=[r.path for r in res],
            slices=[sorted(r.slices) for r in res] if {mw} is not None else None,
-           local_sweeps=opt.last_stats['sweeps'])
+           local_sweeps=opt.last_stats['sweeps'], history=opt.last_stats.get('global_best_history'))
 open(os.path.join({outdir!r}, 'out_%d_%d.json' % (world, rank)), 'w').write(json.dumps(out))
 if world > 1:
     dist.destroy_process_group()
@@ -73,4 +73,7 @@ def test_two_ranks_over_gloo_match_single_process(mw, tmp_path):
         assert r['gathered'] == list(range(7))
         # results do not depend on the number of ranks (seeds and Philox counters use global chain ids)
         assert r['costs'] == single['costs'] and r['paths'] == single['paths'] and r['slices'] == single['slices']
+        # periodic min-reduction: every 20 sweeps, same value on both ranks, non-increasing
+        assert [h[0] for h in r['history']] == [20, 40, 60] and r['history'] == two[0]['history']
+        assert all(a[1] >= b[1] for a, b in zip(r['history'], r['history'][1:]))
     assert two[0]['local_sweeps'] + two[1]['local_sweeps'] == single['local_sweeps'] == 6 * 60

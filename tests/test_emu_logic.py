@@ -65,3 +65,9 @@ def test_emu_generated_trees_disconnected(emu):
 @pytest.mark.parametrize('max_width', [None, 20])
 def test_emu_split_layout(emu, max_width):
     G.test_split_layout_gives_identical_results(max_width)
+
+
+@pytest.mark.parametrize('n,max_width,n_sweeps', [(64, None, 1000), (100, 14, 1000)])
+def test_emu_statistics(emu, n, max_width, n_sweeps):
+    import test_gpu_statistics as S
+    S.test_best_cost_distribution_is_no_worse_than_the_reference(n, max_width, n_sweeps)

@@ -70,7 +70,17 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
         stats['tree_gen_s'] += time.perf_counter() - t0
         eng.set_betas(betas)
         n_steps = len(betas)
-        if deadline is None:
+        multi = opt.distributed and dist.world()[1] > 1
+        if multi and opt.sync_every:
+            # periodic exchange: min-reduction of the best cost over ranks every sync_every sweeps.
+            # Reporting / early visibility only -- chains never read it, so run statistics stay the reference's.
+            done = 0
+            while done < n_steps and (deadline is None or time.perf_counter() < deadline):
+                done = min(n_steps, done + int(opt.sync_every))
+                eng.run(done)
+                stats.setdefault('global_best_history', []).append(
+                    (done, dist.global_best(float(eng.costs()[1].min()), np.zeros(1, np.int32))[0]))
+        elif deadline is None:
             eng.run(n_steps)
         else:  # timeout: the reference polls a stop flag every sweep (sa.py:201); here between launches
             done, chunk = 0, 16

@@ -211,6 +211,7 @@ class BaseOptimizer:
     tree_builder: str = 'device'  # 'device' (built by each chain's own lanes) | 'host' (C++ threads)
     device: int | None = None  # CUDA device; default LOCAL_RANK or 0
     distributed: bool = True   # shard runs over torch.distributed ranks when a process group exists
+    sync_every: int | None = None  # sweeps between min-reductions of the best cost over ranks (None: only at the end)
 
     def optimize(self, *args, **kwargs):
         raise NotImplementedError()
