@@ -59,6 +59,13 @@ const char* tnb_last_error(const tnb_engine* e);
 int tnb_random_trees(int n_leaves, int n_inds, const uint32_t* leaf_bits, int n_trees, const uint64_t* seeds,
                      int method, int n_threads, int32_t* parent, int32_t* child0, int32_t* child1);
 
+/* Same for any network: index sets of intermediate tensors follow the hyper-count rule of
+ * tnco/ctree.py:138-189 (an index shared by the two contracted tensors survives while other tensors, or the
+ * output, still hold it).  output_bits [W32] marks the open (output) indices; NULL = none. */
+int tnb_random_trees_out(int n_leaves, int n_inds, const uint32_t* leaf_bits, const uint32_t* output_bits,
+                         int n_trees, const uint64_t* seeds, int method, int n_threads, int32_t* parent,
+                         int32_t* child0, int32_t* child1);
+
 /* Tree -> linear (einsum) contraction path; replaces include/tnco/utils.hpp:54-71 get_contraction +
  * tnco/ctree.py:350-388 ContractionTree.path().  The tree's leaf k is tensor tensors_pos[k] of a network of
  * n_tensors tensors (tensors_pos == NULL: identity, n_tensors = n_leaves); positions in the path count all
@@ -89,9 +96,17 @@ void tnb_destroy(tnb_engine* e);
 
 /* Network = what ContractionTree carries besides the tree (include/tnco/ctree.hpp:32-40): per-leaf index
  * sets and dims.  leaf_bits [n_leaves][W32].  dims == NULL: every index has dimension `dim`
- * (ctree.hpp:80-89).  The network must be connected and free of hyper-indices (each index on <= 2 tensors). */
+ * (ctree.hpp:80-89).  The network must be connected.  Output indices: tnb_set_output_inds. */
 int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* leaf_bits, uint64_t dim,
                     const uint64_t* dims);
+
+/* Output (open) indices of the network, [W32] bitset or NULL for none (tnco/ctree.py output_inds).  Together with
+ * the holders of every index this fixes the hyper counts; a network with hyper-indices (an index on 3+ tensors,
+ * or on 2 tensors and open) runs the HYPER kernels, which keep the reference's HyperCache
+ * (include/tnco/optimize/infinite_memory/utils.hpp:68-100).  Call after tnb_set_network; drops the chains. */
+int tnb_set_output_inds(tnb_engine* e, const uint32_t* output_bits);
+/* 1 if the current network + output indices have hyper-indices */
+int tnb_is_hyper(tnb_engine* e);
 
 /* max_width < 0 or +inf: unconstrained (infinite_memory optimizer).  Otherwise the memory-constrained
  * optimizer with float32 width arithmetic (tnco/app/app.py:757) and the greedy slicer, re-slicing on

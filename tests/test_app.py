@@ -180,3 +180,41 @@ def test_mt19937_rng_reproduces_reference_runs(backend):
         oc.run([0 + n * (100 / 200) for n in range(200)])
         costs.append(Decimal('%.6g' % oc.min_total_cost))
     assert sorted(costs) == [r.cost for r in res]
+
+
+@pytest.mark.parametrize('max_width', [None, 12])
+def test_hyper_index_network_through_the_app(backend, max_width):
+    """Networks with hyper-indices and open indices (what the reference's own random test networks look like,
+    tnco/testing/utils.py:183-359): the returned path, replayed symbolically with the hyper-count rule of
+    tnco/ctree.py:169-189, costs what the result says and respects max_width (test_contraction.py:147-181,315-352)."""
+    from helpers import hyper_network
+    from tnco_b200.app import Optimizer
+    from tnco_b200.tn import get_hyper_count
+    ts, ni, out = hyper_network(30, 4)
+    rows = index_rows(ts, ni)
+    for x in out:
+        rows[x].append('*')
+    tn, res = Optimizer(seed=5, max_width=max_width).optimize(rows, betas=(0, 100), n_steps=150, n_runs=6)
+    assert len(res) == 6 and [r.cost for r in res] == sorted(r.cost for r in res)
+    for r in res:
+        hc = dict(get_hyper_count(tn.ts_inds))
+        for x in tn.output_inds:
+            hc[x] += 1
+        slices = frozenset(r.slices) if max_width is not None else frozenset()
+        work = [frozenset(x) for x in tn.ts_inds]
+        total = 0
+        for x, y in r.path:
+            x, y = sorted((x, y))
+            ty, tx = work.pop(y), work.pop(x)
+            assert tx & ty
+            total += 2**len(tx | ty | slices)
+            new = set(tx ^ ty)
+            for s in tx & ty:
+                hc[s] -= 1
+                if hc[s] > 0:
+                    new.add(s)
+            if max_width is not None:
+                assert len(frozenset(new) - slices) <= max_width
+            work.append(frozenset(new))
+        assert len(work) == 1 and work[0] == frozenset(tn.output_inds)
+        assert abs(math.log2(total) - math.log2(float(r.cost))) < 1e-4

@@ -158,9 +158,13 @@ def test_precision_too_low_and_bad_input(backend):
     bad[-1] = bad[-2]
     with pytest.raises(ValueError):
         e2.set_chains(p[None], bad[None], b[None], [1])
-    with pytest.raises(ValueError):  # hyper-index: an index on three tensors
-        lb = bits[:10].copy()
-        lb[0, 0] |= 1
-        lb[1, 0] |= 1
-        lb[2, 0] |= 1
-        Engine().set_network(lb, ni)
+    # hyper-index (an index on three tensors): accepted, runs the HYPER kernels; trees must come from the host
+    lb = bits[:10].copy()
+    lb[0, 0] |= 1
+    lb[1, 0] |= 1
+    lb[2, 0] |= 1
+    e3 = Engine()
+    e3.set_network(lb, ni).set_mode()
+    assert e3.hyper and not e2.hyper
+    with pytest.raises(ValueError, match='hyper'):
+        e3.generate_chains([1, 2])

@@ -71,3 +71,13 @@ def test_emu_split_layout(emu, max_width):
 def test_emu_statistics(emu, n, max_width, n_sweeps):
     import test_gpu_statistics as S
     S.test_best_cost_distribution_is_no_worse_than_the_reference(n, max_width, n_sweeps)
+
+
+@pytest.mark.parametrize('n,max_width', [(40, None), (90, 18)])
+def test_emu_hyper_philox(emu, n, max_width):
+    G.test_philox_hyper_index_networks_are_valid(n, max_width)
+
+
+@pytest.mark.parametrize('name', ['hyper64_inf', 'hyper64_fw40'])
+def test_emu_replay_hyper(emu, name):
+    G.test_replay_of_recorded_draw_stream_is_bit_exact(name)

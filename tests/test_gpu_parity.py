@@ -16,11 +16,11 @@ from oracle import sa_oracle as so
 
 pytestmark = pytest.mark.gpu
 
-CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, '*.npz')) if 'hyper' not in p)
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, '*.npz')))
 
 
 def _engine(g, rng, tile=None, every=None):
-    from tnco_b200.engine import Engine
+    from tnco_b200.engine import Engine, pack_index_set
     if tile:
         os.environ['TNB_TILE'] = str(tile)
     else:
@@ -29,7 +29,9 @@ def _engine(g, rng, tile=None, every=None):
     mw = None if mw < 0 else mw
     n = (g['parent'].shape[0] + 1) // 2
     e = Engine()
-    e.set_network(g['bits'][:n], int(g['n_inds']), dim=int(g['dim']))
+    e.set_network(g['bits'][:n], int(g['n_inds']), dim=int(g['dim']),
+                  output_bits=pack_index_set(g['output_inds'].tolist(), int(g['n_inds'])))
+    assert e.hyper == bool(len(g['output_inds']))
     e.set_mode(max_width=mw, update_slices_every=int(g['every']) if every is None else every, rng=rng)
     e.set_chains(g['parent'][None], g['child0'][None], g['child1'][None], [int(g['seed'])])
     os.environ.pop('TNB_TILE', None)
@@ -40,6 +42,7 @@ def _check_against_golden(g, e, mw):
     n_sweeps = int(g['n_sweeps'])
     e.set_betas([100.0 * s / n_sweeps for s in range(n_sweeps)])
     t, m = e.costs()
+    assert (e.bits(0) == g['bits']).all()   # index sets derived on the device (hyper-count rule) == the input tree's
     assert np.log2(t[0]) == float(g['init_log2_total'])
     if mw is not None:
         assert (e.slices()[0] == g['init_slices']).all()
@@ -79,7 +82,7 @@ def test_every_tile_shape_matches_golden(name, tile):
     _check_against_golden(g, e, mw)
 
 
-@pytest.mark.parametrize('name', ['reg64_inf', 'reg100_fw30', 'reg300_inf'])
+@pytest.mark.parametrize('name', ['reg64_inf', 'reg100_fw30', 'reg300_inf', 'hyper64_inf', 'hyper64_fw40'])
 def test_replay_of_recorded_draw_stream_is_bit_exact(name):
     """north_star: replaying a reference-recorded proposal / uniform-draw sequence yields identical trees.
     The stream is recorded by the oracle (itself pinned to the reference) while it runs the same sweeps."""
@@ -326,3 +329,82 @@ def test_split_layout_gives_identical_results(max_width):
     for k in (1, 2):
         assert all((x == y).all() for x, y in zip(a[k], b[k]))
     assert (a[3] == b[3]).all() and (a[4] == b[4]).all() and (a[5] == b[5]).all()
+
+
+def _hyper_case(n, seed):
+    from helpers import hyper_network, leaf_bits
+    from tnco_b200.engine import pack_index_set
+    ts, ni, out = hyper_network(n, seed)
+    return ts, ni, out, leaf_bits(ts, ni), pack_index_set(out, ni)
+
+
+@pytest.mark.parametrize('n,max_width', [(40, None), (90, None), (90, 18)])
+def test_philox_hyper_index_networks_are_valid(n, max_width):
+    """Networks WITH hyper-indices through the production path (HYPER kernels, host tree builder): cached totals
+    equal an independent evaluation by the oracle on the engine's own index sets, index sets obey the hyper-count
+    rule (they depend on the subtree only), sliced widths fit, leaves fixed, determinism."""
+    from tnco_b200.engine import Engine, random_trees
+    ts, ni, out, lb, ob = _hyper_case(n, 5 + n)
+    seeds = np.arange(40, dtype=np.uint64) + 3
+    for method in (0, 1):
+        p, a, b = random_trees(lb, ni, seeds, method=method, output_bits=ob)
+        for c in (0, 11):
+            _check_tree_valid(p[c], a[c], b[c], n)
+    outs = []
+    for rep in range(2):
+        e = Engine()
+        e.set_network(lb, ni, output_bits=ob).set_mode(max_width=max_width)
+        assert e.hyper and e.config()['tile'] == 32
+        e.set_chains(p, a, b, seeds)
+        e.set_betas(np.linspace(0, 100, 300, endpoint=False))
+        t0, _ = e.costs()
+        e.run(300)
+        t, m = e.costs()
+        P, A, B = e.trees()
+        S = e.slices() if max_width is not None else None
+        seq, pc, mw = e.eval_cost(P, A, B, slices=S)
+        assert np.allclose(np.log2(seq), np.log2(t), atol=1e-9)
+        if max_width is not None:
+            assert (mw <= max_width).all()
+        bP, bA, bB = e.trees(True)
+        bseq, _, bmw = e.eval_cost(bP, bA, bB, slices=e.slices(True) if max_width is not None else None)
+        assert np.allclose(np.log2(bseq), np.log2(m), atol=1e-9)
+        for c in (0, 17, 39):
+            _check_tree_valid(P[c], A[c], B[c], n)
+            nb = e.bits(c)
+            assert (nb[:n] == lb).all()
+            # hyper-count rule: inds(z) = held below z AND (held outside z, or output)
+            below = nb[:n].copy()
+            full = np.zeros((2 * n - 1, lb.shape[1]), np.uint32)
+            full[:n] = lb
+            cnt_total = np.zeros(ni, int)
+            for x in range(n):
+                for i in so_positions(lb[x]):
+                    cnt_total[i] += 1
+            sub = [None] * (2 * n - 1)
+            for x in range(n):
+                sub[x] = {i: 1 for i in so_positions(lb[x])}
+            order = []
+            stack = [2 * n - 2]
+            while stack:
+                z = stack.pop()
+                if z >= n:
+                    order.append(z)
+                    stack += [A[c][z], B[c][z]]
+            for z in reversed(order):
+                d = dict(sub[A[c][z]])
+                for i, k in sub[B[c][z]].items():
+                    d[i] = d.get(i, 0) + k
+                sub[z] = d
+                want = sorted(i for i, k in d.items() if k < cnt_total[i] or i in out)
+                assert so_positions(nb[z]) == want, (c, z)
+            o_seq, o_mw, o_pc = so.tree_cost(A[c], B[c], nb, ni, slices=None if S is None else S[c])
+            assert np.isclose(np.log2(o_seq), np.log2(t[c]), atol=1e-9)
+        outs.append((t.copy(), m.copy(), P.copy()))
+        e.close()
+    assert all((x == y).all() for x, y in zip(outs[0], outs[1]))
+    assert np.log2(outs[0][1]).mean() < np.log2(t0).mean()
+
+
+def so_positions(row):
+    return [w * 32 + b for w, v in enumerate(np.asarray(row).tolist()) for b in range(32) if (v >> b) & 1]

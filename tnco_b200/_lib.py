@@ -25,6 +25,7 @@ SIGNATURES = {
     'tnb_version': (C.c_int, []),
     'tnb_last_error': (C.c_char_p, [C.c_void_p]),
     'tnb_random_trees': (C.c_int, [C.c_int, C.c_int, u32p, C.c_int, u64p, C.c_int, C.c_int, i32p, i32p, i32p]),
+    'tnb_random_trees_out': (C.c_int, [C.c_int, C.c_int, u32p, u32p, C.c_int, u64p, C.c_int, C.c_int, i32p, i32p, i32p]),
     'tnb_tree_to_path': (C.c_int, [C.c_int, C.c_int, i32p, i32p, C.c_int, i32p, i32p]),
     'tnb_merge_paths': (C.c_int, [C.c_int, C.c_int, C.c_int, i32p, i32p, i32p]),
     'tnb_path_to_tree': (C.c_int, [C.c_int, i32p, i32p, i32p, i32p]),
@@ -33,6 +34,8 @@ SIGNATURES = {
     'tnb_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     'tnb_destroy': (None, [C.c_void_p]),
     'tnb_set_network': (C.c_int, [C.c_void_p, C.c_int, C.c_int, u32p, C.c_uint64, u64p]),
+    'tnb_set_output_inds': (C.c_int, [C.c_void_p, u32p]),
+    'tnb_is_hyper': (C.c_int, [C.c_void_p]),
     'tnb_set_mode': (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     'tnb_set_prob': (C.c_int, [C.c_void_p, C.c_int]),
     'tnb_set_update_slices': (C.c_int, [C.c_void_p, C.c_int]),

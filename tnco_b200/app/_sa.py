@@ -12,8 +12,8 @@ from sys import stderr
 import numpy as np
 
 from .. import dist
-from ..engine import (Engine, RNG_MT19937, RNG_PHILOX, TREES_GREEDY, TREES_RANDOM, merge_paths, pack_leaf_bits,
-                      random_trees, tree_to_path, unpack_bits)
+from ..engine import (Engine, RNG_MT19937, RNG_PHILOX, TREES_GREEDY, TREES_RANDOM, merge_paths, pack_index_set,
+                      pack_leaf_bits, random_trees, tree_to_path, unpack_bits)
 from ..tn import get_connected_components
 from .app import cost_to_decimal
 
@@ -48,9 +48,8 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
     dims = [tn.dims[x] for x in inds]
     if any(d != dims[0] for d in dims):
         raise NotImplementedError('tnco_b200: per-index dimensions are not supported yet (uniform dims only).')
-    if any(x in tn.output_inds for x in inds if sum(x in xs for xs in ts) > 1):
-        raise NotImplementedError('tnco_b200: hyper-indices are not supported yet.')
     lb = pack_leaf_bits([[pos[x] for x in xs] for xs in ts], len(inds))
+    out_bits = pack_index_set([pos[x] for x in inds if x in tn.output_inds], len(inds))
     n_runs = len(seeds)
     lo, hi = dist.shard(n_runs) if opt.distributed else (0, n_runs)
     my_seeds = np.asarray(seeds[lo:hi], np.uint64)
@@ -58,14 +57,14 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
     method = TREES_GREEDY if opt.init_trees == 'greedy' else TREES_RANDOM
     eng = Engine(dist.local_device(opt.device))
     try:
-        eng.set_network(lb, len(inds), dim=dims[0])
+        eng.set_network(lb, len(inds), dim=dims[0], output_bits=out_bits)
         eng.set_mode(max_width=opt.max_width if finite else None, update_slices_every=update_slices,
                      rng=RNG_MT19937 if opt.rng == 'mt19937' else RNG_PHILOX)
         t0 = time.perf_counter()
-        if opt.tree_builder == 'device':
+        if opt.tree_builder == 'device' and not eng.hyper:
             eng.generate_chains(my_seeds, chain_id0=lo, method=method)
-        else:
-            P, A, B = random_trees(lb, len(inds), my_seeds, method=method)
+        else:  # host C++ threads; the only builder for networks with hyper-indices
+            P, A, B = random_trees(lb, len(inds), my_seeds, method=method, output_bits=out_bits)
             eng.set_chains(P, A, B, my_seeds, chain_id0=lo)
         stats['tree_gen_s'] += time.perf_counter() - t0
         eng.set_betas(betas)

@@ -23,7 +23,6 @@ namespace tnb {
 #if defined(TNB_EMU)
 struct Rt {
   std::string err;
-  int minb = 28;
   bool init(int) { return true; }
   void* alloc(size_t b) { return std::calloc(std::max<size_t>(b, 1), 1); }
   void free_(void* p) { std::free(p); }
@@ -37,7 +36,6 @@ struct Rt {
 #else
 struct Rt {
   std::string err;
-  int minb = 28;  // occupancy class of the sweep kernel: 28 (72 registers) or 16 (<= 128 registers)
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -105,11 +103,11 @@ constexpr int kSweepBlock = 32;
 // Production (Philox) kernels are held to 72 registers (no spills) so that 28 single-warp blocks fit on an SM:
 // 148 x 28 = 4144 resident chains at TILE = 32.  Parity kernels (fp64 pow, stream bookkeeping) keep 128.
 // MINB = single-warp blocks resident per SM the register allocation must allow (28 -> 72 registers).
-template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2, int MINB>
+template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2, int MINB, bool HYPER>
 __global__ void __launch_bounds__(kSweepBlock, MINB) sa_sweep_kernel(const __grid_constant__ Params P) {
   const int chain = (blockIdx.x * kSweepBlock + threadIdx.x) / TILE;
   if (chain >= P.n_chains) return;
-  chain_sweeps<TILE, WPL, FINITE, Rng, DIM2>(P, chain);
+  chain_sweeps<TILE, WPL, FINITE, Rng, DIM2, HYPER>(P, chain);
 }
 
 // children words between the compact [n_chains][n_int] array (upload / read-back form) and the node records
@@ -145,13 +143,13 @@ static bool launch_treegen_t(Rt& rt, const Params& P) {
 #endif
 }
 
-template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2>
-static bool launch_t(Rt& rt, const Params& P, bool init) {
+template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2, bool HYPER>
+static bool launch_h(Rt& rt, const Params& P, bool init) {
 #if defined(TNB_EMU)
   (void)rt;
   for (int c = 0; c < P.n_chains; ++c) {
     if (init) chain_init<TILE, WPL, FINITE, Rng>(P, c);
-    else chain_sweeps<TILE, WPL, FINITE, Rng, DIM2>(P, c);
+    else chain_sweeps<TILE, WPL, FINITE, Rng, DIM2, HYPER>(P, c);
   }
   return true;
 #else
@@ -159,12 +157,23 @@ static bool launch_t(Rt& rt, const Params& P, bool init) {
   const int blk = init ? kBlock : kSweepBlock;
   const int grid = int((threads + blk - 1) / blk);
   if (grid == 0) return true;
+  // occupancy class: production kernels 28 single-warp blocks per SM (<= 72 registers), parity kernels 16
+  constexpr int MINB = Rng::kFast ? 28 : 16;
   if (init) sa_init_kernel<TILE, WPL, FINITE, Rng><<<grid, kBlock, 0, rt.stream>>>(P);
-  else if (!Rng::kFast) sa_sweep_kernel<TILE, WPL, FINITE, Rng, DIM2, 16><<<grid, kSweepBlock, 0, rt.stream>>>(P);
-  else if (rt.minb >= 28) sa_sweep_kernel<TILE, WPL, FINITE, Rng, DIM2, 28><<<grid, kSweepBlock, 0, rt.stream>>>(P);
-  else sa_sweep_kernel<TILE, WPL, FINITE, Rng, DIM2, 16><<<grid, kSweepBlock, 0, rt.stream>>>(P);
+  else sa_sweep_kernel<TILE, WPL, FINITE, Rng, DIM2, MINB, HYPER><<<grid, kSweepBlock, 0, rt.stream>>>(P);
   return rt.ok(cudaGetLastError(), init ? "sa_init_kernel launch" : "sa_sweep_kernel launch");
 #endif
+}
+
+// HYPER kernels exist for full-warp tiles only (pick_tile gives hyper-index networks TILE = 32)
+template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2>
+static bool launch_t(Rt& rt, const Params& P, bool init) {
+  if constexpr (TILE == 32 || TILE == 1) {
+    if (P.hyper && !init) return launch_h<TILE, WPL, FINITE, Rng, DIM2, true>(rt, P, init);
+  } else {
+    if (P.hyper) { rt.err = "hyper-index networks need TILE = 32"; return false; }
+  }
+  return launch_h<TILE, WPL, FINITE, Rng, DIM2, false>(rt, P, init);
 }
 
 template <int TILE, int WPL>
@@ -289,6 +298,10 @@ struct tnb_engine {
   uint32_t* d_leaf_bits = nullptr;
   double* d_pow_tab = nullptr;
   int16_t* d_net_own = nullptr;  // [2][n_inds] the leaves holding each index (device tree construction)
+  uint16_t* d_hcount0 = nullptr;  // [Ws*32] initial hyper counts
+  std::vector<uint16_t> h_holders;  // [n_inds] tensors holding each index
+  std::vector<uint32_t> h_output;   // [W] output (open) indices
+  bool hyper = false;
   std::vector<uint32_t> h_leaf_bits;  // [n][W]
   // mode
   bool finite = false;
@@ -317,9 +330,10 @@ struct tnb_engine {
 
 namespace tnb {
 
-static int pick_tile(int W, int& wpl) {
+static int pick_tile(int W, int& wpl, bool hyper) {
   wpl = 1;
   int tile = 32;
+  if (hyper) { wpl = (W + 31) / 32; return 32; }
   if (W <= 4) tile = 4;
   else if (W <= 8) tile = 8;
   else if (W <= 32) tile = 32;  // measured: 16-lane tiles lose more to intra-warp divergence than they gain
@@ -358,6 +372,7 @@ static void fill_params(const tnb_engine* e, const ChainSet& cs, Params& P) {
   if (e->finite)
     for (int k = 0; k <= e->n_inds; ++k)
       if (float(e->log2d * double(k)) <= e->max_width) P.kthr = k;
+  P.hyper = e->hyper; P.hyp_off = 4 * e->Ws; P.hcount0 = e->d_hcount0;
   P.net_own = e->d_net_own; P.kpop = cs.kpop; P.tree_fail = cs.tree_fail; P.tree_method = TNB_TREES_GREEDY;
 }
 
@@ -377,7 +392,7 @@ static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_be
   if (e->layout == TNB_LAYOUT_INTERLEAVED) split = false;
   if (e->layout == TNB_LAYOUT_SPLIT) split = true;
   cs.hstride = split ? 16 : e->stride;
-  cs.bstride = split ? 4 * e->Ws : e->stride;
+  cs.bstride = split ? 4 * e->Ws * (e->hyper ? 2 : 1) : e->stride;
   bool ok = alloc_to(rt, cs.par, nc * e->Npad) && alloc_to(rt, cs.rec, nc * ni * size_t(cs.hstride)) &&
             (!split || alloc_to(rt, cs.bits_alloc, nc * ni * size_t(cs.bstride))) &&
             alloc_to(rt, cs.pc, nc * ni) && alloc_to(rt, cs.bch, nc * ni) &&
@@ -391,6 +406,8 @@ static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_be
   if (ok && with_slicer)
     ok = alloc_to(rt, cs.nbig, nc * e->Ws * 32) && alloc_to(rt, cs.posbuf, nc * e->Ws * 32) &&
          alloc_to(rt, cs.cp2, nc * ni);
+  else if (ok && e->hyper)
+    ok = alloc_to(rt, cs.nbig, nc * e->Ws * 32);  // hyper counters of build_sets
   if (ok && with_slicer && e->finite)
     ok = alloc_to(rt, cs.kw, nc * e->Npad) && alloc_to(rt, cs.sz, nc * e->Npad) &&
          alloc_to(rt, cs.word, nc * e->Npad) && alloc_to(rt, cs.wkey, nc * e->Npad);
@@ -439,10 +456,11 @@ static bool make_chains(tnb_engine* e, ChainSet& cs, int n_chains, const int32_t
 
 static bool check_shared(tnb_engine* e, const int32_t* c0, const int32_t* c1, int n_chains) {
   // check_shared_inds (include/tnco/ctree.hpp:101-152): children of every contraction must share an index.
-  // inds(z) = xor of leaf sets for hyper-free networks, computed here on the host for validation only.
+  // inds(z) by the hyper-count rule of tnco/ctree.py:169-189, computed here on the host for validation only.
   if (e->dsi) return true;
   const int N = e->N, n = e->n, W = e->W;
   std::vector<uint32_t> bits(size_t(N) * W);
+  std::vector<int> cnt(size_t(W) * 32, 0);
   std::vector<int32_t> order;
   std::vector<int32_t> stack;
   std::vector<uint8_t> vis(N);
@@ -450,6 +468,8 @@ static bool check_shared(tnb_engine* e, const int32_t* c0, const int32_t* c1, in
     const int32_t *a = c0 + size_t(c) * N, *b = c1 + size_t(c) * N;
     std::memcpy(bits.data(), e->h_leaf_bits.data(), sizeof(uint32_t) * size_t(n) * W);
     std::fill(vis.begin(), vis.end(), 0);
+    for (int i = 0; i < e->n_inds; ++i)
+      cnt[size_t(i)] = int(e->h_holders[size_t(i)]) - 1 + int((e->h_output[size_t(i) >> 5] >> (i & 31)) & 1u);
     stack.assign(1, N - 1);
     while (!stack.empty()) {
       const int z = stack.back();
@@ -460,7 +480,13 @@ static bool check_shared(tnb_engine* e, const int32_t* c0, const int32_t* c1, in
           for (int w = 0; w < W; ++w) {
             const uint32_t x = bits[size_t(a[z]) * W + w], y = bits[size_t(b[z]) * W + w];
             inter |= (x & y) != 0;
-            bits[size_t(z) * W + w] = x ^ y;
+            uint32_t keep = 0u, v = x & y;
+            while (v) {
+              const int bit = __builtin_ctz(v);
+              v &= v - 1;
+              if (--cnt[size_t(w) * 32 + bit] > 0) keep |= 1u << bit;
+            }
+            bits[size_t(z) * W + w] = (x ^ y) | keep;
           }
           if (!inter)
             return e->fail("invalid tree: contracted tensors share no index (check_shared_inds), chain " +
@@ -529,6 +555,21 @@ static bool ensure_init(tnb_engine* e) {
   return true;
 }
 
+// hyper counts (holders - 1, +1 for output indices), the hyper flag and everything that depends on it
+static bool refresh_hyper(tnb_engine* e) {
+  std::vector<uint16_t> hc(size_t(e->Ws) * 32, 0);
+  e->hyper = false;
+  for (int i = 0; i < e->n_inds; ++i) {
+    const int c = int(e->h_holders[size_t(i)]) - 1 + int((e->h_output[size_t(i) >> 5] >> (i & 31)) & 1u);
+    hc[size_t(i)] = uint16_t(c < 0 ? 0 : c);
+    e->hyper |= c >= 2;
+  }
+  e->tile = pick_tile(e->W, e->wpl, e->hyper);
+  e->stride = 16 + 4 * e->Ws * (e->hyper ? 2 : 1);
+  if (!e->rt.h2d(e->d_hcount0, hc.data(), hc.size() * sizeof(uint16_t)) || !e->rt.sync()) return e->rtfail();
+  return true;
+}
+
 }  // namespace tnb
 
 // ============================================================================================ C-ABI
@@ -555,6 +596,7 @@ void tnb_destroy(tnb_engine* e) {
   e->rt.free_(e->d_leaf_bits);
   e->rt.free_(e->d_pow_tab);
   e->rt.free_(e->d_net_own);
+  e->rt.free_(e->d_hcount0);
   e->rt.free_(e->d_betas);
   e->rt.free_(e->d_flush);
   e->rt.destroy();
@@ -575,8 +617,8 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* lea
   if (2 * n_leaves - 1 > 32767) return e->fail("tnb_set_network: at most 16384 tensors"), -2;
   const int W = (n_inds + 31) / 32;
   if (W > 128) return e->fail("tnb_set_network: at most 4096 indices"), -2;
-  // hyper-index check: every index on at most two tensors
-  std::vector<uint8_t> cnt(size_t(W) * 32, 0);
+  // holders of every index (hyper-index = on 3+ tensors, or on 2 and open)
+  std::vector<uint16_t> cnt(size_t(W) * 32, 0);
   std::vector<int16_t> own(size_t(2) * n_inds, int16_t(-1));
   for (int t = 0; t < n_leaves; ++t)
     for (int w = 0; w < W; ++w) {
@@ -585,26 +627,16 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* lea
         const int i = w * 32 + __builtin_ctz(v);
         v &= v - 1;
         if (i >= n_inds) return e->fail("tnb_set_network: leaf_bits has a bit beyond n_inds"), -1;
-        if (++cnt[size_t(i)] > 2)
-          return e->fail("tnb_set_network: hyper-indices (an index on more than two tensors) are not supported yet"), -2;
-        own[size_t(cnt[size_t(i)] - 1) * n_inds + i] = int16_t(t);
+        if (++cnt[size_t(i)] <= 2) own[size_t(cnt[size_t(i)] - 1) * n_inds + i] = int16_t(t);
       }
     }
   e->cs.release(e->rt);
   e->initialized = false;
   e->n = n_leaves; e->N = 2 * n_leaves - 1; e->n_int = n_leaves - 1; e->n_inds = n_inds; e->W = W;
   e->Ws = (W + 3) / 4 * 4;
-  e->stride = 16 + 4 * e->Ws;
   e->Npad = (e->N + 7) / 8 * 8;
-  e->tile = pick_tile(W, e->wpl);
-  {
-    // Occupancy class of the production kernel: 28 single-warp blocks per SM (72 registers, no spills) -- all
-    // 4096 chains of the benchmark configuration are then resident in one wave (27.7 per SM).  The 16-block
-    // class (<= 128 registers) is kept for experiments (TNB_MINB=16); it was faster only while the kernel still
-    // carried the partial-cost cache (profiles/README.md).
-    e->rt.minb = 28;
-    if (const char* f = std::getenv("TNB_MINB")) e->rt.minb = std::atoi(f) >= 28 ? 28 : 16;
-  }
+  e->h_holders.assign(cnt.begin(), cnt.begin() + n_inds);
+  e->h_output.assign(size_t(W), 0u);
   e->dim = dim;
   e->log2d = std::log2(double(dim));
   e->h_leaf_bits.assign(leaf_bits, leaf_bits + size_t(n_leaves) * W);
@@ -615,8 +647,12 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* lea
   e->rt.free_(e->d_pow_tab);
   e->rt.free_(e->d_net_own);
   e->d_leaf_bits = nullptr; e->d_pow_tab = nullptr; e->d_net_own = nullptr;
-  if (!alloc_to(e->rt, e->d_net_own, own.size()) || !e->rt.h2d(e->d_net_own, own.data(), own.size() * sizeof(int16_t)))
+  e->rt.free_(e->d_hcount0);
+  e->d_hcount0 = nullptr;
+  if (!alloc_to(e->rt, e->d_net_own, own.size()) || !e->rt.h2d(e->d_net_own, own.data(), own.size() * sizeof(int16_t)) ||
+      !alloc_to(e->rt, e->d_hcount0, size_t(e->Ws) * 32))
     return e->rtfail(), -3;
+  if (!refresh_hyper(e)) return -3;
   if (!alloc_to(e->rt, e->d_leaf_bits, padded.size())) return e->rtfail(), -3;
   std::vector<double> tab(size_t(n_inds) + 1);
   for (int k = 0; k <= n_inds; ++k) tab[size_t(k)] = std::pow(double(dim), double(k));
@@ -626,6 +662,20 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* lea
     return e->rtfail(), -3;
   return 0;
 }
+
+int tnb_set_output_inds(tnb_engine* e, const uint32_t* output_bits) {
+  if (!e) return -1;
+  if (e->n == 0) return e->fail("tnb_set_output_inds: call tnb_set_network first"), -1;
+  e->cs.release(e->rt);
+  e->initialized = false;
+  e->h_output.assign(size_t(e->W), 0u);
+  if (output_bits)
+    for (int i = 0; i < e->n_inds; ++i)
+      if ((output_bits[i >> 5] >> (i & 31)) & 1u) e->h_output[size_t(i) >> 5] |= 1u << (i & 31);
+  return refresh_hyper(e) ? 0 : -3;
+}
+
+int tnb_is_hyper(tnb_engine* e) { return e && e->hyper ? 1 : 0; }
 
 int tnb_set_mode(tnb_engine* e, double max_width, int update_slices_every, int disable_shared_inds, int prob_kind,
                  int rng_kind, int layout) {
@@ -677,6 +727,9 @@ int tnb_generate_chains(tnb_engine* e, int n_chains, const uint64_t* seeds, uint
   if (e->n == 0) return e->fail("tnb_generate_chains: call tnb_set_network first"), -1;
   if (n_chains < 1 || !seeds || (method != TNB_TREES_GREEDY && method != TNB_TREES_RANDOM))
     return e->fail("tnb_generate_chains: invalid arguments"), -1;
+  if (e->hyper)
+    return e->fail("tnb_generate_chains: device tree construction is not supported for hyper-index networks "
+                   "(use tnb_random_trees_out + tnb_set_chains)"), -2;
   ChainSet& cs = e->cs;
   cs.release(e->rt);
   e->initialized = false;

@@ -63,12 +63,16 @@ static inline int popc_row(const uint32_t* a, int W) {
 struct Net {
   int n, n_inds, W;
   const uint32_t* leaf_bits;
-  std::vector<int32_t> own0, own1;  // the (<=2) leaves holding each index
+  std::vector<int32_t> own0, own1;            // the first two leaves holding each index
+  std::vector<std::vector<int32_t>> holders;  // all leaves holding each index
+  std::vector<int> hcount0;                   // hyper count: holders - 1 (+1 for output indices), ctree.py:138-156
+  bool hyper = false;                         // some index has hyper count >= 2
 };
 
-static bool build_net(Net& net, std::string& err) {
+static bool build_net(Net& net, const uint32_t* output_bits, std::string& err) {
   net.own0.assign(net.n_inds, -1);
   net.own1.assign(net.n_inds, -1);
+  net.holders.assign(net.n_inds, {});
   for (int t = 0; t < net.n; ++t)
     for (int w = 0; w < net.W; ++w) {
       uint32_t v = net.leaf_bits[size_t(t) * net.W + w];
@@ -78,10 +82,137 @@ static bool build_net(Net& net, std::string& err) {
         if (i >= net.n_inds) { err = "leaf_bits has a bit beyond n_inds"; return false; }
         if (net.own0[i] < 0) net.own0[i] = t;
         else if (net.own1[i] < 0) net.own1[i] = t;
-        else { err = "hyper-indices (an index on more than two tensors) are not supported"; return false; }
+        net.holders[i].push_back(t);
       }
     }
+  net.hcount0.assign(net.n_inds, 0);
+  for (int i = 0; i < net.n_inds; ++i) {
+    const int out = output_bits ? int((output_bits[i >> 5] >> (i & 31)) & 1u) : 0;
+    net.hcount0[i] = std::max(0, int(net.holders[i].size()) - 1 + out);
+    net.hyper |= net.hcount0[i] >= 2;
+  }
   return true;
+}
+
+// One tree for a network WITH hyper-indices (general but slower than one_tree): clusters holding each index are
+// tracked explicitly and intermediate index sets follow the hyper-count rule of tnco/ctree.py:169-189.
+static bool one_tree_hyper(const Net& net, uint64_t seed, int method, int32_t* par, int32_t* c0, int32_t* c1) {
+  const int n = net.n, N = 2 * n - 1, W = net.W;
+  SplitMix rng(seed * 0x9E3779B97F4A7C15ull + 0x7654321ull + uint64_t(method));
+  std::fill(par, par + N, -1);
+  std::fill(c0, c0 + N, -1);
+  std::fill(c1, c1 + N, -1);
+  if (n == 1) return true;
+  std::vector<uint32_t> bits(size_t(N) * W, 0u);
+  std::memcpy(bits.data(), net.leaf_bits, sizeof(uint32_t) * size_t(n) * W);
+  std::vector<int> cnt(net.hcount0);
+  std::vector<std::vector<int32_t>> cur(net.holders);  // clusters currently holding each index
+  std::vector<uint8_t> alive(N, 0);
+  std::fill(alive.begin(), alive.begin() + n, 1);
+  int nxt = n;
+  auto out_size = [&](int a, int b) {  // popcount of the index set the contraction of a and b would get
+    const uint32_t *ba = &bits[size_t(a) * W], *bb = &bits[size_t(b) * W];
+    int k = 0;
+    for (int w = 0; w < W; ++w) {
+      k += __builtin_popcount(ba[w] ^ bb[w]);
+      uint32_t v = ba[w] & bb[w];
+      while (v) {
+        const int i = w * 32 + __builtin_ctz(v);
+        v &= v - 1;
+        k += cnt[i] - 1 > 0;
+      }
+    }
+    return k;
+  };
+  auto merge = [&](int a, int b) {
+    const int z = nxt++;
+    uint32_t* bz = &bits[size_t(z) * W];
+    const uint32_t *ba = &bits[size_t(a) * W], *bb = &bits[size_t(b) * W];
+    for (int w = 0; w < W; ++w) {
+      uint32_t keep = 0u, v = ba[w] & bb[w];
+      while (v) {
+        const int bit = __builtin_ctz(v);
+        v &= v - 1;
+        if (--cnt[w * 32 + bit] > 0) keep |= 1u << bit;
+      }
+      bz[w] = (ba[w] ^ bb[w]) | keep;
+      uint32_t u = ba[w] | bb[w];
+      while (u) {
+        const int bit = __builtin_ctz(u);
+        u &= u - 1;
+        auto& h = cur[size_t(w) * 32 + bit];
+        h.erase(std::remove_if(h.begin(), h.end(), [&](int32_t x) { return x == a || x == b; }), h.end());
+        if ((bz[w] >> bit) & 1u) h.push_back(z);
+      }
+    }
+    c0[z] = a; c1[z] = b; par[a] = z; par[b] = z;
+    alive[a] = alive[b] = 0; alive[z] = 1;
+    return z;
+  };
+  if (method == TNB_TREES_RANDOM) {
+    std::vector<int32_t> order(net.n_inds);
+    for (int i = 0; i < net.n_inds; ++i) order[i] = i;
+    while (nxt < N) {
+      for (size_t i = order.size(); i > 1; --i) std::swap(order[i - 1], order[rng.below(uint32_t(i))]);
+      bool progressed = false;
+      for (int32_t i : order) {
+        auto& h = cur[size_t(i)];
+        if (h.size() < 2) continue;
+        const uint32_t x = rng.below(uint32_t(h.size()));
+        uint32_t y = rng.below(uint32_t(h.size() - 1));
+        if (y >= x) ++y;
+        merge(h[x], h[y]);
+        progressed = true;
+        if (nxt == N) break;
+      }
+      if (!progressed) return false;
+    }
+    return true;
+  }
+  struct Cand {
+    double score;
+    uint32_t tie;
+    int32_t a, b;
+    bool operator<(const Cand& o) const { return score != o.score ? score > o.score : tie > o.tie; }
+  };
+  std::priority_queue<Cand> pq;
+  std::vector<int> kcache(N, 0);
+  for (int t = 0; t < n; ++t) kcache[t] = popc_row(&bits[size_t(t) * W], W);
+  auto sz = [](int k) { return std::ldexp(1.0, std::min(k, 1000)); };
+  auto push = [&](int a, int b) {
+    pq.push(Cand{sz(out_size(a, b)) - sz(kcache[a]) - sz(kcache[b]), uint32_t(rng.next() >> 32), a, b});
+  };
+  std::vector<int32_t> seen(N, -1);
+  for (int t = 0; t < n; ++t) {  // every pair of leaves sharing an index, once
+    for (int w = 0; w < W; ++w) {
+      uint32_t v = bits[size_t(t) * W + w];
+      while (v) {
+        const int i = w * 32 + __builtin_ctz(v);
+        v &= v - 1;
+        for (int32_t o : cur[size_t(i)])
+          if (o > t && seen[o] != t) { seen[o] = t; push(t, o); }
+      }
+    }
+  }
+  std::fill(seen.begin(), seen.end(), -1);
+  while (nxt < N && !pq.empty()) {
+    const Cand c = pq.top();
+    pq.pop();
+    if (!alive[c.a] || !alive[c.b]) continue;
+    const int z = (c.tie & 1) ? merge(c.a, c.b) : merge(c.b, c.a);
+    const uint32_t* bz = &bits[size_t(z) * W];
+    kcache[z] = popc_row(bz, W);
+    for (int w = 0; w < W; ++w) {
+      uint32_t v = bz[w];
+      while (v) {
+        const int i = w * 32 + __builtin_ctz(v);
+        v &= v - 1;
+        for (int32_t o : cur[size_t(i)])
+          if (o != z && seen[o] != z) { seen[o] = z; push(z, o); }
+      }
+    }
+  }
+  return nxt == N;
 }
 
 // One tree.  method 0: greedy on size(out)-size(a)-size(b) with random tie-breaks; 1: random edge order.
@@ -211,20 +342,29 @@ void tnb_mt19937_state(uint32_t seed, uint64_t n_draws, uint32_t* state624, int3
 
 int tnb_random_trees(int n_leaves, int n_inds, const uint32_t* leaf_bits, int n_trees, const uint64_t* seeds,
                      int method, int n_threads, int32_t* parent, int32_t* child0, int32_t* child1) {
+  return tnb_random_trees_out(n_leaves, n_inds, leaf_bits, nullptr, n_trees, seeds, method, n_threads, parent, child0,
+                              child1);
+}
+
+int tnb_random_trees_out(int n_leaves, int n_inds, const uint32_t* leaf_bits, const uint32_t* output_bits, int n_trees,
+                         const uint64_t* seeds, int method, int n_threads, int32_t* parent, int32_t* child0,
+                         int32_t* child1) {
   if (n_leaves < 1 || n_inds < 0 || n_trees < 0 || !leaf_bits || !seeds) {
     set_global_error("tnb_random_trees: invalid arguments");
     return -1;
   }
-  Net net{n_leaves, n_inds, (n_inds + 31) / 32, leaf_bits, {}, {}};
+  Net net;
+  net.n = n_leaves; net.n_inds = n_inds; net.W = (n_inds + 31) / 32; net.leaf_bits = leaf_bits;
   std::string err;
-  if (!build_net(net, err)) { set_global_error("tnb_random_trees: " + err); return -2; }
+  if (!build_net(net, output_bits, err)) { set_global_error("tnb_random_trees: " + err); return -2; }
   const int N = 2 * n_leaves - 1;
   if (n_threads <= 0) n_threads = int(std::max(1u, std::thread::hardware_concurrency()));
   n_threads = std::max(1, std::min(n_threads, n_trees));
   std::vector<int> ok(size_t(n_threads), 1);
   auto work = [&](int tid) {
     for (int t = tid; t < n_trees; t += n_threads)
-      if (!one_tree(net, seeds[t], method, parent + size_t(t) * N, child0 + size_t(t) * N, child1 + size_t(t) * N))
+      if (!(net.hyper ? one_tree_hyper : one_tree)(net, seeds[t], method, parent + size_t(t) * N,
+                                                   child0 + size_t(t) * N, child1 + size_t(t) * N))
         ok[size_t(tid)] = 0;
   };
   if (n_threads == 1) work(0);

@@ -29,6 +29,11 @@ struct Params {
   float max_width;
   // chains
   int n_chains, Npad;
+  // hyper-indices (an index on 3+ tensors, or on 2 and open): HYPER kernels keep, next to every internal node's
+  // index set, hyper[z] = inds[z] & inds[c0] & inds[c1] (HyperCache, infinite_memory/utils.hpp:68-100)
+  int hyper;                // network has hyper-indices
+  int hyp_off;              // byte offset of the hyper row from the node's index-set row (= 4*Ws)
+  const uint16_t* hcount0;  // [Ws*32] initial hyper count of every index: holders - 1 (+1 if output), ctree.py:138-156
   int16_t* par;    // [n_chains][Npad]
   // Per internal node a 16-byte header {+0 u32 child0 | child1 << 16, +4 unused, +8 f64 contraction cost} and
   // an index set u32[Ws].  INTERLEAVED layout (state fits L2): one record {header, index set} of
@@ -266,6 +271,17 @@ struct ChainView {
     for (int k = 0; k < WPL; ++k)
       if (lane_ok[k]) dst[k * TILE] = v[k];
   }
+  TNB_D TNB_INLINE void load_hyp(int node, uint32_t (&o)[WPL]) const {  // internal nodes only
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(rec_lane + unsigned(node) * bstride + unsigned(P.hyp_off));
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) o[k] = lane_ok[k] ? src[k * TILE] : 0u;
+  }
+  TNB_D TNB_INLINE void store_hyp(int node, const uint32_t (&v)[WPL]) const {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(rec_lane + unsigned(node) * bstride + unsigned(P.hyp_off));
+#pragma unroll
+    for (int k = 0; k < WPL; ++k)
+      if (lane_ok[k]) dst[k * TILE] = v[k];
+  }
   // header fields of internal node z
   TNB_D TNB_INLINE uint32_t& ch(int z) const { return *reinterpret_cast<uint32_t*>(rec + unsigned(z) * hstride); }
   TNB_D TNB_INLINE double& cc(int z) const { return *reinterpret_cast<double*>(rec + unsigned(z) * hstride + 8); }
@@ -321,22 +337,24 @@ struct ScratchSink {
   TNB_D TNB_INLINE void put(int z, double cost, double pcost) const { dst[z - n] = make_dbl2(cost, pcost); }
 };
 
-template <int TILE, int WPL, bool BUILD, class Sink>
+template <int TILE, int WPL, bool WIDTHS, class Sink>
 TNB_D void cost_pass(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL], const Sink& dst, double& seq,
                      uint32_t& maxk) {
   const Params& P = c.P;
   seq = 0.0;
   maxk = 0;
   for (int z = c.po_first(); z >= 0; z = c.po_next(z)) {
-    uint32_t x[WPL];
-    if (z < P.n) {
-      if (BUILD) {
-        c.load_bits(z, x);
-        uint32_t k = 0;
+    uint32_t kw_ = 0;
+    if (WIDTHS) {  // sliced popcount of the node's own index set (widest node)
+      uint32_t x[WPL];
+      c.load_bits(z, x);
 #pragma unroll
-        for (int i = 0; i < WPL; ++i) k += popc32(x[i] & ~S[i]);
-        k = c.t.sum(k);
-        maxk = k > maxk ? k : maxk;
+      for (int i = 0; i < WPL; ++i) kw_ += uint32_t(popc32(x[i] & ~S[i]));
+    }
+    if (z < P.n) {
+      if (WIDTHS) {
+        kw_ = c.t.sum(kw_);
+        maxk = kw_ > maxk ? kw_ : maxk;
       }
       continue;
     }
@@ -345,19 +363,8 @@ TNB_D void cost_pass(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL], co
     uint32_t xa[WPL], xb[WPL];
     c.load_bits(a, xa);
     c.load_bits(b, xb);
-    uint32_t kk = popc_or3<WPL>(xa, xb, S);
-    if (BUILD) {
-      uint32_t k = 0;
-#pragma unroll
-      for (int i = 0; i < WPL; ++i) {
-        x[i] = xa[i] ^ xb[i];
-        k += popc32(x[i] & ~S[i]);
-      }
-      c.store_bits(z, x);
-      kk |= k << 16;
-    }
-    kk = c.t.sum(kk);
-    if (BUILD) {
+    uint32_t kk = c.t.sum(popc_or3<WPL>(xa, xb, S) | (kw_ << 16));
+    if (WIDTHS) {
       const uint32_t k = kk >> 16;
       maxk = k > maxk ? k : maxk;
       kk &= 0xffffu;
@@ -370,19 +377,44 @@ TNB_D void cost_pass(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL], co
   }
 }
 
-// Index sets of internal nodes only (needed before the slicer can run at construction time).
-template <int TILE, int WPL>
-TNB_D void build_bits(const ChainView<TILE, WPL>& c) {
+// Index sets (and, with HYPER, hyper rows) of all internal nodes from the topology, in post-order -- what
+// ContractionTree.__init__ derives from a path (tnco/ctree.py:169-189): inds(z) = inds(a) ^ inds(b), plus every
+// shared index whose hyper count is still positive after this contraction.  The counters are lane-private
+// (a lane counts the indices of its own words), initialised from the network's hyper counts.
+template <int TILE, int WPL, bool HYPER>
+TNB_D void build_sets(const ChainView<TILE, WPL>& c) {
   const Params& P = c.P;
+  uint16_t* cnt = HYPER ? P.nbig + size_t(c.chain) * P.Ws * 32 : nullptr;
+  if (HYPER) {
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      const int w = c.t.tl + k * TILE;
+      if (w < P.W)
+        for (int b = 0; b < 32; ++b) cnt[w * 32 + b] = P.hcount0[w * 32 + b];
+    }
+  }
   for (int z = c.po_first(); z >= 0; z = c.po_next(z)) {
     if (z < P.n) continue;
     const uint32_t cc_ = c.ch(z);
-    uint32_t xa[WPL], xb[WPL];
+    uint32_t xa[WPL], xb[WPL], keep[WPL];
     c.load_bits(int(cc_ & 0xffffu), xa);
     c.load_bits(int(cc_ >> 16), xb);
 #pragma unroll
-    for (int i = 0; i < WPL; ++i) xa[i] ^= xb[i];
+    for (int i = 0; i < WPL; ++i) {
+      keep[i] = 0u;
+      if (HYPER) {
+        const int w = c.t.tl + i * TILE;
+        uint32_t v = xa[i] & xb[i];
+        while (v) {
+          const int b = ctz32(v);
+          v &= v - 1;
+          if (--cnt[w * 32 + b] > 0) keep[i] |= 1u << b;
+        }
+      }
+      xa[i] = (xa[i] ^ xb[i]) | keep[i];
+    }
     c.store_bits(z, xa);
+    if (HYPER) c.store_hyp(z, keep);  // == inds(z) & inds(a) & inds(b)
   }
 }
 
@@ -973,12 +1005,13 @@ TNB_D void chain_init(const Params& P, int chain) {
     if (P.out_maxw) P.out_maxw[chain] = 0.0;
     return;
   }
+  if (P.hyper) build_sets<TILE, WPL, true>(c);
+  else build_sets<TILE, WPL, false>(c);
   if (FINITE) {
     if (P.slices_given) {
       load_slices(c, S);
     } else {
       // reference ctor order: seed PRNG -> WidthCache -> slices (consumes the PRNG) -> CostCache
-      build_bits(c);
       Rng rng;
       rng.load(P, chain);
       get_slices_dev(c, rng, S);
@@ -1027,7 +1060,7 @@ TNB_D double sum_ccost(const ChainView<TILE, WPL>& c) {
 // walks.  The inputs of level k+1 (parent A', its children word and contraction cost, the sibling's index set
 // and partial cost) do not depend on the move at level k, so they are loaded during level k in three stages and
 // are in registers when level k+1 starts.
-template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2>
+template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2, bool HYPER = false>
 TNB_D void chain_sweeps(const Params& P, int chain) {
   ChainView<TILE, WPL> c(P, chain);
   const Tile<TILE>& t = c.t;
@@ -1065,8 +1098,10 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   bool in_sweep = false;
   int B = 0, A = -1, C = 0, p0 = 0, p1 = 0, a0 = 0, a1 = 0;
   uint32_t b0[WPL], b1[WPL], bC[WPL];
+  // HYPER: inds[A], hyper[A] (loaded per level) and hyper[B] (carried: next level's B is this level's A)
+  uint32_t bA[WPL], hA[WPL], hB[WPL];
 #pragma unroll
-  for (int k = 0; k < WPL; ++k) b0[k] = b1[k] = bC[k] = 0u;
+  for (int k = 0; k < WPL; ++k) b0[k] = b1[k] = bC[k] = bA[k] = hA[k] = hB[k] = 0u;
   double pc0 = 0.0, pc1 = 0.0, pcC = 0.0, ccA = 0.0, ccB = 0.0, total = 0.0, root_pc = 0.0, beta = 0.0;
   float inv_beta_f = 0.f;
 
@@ -1087,7 +1122,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
 #pragma unroll
               for (int k = 0; k < WPL; ++k) diff |= S2[k] != S[k];
               if (t.any(diff)) {  // same slices -> same costs: nothing to decide
-                if (DIM2 && P.n_inds <= 1000) {
+                if (DIM2 && !HYPER && P.n_inds <= 1000) {
                   int* dz = reinterpret_cast<int*>(P.wkey + size_t(chain) * P.Npad);
                   const int shift0 = mark_slice_diff(c, S, S2, dz, P.word + size_t(chain) * P.Npad);
                   const double r2 = sum_shifted<TILE, WPL, false>(c, dz, shift0);
@@ -1171,6 +1206,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         sz1 = szp[p1];
       }
       ccB = c.cc(B);
+      if (HYPER) c.load_hyp(B, hB);
       A = c.par[B];
       in_sweep = true;
       if (A >= 0) {
@@ -1179,6 +1215,10 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         a1 = int(aw >> 16);
         C = (a0 == B) ? a1 : a0;
         c.load_bits(C, bC);
+        if (HYPER) {
+          c.load_bits(A, bA);
+          c.load_hyp(A, hA);
+        }
         if (PC) pcC = c.pc_of(C);
         if (FS) szC = szp[C];
         ccA = c.cc(A);
@@ -1207,7 +1247,8 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     for (int k = 0; k < WPL; ++k) {
       bD[k] = pick0 ? b0[k] : b1[k];
       bE[k] = pick0 ? b1[k] : b0[k];
-      nb[k] = bD[k] ^ bC[k];  // new inds of B (infinite_memory/optimizer.hpp:147; no hyper-indices)
+      nb[k] = bD[k] ^ bC[k];  // new inds of B (infinite_memory/optimizer.hpp:147)
+      if (HYPER) nb[k] |= hA[k] | hB[k];
       kpack += uint32_t(popc32(nb[k] | bE[k] | S[k])) | (uint32_t(popc32(bD[k] | bC[k] | S[k])) << 16);
       if (FINITE) ks += uint32_t(popc32(nb[k] & ~S[k]));
       if (FS) ks += uint32_t(popc32(nb[k])) << 16;  // unsliced popcount of the new B rides in the same reduction
@@ -1280,6 +1321,15 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       c.par[C] = int16_t(B);
       c.par[E] = int16_t(A);
       c.store_bits(B, nb);
+      if (HYPER) {  // :170-172 with E_old now under A and C_old now under B
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) {
+          hA[k] = bA[k] & nb[k] & bE[k];
+          hB[k] = nb[k] & bD[k] & bC[k];
+        }
+        c.store_hyp(A, hA);
+        c.store_hyp(B, hB);
+      }
       ccB = nB;
       ccA = nA;
       total += delta;
@@ -1300,7 +1350,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < WPL; ++k) bB[k] = bD[k] ^ bE[k];
+      for (int k = 0; k < WPL; ++k) bB[k] = HYPER ? ((bD[k] ^ bE[k]) | hB[k]) : (bD[k] ^ bE[k]);
     }
     // propagate partial costs (:185-188), post-swap names
     double pcB = 0.0;
@@ -1341,6 +1391,12 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       a1 = int(awn >> 16);
       C = (a0 == B) ? a1 : a0;
       c.load_bits(C, bC);
+      if (HYPER) {
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) hB[k] = hA[k];
+        c.load_bits(A, bA);
+        c.load_hyp(A, hA);
+      }
       if (PC) pcC = c.pc_of(C);
       if (FS) szC = szp[C];
       ccA = ccAn;

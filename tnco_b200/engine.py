@@ -42,16 +42,27 @@ def unpack_bits(row):
 
 
 # ------------------------------------------------------------------------------------------ host helpers
-def random_trees(leaf_bits, n_inds, seeds, method=TREES_GREEDY, n_threads=0):
-    """Initial contraction trees, one per seed: (parent, child0, child1), each [n_trees][2n-1] int32."""
+def pack_index_set(positions, n_inds):
+    """Index positions -> [W32] uint32 bitset."""
+    out = np.zeros((int(n_inds) + 31) // 32, np.uint32)
+    for x in positions:
+        out[x >> 5] |= np.uint32(1 << (x & 31))
+    return out
+
+
+def random_trees(leaf_bits, n_inds, seeds, method=TREES_GREEDY, n_threads=0, output_bits=None):
+    """Initial contraction trees, one per seed: (parent, child0, child1), each [n_trees][2n-1] int32.
+    ``output_bits``: [W32] bitset of the open indices (only matters for networks with hyper-indices)."""
     L = _lib.lib()
     lb = _c(leaf_bits, np.uint32)
     n = lb.shape[0]
     seeds = _c(seeds, np.uint64)
     T, N = len(seeds), 2 * n - 1
     p, a, b = (np.empty((T, N), np.int32) for _ in range(3))
-    rc = L.tnb_random_trees(n, int(n_inds), _ptr(lb, C.c_uint32), T, _ptr(seeds, C.c_uint64), int(method),
-                            int(n_threads), _ptr(p, C.c_int32), _ptr(a, C.c_int32), _ptr(b, C.c_int32))
+    ob = None if output_bits is None else _c(output_bits, np.uint32)
+    rc = L.tnb_random_trees_out(n, int(n_inds), _ptr(lb, C.c_uint32), _ptr(ob, C.c_uint32), T,
+                                _ptr(seeds, C.c_uint64), int(method), int(n_threads), _ptr(p, C.c_int32),
+                                _ptr(a, C.c_int32), _ptr(b, C.c_int32))
     if rc:
         raise ValueError(L.tnb_last_error(None).decode())
     return p, a, b
@@ -146,11 +157,11 @@ class Engine:
     def _chk(self, rc):
         if rc:
             msg = self._L.tnb_last_error(self._h).decode()
-            if 'Precision is too low' in msg or 'invalid' in msg or 'not supported' in msg or 'not connected' in msg:
+            if any(k in msg for k in ('Precision is too low', 'invalid', 'not supported', 'not connected')):
                 raise ValueError(msg)
             raise EngineError(msg)
 
-    def set_network(self, leaf_bits, n_inds, dim=2, dims=None):
+    def set_network(self, leaf_bits, n_inds, dim=2, dims=None, output_bits=None):
         lb = _c(leaf_bits, np.uint32)
         self.n, self.n_inds = lb.shape[0], int(n_inds)
         self.N, self.W = 2 * self.n - 1, (self.n_inds + 31) // 32
@@ -159,7 +170,17 @@ class Engine:
         d = None if dims is None else _c(dims, np.uint64)
         self._chk(self._L.tnb_set_network(self._h, self.n, self.n_inds, _ptr(lb, C.c_uint32), int(dim),
                                           _ptr(d, C.c_uint64)))
+        if output_bits is not None:
+            ob = _c(output_bits, np.uint32).reshape(-1)
+            if ob.shape != (self.W,):
+                raise ValueError('output_bits must be [ceil(n_inds/32)]')
+            self._chk(self._L.tnb_set_output_inds(self._h, _ptr(ob, C.c_uint32)))
         return self
+
+    @property
+    def hyper(self):
+        """True if the network (with its output indices) has hyper-indices."""
+        return bool(self._L.tnb_is_hyper(self._h))
 
     def set_mode(self, max_width=None, update_slices_every=10, disable_shared_inds=False, prob=PROB_MH,
                  rng=RNG_PHILOX, layout=LAYOUT_AUTO):

@@ -12,7 +12,7 @@ import numpy as np
 
 from ..._lib import RNG_MT19937
 from ...ctree import ContractionTree
-from ...engine import Engine, mt19937_state_str, unpack_bits
+from ...engine import Engine, mt19937_state_str, pack_index_set, unpack_bits
 from ..prob import BaseProbability
 
 
@@ -43,7 +43,9 @@ class Optimizer:
             raise NotImplementedError('tnco_b200: per-index dimensions are not supported yet.')
         lb, ni = ctree.leaf_bits()
         self._e = Engine(device)
-        self._e.set_network(lb, ni, dim=dims.pop())
+        pos = {x: k for k, x in enumerate(ctree._inds_order)}
+        self._e.set_network(lb, ni, dim=dims.pop(),
+                            output_bits=pack_index_set([pos[x] for x in ctree.output_inds()], ni))
         self._e.set_mode(max_width=getattr(cmodel, 'max_width', None) if self._finite else None,
                          update_slices_every=1, disable_shared_inds=self._dsi, rng=RNG_MT19937)
         p, a, b = ctree.arrays()
