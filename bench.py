@@ -276,7 +276,7 @@ def run_ours(args):
 
     # ---- e2e through the public API, host buffers in, result objects out
     rows = index_rows(ts, ni)
-    e2e_props, e2e_s = 0, 0.0
+    e2e_props, e2e_s, e2e_parts = 0, 0.0, {}
     for i in range(args.e2e_warmup + args.e2e_steps):
         opt = Optimizer(method='sa', seed=1000 + i)
         tdist.barrier()
@@ -286,6 +286,9 @@ def run_ours(args):
         if i >= args.e2e_warmup:
             e2e_props += tdist.all_reduce_sum(opt.last_stats['proposals'])
             e2e_s += dt
+            e2e_parts = {k: round(1e3 * opt.last_stats.get(k, 0.0), 1) for k in ('engine_s', 'exchange_s', 'assemble_s')}
+            e2e_parts['kernel_ms'] = round(opt.last_stats['kernel_ms'], 1)
+            e2e_parts['wall_ms'] = round(1e3 * dt, 1)
     N = 2 * n - 1
     npad, ws = (N + 7) // 8 * 8, (W + 3) // 4 * 4
     h2d = C * 8 + S * 8 + n * ws * 4 + (ni + 1) * 8 + 2 * ni * 2   # seeds, betas, network (trees are built on the device)
@@ -315,7 +318,8 @@ def run_ours(args):
                             state_bytes_per_chain=cfg['state_bytes_per_chain'], parallelism=f'chains sharded x{world}'),
                 clocks=clk.summary(),
                 e2e=dict(value=e2e_props / max(e2e_s, 1e-9), unit='proposals/s', h2d_bytes_per_step=h2d,
-                         d2h_bytes_per_step=d2h, api="Optimizer(method='sa').optimize(rows, betas=(0,100), n_steps, n_runs)"),
+                         d2h_bytes_per_step=d2h, api="Optimizer(method='sa').optimize(rows, betas=(0,100), n_steps, n_runs)",
+                         last_step_ms=e2e_parts),
                 gpu_launches=launches,
                 roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
                               traffic=traffic, kernel='sa_sweep_kernel', peak_source=peak_src,

@@ -55,6 +55,7 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
     my_seeds = np.asarray(seeds[lo:hi], np.uint64)
     n_local = hi - lo
     method = TREES_GREEDY if opt.init_trees == 'greedy' else TREES_RANDOM
+    t_eng = time.perf_counter()
     eng = Engine(dist.local_device(opt.device))
     try:
         eng.set_network(lb, len(inds), dim=dims[0], output_bits=out_bits)
@@ -101,6 +102,8 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
         stats['config'] = eng.config()
     finally:
         eng.close()
+    stats['engine_s'] = stats.get('engine_s', 0.0) + time.perf_counter() - t_eng
+    t_x = time.perf_counter()
     # the one exchange step: global min + broadcast of the winning tree (reporting only)
     if opt.distributed and dist.world()[1] > 1:
         k = int(np.argmin(mins))
@@ -109,6 +112,7 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
         mins = dist.all_gather_rows(mins, n_runs)
         ba, bb = dist.all_gather_rows(ba, n_runs), dist.all_gather_rows(bb, n_runs)
         sl = dist.all_gather_rows(sl, n_runs)
+    stats['exchange_s'] = stats.get('exchange_s', 0.0) + time.perf_counter() - t_x
     return dict(mins=mins, c0=ba, c1=bb, slices=sl, inds=inds, comp=np.asarray(comp, np.int32), n_tensors=len(tn),
                 whole=(len(comp) == len(tn)))
 
@@ -187,6 +191,7 @@ def optimize(opt, results_cls, tn, betas, n_steps, n_runs, n_projs, update_slice
         return results_cls(**kw)
 
     results = [make(int(r)) for r in order]
+    stats['assemble_s'] = time.perf_counter() - t_start - runtime
     if opt.verbose == 1:
         print(' Done!', file=stderr, flush=True)
     stats['runtime_s'] = runtime

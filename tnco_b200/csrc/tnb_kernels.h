@@ -1097,6 +1097,10 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   const int f_dsi = P.dsi, f_prob = P.prob_kind;
   bool in_sweep = false;
   int B = 0, A = -1, C = 0, p0 = 0, p1 = 0, a0 = 0, a1 = 0;
+  // one level ahead (loop-carried): An = parent(A) and its header, loaded during the previous level
+  int An = -1;
+  uint32_t awn = 0u;
+  double ccAn = 0.0;
   uint32_t b0[WPL], b1[WPL], bC[WPL];
   // HYPER: inds[A], hyper[A] (loaded per level) and hyper[B] (carried: next level's B is this level's A)
   uint32_t bA[WPL], hA[WPL], hB[WPL];
@@ -1222,12 +1226,35 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         if (PC) pcC = c.pc_of(C);
         if (FS) szC = szp[C];
         ccA = c.cc(A);
+        An = c.par[A];
+        if (An >= 0) {
+          awn = c.ch(An);
+          ccAn = c.cc(An);
+        }
       }
     } else {
     // -------------------------------------------------------------------- one level (A >= 0)
     // (if/else, not `continue`: both kinds of iteration join again here so the tiles of a warp re-converge)
     // get_ctree_nn (optimize/optimizer.hpp:86-172): A = parent(B), C = sibling(B), D/E = children of B
-    const int An = c.par[A];  // stage 1 of the next level's inputs
+    // Inputs of the NEXT level, issued before this level's own work so that every load has (at least) the whole
+    // level to land.  They depend only on the chain of ancestors, which no move below them modifies:
+    //   Ann = parent(An);  the sibling of A under An (from An's header, in registers) and its index set.
+    const int Ann = An >= 0 ? int(c.par[An]) : -1;
+    int Cn = 0;
+    uint32_t bCn[WPL], bAn[WPL], hAn[WPL];
+    double pcCn = 0.0;
+    int szCn = 0;
+    if (An >= 0) {
+      const int x0 = int(awn & 0xffffu), x1 = int(awn >> 16);
+      Cn = (x0 == A) ? x1 : x0;
+      c.load_bits(Cn, bCn);
+      if (HYPER) {
+        c.load_bits(An, bAn);
+        c.load_hyp(An, hAn);
+      }
+      if (PC) pcCn = c.pc_of(Cn);
+      if (FS) szCn = szp[Cn];
+    }
     const bool bslot0 = (a0 == B);
     bool l0 = false, l1 = false;
 #pragma unroll
@@ -1268,12 +1295,12 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       gate = c.width_of(int(ks)) <= P.max_width;
       if (!gate) ++q_wrej;
     }
-    // stage 2: children word and contraction cost of the next parent
-    uint32_t awn = 0u;
-    double ccAn = 0.0;
-    if (An >= 0) {
-      awn = c.ch(An);
-      ccAn = c.cc(An);
+    // header of the parent after next (Ann was requested at the top of this level)
+    uint32_t awnn = 0u;
+    double ccAnn = 0.0;
+    if (Ann >= 0) {
+      awnn = c.ch(Ann);
+      ccAnn = c.cc(Ann);
     }
     bool acc = false;
     double nA = 0.0, nB = 0.0, delta = 0.0;
@@ -1386,21 +1413,27 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     ccB = ccA;
     B = A;
     A = An;
-    if (An >= 0) {  // stage 3: the next sibling's index set and partial cost
+    if (An >= 0) {  // rotate the pipeline: what was loaded for the next level becomes current
       a0 = int(awn & 0xffffu);
       a1 = int(awn >> 16);
-      C = (a0 == B) ? a1 : a0;
-      c.load_bits(C, bC);
+      C = Cn;
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) bC[k] = bCn[k];
       if (HYPER) {
 #pragma unroll
-        for (int k = 0; k < WPL; ++k) hB[k] = hA[k];
-        c.load_bits(A, bA);
-        c.load_hyp(A, hA);
+        for (int k = 0; k < WPL; ++k) {
+          hB[k] = hA[k];
+          bA[k] = bAn[k];
+          hA[k] = hAn[k];
+        }
       }
-      if (PC) pcC = c.pc_of(C);
-      if (FS) szC = szp[C];
+      if (PC) pcC = pcCn;
+      if (FS) szC = szCn;
       ccA = ccAn;
     }
+    An = Ann;
+    awn = awnn;
+    ccAn = ccAnn;
     }  // level
   }
   rng.store(P, chain);
