@@ -833,8 +833,11 @@ TNB_D void snapshot_best(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL]
   const Params& P = c.P;
   const uint32_t* src = reinterpret_cast<const uint32_t*>(c.par);
   uint32_t* dst = reinterpret_cast<uint32_t*>(P.bpar + size_t(c.chain) * P.Npad);
+  // (unrolled: the copies are independent, several loads in flight instead of one load-store round trip at a time)
+#pragma unroll 8
   for (int i = c.t.tl; i < P.Npad / 2; i += TILE) dst[i] = src[i];
   uint32_t* dch = P.bch + size_t(c.chain) * P.n_int;
+#pragma unroll 8
   for (int i = c.t.tl; i < P.n_int; i += TILE) dch[i] = c.ch(P.n + i);
   if (finite) {
     uint32_t* ds = P.bslices + size_t(c.chain) * P.Ws;
