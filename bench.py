@@ -26,7 +26,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = 'C2: 2D-grid 6x6 random circuit depth 12 TN (180 tensors, 324 indices, d=2), unconstrained SA'
+WORKLOADS = {
+    # BASELINE.json configs[1]: the default (the configuration `metric` is quoted on that fits one GPU)
+    'C2': dict(text='C2: 2D-grid 6x6 random circuit depth 12 TN (180 tensors, 324 indices, d=2), unconstrained SA',
+               make=lambda nw: nw.grid_rqc(6, 6, 12), max_width=None),
+    # BASELINE.json configs[3] / north_star target: Sycamore-53 m=20, memory-constrained (max width 2^32)
+    'C4': dict(text='C4: Sycamore-style 53-qubit m=20 TN (430 tensors, 807 indices, d=2), memory-constrained SA, '
+                    'max_width=32, update_slices=10', make=lambda nw: nw.sycamore(20), max_width=32.0),
+}
+WORKLOAD = WORKLOADS['C2']['text']
+_SEL = {'name': 'C2'}
 
 
 # ------------------------------------------------------------------------------------------ helpers
@@ -96,7 +105,7 @@ class ClockSampler:
 def workload():
     from tnco_b200 import networks
     from tnco_b200.engine import pack_leaf_bits
-    ts, ni = networks.grid_rqc(6, 6, 12)
+    ts, ni = WORKLOADS[_SEL['name']]['make'](networks)
     return ts, ni, pack_leaf_bits(ts, ni)
 
 
@@ -117,7 +126,7 @@ def bytes_per_proposal(W, levels_per_sweep, p_acc):
 # ------------------------------------------------------------------------------------------ CPU reference arm
 def _ref_worker(args):
     """One run of the reference, driven exactly like `core_` (tnco/app/infinite_memory/sa.py:199-209)."""
-    kind, P, A, B, nb, ni, seed, n_sweeps, count = args
+    kind, P, A, B, nb, ni, seed, n_sweeps, count, mw = args
     import numpy as np  # noqa
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
@@ -125,28 +134,31 @@ def _ref_worker(args):
     log2c = np.zeros(1, np.float32)
     if kind == 'reference':
         from helpers import RefChain
-        rc = RefChain(P, A, B, nb, ni, seed=seed)
+        rc = RefChain(P, A, B, nb, ni, seed=seed, max_width=mw)
         opt, mh = rc.opt, rc.mh
         t0 = time.perf_counter()
         for n in range(n_sweeps):
             mh.beta = n * (100.0 / n_sweeps)
-            opt.update(mh)
+            if mw is None:
+                opt.update(mh)
+            else:
+                opt.update(mh, update_slices=(n % 10 == 0))   # finite_width/sa.py:228
             status[0] = n / n_sweeps
             log2c[0] = opt.log2_min_total_cost
         dt = time.perf_counter() - t0
         best = opt.log2_min_total_cost
     else:
         from oracle import sa_oracle as so
-        oc = so.Chain(P, A, B, nb, ni, seed=seed)
+        oc = so.Chain(P, A, B, nb, ni, seed=seed, max_width=mw)
         t0 = time.perf_counter()
-        oc.run([n * (100.0 / n_sweeps) for n in range(n_sweeps)])
+        oc.run([n * (100.0 / n_sweeps) for n in range(n_sweeps)], update_slices_every=10)
         dt = time.perf_counter() - t0
         best = oc.log2_min_total_cost
     props = 0
     if count:  # exact proposal count from the bit-identical restatement (untimed)
         from oracle import sa_oracle as so
-        oc = so.Chain(P, A, B, nb, ni, seed=seed)
-        oc.run([n * (100.0 / n_sweeps) for n in range(n_sweeps)])
+        oc = so.Chain(P, A, B, nb, ni, seed=seed, max_width=mw)
+        oc.run([n * (100.0 / n_sweeps) for n in range(n_sweeps)], update_slices_every=10)
         props = oc.counters()['proposals']
     return dt, props, best
 
@@ -173,11 +185,11 @@ def cpu_reference_rate(n_sweeps, n_runs=None, repeats=1):
         nbs.append(nb)
     out = []
     with Parallel(n_jobs=cores, backend='loky') as par:
-        par(delayed(_ref_worker)((kind, P[k], A[k], B[k], nbs[k], ni, int(seeds[k]), 50, False))
+        par(delayed(_ref_worker)((kind, P[k], A[k], B[k], nbs[k], ni, int(seeds[k]), 50, False, WORKLOADS[_SEL['name']]['max_width']))
             for k in range(n_runs))  # pool warm-up
         for rep in range(repeats):
             t0 = time.perf_counter()
-            res = par(delayed(_ref_worker)((kind, P[k], A[k], B[k], nbs[k], ni, int(seeds[k]), n_sweeps, True))
+            res = par(delayed(_ref_worker)((kind, P[k], A[k], B[k], nbs[k], ni, int(seeds[k]), n_sweeps, True, WORKLOADS[_SEL['name']]['max_width']))
                       for k in range(n_runs))
             wall = time.perf_counter() - t0
             props = sum(r[1] for r in res)
@@ -205,7 +217,7 @@ def run_reference_arm(args):
     line = dict(metric='SA proposals/sec', value=value, unit='proposals/s', n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * secs / args.steps, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='f64', data='synthetic', impl='reference',
-                config=dict(workload=WORKLOAD, chains=n_runs, sweeps_per_step=n_sweeps, betas=[0, 100]),
+                config=dict(workload=WORKLOADS[_SEL['name']]['text'], chains=n_runs, sweeps_per_step=n_sweeps, betas=[0, 100]),
                 cpu_baseline=dict(value=value, unit='proposals/s', cores=cores, kind=kind,
                                   sample=f'{n_runs} runs (one per core, joblib loky) x {n_sweeps} sweeps per step, '
                                          'in-loop time of the slowest run'),
@@ -236,7 +248,8 @@ def run_ours(args):
     seeds = (np.arange(C, dtype=np.uint64) + 1) + np.uint64(rank * C)
 
     eng = Engine(local)
-    eng.set_network(lb, ni).set_mode()
+    mw = WORKLOADS[_SEL['name']]['max_width']
+    eng.set_network(lb, ni).set_mode(max_width=mw)
     eng.set_betas(betas)
     cfg = eng.config()
 
@@ -278,7 +291,7 @@ def run_ours(args):
     rows = index_rows(ts, ni)
     e2e_props, e2e_s, e2e_parts = 0, 0.0, {}
     for i in range(args.e2e_warmup + args.e2e_steps):
-        opt = Optimizer(method='sa', seed=1000 + i)
+        opt = Optimizer(method='sa', seed=1000 + i, max_width=mw)
         tdist.barrier()
         t0 = time.perf_counter()
         tn, res = opt.optimize(rows, betas=(0, 100), n_steps=S, n_runs=C * world)
@@ -303,7 +316,7 @@ def run_ours(args):
     traffic, issue = None, None
     try:
         prof = json.load(open(os.path.join(ROOT, 'profiles', 'sweep_kernel_traffic.json')))
-        traffic = prof['dram_bytes_per_launch']
+        traffic = prof['dram_bytes_per_launch'] if _SEL['name'] == 'C2' else None
         # the roof that actually binds this L2-resident workload: warp-instruction issue (4 schedulers x 148 SMs,
         # one instruction per cycle each); instructions per proposal from the committed ncu capture
         ipp = prof['warp_instructions_per_proposal']
@@ -312,7 +325,7 @@ def run_ours(args):
     line = dict(metric='SA proposals/sec', value=props_all / (ms_max * 1e-3), unit='proposals/s', n_gpus=world,
                 steps=args.steps, warmup=args.warmup, ms_per_step=ms_max / args.steps, higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
-                config=dict(workload=WORKLOAD, chains_per_gpu=C, sweeps_per_step=S, betas=[0, 100],
+                config=dict(workload=WORKLOADS[_SEL['name']]['text'], chains_per_gpu=C, sweeps_per_step=S, betas=[0, 100],
                             rng='philox4x32-10', l2='flushed before every step (256 MiB memset)',
                             tile=cfg['tile'], words_per_lane=cfg['words_per_lane'],
                             state_bytes_per_chain=cfg['state_bytes_per_chain'], parallelism=f'chains sharded x{world}'),
@@ -324,9 +337,12 @@ def run_ours(args):
                 roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
                               traffic=traffic, kernel='sa_sweep_kernel', peak_source=peak_src,
                               bytes_per_proposal=bpp, levels_per_sweep=L, accept_ratio=pacc,
-                              note='chain state (50 MB) is L2-resident; the kernel is latency/issue bound, see DESIGN.md'),
+                              note=('chain state (%d MB) is L2-resident; the kernel is latency/issue bound, see DESIGN.md'
+                                    if C * cfg['state_bytes_per_chain'] <= (96 << 20) else
+                                    'chain state (%d MB) is HBM-resident (split layout), latency bound, see DESIGN.md')
+                              % (C * cfg['state_bytes_per_chain'] // 1000000)),
                 best_log2_flops=gbest and float(np.log2(gbest)), proposals_per_step=props / args.steps)
-    if ipp:
+    if ipp and args.workload == 'C2':
         mhz = line['clocks'].get('sm_mhz') or line['clocks'].get('sm_max_mhz') or 1965.0
         peak_issue = 148 * 4 * mhz * 1e6
         line['roofline']['issue'] = dict(bound='warp-instruction issue', warp_instr_per_proposal=ipp,
@@ -359,7 +375,9 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--e2e-warmup', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='C2', choices=sorted(WORKLOADS), help='C2 = BASELINE.json configs[1] (default)')
     args = ap.parse_args()
+    _SEL['name'] = args.workload
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3
     if args.impl == 'reference':

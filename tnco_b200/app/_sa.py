@@ -104,16 +104,19 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
         eng.close()
     stats['engine_s'] = stats.get('engine_s', 0.0) + time.perf_counter() - t_eng
     t_x = time.perf_counter()
+    # best trees travel and wait in the engine's compact form: one word child0 | child1 << 16 per internal node
+    n = len(comp)
+    chw = (ba[:, n:].astype(np.uint32) | (bb[:, n:].astype(np.uint32) << np.uint32(16)))
     # the one exchange step: global min + broadcast of the winning tree (reporting only)
     if opt.distributed and dist.world()[1] > 1:
         k = int(np.argmin(mins))
         payload = np.concatenate([bp[k], ba[k], bb[k], sl[k].view(np.int32)])
         stats['global_best'] = dist.global_best(float(mins[k]), payload)[0]
         mins = dist.all_gather_rows(mins, n_runs)
-        ba, bb = dist.all_gather_rows(ba, n_runs), dist.all_gather_rows(bb, n_runs)
+        chw = dist.all_gather_rows(chw, n_runs)
         sl = dist.all_gather_rows(sl, n_runs)
     stats['exchange_s'] = stats.get('exchange_s', 0.0) + time.perf_counter() - t_x
-    return dict(mins=mins, c0=ba, c1=bb, slices=sl, inds=inds, comp=np.asarray(comp, np.int32), n_tensors=len(tn),
+    return dict(mins=mins, chw=chw, slices=sl, inds=inds, comp=np.asarray(comp, np.int32), n_tensors=len(tn),
                 whole=(len(comp) == len(tn)))
 
 
@@ -125,7 +128,11 @@ def _pairs(a):
 
 def _comp_path(pc, r):
     """Linear path of run r of one component over all tensors (ContractionTree.path(), ctree.py:350-388)."""
-    return tree_to_path(pc['c0'][r], pc['c1'][r], n_tensors=pc['n_tensors'], tensors_pos=pc['comp'])
+    n = len(pc['comp'])
+    c0, c1 = np.full(2 * n - 1, -1, np.int32), np.full(2 * n - 1, -1, np.int32)
+    c0[n:] = pc['chw'][r] & np.uint32(0xffff)
+    c1[n:] = pc['chw'][r] >> np.uint32(16)
+    return tree_to_path(c0, c1, n_tensors=pc['n_tensors'], tensors_pos=pc['comp'])
 
 
 def _comp_slices(pc, r):
@@ -161,36 +168,36 @@ def optimize(opt, results_cls, tn, betas, n_steps, n_runs, n_projs, update_slice
     live = [pc for pc in per_comp if pc is not None]
     # total cost per run = sum of the 6-significant-digit Decimals the reference prints (sa.py:215-220)
     if len(live) == 1:
-        keys = np.array([float('%.6g' % v) for v in live[0]['mins']])
+        keys = np.char.mod('%.6g', np.asarray(live[0]['mins'], np.float64)).astype(np.float64)
     else:
         keys = np.array([float(sum(cost_to_decimal(pc['mins'][r]) for pc in live)) for r in range(R)]) if live \
             else np.zeros(R)
     order = np.argsort(keys, kind='stable')  # == sorted(results) on cost (app.py:83-87, sa.py:257)
 
-    def make(r):
-        def d_costs():
+    def field(name, r):
+        """One field of the result record of run r, computed when first looked at."""
+        if name == 'runtime_s':
+            return runtime
+        if name == 'disconnected_costs':
             return [0 if pc is None else cost_to_decimal(pc['mins'][r]) for pc in per_comp]
-
-        def d_paths():
+        if name == 'cost':
+            return sum(field('disconnected_costs', r))
+        if name == 'disconnected_paths':
             return [[] if pc is None else _pairs(_comp_path(pc, r)) for pc in per_comp]
-
-        def path():
+        if name == 'path':
             if len(live) == 1 and live[0]['whole']:  # one component spanning the network: its path, pairs sorted
                 return _pairs(np.sort(_comp_path(live[0], r), axis=1))
             cat = np.concatenate([_comp_path(pc, r) for pc in live], axis=0)[None] if live else \
                 np.zeros((1, 0, 2), np.int32)
             # tn_utils.merge_contraction_paths (sa.py:230), in C++
             return _pairs(merge_paths(len(tn), [len(pc['comp']) - 1 for pc in live], cat)[0])
+        if name == 'disconnected_slices':
+            return [frozenset() if pc is None else _comp_slices(pc, r) for pc in per_comp]
+        if name == 'slices':
+            return fts.reduce(op.or_, field('disconnected_slices', r), frozenset())
+        raise AttributeError(name)
 
-        kw = dict(cost=lambda: sum(d_costs()), runtime_s=runtime, disconnected_costs=d_costs,
-                  disconnected_paths=d_paths, path=path)
-        if finite:
-            def d_slices():
-                return [frozenset() if pc is None else _comp_slices(pc, r) for pc in per_comp]
-            kw.update(disconnected_slices=d_slices, slices=lambda: fts.reduce(op.or_, d_slices(), frozenset()))
-        return results_cls(**kw)
-
-    results = [make(int(r)) for r in order]
+    results = [results_cls._from_source(field, r) for r in order.tolist()]
     stats['assemble_s'] = time.perf_counter() - t_start - runtime
     if opt.verbose == 1:
         print(' Done!', file=stderr, flush=True)

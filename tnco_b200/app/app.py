@@ -59,14 +59,27 @@ class _LazyFields:
         for k in names:
             object.__setattr__(self, '_' + k, vals[k])
 
+    @classmethod
+    def _from_source(cls, source, key):
+        """Record whose every field is ``source(field_name, key)``, evaluated and cached on first access (one
+        shared callable instead of per-record closures: optimize() creates one record per run)."""
+        o = object.__new__(cls)
+        object.__setattr__(o, '_src', (source, key))
+        return o
+
     def __setattr__(self, k, v):
         raise AttributeError('results are read-only')
 
     def _get(self, k):
-        v = object.__getattribute__(self, '_' + k)
-        if callable(v):
-            v = v()
-            object.__setattr__(self, '_' + k, v)
+        d = object.__getattribute__(self, '__dict__')
+        if '_' + k in d:
+            v = d['_' + k]
+            if callable(v):
+                v = v()
+                d['_' + k] = v
+            return v
+        source, key = d['_src']
+        v = d['_' + k] = source(k, key)
         return v
 
     def __getattr__(self, k):
