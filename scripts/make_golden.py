@@ -32,6 +32,10 @@ CASES = [
     ('reg300_inf', 300, 9, 1000, None, False, 2, 10),
     ('reg200_fw35', 200, 10, 800, 0.35, False, 2, 10),
     ('reg1000_inf', 1000, 11, 300, None, False, 2, 10),
+    # dim = 0: per-index dimensions drawn from {2, 4, 8} (the reference's dims-vector code paths)
+    ('dims64_inf', 64, 13, 1500, None, False, 0, 10),
+    ('dims64_fw45', 64, 14, 1200, 0.45, False, 0, 10),
+    ('dimshyper48_fw50', 48, 15, 1000, 0.5, True, 0, 10),
 ]
 
 
@@ -42,18 +46,29 @@ def digest(state_str):
 def main():
     assert ref_core() is not None, 'build oracle/_ref first (make -C oracle ref)'
     os.makedirs(GOLDEN, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, n, seed, n_sweeps, frac, hyper, dim, every in CASES:
+        if only and name not in only:
+            continue
         if hyper:
             ts, ni, out = hyper_network(n, seed)
         else:
             ts, ni = regular_network(n, seed)
             out = []
         p, a, b, bits = random_tree(ts, ni, seed + 1, out)
+        dims = None
+        if dim == 0:
+            dims = np.random.default_rng(seed).choice([2, 4, 8], size=ni).astype(np.uint64)
         mw = None
         if frac is not None:
-            w0 = max(sum(bin(int(v)).count('1') for v in row) for row in bits)
-            mw = float(int(w0 * frac)) * float(np.log2(dim))
-        rc = RefChain(p, a, b, bits, ni, dim=dim, max_width=mw, seed=seed)
+            if dims is None:
+                w0 = max(sum(bin(int(v)).count('1') for v in row) for row in bits)
+                mw = float(int(w0 * frac)) * float(np.log2(dim))
+            else:
+                l2 = np.log2(dims.astype(float))
+                w0 = max(sum(l2[i] for i in range(ni) if (int(row[i >> 5]) >> (i & 31)) & 1) for row in bits)
+                mw = float(int(w0 * frac))
+        rc = RefChain(p, a, b, bits, ni, dim=dim if dims is None else 2, dims=dims, max_width=mw, seed=seed)
         cps = sorted(set([0, 1, 2, 10, 11, n_sweeps // 3, n_sweeps // 2, n_sweeps - 1]))
         rec = dict(parent=[], child0=[], child1=[], log2_total=[], log2_min=[], prng_crc=[], slices=[],
                    min_slices=[])
@@ -77,7 +92,7 @@ def main():
             ts_arr[i, :len(x)] = x
         np.savez_compressed(
             os.path.join(GOLDEN, name + '.npz'), ts_inds=ts_arr, n_inds=ni, output_inds=np.array(out, np.int32),
-            parent=p, child0=a, child1=b, bits=bits, dim=dim, max_width=np.float64(-1 if mw is None else mw),
+            parent=p, child0=a, child1=b, bits=bits, dim=dim, dims=np.zeros(0, np.uint64) if dims is None else dims, max_width=np.float64(-1 if mw is None else mw),
             seed=seed, n_sweeps=n_sweeps, beta0=0.0, beta1=100.0, every=every, checkpoints=np.array(cps),
             init_log2_total=init_log2, init_slices=init_slices,
             cp_parent=np.array(rec['parent']), cp_child0=np.array(rec['child0']),

@@ -218,3 +218,35 @@ def test_hyper_index_network_through_the_app(backend, max_width):
             work.append(frozenset(new))
         assert len(work) == 1 and work[0] == frozenset(tn.output_inds)
         assert abs(math.log2(total) - math.log2(float(r.cost))) < 1e-4
+
+
+@pytest.mark.parametrize('max_width', [None, 14])
+def test_per_index_dims_through_the_app(backend, max_width):
+    """Indices of different (power-of-two) dimensions: cost = sum over steps of the PRODUCT of the dimensions of
+    x | y [| slices], width = sum of log2 dims (cost_model/simple.hpp:46-54, finite_width/cost_model/simple.hpp:47-55)."""
+    import numpy as np
+    from tnco_b200.app import Optimizer
+    ts, ni = regular_network(26, 8)
+    dims = np.random.default_rng(1).choice([2, 4, 8], size=ni).tolist()
+    rows = index_rows(ts, ni)
+    for i, d in enumerate(dims):
+        rows[i][0] = d
+    tn, res = Optimizer(seed=3, max_width=max_width).optimize(rows, betas=(0, 100), n_steps=150, n_runs=5)
+    assert [r.cost for r in res] == sorted(r.cost for r in res)
+    for r in res:
+        slices = frozenset(r.slices) if max_width is not None else frozenset()
+        work = [frozenset(x) for x in tn.ts_inds]
+        total = 0
+        for x, y in r.path:
+            x, y = sorted((x, y))
+            ty, tx = work.pop(y), work.pop(x)
+            assert tx & ty
+            total += math.prod(tn.dims[i] for i in tx | ty | slices)
+            new = tx ^ ty
+            if max_width is not None:
+                assert sum(math.log2(tn.dims[i]) for i in new - slices) <= max_width
+            work.append(new)
+        assert abs(math.log2(total) - math.log2(float(r.cost))) < 1e-4
+    with pytest.raises(NotImplementedError, match='power'):
+        rows[0][0] = 3
+        Optimizer(seed=3).optimize(rows, betas=(0, 100), n_steps=5, n_runs=1)

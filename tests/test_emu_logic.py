@@ -81,3 +81,14 @@ def test_emu_hyper_philox(emu, n, max_width):
 @pytest.mark.parametrize('name', ['hyper64_inf', 'hyper64_fw40'])
 def test_emu_replay_hyper(emu, name):
     G.test_replay_of_recorded_draw_stream_is_bit_exact(name)
+
+
+@pytest.mark.parametrize('n,max_width,hyper', [(80, None, False), (80, 30, False), (60, 26, True)])
+def test_emu_per_index_dims(emu, n, max_width, hyper):
+    G.test_philox_per_index_dims(n, max_width, hyper)
+    G.test_per_index_dims_must_be_powers_of_two()
+
+
+@pytest.mark.parametrize('name', ['dims64_fw45', 'dimshyper48_fw50'])
+def test_emu_replay_dims(emu, name):
+    G.test_replay_of_recorded_draw_stream_is_bit_exact(name)

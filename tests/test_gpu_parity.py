@@ -29,7 +29,8 @@ def _engine(g, rng, tile=None, every=None):
     mw = None if mw < 0 else mw
     n = (g['parent'].shape[0] + 1) // 2
     e = Engine()
-    e.set_network(g['bits'][:n], int(g['n_inds']), dim=int(g['dim']),
+    dims = g['dims'] if 'dims' in g.files and len(g['dims']) else None   # per-index dims fixtures (dim == 0)
+    e.set_network(g['bits'][:n], int(g['n_inds']), dim=int(g['dim']) or 2, dims=dims,
                   output_bits=pack_index_set(g['output_inds'].tolist(), int(g['n_inds'])))
     assert e.hyper == bool(len(g['output_inds']))
     e.set_mode(max_width=mw, update_slices_every=int(g['every']) if every is None else every, rng=rng)
@@ -82,7 +83,8 @@ def test_every_tile_shape_matches_golden(name, tile):
     _check_against_golden(g, e, mw)
 
 
-@pytest.mark.parametrize('name', ['reg64_inf', 'reg100_fw30', 'reg300_inf', 'hyper64_inf', 'hyper64_fw40'])
+@pytest.mark.parametrize('name', ['reg64_inf', 'reg100_fw30', 'reg300_inf', 'hyper64_inf', 'hyper64_fw40',
+                                  'dims64_fw45', 'dimshyper48_fw50'])
 def test_replay_of_recorded_draw_stream_is_bit_exact(name):
     """north_star: replaying a reference-recorded proposal / uniform-draw sequence yields identical trees.
     The stream is recorded by the oracle (itself pinned to the reference) while it runs the same sweeps."""
@@ -91,13 +93,14 @@ def test_replay_of_recorded_draw_stream_is_bit_exact(name):
     mw = float(g['max_width'])
     mw = None if mw < 0 else mw
     n_sweeps = 400
-    oc = so.Chain(g['parent'], g['child0'], g['child1'], g['bits'], int(g['n_inds']), dim=int(g['dim']),
-                  max_width=mw, seed=int(g['seed']))
+    dims = g['dims'] if 'dims' in g.files and len(g['dims']) else None
+    oc = so.Chain(g['parent'], g['child0'], g['child1'], g['bits'], int(g['n_inds']), dim=int(g['dim']) or 2,
+                  dims=dims, max_width=mw, seed=int(g['seed']))
     # the constructor's slicer draws precede the recording; re-create the full stream from the seed instead
     betas = [100.0 * s / n_sweeps for s in range(n_sweeps)]
     oc.run(betas, update_slices_every=int(g['every']))
     words = oc.counters()['words_drawn']
-    stream = so.mt_stream(int(g['seed']), words + 8 * int(g['n_inds']) + 64 + 3 * len(g['parent']))
+    stream = so.mt_stream(int(g['seed']), words + 40 * int(g['n_inds']) + 64 + 3 * len(g['parent']))  # tail >= the engine's per-sweep reserve
     e, _ = _engine(g, RNG_REPLAY)
     e.set_stream(stream[None])
     e.set_betas(betas)
@@ -408,3 +411,68 @@ def test_philox_hyper_index_networks_are_valid(n, max_width):
 
 def so_positions(row):
     return [w * 32 + b for w, v in enumerate(np.asarray(row).tolist()) for b in range(32) if (v >> b) & 1]
+
+
+@pytest.mark.parametrize('n,max_width,hyper', [(80, None, False), (80, 30, False), (60, 26, True)])
+def test_philox_per_index_dims(n, max_width, hyper):
+    """Per-index dimensions (powers of two): production path against the oracle's dims-vector cost model
+    (infinite_memory/cost_model/simple.hpp:46-54, finite_width/cost_model/simple.hpp:47-55) on the engine's own trees
+    and index sets; sliced widths (sum of log2 dims) fit; whole indices are sliced; determinism."""
+    from helpers import leaf_bits
+    from tnco_b200.engine import Engine, random_trees
+    if hyper:
+        ts, ni, out, lb, ob = _hyper_case(n, 31)
+    else:
+        ts, ni = regular_network(n, 31)
+        lb, ob, out = leaf_bits(ts, ni), None, []
+    dims = np.random.default_rng(5).choice([2, 4, 8, 16], size=ni).astype(np.uint64)
+    l2 = np.log2(dims.astype(float))
+    seeds = np.arange(32, dtype=np.uint64) + 2
+    p, a, b = random_trees(lb, ni, seeds, output_bits=ob)
+    outs = []
+    for rep in range(2):
+        e = Engine()
+        e.set_network(lb, ni, dims=dims, output_bits=ob).set_mode(max_width=max_width)
+        e.set_chains(p, a, b, seeds)
+        e.set_betas(np.linspace(0, 100, 300, endpoint=False))
+        t0, _ = e.costs()
+        e.run(300)
+        t, m = e.costs()
+        P, A, B = e.trees()
+        S = e.slices() if max_width is not None else None
+        seq, pc, mw = e.eval_cost(P, A, B, slices=S)
+        assert np.allclose(np.log2(seq), np.log2(t), atol=1e-9)
+        for c in (0, 9, 31):
+            nb = e.bits(c)
+            assert (nb[:n] == lb).all()
+            o_seq, o_mw, o_pc = so.tree_cost(A[c], B[c], nb, ni, dims=dims, slices=None if S is None else S[c])
+            assert np.isclose(np.log2(o_seq), np.log2(t[c]), atol=1e-9)
+            assert np.isclose(o_mw, mw[c])
+            if max_width is not None:
+                assert o_mw <= max_width
+                # max log2 width recomputed from the index sets, slices removed
+                keep = [i for i in range(ni) if not (int(S[c][i >> 5]) >> (i & 31)) & 1]
+                w = max(sum(l2[i] for i in keep if (int(row[i >> 5]) >> (i & 31)) & 1) for row in nb)
+                assert w <= max_width
+        bP, bA, bB = e.trees(True)
+        bseq, _, bmw = e.eval_cost(bP, bA, bB, slices=e.slices(True) if max_width is not None else None)
+        assert np.allclose(np.log2(bseq), np.log2(m), atol=1e-9)
+        if max_width is not None:
+            assert (bmw <= max_width).all() and e.progress()['width_rejects'].sum() > 0
+        outs.append((t.copy(), m.copy(), P.copy()))
+        e.close()
+    assert all((x == y).all() for x, y in zip(outs[0], outs[1]))
+    assert np.log2(outs[0][1]).mean() < np.log2(t0).mean()
+
+
+def test_per_index_dims_must_be_powers_of_two():
+    from helpers import leaf_bits
+    from tnco_b200.engine import Engine
+    ts, ni = regular_network(10, 1)
+    dims = np.full(ni, 2, np.uint64)
+    dims[3] = 3
+    e = Engine()
+    with pytest.raises(ValueError, match='power of'):
+        e.set_network(leaf_bits(ts, ni), ni, dims=dims)
+    e.set_network(leaf_bits(ts, ni), ni, dims=np.full(ni, 3, np.uint64))   # uniform: any integer dimension
+    e.close()

@@ -45,9 +45,11 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
     ts = [tn.ts_inds[t] for t in comp]
     inds = list(dict.fromkeys(x for xs in ts for x in xs))
     pos = {x: k for k, x in enumerate(inds)}
-    dims = [tn.dims[x] for x in inds]
-    if any(d != dims[0] for d in dims):
-        raise NotImplementedError('tnco_b200: per-index dimensions are not supported yet (uniform dims only).')
+    dims = [int(tn.dims[x]) for x in inds]
+    uniform = all(d == dims[0] for d in dims)
+    if not uniform and any(d < 2 or d & (d - 1) for d in dims):
+        raise NotImplementedError('tnco_b200: per-index dimensions are supported when every dimension is a power '
+                                  'of two >= 2 (or all dimensions are equal).')
     lb = pack_leaf_bits([[pos[x] for x in xs] for xs in ts], len(inds))
     out_bits = pack_index_set([pos[x] for x in inds if x in tn.output_inds], len(inds))
     n_runs = len(seeds)
@@ -58,7 +60,7 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
     t_eng = time.perf_counter()
     eng = Engine(dist.local_device(opt.device))
     try:
-        eng.set_network(lb, len(inds), dim=dims[0], output_bits=out_bits)
+        eng.set_network(lb, len(inds), dim=dims[0], dims=None if uniform else dims, output_bits=out_bits)
         eng.set_mode(max_width=opt.max_width if finite else None, update_slices_every=update_slices,
                      rng=RNG_MT19937 if opt.rng == 'mt19937' else RNG_PHILOX)
         t0 = time.perf_counter()

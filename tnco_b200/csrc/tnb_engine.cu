@@ -302,6 +302,30 @@ struct tnb_engine {
   std::vector<uint16_t> h_holders;  // [n_inds] tensors holding each index
   std::vector<uint32_t> h_output;   // [W] output (open) indices
   bool hyper = false;
+  // Per-index dimensions that are powers of two: index i of dimension 2^w is carried as w adjacent binary
+  // ("virtual") indices [voff[i], voff[i] + vw[i]) that are always set together, so that cost = 2^popcount and
+  // width = popcount keep holding and the sweep kernels are untouched; only the slicers know about the groups.
+  // n_inds / W / Ws count virtual indices; n_inds_u / Wu are the caller's.  Without per-index dims they coincide.
+  int n_inds_u = 0, Wu = 0;
+  bool grouped = false;
+  std::vector<int> voff, vw;
+  uint32_t* d_leader = nullptr;  // [Ws] first virtual bit of every index
+  uint8_t* d_gw = nullptr;       // [Ws*32] log2(dim) at the leader positions
+
+  // caller's index space <-> virtual index space (rows of Wu / W words)
+  void expand_row(const uint32_t* u, uint32_t* v) const {
+    for (int w = 0; w < W; ++w) v[w] = 0u;
+    for (int i = 0; i < n_inds_u; ++i)
+      if ((u[i >> 5] >> (i & 31)) & 1u)
+        for (int k = voff[size_t(i)]; k < voff[size_t(i)] + vw[size_t(i)]; ++k) v[k >> 5] |= 1u << (k & 31);
+  }
+  void contract_row(const uint32_t* v, uint32_t* u) const {
+    for (int w = 0; w < Wu; ++w) u[w] = 0u;
+    for (int i = 0; i < n_inds_u; ++i) {
+      const int k = voff[size_t(i)];
+      if ((v[k >> 5] >> (k & 31)) & 1u) u[i >> 5] |= 1u << (i & 31);
+    }
+  }
   std::vector<uint32_t> h_leaf_bits;  // [n][W]
   // mode
   bool finite = false;
@@ -372,6 +396,7 @@ static void fill_params(const tnb_engine* e, const ChainSet& cs, Params& P) {
   if (e->finite)
     for (int k = 0; k <= e->n_inds; ++k)
       if (float(e->log2d * double(k)) <= e->max_width) P.kthr = k;
+  P.grouped = e->grouped; P.leader = e->d_leader; P.gw = e->d_gw;
   P.hyper = e->hyper; P.hyp_off = 4 * e->Ws; P.hcount0 = e->d_hcount0;
   P.net_own = e->d_net_own; P.kpop = cs.kpop; P.tree_fail = cs.tree_fail; P.tree_method = TNB_TREES_GREEDY;
 }
@@ -597,26 +622,61 @@ void tnb_destroy(tnb_engine* e) {
   e->rt.free_(e->d_pow_tab);
   e->rt.free_(e->d_net_own);
   e->rt.free_(e->d_hcount0);
+  e->rt.free_(e->d_leader);
+  e->rt.free_(e->d_gw);
   e->rt.free_(e->d_betas);
   e->rt.free_(e->d_flush);
   e->rt.destroy();
   delete e;
 }
 
-int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* leaf_bits, uint64_t dim,
+int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds_u, const uint32_t* leaf_bits_u, uint64_t dim,
                     const uint64_t* dims) {
   if (!e) return -1;
-  if (n_leaves < 1 || n_inds < 1 || !leaf_bits) return e->fail("tnb_set_network: invalid arguments"), -1;
+  if (n_leaves < 1 || n_inds_u < 1 || !leaf_bits_u) return e->fail("tnb_set_network: invalid arguments"), -1;
+  const int Wu = (n_inds_u + 31) / 32;
+  // per-index dims: uniform -> scalar dim (include/tnco/ctree.hpp:80-89); powers of two -> virtual binary indices
+  std::vector<int> vw(size_t(n_inds_u), 1), voff(size_t(n_inds_u), 0);
+  bool grouped = false;
   if (dims) {
     bool uniform = true;
-    for (int i = 1; i < n_inds; ++i) uniform &= dims[i] == dims[0];
-    if (!uniform) return e->fail("tnb_set_network: per-index dims are not supported yet (uniform dim only)"), -2;
-    dim = dims[0];
+    for (int i = 1; i < n_inds_u; ++i) uniform &= dims[i] == dims[0];
+    if (uniform) {
+      dim = dims[0];
+    } else {
+      for (int i = 0; i < n_inds_u; ++i) {
+        const uint64_t d = dims[i];
+        if (d < 2 || (d & (d - 1)) != 0)
+          return e->fail("tnb_set_network: per-index dims are not supported unless every dimension is a power of "
+                         "two >= 2 (index " + std::to_string(i) + " has dimension " + std::to_string(d) + ")"), -2;
+        vw[size_t(i)] = __builtin_ctzll(d);
+      }
+      grouped = true;
+      dim = 2;
+    }
   }
   if (dim < 1) return e->fail("tnb_set_network: dim must be positive"), -1;
   if (2 * n_leaves - 1 > 32767) return e->fail("tnb_set_network: at most 16384 tensors"), -2;
+  int n_inds = 0;
+  for (int i = 0; i < n_inds_u; ++i) {
+    voff[size_t(i)] = n_inds;
+    n_inds += vw[size_t(i)];
+  }
   const int W = (n_inds + 31) / 32;
-  if (W > 128) return e->fail("tnb_set_network: at most 4096 indices"), -2;
+  if (W > 128) return e->fail("tnb_set_network: at most 4096 (binary) indices"), -2;
+  for (int t = 0; t < n_leaves; ++t)
+    for (int i = n_inds_u; i < Wu * 32; ++i)
+      if ((leaf_bits_u[size_t(t) * Wu + (i >> 5)] >> (i & 31)) & 1u)
+        return e->fail("tnb_set_network: leaf_bits has a bit beyond n_inds"), -1;
+  e->cs.release(e->rt);
+  e->initialized = false;
+  e->n = n_leaves; e->N = 2 * n_leaves - 1; e->n_int = n_leaves - 1; e->n_inds = n_inds; e->W = W;
+  e->n_inds_u = n_inds_u; e->Wu = Wu; e->grouped = grouped; e->vw = vw; e->voff = voff;
+  e->Ws = (W + 3) / 4 * 4;
+  e->Npad = (e->N + 7) / 8 * 8;
+  // everything below lives in the virtual index space
+  std::vector<uint32_t> leaf_bits(size_t(n_leaves) * W);
+  for (int t = 0; t < n_leaves; ++t) e->expand_row(leaf_bits_u + size_t(t) * Wu, &leaf_bits[size_t(t) * W]);
   // holders of every index (hyper-index = on 3+ tensors, or on 2 and open)
   std::vector<uint16_t> cnt(size_t(W) * 32, 0);
   std::vector<int16_t> own(size_t(2) * n_inds, int16_t(-1));
@@ -626,31 +686,32 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* lea
       while (v) {
         const int i = w * 32 + __builtin_ctz(v);
         v &= v - 1;
-        if (i >= n_inds) return e->fail("tnb_set_network: leaf_bits has a bit beyond n_inds"), -1;
         if (++cnt[size_t(i)] <= 2) own[size_t(cnt[size_t(i)] - 1) * n_inds + i] = int16_t(t);
       }
     }
-  e->cs.release(e->rt);
-  e->initialized = false;
-  e->n = n_leaves; e->N = 2 * n_leaves - 1; e->n_int = n_leaves - 1; e->n_inds = n_inds; e->W = W;
-  e->Ws = (W + 3) / 4 * 4;
-  e->Npad = (e->N + 7) / 8 * 8;
   e->h_holders.assign(cnt.begin(), cnt.begin() + n_inds);
   e->h_output.assign(size_t(W), 0u);
   e->dim = dim;
   e->log2d = std::log2(double(dim));
-  e->h_leaf_bits.assign(leaf_bits, leaf_bits + size_t(n_leaves) * W);
+  e->h_leaf_bits = leaf_bits;
   std::vector<uint32_t> padded(size_t(n_leaves) * e->Ws, 0u);
   for (int t = 0; t < n_leaves; ++t)
-    std::memcpy(&padded[size_t(t) * e->Ws], leaf_bits + size_t(t) * W, sizeof(uint32_t) * size_t(W));
-  e->rt.free_(e->d_leaf_bits);
-  e->rt.free_(e->d_pow_tab);
-  e->rt.free_(e->d_net_own);
-  e->d_leaf_bits = nullptr; e->d_pow_tab = nullptr; e->d_net_own = nullptr;
-  e->rt.free_(e->d_hcount0);
-  e->d_hcount0 = nullptr;
+    std::memcpy(&padded[size_t(t) * e->Ws], &leaf_bits[size_t(t) * W], sizeof(uint32_t) * size_t(W));
+  std::vector<uint32_t> leader(size_t(e->Ws), 0u);
+  std::vector<uint8_t> gw(size_t(e->Ws) * 32, 0);
+  for (int i = 0; i < n_inds_u; ++i) {
+    const int k = voff[size_t(i)];
+    leader[size_t(k) >> 5] |= 1u << (k & 31);
+    gw[size_t(k)] = uint8_t(vw[size_t(i)]);
+  }
+  void* old[] = {e->d_leaf_bits, e->d_pow_tab, e->d_net_own, e->d_hcount0, e->d_leader, e->d_gw};
+  for (void* q : old) e->rt.free_(q);
+  e->d_leaf_bits = nullptr; e->d_pow_tab = nullptr; e->d_net_own = nullptr; e->d_hcount0 = nullptr;
+  e->d_leader = nullptr; e->d_gw = nullptr;
   if (!alloc_to(e->rt, e->d_net_own, own.size()) || !e->rt.h2d(e->d_net_own, own.data(), own.size() * sizeof(int16_t)) ||
-      !alloc_to(e->rt, e->d_hcount0, size_t(e->Ws) * 32))
+      !alloc_to(e->rt, e->d_hcount0, size_t(e->Ws) * 32) || !alloc_to(e->rt, e->d_leader, leader.size()) ||
+      !alloc_to(e->rt, e->d_gw, gw.size()) || !e->rt.h2d(e->d_leader, leader.data(), leader.size() * sizeof(uint32_t)) ||
+      !e->rt.h2d(e->d_gw, gw.data(), gw.size()))
     return e->rtfail(), -3;
   if (!refresh_hyper(e)) return -3;
   if (!alloc_to(e->rt, e->d_leaf_bits, padded.size())) return e->rtfail(), -3;
@@ -669,9 +730,11 @@ int tnb_set_output_inds(tnb_engine* e, const uint32_t* output_bits) {
   e->cs.release(e->rt);
   e->initialized = false;
   e->h_output.assign(size_t(e->W), 0u);
-  if (output_bits)
-    for (int i = 0; i < e->n_inds; ++i)
-      if ((output_bits[i >> 5] >> (i & 31)) & 1u) e->h_output[size_t(i) >> 5] |= 1u << (i & 31);
+  if (output_bits) {
+    std::vector<uint32_t> u(output_bits, output_bits + e->Wu);
+    if (e->n_inds_u & 31) u[size_t(e->Wu) - 1] &= (1u << (e->n_inds_u & 31)) - 1u;
+    e->expand_row(u.data(), e->h_output.data());
+  }
   return refresh_hyper(e) ? 0 : -3;
 }
 
@@ -894,16 +957,15 @@ int tnb_get_bits(tnb_engine* e, int chain, uint32_t* node_bits) {
   if (!e) return -1;
   if (!ensure_init(e)) return -2;
   if (chain < 0 || chain >= e->cs.n_chains) return e->fail("tnb_get_bits: chain range"), -1;
-  const int W = e->W, Ws = e->Ws;
-  std::memcpy(node_bits, e->h_leaf_bits.data(), sizeof(uint32_t) * size_t(e->n) * W);
-  (void)Ws;
+  const int W = e->W, Wu = e->Wu;
+  for (int t = 0; t < e->n; ++t) e->contract_row(&e->h_leaf_bits[size_t(t) * W], node_bits + size_t(t) * Wu);
   const size_t ni = size_t(std::max(e->n_int, 1));
   const size_t bs = size_t(e->cs.bstride);
   std::vector<char> hb(ni * bs);
   if (!e->rt.d2h(hb.data(), e->cs.bitsb + size_t(chain) * ni * bs, hb.size() - (e->cs.bits_alloc ? 0 : 16)))
     return e->rtfail(), -3;
   for (int z = 0; z < e->n_int; ++z)
-    std::memcpy(node_bits + size_t(e->n + z) * W, &hb[size_t(z) * bs], sizeof(uint32_t) * size_t(W));
+    e->contract_row(reinterpret_cast<const uint32_t*>(&hb[size_t(z) * bs]), node_bits + size_t(e->n + z) * Wu);
   return 0;
 }
 
@@ -914,7 +976,7 @@ int tnb_get_slices(tnb_engine* e, int best, int chain0, int n, uint32_t* slices)
   std::vector<uint32_t> hs(size_t(n) * e->Ws);
   if (!e->rt.d2h(hs.data(), (best ? e->cs.bslices : e->cs.slices) + size_t(chain0) * e->Ws, hs.size() * sizeof(uint32_t)))
     return e->rtfail(), -3;
-  for (int c = 0; c < n; ++c) std::memcpy(slices + size_t(c) * e->W, &hs[size_t(c) * e->Ws], sizeof(uint32_t) * size_t(e->W));
+  for (int c = 0; c < n; ++c) e->contract_row(&hs[size_t(c) * e->Ws], slices + size_t(c) * e->Wu);
   return 0;
 }
 
@@ -959,7 +1021,7 @@ int tnb_eval_cost(tnb_engine* e, int n_trees, const int32_t* parent, const int32
   if (rc == 0 && slices) {
     std::vector<uint32_t> hs(size_t(n_trees) * e->Ws, 0u);
     for (int c = 0; c < n_trees; ++c)
-      std::memcpy(&hs[size_t(c) * e->Ws], slices + size_t(c) * e->W, sizeof(uint32_t) * size_t(e->W));
+      e->expand_row(slices + size_t(c) * e->Wu, &hs[size_t(c) * e->Ws]);
     if (!e->rt.h2d(tmp.slices, hs.data(), hs.size() * sizeof(uint32_t)) || !e->rt.sync()) { e->rtfail(); rc = -3; }
   }
   if (rc == 0) {

@@ -31,6 +31,10 @@ struct Params {
   int n_chains, Npad;
   // hyper-indices (an index on 3+ tensors, or on 2 and open): HYPER kernels keep, next to every internal node's
   // index set, hyper[z] = inds[z] & inds[c0] & inds[c1] (HyperCache, infinite_memory/utils.hpp:68-100)
+  // per-index dims (powers of two) as groups of adjacent binary indices: only the slicers look at these
+  int grouped;
+  const uint32_t* leader;   // [Ws] first bit of every group
+  const uint8_t* gw;        // [Ws*32] group size (log2 of the index dimension) at the leader positions
   int hyper;                // network has hyper-indices
   int hyp_off;              // byte offset of the hyper row from the node's index-set row (= 4*Ws)
   const uint16_t* hcount0;  // [Ws*32] initial hyper count of every index: holders - 1 (+1 if output), ctree.py:138-156
@@ -418,6 +422,14 @@ TNB_D void build_sets(const ChainView<TILE, WPL>& c) {
   }
 }
 
+// bits of word `w` covered by the bit range [idx, idx + g)
+TNB_D TNB_INLINE uint32_t span_mask(int idx, int g, int w) {
+  const int lo = idx > 32 * w ? idx : 32 * w, hi = idx + g < 32 * w + 32 ? idx + g : 32 * w + 32;
+  if (lo >= hi) return 0u;
+  const uint32_t ones = hi - lo >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u);
+  return ones << (lo - 32 * w);
+}
+
 // Greedy slicer (finite_width/greedy/utils.hpp:24-125, skip_slices = nullopt, uniform dims), including
 // libstdc++'s std::shuffle / uniform_int_distribution draw pattern so that stream modes stay bit-exact.
 template <int TILE, int WPL, class Rng>
@@ -470,14 +482,15 @@ TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2
     if (!(c.width_of(int(k)) > P.max_width)) continue;
     float sw = c.width_of(int(ks));
     if (!(sw > P.max_width)) continue;
-    // ascending positions of the still unsliced indices of this node
+    // ascending positions of the still unsliced indices of this node (group leaders when dims differ per index)
     uint32_t np = 0;
 #pragma unroll
     for (int i = 0; i < WPL; ++i) {
-      uint32_t tot;
-      uint32_t off = np + t.excl_scan_sum(uint32_t(popc32(x[i])), tot);
       const int w = t.tl + i * TILE;
       uint32_t v = x[i];
+      if (P.grouped) v &= w < P.W ? P.leader[w] : 0u;
+      uint32_t tot;
+      uint32_t off = np + t.excl_scan_sum(uint32_t(popc32(v)), tot);
       while (v) {
         pos[off++] = int16_t(w * 32 + ctz32(v));
         v &= v - 1;
@@ -518,12 +531,14 @@ TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2
         swp(i, xx % (r + 1));
         ++i;
       }
-      // std::stable_sort by n_big_tensors, descending (:85); insertion sort is stable
+      // std::stable_sort by n_big_tensors, descending, then (dims vector) by log2 dim, descending (:52-62,:85);
+      // insertion sort is stable
       for (uint32_t a = 1; a < np; ++a) {
         const int16_t key = pos[a];
         const uint16_t kb = nbig[key];
+        const int gk = P.grouped ? int(P.gw[key]) : 0;
         int b = int(a) - 1;
-        while (b >= 0 && kb > nbig[pos[b]]) {
+        while (b >= 0 && (kb > nbig[pos[b]] || (P.grouped && kb == nbig[pos[b]] && gk > int(P.gw[pos[b]])))) {
           pos[b + 1] = pos[b];
           --b;
         }
@@ -535,16 +550,15 @@ TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2
     uint32_t m = 0;
     const float dw = float(-P.log2d);  // get_delta_width for a present index (fw simple.hpp:60-76)
     while (m < np) {
-      sw += dw;
+      sw += P.grouped ? -float(int(P.gw[pos[m]])) : dw;
       ++m;
       if (sw <= P.max_width) break;
     }
     for (uint32_t j = 0; j < m; ++j) {
       const int idx = pos[j];
-      const int w = idx >> 5;
+      const int g = P.grouped ? int(P.gw[idx]) : 1;
 #pragma unroll
-      for (int i = 0; i < WPL; ++i)
-        if (w == t.tl + i * TILE) S2[i] |= 1u << (idx & 31);
+      for (int i = 0; i < WPL; ++i) S2[i] |= span_mask(idx, g, t.tl + i * TILE);
     }
     t.sync();
   }
@@ -646,10 +660,16 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, Rng& rng,
       ks += uint32_t(popc32(x[k]));
     }
     ks = t.sum(ks);
-    for (int m = int(ks) - P.kthr; m > 0; --m) {
+    for (int m = int(ks) - P.kthr; m > 0;) {  // m = binary indices still to be removed from this node
       uint32_t cand[WPL];
 #pragma unroll
-      for (int k = 0; k < WPL; ++k) cand[k] = x[k];
+      for (int k = 0; k < WPL; ++k) {
+        cand[k] = x[k];
+        if (P.grouped) {  // one candidate per index: its leader bit
+          const int w = t.tl + k * TILE;
+          cand[k] &= w < P.W ? P.leader[w] : 0u;
+        }
+      }
 #pragma unroll
       for (int b = NB - 1; b >= 0; --b) {
         bool hit = false;
@@ -660,6 +680,24 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, Rng& rng,
           for (int k = 0; k < WPL; ++k) cand[k] &= cnt[k][b];
         }
       }
+      if (P.grouped) {  // second sort key: the largest dimension among the most frequent (:57-60)
+        uint32_t gmax = 0;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) {
+          const int w = t.tl + k * TILE;
+          for (uint32_t v = cand[k]; v; v &= v - 1) {
+            const uint32_t g = P.gw[w * 32 + ctz32(v)];
+            gmax = g > gmax ? g : gmax;
+          }
+        }
+        gmax = t.max_u32(gmax);
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) {
+          const int w = t.tl + k * TILE;
+          for (uint32_t v = cand[k]; v; v &= v - 1)
+            if (P.gw[w * 32 + ctz32(v)] != gmax) cand[k] &= ~(1u << ctz32(v));
+        }
+      }
       uint32_t mine = 0;
 #pragma unroll
       for (int k = 0; k < WPL; ++k) mine += uint32_t(popc32(cand[k]));
@@ -668,16 +706,35 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, Rng& rng,
       uint32_t r = mulhi32(rng.local_next(), tot);  // every lane draws the same word
       bool done = !(r >= off && r < off + mine);
       r -= off;
+      uint32_t picked = 0;  // 1 + position of the chosen bit (on the lane that owns it)
 #pragma unroll
       for (int k = 0; k < WPL; ++k) {
         const uint32_t pk = uint32_t(popc32(cand[k]));
         if (!done && r < pk) {
-          const uint32_t bit = 1u << nth_set_bit(cand[k], r);
-          S2[k] |= bit;
-          x[k] &= ~bit;
+          const int bpos = nth_set_bit(cand[k], r);
+          if (P.grouped) {
+            picked = uint32_t((t.tl + k * TILE) * 32 + bpos) + 1u;
+          } else {
+            S2[k] |= 1u << bpos;
+            x[k] &= ~(1u << bpos);
+          }
           done = true;
         }
         r -= pk;
+      }
+      if (P.grouped) {  // the whole index goes: every lane clears its share of the group
+        picked = t.max_u32(picked);
+        if (picked == 0u) break;  // (no candidate left; cannot happen while m > 0)
+        const int idx = int(picked - 1u), g = int(P.gw[idx]);
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) {
+          const uint32_t msk = span_mask(idx, g, t.tl + k * TILE);
+          S2[k] |= msk;
+          x[k] &= ~msk;
+        }
+        m -= g;
+      } else {
+        --m;
       }
     }
   }

@@ -38,13 +38,14 @@ class Optimizer:
         self._seed = secrets.randbits(32) if seed is None else int(seed) % 2**32
         self._ctree0, self._cmodel = ctree, cmodel
         self._dsi, self._atol = bool(disable_shared_inds), atol
-        dims = set(ctree.dims.values())
-        if len(dims) != 1:
-            raise NotImplementedError('tnco_b200: per-index dimensions are not supported yet.')
+        dims = [int(ctree.dims[x]) for x in ctree._inds_order]
+        uniform = len(set(dims)) == 1
+        if not uniform and any(d < 2 or d & (d - 1) for d in dims):
+            raise NotImplementedError('tnco_b200: per-index dimensions must all be powers of two >= 2.')
         lb, ni = ctree.leaf_bits()
         self._e = Engine(device)
         pos = {x: k for k, x in enumerate(ctree._inds_order)}
-        self._e.set_network(lb, ni, dim=dims.pop(),
+        self._e.set_network(lb, ni, dim=dims[0], dims=None if uniform else dims,
                             output_bits=pack_index_set([pos[x] for x in ctree.output_inds()], ni))
         self._e.set_mode(max_width=getattr(cmodel, 'max_width', None) if self._finite else None,
                          update_slices_every=1, disable_shared_inds=self._dsi, rng=RNG_MT19937)
