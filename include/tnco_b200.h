@@ -151,6 +151,9 @@ int tnb_get_timing(tnb_engine* e, double* kernel_ms, int64_t* launches);
 int tnb_get_costs(tnb_engine* e, double* total, double* min_total);
 /* per chain [n][2*n_leaves-1]; best != 0: the reference's min_ctree */
 int tnb_get_trees(tnb_engine* e, int best, int chain0, int n, int32_t* parent, int32_t* child0, int32_t* child1);
+/* the same trees in the engine's compact form: one word child0 | child1 << 16 per INTERNAL node,
+ * [n][n_leaves-1] (node n_leaves + i at column i); a tenth of the bytes of tnb_get_trees, for bulk read-back */
+int tnb_get_trees_packed(tnb_engine* e, int best, int chain0, int n, uint32_t* children);
 /* index sets of every node of the CURRENT tree of one chain, [2*n_leaves-1][W32] */
 int tnb_get_bits(tnb_engine* e, int chain, uint32_t* node_bits);
 /* per chain [n][W32]; best != 0: min_slices */

@@ -47,6 +47,7 @@ SIGNATURES = {
     'tnb_get_timing': (C.c_int, [C.c_void_p, f64p, i64p]),
     'tnb_get_costs': (C.c_int, [C.c_void_p, f64p, f64p]),
     'tnb_get_trees': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p]),
+    'tnb_get_trees_packed': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, u32p]),
     'tnb_get_bits': (C.c_int, [C.c_void_p, C.c_int, u32p]),
     'tnb_get_slices': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, u32p]),
     'tnb_get_progress': (C.c_int, [C.c_void_p, i64p, u64p, u64p, u64p, u64p]),

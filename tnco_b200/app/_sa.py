@@ -12,7 +12,7 @@ from sys import stderr
 import numpy as np
 
 from .. import dist
-from ..engine import (Engine, RNG_MT19937, RNG_PHILOX, TREES_GREEDY, TREES_RANDOM, merge_paths, pack_index_set,
+from ..engine import (RNG_MT19937, RNG_PHILOX, cached_engine, TREES_GREEDY, TREES_RANDOM, merge_paths, pack_index_set,
                       pack_leaf_bits, random_trees, tree_to_path, unpack_bits)
 from ..tn import get_connected_components
 from .app import cost_to_decimal
@@ -58,7 +58,7 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
     n_local = hi - lo
     method = TREES_GREEDY if opt.init_trees == 'greedy' else TREES_RANDOM
     t_eng = time.perf_counter()
-    eng = Engine(dist.local_device(opt.device))
+    eng = cached_engine(dist.local_device(opt.device))
     try:
         eng.set_network(lb, len(inds), dim=dims[0], dims=None if uniform else dims, output_bits=out_bits)
         eng.set_mode(max_width=opt.max_width if finite else None, update_slices_every=update_slices,
@@ -99,21 +99,21 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
         for k in ('proposals', 'accepts', 'sweeps'):
             stats[k] += c[k]
         _, mins = eng.costs()
-        bp, ba, bb = eng.trees(best=True)
+        # best trees travel and wait in the engine's compact form: one word child0 | child1 << 16 per internal node
+        chw = eng.trees_packed(best=True)
+        kbest = int(np.argmin(mins))
+        bp, ba, bb = eng.trees(best=True, chain0=kbest, n=1)
         sl = eng.slices(best=True) if finite else np.zeros((n_local, eng.W), np.uint32)
         stats['config'] = eng.config()
-    finally:
-        eng.close()
+    except BaseException:
+        eng.close()  # do not hand a half-configured engine to the next call
+        raise
     stats['engine_s'] = stats.get('engine_s', 0.0) + time.perf_counter() - t_eng
     t_x = time.perf_counter()
-    # best trees travel and wait in the engine's compact form: one word child0 | child1 << 16 per internal node
-    n = len(comp)
-    chw = (ba[:, n:].astype(np.uint32) | (bb[:, n:].astype(np.uint32) << np.uint32(16)))
     # the one exchange step: global min + broadcast of the winning tree (reporting only)
     if opt.distributed and dist.world()[1] > 1:
-        k = int(np.argmin(mins))
-        payload = np.concatenate([bp[k], ba[k], bb[k], sl[k].view(np.int32)])
-        stats['global_best'] = dist.global_best(float(mins[k]), payload)[0]
+        payload = np.concatenate([bp[0], ba[0], bb[0], sl[kbest].view(np.int32)])
+        stats['global_best'] = dist.global_best(float(mins[kbest]), payload)[0]
         mins = dist.all_gather_rows(mins, n_runs)
         chw = dist.all_gather_rows(chw, n_runs)
         sl = dist.all_gather_rows(sl, n_runs)

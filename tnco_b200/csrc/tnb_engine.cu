@@ -11,7 +11,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "tnb_internal.h"
@@ -61,14 +63,54 @@ struct Rt {
     if (!ok(cudaEventCreate(&ev0), "cudaEventCreate") || !ok(cudaEventCreate(&ev1), "cudaEventCreate")) return false;
     return true;
   }
+  // Device allocations are recycled through an exact-size free list: cudaMalloc / cudaFree synchronise the device
+  // and were the most variable part (10-350 ms) of a back-to-back optimize() call that needs the same arrays again.
+  std::multimap<size_t, void*> pool;
+  std::unordered_map<void*, size_t> sizes;
+  size_t pooled = 0;
+  static constexpr size_t kPoolCap = size_t(16) << 30;
   void* alloc(size_t b) {
+    b = std::max<size_t>(b, 16);
     void* p = nullptr;
     cudaSetDevice(device);
-    if (!ok(cudaMalloc(&p, std::max<size_t>(b, 16)), "cudaMalloc")) return nullptr;
-    cudaMemsetAsync(p, 0, std::max<size_t>(b, 16), stream);
+    auto it = pool.find(b);
+    if (it != pool.end()) {
+      p = it->second;
+      pool.erase(it);
+      pooled -= b;
+    } else {
+      if (cudaMalloc(&p, b) != cudaSuccess) {  // out of memory: give the cached blocks back and retry once
+        cudaGetLastError();
+        trim();
+        if (!ok(cudaMalloc(&p, b), "cudaMalloc")) return nullptr;
+      }
+      sizes[p] = b;
+    }
+    cudaMemsetAsync(p, 0, b, stream);
     return p;
   }
-  void free_(void* p) { if (p) cudaFree(p); }
+  void free_(void* p) {
+    if (!p) return;
+    auto it = sizes.find(p);
+    if (it == sizes.end()) { cudaFree(p); return; }
+    if (pooled + it->second > kPoolCap) {
+      cudaStreamSynchronize(stream);
+      cudaFree(p);
+      sizes.erase(it);
+      return;
+    }
+    pool.emplace(it->second, p);  // later kernels of this stream are ordered after the ones still using it
+    pooled += it->second;
+  }
+  void trim() {
+    cudaStreamSynchronize(stream);
+    for (auto& kv : pool) {
+      cudaFree(kv.second);
+      sizes.erase(kv.second);
+    }
+    pool.clear();
+    pooled = 0;
+  }
   bool h2d(void* d, const void* h, size_t b) {
     return b == 0 || ok(cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, stream), "cudaMemcpy H2D");
   }
@@ -80,6 +122,7 @@ struct Rt {
   bool fill_ff(void* d, size_t b) { return b == 0 || ok(cudaMemsetAsync(d, 0xff, b, stream), "cudaMemset"); }
   bool sync() { return ok(cudaStreamSynchronize(stream), "cudaStreamSynchronize"); }
   void destroy() {
+    trim();
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -951,6 +994,21 @@ int tnb_get_trees(tnb_engine* e, int best, int chain0, int n, int32_t* parent, i
       }
     }
   return 0;
+}
+
+int tnb_get_trees_packed(tnb_engine* e, int best, int chain0, int n, uint32_t* children) {
+  if (!e) return -1;
+  if (!ensure_init(e)) return -2;
+  if (chain0 < 0 || n < 0 || chain0 + n > e->cs.n_chains || !children) return e->fail("tnb_get_trees_packed: arguments"), -1;
+  if (e->n_int == 0 || n == 0) return 0;
+  const size_t ni = size_t(e->n_int), count = size_t(n) * ni;
+  if (best) return e->rt.d2h(children, e->cs.bch + size_t(chain0) * ni, count * sizeof(uint32_t)) ? 0 : (e->rtfail(), -3);
+  uint32_t* tmp = nullptr;
+  if (!alloc_to(e->rt, tmp, count)) return e->rtfail(), -3;
+  const bool got = ch_copy(e->rt, tmp, e->cs.rec + size_t(chain0) * ni * size_t(e->cs.hstride), e->cs.hstride, count, false) &&
+                   e->rt.d2h(children, tmp, count * sizeof(uint32_t));
+  e->rt.free_(tmp);
+  return got ? 0 : (e->rtfail(), -3);
 }
 
 int tnb_get_bits(tnb_engine* e, int chain, uint32_t* node_bits) {

@@ -1074,7 +1074,16 @@ TNB_D void chain_init(const Params& P, int chain) {
       // reference ctor order: seed PRNG -> WidthCache -> slices (consumes the PRNG) -> CostCache
       Rng rng;
       rng.load(P, chain);
-      get_slices_dev(c, rng, S);
+      if constexpr (Rng::kFast) {
+        if (P.kw) {  // production: the same greedy rule through the fast slicer
+          build_kw_sz(c);
+          get_slices_fast(c, rng, S);
+        } else {
+          get_slices_dev(c, rng, S);
+        }
+      } else {
+        get_slices_dev(c, rng, S);
+      }
       rng.store(P, chain);
       store_slices(c, S);
     }
@@ -1087,7 +1096,7 @@ TNB_D void chain_init(const Params& P, int chain) {
   P.min_total[chain] = seq;  // get_cost(min_ctree) sums in traversal order (infinite_memory/utils.hpp:102-116)
   if (P.out_seq) P.out_seq[chain] = seq;
   if (P.out_maxw) P.out_maxw[chain] = P.log2d * double(maxk);
-  if (FINITE && P.kw) build_kw_sz(c);
+  if (FINITE && P.kw && (!Rng::kFast || P.slices_given)) build_kw_sz(c);
   if (P.bpar) snapshot_best(c, S, FINITE);
 }
 

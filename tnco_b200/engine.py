@@ -4,6 +4,7 @@ Host code only marshals buffers; all optimisation work happens in the CUDA libra
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import math
 
@@ -129,6 +130,28 @@ def mt19937_state_str(seed, n_draws):
 
 
 # ------------------------------------------------------------------------------------------ engine
+_ENGINES = {}
+
+
+def cached_engine(device=0):
+    """One long-lived Engine per device for back-to-back ``optimize()`` calls: creating / destroying the CUDA stream
+    and (re)allocating device memory per call costs tens to hundreds of milliseconds.  The engine keeps its device
+    memory until ``release_cached_engines()`` (also run at interpreter exit)."""
+    e = _ENGINES.get(int(device))
+    if e is not None and e._L is not _lib.lib():  # the bound library changed (tests switch to the emulation build)
+        e.close()
+        e = None
+    if e is None or not getattr(e, '_h', None):
+        e = _ENGINES[int(device)] = Engine(device)
+    return e
+
+
+def release_cached_engines():
+    for e in list(_ENGINES.values()):
+        e.close()
+    _ENGINES.clear()
+
+
 class Engine:
     """Batched SA chains on one B200."""
 
@@ -245,6 +268,13 @@ class Engine:
                                         _ptr(a, C.c_int32), _ptr(b, C.c_int32)))
         return p, a, b
 
+    def trees_packed(self, best=False, chain0=0, n=None):
+        """[n][n_leaves-1] uint32, child0 | child1 << 16 of internal node n_leaves + i at column i."""
+        n = self.n_chains - chain0 if n is None else n
+        o = np.empty((n, max(self.n - 1, 0)), np.uint32)
+        self._chk(self._L.tnb_get_trees_packed(self._h, int(best), int(chain0), int(n), _ptr(o, C.c_uint32)))
+        return o
+
     def bits(self, chain):
         o = np.empty((self.N, self.W), np.uint32)
         self._chk(self._L.tnb_get_bits(self._h, int(chain), _ptr(o, C.c_uint32)))
@@ -287,3 +317,6 @@ class Engine:
         self._chk(self._L.tnb_get_config(self._h, *[C.byref(x) for x in v]))
         return dict(tile=v[0].value, words_per_lane=v[1].value, layout=v[2].value,
                     state_bytes_per_chain=v[3].value)
+
+
+atexit.register(release_cached_engines)
