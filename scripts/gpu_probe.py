@@ -12,7 +12,7 @@ from tnco_b200 import networks  # noqa: E402
 from tnco_b200.engine import Engine, pack_leaf_bits, random_trees  # noqa: E402
 
 
-def probe(cfg, n_chains, n_sweeps, max_width=None, tile=None, trees='greedy'):
+def probe(cfg, n_chains, n_sweeps, max_width=None, tile=None, trees='greedy', layout=0):
     ts, ni = networks.CONFIGS[cfg]['make']()
     lb = pack_leaf_bits(ts, ni)
     seeds = np.arange(n_chains, dtype=np.uint64) + 1
@@ -27,7 +27,7 @@ def probe(cfg, n_chains, n_sweeps, max_width=None, tile=None, trees='greedy'):
     e = Engine()
     e.set_network(lb, ni)
     os.environ.pop('TNB_TILE', None)
-    e.set_mode(max_width=max_width)
+    e.set_mode(max_width=max_width, layout=layout)
     e.set_chains(p, a, b, seeds)
     e.set_betas(np.linspace(0, 100, n_sweeps, endpoint=False))
     t, m = e.costs()
