@@ -315,12 +315,13 @@ struct ChainSet {
   int16_t *posbuf = nullptr, *kpop = nullptr, *kw = nullptr, *sz = nullptr, *word = nullptr;
   uint32_t* wkey = nullptr;
   int* tree_fail = nullptr;
+  double* escore = nullptr;
   uint32_t* stream = nullptr;
   unsigned long long stream_len = 0;
 
   void release(Rt& rt) {
     void* ps[] = {par, bpar, rec, bits_alloc, bch, pc, slices, bslices, cp2, total, min_total, out_seq, out_maxw, seeds,
-                  rng_ctr, n_prop, n_acc, n_wrej, cursor, sweep_idx, overrun, nbig, posbuf, kpop, tree_fail, stream, kw, sz, word, wkey};
+                  rng_ctr, n_prop, n_acc, n_wrej, cursor, sweep_idx, overrun, nbig, posbuf, kpop, tree_fail, escore, stream, kw, sz, word, wkey};
     for (void* p : ps) rt.free_(p);
     *this = ChainSet();
   }
@@ -441,7 +442,7 @@ static void fill_params(const tnb_engine* e, const ChainSet& cs, Params& P) {
       if (float(e->log2d * double(k)) <= e->max_width) P.kthr = k;
   P.grouped = e->grouped; P.leader = e->d_leader; P.gw = e->d_gw;
   P.hyper = e->hyper; P.hyp_off = 4 * e->Ws; P.hcount0 = e->d_hcount0;
-  P.net_own = e->d_net_own; P.kpop = cs.kpop; P.tree_fail = cs.tree_fail; P.tree_method = TNB_TREES_GREEDY;
+  P.net_own = e->d_net_own; P.kpop = cs.kpop; P.escore = cs.escore; P.tree_fail = cs.tree_fail; P.tree_method = TNB_TREES_GREEDY;
 }
 
 template <class T>
@@ -841,7 +842,7 @@ int tnb_generate_chains(tnb_engine* e, int n_chains, const uint64_t* seeds, uint
   e->initialized = false;
   e->chain_id0 = chain_id0;
   if (!alloc_chains(e, cs, n_chains, true, true) || !alloc_to(e->rt, cs.kpop, size_t(n_chains) * e->Npad) ||
-      !alloc_to(e->rt, cs.tree_fail, size_t(n_chains))) {
+      !alloc_to(e->rt, cs.tree_fail, size_t(n_chains)) || !alloc_to(e->rt, cs.escore, size_t(n_chains) * e->Ws * 32)) {
     e->rtfail();
     cs.release(e->rt);
     return -3;

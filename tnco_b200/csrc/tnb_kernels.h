@@ -80,6 +80,7 @@ struct Params {
   // initial-tree construction on the device
   const int16_t* net_own;  // [2][n_inds] the (<= 2) leaves holding each index, -1 if none
   int16_t* kpop;           // [n_chains][Npad] popcount of every cluster's index set
+  double* escore;          // [n_chains][Ws*32] cached greedy score of every live edge
   int tree_method;         // TNB_TREES_GREEDY / TNB_TREES_RANDOM
   int* tree_fail;          // [n_chains] set when the network turned out to be disconnected
   // init / eval
@@ -946,6 +947,8 @@ TNB_D void chain_treegen(const Params& P, int chain) {
   int16_t* own0 = reinterpret_cast<int16_t*>(P.nbig + size_t(chain) * P.Ws * 32);
   int16_t* own1 = P.posbuf + size_t(chain) * P.Ws * 32;
   int16_t* kpop = P.kpop + size_t(chain) * P.Npad;
+  double* escore = P.escore + size_t(chain) * P.Ws * 32;  // cached score of every live edge, +inf otherwise
+  const double kDead = 1.0e308;
   const unsigned long long seed = P.seeds[chain];
   const uint32_t s0 = mix32(uint32_t(seed) ^ 0x9e3779b9u), s1 = mix32(uint32_t(seed >> 32) + 0x7f4a7c15u);
   for (int i = t.tl; i < P.n_inds; i += TILE) {
@@ -964,50 +967,49 @@ TNB_D void chain_treegen(const Params& P, int chain) {
     return x < n ? P.leaf_bits + size_t(x) * P.Ws
                  : reinterpret_cast<const uint32_t*>(c.rec_lane - 4 * t.tl + unsigned(x) * c.bstride);
   };
-  // big networks: score a strided sample of ~1024 edges per step instead of all of them
-  const int stride_edges = P.n_inds > 1024 ? (P.n_inds + 1023) / 1024 : 1;
+  auto pow2 = [](int k) { return bits_to_f64((unsigned long long)(1023 + (k > 1000 ? 1000 : k)) << 52); };
+  // score of contracting clusters a and b along a shared index (opt_einsum greedy: size(out) - size(a) - size(b))
+  auto score = [&](int a, int b) -> double {
+    if (P.tree_method != 0) return 0.0;
+    const uint32_t *ra = row(a), *rb = row(b);
+    int ko = 0;
+    for (int w = 0; w < W; ++w) ko += popc32(ra[w] ^ rb[w]);
+    return pow2(ko) - pow2(kpop[a]) - pow2(kpop[b]);
+  };
+  // every edge is scored once here; afterwards only the edges of the freshly merged cluster are re-scored
+  for (int i = t.tl; i < P.n_inds; i += TILE) {
+    const int a = own0[i], b = own1[i];
+    escore[i] = (a < 0 || b < 0 || a == b) ? kDead : score(a, b);
+  }
+  t.sync();
   for (int step = 0; step < n - 1; ++step) {
     const int z = n + step;
-    double best = 1.0e308;
+    double best = kDead;
     uint32_t best_tie = 0xffffffffu;
     int best_i = -1;
     const uint32_t hs = mix32(s0 + uint32_t(step) * 0x632be5abu);
-    for (int pass = 0; pass < 2 && best_i < 0; ++pass) {  // pass 1 (full scan) only if the sample found nothing
-      const int st = pass == 0 ? stride_edges : 1;
-      const int off = pass == 0 && st > 1 ? int(hs % uint32_t(st)) : 0;
-      for (int i = off + t.tl * st; i < P.n_inds; i += TILE * st) {
-        const int a = own0[i], b = own1[i];
-        if (a < 0 || b < 0 || a == b) continue;
-        const uint32_t tie = mix32(hs ^ (uint32_t(i) * 0x9e3779b1u) ^ s1);
-        double score = 0.0;
-        if (P.tree_method == 0) {
-          const uint32_t *ra = row(a), *rb = row(b);
-          int ko = 0;
-          for (int w = 0; w < W; ++w) ko += popc32(ra[w] ^ rb[w]);
-          const int ka = kpop[a], kb = kpop[b];
-          score = bits_to_f64((unsigned long long)(1023 + (ko > 1000 ? 1000 : ko)) << 52) -
-                  bits_to_f64((unsigned long long)(1023 + (ka > 1000 ? 1000 : ka)) << 52) -
-                  bits_to_f64((unsigned long long)(1023 + (kb > 1000 ? 1000 : kb)) << 52);
-        }
-        if (score < best || (score == best && tie < best_tie)) {
-          best = score;
-          best_tie = tie;
-          best_i = i;
-        }
+    for (int i = t.tl; i < P.n_inds; i += TILE) {
+      const double sc = escore[i];
+      if (!(sc < kDead)) continue;
+      const uint32_t tie = mix32(hs ^ (uint32_t(i) * 0x9e3779b1u) ^ s1);
+      if (sc < best || (sc == best && tie < best_tie)) {
+        best = sc;
+        best_tie = tie;
+        best_i = i;
       }
-      // tile arg-min over (score, tie); lanes without a candidate carry best_i = -1
+    }
+    // tile arg-min over (score, tie); lanes without a candidate carry best_i = -1
 #if !defined(TNB_EMU)
 #pragma unroll
-      for (int d = TILE / 2; d > 0; d >>= 1) {
-        const unsigned m = TILE == 32 ? 0xffffffffu : t.mask;
-        const double os = __shfl_xor_sync(m, best, d, TILE);
-        const uint32_t ot = __shfl_xor_sync(m, best_tie, d, TILE);
-        const int oi = __shfl_xor_sync(m, best_i, d, TILE);
-        const bool take = oi >= 0 && (best_i < 0 || os < best || (os == best && (ot < best_tie || (ot == best_tie && oi < best_i))));
-        if (take) { best = os; best_tie = ot; best_i = oi; }
-      }
-#endif
+    for (int d = TILE / 2; d > 0; d >>= 1) {
+      const unsigned m = TILE == 32 ? 0xffffffffu : t.mask;
+      const double os = __shfl_xor_sync(m, best, d, TILE);
+      const uint32_t ot = __shfl_xor_sync(m, best_tie, d, TILE);
+      const int oi = __shfl_xor_sync(m, best_i, d, TILE);
+      const bool take = oi >= 0 && (best_i < 0 || os < best || (os == best && (ot < best_tie || (ot == best_tie && oi < best_i))));
+      if (take) { best = os; best_tie = ot; best_i = oi; }
     }
+#endif
     if (best_i < 0) {  // no live edge left: the network is disconnected
       P.tree_fail[chain] = 1;
       return;
@@ -1015,17 +1017,17 @@ TNB_D void chain_treegen(const Params& P, int chain) {
     int a = own0[best_i], b = own1[best_i];
     if (best_tie & 1u) { const int tmp = a; a = b; b = tmp; }
     // merge: index set of z, popcount, topology
-    uint32_t xa[WPL], xb[WPL];
+    uint32_t xa[WPL], xb[WPL], xz[WPL];
     c.load_bits(a, xa);
     c.load_bits(b, xb);
     uint32_t k = 0;
 #pragma unroll
     for (int q = 0; q < WPL; ++q) {
-      const uint32_t x = xa[q] ^ xb[q];
-      k += uint32_t(popc32(x));
+      xz[q] = xa[q] ^ xb[q];
+      k += uint32_t(popc32(xz[q]));
       // owners: surviving indices now belong to z, contracted ones (in both) die
       const int w = t.tl + q * TILE;
-      uint32_t v = x;
+      uint32_t v = xz[q];
       while (v) {
         const int idx = w * 32 + ctz32(v);
         v &= v - 1;
@@ -1038,16 +1040,30 @@ TNB_D void chain_treegen(const Params& P, int chain) {
         v &= v - 1;
         own0[idx] = int16_t(-1);
         own1[idx] = int16_t(-1);
+        escore[idx] = kDead;
       }
-      xa[q] = x;
     }
-    c.store_bits(z, xa);
+    c.store_bits(z, xz);
     k = t.sum(k);
     kpop[z] = int16_t(k);
     c.par[a] = int16_t(z);
     c.par[b] = int16_t(z);
     c.ch(z) = uint32_t(a) | (uint32_t(b) << 16);
-    t.sync();  // owners / rows written by other lanes are read by everybody in the next step
+    t.sync();  // the row of z (written word by word by its owners) is read whole below
+    // re-score the edges of z: each lane takes the surviving indices of its own words
+#pragma unroll
+    for (int q = 0; q < WPL; ++q) {
+      const int w = t.tl + q * TILE;
+      uint32_t v = xz[q];
+      while (v) {
+        const int idx = w * 32 + ctz32(v);
+        v &= v - 1;
+        const int o0 = own0[idx], o1 = own1[idx];
+        const int other = o0 == z ? o1 : o0;
+        escore[idx] = (other < 0 || other == z) ? kDead : score(z, other);
+      }
+    }
+    t.sync();  // owners / scores written by other lanes are read by everybody in the next step
   }
 }
 
