@@ -92,3 +92,7 @@ def test_emu_per_index_dims(emu, n, max_width, hyper):
 @pytest.mark.parametrize('name', ['dims64_fw45', 'dimshyper48_fw50'])
 def test_emu_replay_dims(emu, name):
     G.test_replay_of_recorded_draw_stream_is_bit_exact(name)
+
+
+def test_emu_packed_trees_and_cache(emu):
+    G.test_packed_tree_readback_and_cached_engine()

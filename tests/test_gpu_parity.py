@@ -476,3 +476,28 @@ def test_per_index_dims_must_be_powers_of_two():
         e.set_network(leaf_bits(ts, ni), ni, dims=dims)
     e.set_network(leaf_bits(ts, ni), ni, dims=np.full(ni, 3, np.uint64))   # uniform: any integer dimension
     e.close()
+
+
+def test_packed_tree_readback_and_cached_engine():
+    """tnb_get_trees_packed == tnb_get_trees (both current and best trees); cached_engine hands out one engine per
+    device and survives back-to-back reconfiguration."""
+    from helpers import leaf_bits
+    from tnco_b200.engine import cached_engine, release_cached_engines
+    ts, ni = regular_network(50, 3)
+    lb = leaf_bits(ts, ni)
+    e = cached_engine(0)
+    assert cached_engine(0) is e
+    for rep in range(2):
+        e.set_network(lb, ni).set_mode(max_width=None if rep == 0 else 12)
+        e.generate_chains(np.arange(20, dtype=np.uint64) + rep)
+        e.set_betas(np.linspace(0, 100, 100, endpoint=False))
+        e.run(100)
+        for best in (False, True):
+            p, a, b = e.trees(best=best)
+            w = e.trees_packed(best=best)
+            assert ((w & 0xffff) == a[:, 50:]).all() and ((w >> 16) == b[:, 50:]).all()
+            w2 = e.trees_packed(best=best, chain0=7, n=3)
+            assert (w2 == w[7:10]).all()
+    release_cached_engines()
+    assert cached_engine(0) is not e
+    release_cached_engines()

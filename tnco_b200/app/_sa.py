@@ -42,16 +42,17 @@ def expand_betas(betas, n_steps):
 def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, deadline, stats):
     """All runs of one connected component.  Returns per run: min cost (float), best tree -> path over all
     tensors of tn, slices (index names)."""
-    ts = [tn.ts_inds[t] for t in comp]
+    all_ts, all_dims, outs = tn.ts_inds, tn.dims, tn.output_inds   # (properties that rebuild their value: read once)
+    ts = [all_ts[t] for t in comp]
     inds = list(dict.fromkeys(x for xs in ts for x in xs))
     pos = {x: k for k, x in enumerate(inds)}
-    dims = [int(tn.dims[x]) for x in inds]
+    dims = [int(all_dims[x]) for x in inds]
     uniform = all(d == dims[0] for d in dims)
     if not uniform and any(d < 2 or d & (d - 1) for d in dims):
         raise NotImplementedError('tnco_b200: per-index dimensions are supported when every dimension is a power '
                                   'of two >= 2 (or all dimensions are equal).')
     lb = pack_leaf_bits([[pos[x] for x in xs] for xs in ts], len(inds))
-    out_bits = pack_index_set([pos[x] for x in inds if x in tn.output_inds], len(inds))
+    out_bits = pack_index_set([pos[x] for x in inds if x in outs], len(inds))
     n_runs = len(seeds)
     lo, hi = dist.shard(n_runs) if opt.distributed else (0, n_runs)
     my_seeds = np.asarray(seeds[lo:hi], np.uint64)
