@@ -132,6 +132,7 @@ struct Rt {
 
 // ------------------------------------------------------------------------------------------ kernels
 constexpr int kBlock = 128;
+constexpr size_t kTailWords = 256;  // padding words behind every array that load_bits reads rows from
 
 #if !defined(TNB_EMU)
 template <int TILE, int WPL, bool FINITE, class Rng>
@@ -462,8 +463,9 @@ static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_be
   if (e->layout == TNB_LAYOUT_SPLIT) split = true;
   cs.hstride = split ? 16 : e->stride;
   cs.bstride = split ? 4 * e->Ws * (e->hyper ? 2 : 1) : e->stride;
-  bool ok = alloc_to(rt, cs.par, nc * e->Npad) && alloc_to(rt, cs.rec, nc * ni * size_t(cs.hstride)) &&
-            (!split || alloc_to(rt, cs.bits_alloc, nc * ni * size_t(cs.bstride))) &&
+  // (+ tail: load_bits reads whole tiles of words and masks the ones beyond the row)
+  bool ok = alloc_to(rt, cs.par, nc * e->Npad) && alloc_to(rt, cs.rec, nc * ni * size_t(cs.hstride) + 4 * kTailWords) &&
+            (!split || alloc_to(rt, cs.bits_alloc, nc * ni * size_t(cs.bstride) + 4 * kTailWords)) &&
             alloc_to(rt, cs.pc, nc * ni) && alloc_to(rt, cs.bch, nc * ni) &&
             alloc_to(rt, cs.slices, nc * e->Ws) && alloc_to(rt, cs.total, nc) && alloc_to(rt, cs.min_total, nc) &&
             alloc_to(rt, cs.out_seq, nc) && alloc_to(rt, cs.out_maxw, nc) && alloc_to(rt, cs.seeds, nc) &&
@@ -758,7 +760,7 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds_u, const uint32_t* l
       !e->rt.h2d(e->d_gw, gw.data(), gw.size()))
     return e->rtfail(), -3;
   if (!refresh_hyper(e)) return -3;
-  if (!alloc_to(e->rt, e->d_leaf_bits, padded.size())) return e->rtfail(), -3;
+  if (!alloc_to(e->rt, e->d_leaf_bits, padded.size() + kTailWords)) return e->rtfail(), -3;
   std::vector<double> tab(size_t(n_inds) + 1);
   for (int k = 0; k <= n_inds; ++k) tab[size_t(k)] = std::pow(double(dim), double(k));
   if (!alloc_to(e->rt, e->d_pow_tab, tab.size())) return e->rtfail(), -3;
