@@ -304,6 +304,15 @@ struct ChainView {
   // header fields of internal node z
   TNB_D TNB_INLINE uint32_t& ch(int z) const { return *reinterpret_cast<uint32_t*>(rec + unsigned(z) * hstride); }
   TNB_D TNB_INLINE double& cc(int z) const { return *reinterpret_cast<double*>(rec + unsigned(z) * hstride + 8); }
+  TNB_D TNB_INLINE void store_header(int z, uint32_t children, double cost) const {
+#if defined(TNB_EMU)
+    ch(z) = children;
+    cc(z) = cost;
+#else
+    const unsigned long long cb = (unsigned long long)__double_as_longlong(cost);
+    *reinterpret_cast<uint4*>(rec + unsigned(z) * hstride) = make_uint4(children, 0u, uint32_t(cb), uint32_t(cb >> 32));
+#endif
+  }
   TNB_D TNB_INLINE double pc_of(int node) const { return node < n ? 0.0 : pcv[node]; }
   TNB_D TNB_INLINE double cost_of(int k) const {
     // pow(dim, k) (infinite_memory/cost_model/simple.hpp:45) from the host-computed table (std::pow)
@@ -1442,8 +1451,13 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       // Tree::swap_with_nn(E): E <-> C, child slots preserved (tree.hpp:141-192)
       if (bslot0) a1 = E; else a0 = E;
       if (pick0) p1 = C; else p0 = C;
-      c.ch(A) = uint32_t(a0) | (uint32_t(a1) << 16);
-      c.ch(B) = uint32_t(p0) | (uint32_t(p1) << 16);
+      if (PC) {
+        c.ch(A) = uint32_t(a0) | (uint32_t(a1) << 16);
+        c.ch(B) = uint32_t(p0) | (uint32_t(p1) << 16);
+      } else {  // production: children word and new contraction cost of a node leave as ONE 16-byte header store
+        c.store_header(A, uint32_t(a0) | (uint32_t(a1) << 16), nA);
+        c.store_header(B, uint32_t(p0) | (uint32_t(p1) << 16), nB);
+      }
       c.par[C] = int16_t(B);
       c.par[E] = int16_t(A);
       c.store_bits(B, nb);
@@ -1488,9 +1502,6 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       c.cc(A) = ccA;
       c.pcv[A] = pcA;
       root_pc = pcA;
-    } else if (acc) {
-      c.cc(B) = ccB;
-      c.cc(A) = ccA;
     }
     // next level: B <- A, whose children are (a0, a1) = {B, C} in slot order
     p0 = a0;
