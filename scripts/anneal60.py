@@ -61,6 +61,11 @@ def cpu_arm(lb, ni, mw, budget, every=10):
         cal = par(delayed(_cpu_worker)((P[k], A[k], B[k], nbs[k], ni, int(seeds[k]), 3000, mw, every, 1e9))
                   for k in range(cores))
         rate = 3000 / max(c[0] for c in cal)   # sweeps/s of the slowest run with every core busy
+        # second pass: a whole beta ramp of ~5 s (sweeps get cheaper as the trees improve, a short ramp underestimates)
+        n2 = max(3000, int(rate * 5.0))
+        cal = par(delayed(_cpu_worker)((P[k], A[k], B[k], nbs[k], ni, int(seeds[k]), n2, mw, every, 1e9))
+                  for k in range(cores))
+        rate = n2 / max(c[0] for c in cal)
         n_sweeps = max(1000, int(rate * budget * 0.97))
         t0 = time.perf_counter()
         res = par(delayed(_cpu_worker)((P[k], A[k], B[k], nbs[k], ni, int(seeds[k]), n_sweeps, mw, every, budget))
@@ -83,7 +88,13 @@ def gpu_arm(lb, ni, mw, budget, n_chains, every=10):
     e.set_betas(np.linspace(0, 100, 300, endpoint=False))
     e.run(300)
     ms, _ = e.timing()
-    n_sweeps = max(1000, int(300 / (ms * 1e-3) * budget * 0.93))
+    n2 = max(300, int(300 / (ms * 1e-3) * 3.0))   # second pass: a whole beta ramp of ~3 s
+    e.generate_chains(seeds)
+    e.set_betas(np.linspace(0, 100, n2, endpoint=False))
+    e.timing()
+    e.run(n2)
+    ms, _ = e.timing()
+    n_sweeps = max(1000, int(n2 / (ms * 1e-3) * budget * 0.96))
     # the timed anneal
     t0 = time.perf_counter()
     e.generate_chains(seeds)
