@@ -1217,6 +1217,11 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   double pc0 = 0.0, pc1 = 0.0, pcC = 0.0, ccA = 0.0, ccB = 0.0, total = 0.0, root_pc = 0.0, beta = 0.0;
   float inv_beta_f = 0.f;
 
+  // Two copies of the loop body for the unconstrained kernels: the rotation of the loop-carried registers (a fifth
+  // of a level's instructions were MOVs) then happens by renaming.  (The finite-width kernel, with the re-slicer in
+  // its boundary branch, loses a third of its speed to the doubled body.)
+  constexpr int kUnroll = FINITE ? 1 : 2;
+#pragma unroll kUnroll
   while (true) {
     if (A < 0) {
       // ------------------------------------------------------------------ sweep boundary
