@@ -446,6 +446,11 @@ TNB_D void build_sets(const ChainView<TILE, WPL>& c) {
   }
 }
 
+TNB_D TNB_INLINE uint32_t mix32(uint32_t x) {  // murmur3 finaliser
+  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+
 // bits of word `w` covered by the bit range [idx, idx + g)
 TNB_D TNB_INLINE uint32_t span_mask(int idx, int g, int w) {
   const int lo = idx > 32 * w ? idx : 32 * w, hi = idx + g < 32 * w + 32 ? idx + g : 32 * w + 32;
@@ -670,6 +675,8 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, Rng& rng,
   }
   t.sync();
   // (3) greedy selection (:60-104)
+  const uint32_t draw0 = rng.local_next();
+  uint32_t n_draw = 0;
   uint32_t xnext[WPL];
   c.load_bits(word[0], xnext);
   for (int j = 0; j < nw; ++j) {
@@ -725,9 +732,24 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, Rng& rng,
       uint32_t mine = 0;
 #pragma unroll
       for (int k = 0; k < WPL; ++k) mine += uint32_t(popc32(cand[k]));
+      if (!P.grouped) {
+        // Every candidate of the most frequent class goes anyway when the class is not larger than what is still
+        // to be removed (the order inside a class is only the random tie-break): take the class in one step.
+        const uint32_t all = t.sum(mine);
+        if (all != 0u && int(all) <= m) {
+#pragma unroll
+          for (int k = 0; k < WPL; ++k) {
+            S2[k] |= cand[k];
+            x[k] &= ~cand[k];
+          }
+          m -= int(all);
+          continue;
+        }
+      }
       uint32_t tot;
       const uint32_t off = t.excl_scan_sum(mine, tot);
-      uint32_t r = mulhi32(rng.local_next(), tot);  // every lane draws the same word
+      // tie-break draw: one Philox word per re-slice, hashed with the pick number (every lane computes the same)
+      uint32_t r = mulhi32(mix32(draw0 + 0x9e3779b9u * ++n_draw), tot);
       bool done = !(r >= off && r < off + mine);
       r -= off;
       uint32_t picked = 0;  // 1 + position of the chosen bit (on the lane that owns it)
@@ -823,39 +845,43 @@ TNB_D TNB_NOINLINE int mark_slice_diff(const ChainView<TILE, WPL>& c, const uint
     }
   }
   t.sync();
-  const char* bits0 = c.rec_lane - 4 * t.tl;
+  // The two leaves holding idx climb towards each other, the one with the smaller subtree first (an ancestor always
+  // has the larger leaf count), and meet in the node that contracts idx; every node entered on the way has idx in
+  // one of its children.  Only par[] and sz[] are read: small arrays that stay in L2 even when the index sets
+  // live in HBM (testing the bit of idx in every node's index set cost one HBM round trip per step).
+  const int16_t* sz = P.sz + size_t(c.chain) * P.Npad;
   for (int j = t.tl; j < int(nd); j += TILE) {
     const int e = uint16_t(list[j]);
     const int idx = e & 0x7fff, sgn = (e & 0x8000) ? 1 : -1;
-    const unsigned wofs = unsigned(idx) >> 5;
-    const uint32_t bit = 1u << (idx & 31);
-    const int u = P.net_own[idx], v = P.net_own[P.n_inds + idx];
-    int y = u;
-    while (true) {
-      const int p = c.par[y];
-      if (p < 0) break;
+    int a = P.net_own[idx], b = P.net_own[P.n_inds + idx];
+    auto mark = [&](int z) {
 #if defined(TNB_EMU)
-      dz[p - c.n] += sgn;
+      dz[z - c.n] += sgn;
 #else
-      atomicAdd(dz + (p - c.n), sgn);
+      atomicAdd(dz + (z - c.n), sgn);
 #endif
-      y = p;
-      if (!(*reinterpret_cast<const uint32_t*>(bits0 + unsigned(y) * c.bstride + 4 * wofs) & bit)) break;
-    }
-    const int top = y;  // the node that contracts idx (or the root for an open index)
-    if (v >= 0) {
-      y = v;
+    };
+    if (b < 0) {  // open index: it stays in every node up to the root
       while (true) {
-        const int p = c.par[y];
-        if (p < 0 || p == top) break;
-#if defined(TNB_EMU)
-        dz[p - c.n] += sgn;
-#else
-        atomicAdd(dz + (p - c.n), sgn);
-#endif
-        y = p;
+        a = c.par[a];
+        if (a < 0) break;
+        mark(a);
+      }
+      continue;
+    }
+    int sa = 1, sb = 1;
+    while (a != b) {
+      if (sa <= sb) {
+        a = c.par[a];
+        sa = sz[a];
+        if (a != b) mark(a);
+      } else {
+        b = c.par[b];
+        sb = sz[b];
+        if (a != b) mark(b);
       }
     }
+    // (the contracting node was marked by whichever walker reached it first, exactly once)
   }
   t.sync();
   return 2 * int(n_add) - int(nd);  // |S2 \ S| - |S \ S2|
@@ -950,10 +976,7 @@ TNB_D void store_slices(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL])
 }
 
 // ------------------------------------------------------------------------------------------ initial trees
-TNB_D TNB_INLINE uint32_t mix32(uint32_t x) {  // murmur3 finaliser
-  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
-  return x;
-}
+
 
 // One initial contraction tree per chain, built by the chain's own tile (replaces the host-side
 // get_random_contraction_path + ContractionTree construction, tnco/utils/tn.py:109-273, tnco/ctree.py:108-226, for
