@@ -27,7 +27,7 @@ def probe(cfg, n_chains, n_sweeps, max_width=None, tile=None, trees='greedy', la
     e = Engine()
     e.set_network(lb, ni)
     os.environ.pop('TNB_TILE', None)
-    e.set_mode(max_width=max_width, layout=layout)
+    e.set_mode(max_width=max_width, layout=layout, update_slices_every=int(os.environ.get('TNB_EVERY', '10')))
     e.set_chains(p, a, b, seeds)
     e.set_betas(np.linspace(0, 100, n_sweeps, endpoint=False))
     t, m = e.costs()
