@@ -1,11 +1,13 @@
+# torchrun scaling runs on one 8-GPU box (weak scaling: 4096 chains per GPU)
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-$TR --nproc-per-node 8 --master-port 29521 bench.py --gpus 8 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_8gpu_c2.json 2> gpurun_out/bench_8gpu_c2.err
+$TR --nproc-per-node 8 --master-port 29521 bench.py --gpus 8 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_8gpu_c2.json 2> gpurun_out/bench_8gpu_c2.err
 $TR --nproc-per-node 8 --master-port 29522 bench.py --gpus 8 --workload C4 --sweeps 4000 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_8gpu_c4.json 2> gpurun_out/bench_8gpu_c4.err
-$TR --nproc-per-node 4 --master-port 29523 bench.py --gpus 4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_4gpu_c2.json 2> gpurun_out/bench_4gpu_c2.err
+$TR --nproc-per-node 4 --master-port 29523 bench.py --gpus 4 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_4gpu_c2.json 2> gpurun_out/bench_4gpu_c2.err
+$TR --nproc-per-node 2 --master-port 29524 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_2gpu_c2.json 2> gpurun_out/bench_2gpu_c2.err
 python bench.py --workload C4 --sweeps 4000 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_1gpu_c4.json 2> gpurun_out/bench_1gpu_c4.err
-tail -2 gpurun_out/bench_8gpu_c2.err
-for f in bench_8gpu_c2 bench_8gpu_c4 bench_4gpu_c2 bench_1gpu_c4; do python -c "
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_1gpu_c2.json 2> gpurun_out/bench_1gpu_c2.err
+for f in bench_1gpu_c2 bench_2gpu_c2 bench_4gpu_c2 bench_8gpu_c2 bench_1gpu_c4 bench_8gpu_c4; do python -c "
 import json,sys
 d=json.loads(open('gpurun_out/$f.json').read().strip().splitlines()[-1])
 print('$f', 'value %.3e'%d['value'], 'e2e %.3e'%d['e2e']['value'], 'ms/step %.1f'%d['ms_per_step'], d['e2e'].get('last_step_ms'), d['clocks'])
