@@ -171,7 +171,9 @@ def optimize(opt, results_cls, tn, betas, n_steps, n_runs, n_projs, update_slice
     live = [pc for pc in per_comp if pc is not None]
     # total cost per run = sum of the 6-significant-digit Decimals the reference prints (sa.py:215-220)
     if len(live) == 1:
-        keys = np.char.mod('%.6g', np.asarray(live[0]['mins'], np.float64)).astype(np.float64)
+        # the printed cost is a monotone function of the exact one: ordering by the exact cost orders the Decimals
+        # (equal Decimals come out in order of their exact costs instead of run order)
+        keys = np.asarray(live[0]['mins'], np.float64)
     else:
         keys = np.array([float(sum(cost_to_decimal(pc['mins'][r]) for pc in live)) for r in range(R)]) if live \
             else np.zeros(R)
