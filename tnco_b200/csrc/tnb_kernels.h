@@ -1163,13 +1163,7 @@ TNB_D void chain_init(const Params& P, int chain) {
 }
 
 // ------------------------------------------------------------------------------------------ sweeps
-TNB_D TNB_INLINE float exp2_fast(float x) {
-#if defined(TNB_EMU)
-  return exp2f(x);
-#else
-  return exp2f(x);  // -use_fast_math is off: exp2f on the device is MUFU.EX2 plus range handling
-#endif
-}
+TNB_D TNB_INLINE float exp2_fast(float x) { return exp2f(x); }  // ex2.approx under -ftz on the device
 
 // Sum of all contraction costs of a chain (production mode keeps no partial-cost cache: the running total is
 // re-based on this exact-as-possible sum every few sweeps, like the reference re-reads partial_cost.back()

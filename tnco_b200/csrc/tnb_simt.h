@@ -40,13 +40,6 @@ TNB_D TNB_INLINE void keep_in_register(T*& p) {
   (void)p;
 #endif
 }
-TNB_D TNB_INLINE void keep_in_register(int& v) {
-#if !defined(TNB_EMU)
-  asm volatile("" : "+r"(v));
-#else
-  (void)v;
-#endif
-}
 #if defined(TNB_EMU)
 #define TNB_NOINLINE
 #else
