@@ -117,18 +117,18 @@ template <int TILE>
 struct RngPhilox {
   static constexpr bool kFast = true;  // log-domain fp32 acceptance test (see chain_sweeps)
   uint32_t k0, k1, g0, g1;
-  unsigned long long blk;  // index of the block of TILE vectors held in registers
-  uint32_t pos;            // next vector within the block; == TILE: block exhausted
-  bool fresh;              // registers hold block `blk`
+  unsigned long long base;  // event index of the vector held by lane 0 (lane tl holds vector base + tl)
+  uint32_t pos;             // events consumed since `base`; == TILE: the held vectors are used up
+  bool fresh;               // registers hold the vectors [base, base + TILE)
   uint32_t r0, r1, r2;
   uint32_t e0, esrc;
   float rf, ef;  // -log2(u) of this lane's vector / of the current event
   TNB_D void set_counter(unsigned long long v) {
-    blk = v / TILE;
-    pos = uint32_t(v % TILE);
+    base = v;
+    pos = 0;
     fresh = false;
   }
-  TNB_D unsigned long long counter() const { return blk * TILE + pos; }
+  TNB_D unsigned long long counter() const { return base + pos; }
   TNB_D void load(const Params& P, int chain) {
     const unsigned long long s = P.seeds[chain], g = P.chain_id0 + (unsigned long long)chain;
     k0 = uint32_t(s); k1 = uint32_t(s >> 32); g0 = uint32_t(g); g1 = uint32_t(g >> 32);
@@ -139,7 +139,7 @@ struct RngPhilox {
   TNB_D void store(const Params& P, int chain) const { P.rng_ctr[chain] = counter(); }
   TNB_D bool can_start(const Params&) const { return true; }
   TNB_D void generate(const Tile<TILE>& t) {
-    const unsigned long long idx = blk * TILE + (unsigned long long)t.tl;
+    const unsigned long long idx = base + (unsigned long long)t.tl;
     uint32_t r3;
     philox4x32_10(uint32_t(idx), uint32_t(idx >> 32), g0, g1, k0, k1, r0, r1, r2, r3);
     // u = (r1 + 0.5) / 2^32 in (0,1);  -log2(u) = 32 - log2(r1 + 0.5), computed once per vector
@@ -150,9 +150,20 @@ struct RngPhilox {
 #endif
     fresh = true;
   }
+  // Sub-warp tiles: every TILE iterations of the sweep loop ALL tiles of the warp refill together (an iteration
+  // consumes at most one event, so nobody runs dry in between).  Refilling lazily, tile by tile, made the 70
+  // instructions of a refill run with 1/8 of the lanes active several times per iteration (C1: 13.5 of 32 lanes
+  // active on average).  Event e always uses vector e, so results do not depend on when a refill happens.
+  TNB_D TNB_INLINE void tick(const Tile<TILE>& t, uint32_t iteration) {
+    if (TILE < 32 && (iteration & uint32_t(TILE - 1)) == 0u && (pos != 0u || !fresh)) {
+      base += pos;
+      pos = 0;
+      generate(t);
+    }
+  }
   TNB_D TNB_INLINE void event(const Tile<TILE>& t) {
     if (pos == TILE) {
-      ++blk;
+      base += TILE;
       pos = 0;
       fresh = false;
     }
@@ -210,6 +221,7 @@ struct RngStream {
     return w[cur++];
   }
   TNB_D TNB_INLINE uint32_t leaf_word(const Tile<TILE>&) { return next(); }
+  TNB_D TNB_INLINE void tick(const Tile<TILE>&, uint32_t) {}
   TNB_D TNB_INLINE void begin_level(const Tile<TILE>&) {}
   TNB_D TNB_INLINE uint32_t coin_word(const Tile<TILE>&) { return next(); }
   TNB_D TNB_INLINE double uniform(const Tile<TILE>&) {
@@ -1238,8 +1250,10 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   // of a level's instructions were MOVs) then happens by renaming.  (The finite-width kernel, with the re-slicer in
   // its boundary branch, loses a third of its speed to the doubled body.)
   constexpr int kUnroll = FINITE ? 1 : 2;
+  uint32_t iteration = 0;
 #pragma unroll kUnroll
   while (true) {
+    rng.tick(t, iteration++);
     if (A < 0) {
       // ------------------------------------------------------------------ sweep boundary
       if (in_sweep) {
