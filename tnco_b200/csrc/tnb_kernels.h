@@ -169,11 +169,11 @@ struct RngPhilox {
     }
     if (!fresh) generate(t);
     esrc = pos;
-    e0 = t.bcast(r0, int(pos));
+    e0 = t.bcast_c(r0, int(pos));
 #if defined(TNB_EMU)
     ef = rf;
 #else
-    ef = __uint_as_float(t.bcast(__float_as_uint(rf), int(pos)));
+    ef = __uint_as_float(t.bcast_c(__float_as_uint(rf), int(pos)));
 #endif
     ++pos;
   }
@@ -1406,7 +1406,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       l0 |= (b0[k] & bC[k]) != 0u;
       l1 |= (b1[k] & bC[k]) != 0u;
     }
-    const bool i0 = t.any(l0), i1 = t.any(l1);
+    const bool i0 = t.any_c(l0), i1 = t.any_c(l1);
     rng.begin_level(t);
     bool pick0;
     if (f_dsi || (i0 && i1)) pick0 = (rng.coin_word(t) & 1u) != 0u;
@@ -1431,7 +1431,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     ++q_prop;
     bool gate = true;
     if (FINITE) {  // finite_width/greedy/optimizer.hpp:176-188
-      ks = t.sum(ks);
+      ks = t.sum_c(ks);
       if (FS) {
         ku = ks >> 16;
         ks &= 0xffffu;
@@ -1449,7 +1449,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     bool acc = false;
     double nA = 0.0, nB = 0.0, delta = 0.0;
     if (gate) {
-      kpack = t.sum(kpack);
+      kpack = t.sum_c(kpack);
       if (DIM2) {  // dim == 2: the exact power of two built from its exponent (+inf past 2^1023, like pow)
         const uint32_t ka = kpack & 0xffffu, kb = kpack >> 16;
         nA = bits_to_f64((unsigned long long)(1023u + (ka > 1024u ? 1024u : ka)) << 52);
