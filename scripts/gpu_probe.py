@@ -26,9 +26,9 @@ def probe(cfg, n_chains, n_sweeps, max_width=None, tile=None, trees='greedy', la
         os.environ['TNB_TILE'] = str(tile)
     e = Engine()
     e.set_network(lb, ni)
-    os.environ.pop('TNB_TILE', None)
     e.set_mode(max_width=max_width, layout=layout, update_slices_every=int(os.environ.get('TNB_EVERY', '10')))
     e.set_chains(p, a, b, seeds)
+    os.environ.pop('TNB_TILE', None)   # (the tile shape is fixed when the chains are created)
     e.set_betas(np.linspace(0, 100, n_sweeps, endpoint=False))
     t, m = e.costs()
     init_log2 = float(np.log2(t).mean())

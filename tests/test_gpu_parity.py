@@ -215,9 +215,11 @@ def test_philox_finite_width_chains_are_valid(n, max_width, tile):
             os.environ['TNB_TILE'] = str(tile)
         e = Engine()
         e.set_network(lb, ni)
-        os.environ.pop('TNB_TILE', None)
         e.set_mode(max_width=max_width, update_slices_every=10)
         e.set_chains(p, a, b, seeds)
+        os.environ.pop('TNB_TILE', None)   # (the tile shape is fixed when the chains are created)
+        if tile:
+            assert e.config()['tile'] == tile
         e.set_betas(np.linspace(0, 100, 400, endpoint=False))
         t0, _ = e.costs()
         e.run(200)
@@ -501,3 +503,32 @@ def test_packed_tree_readback_and_cached_engine():
     release_cached_engines()
     assert cached_engine(0) is not e
     release_cached_engines()
+
+
+def test_tile_shape_follows_the_batch_size():
+    """Lanes per chain are chosen per batch: the widest tile whose batch fits one wave of resident warps, else the
+    narrowest that holds the index set -- and the choice never changes results (same seeds, Philox)."""
+    from helpers import leaf_bits
+    from tnco_b200.engine import Engine
+    ts, ni = regular_network(64, 0)      # 96 indices: 3 words, tiles of 4 .. 32 lanes are possible
+    lb = leaf_bits(ts, ni)
+    seeds = np.arange(48, dtype=np.uint64) + 1
+    outs = {}
+    for tile in (4, 8, 16, 32):
+        os.environ['TNB_TILE'] = str(tile)
+        e = Engine()
+        e.set_network(lb, ni).set_mode()
+        e.generate_chains(seeds)
+        os.environ.pop('TNB_TILE', None)
+        assert e.config()['tile'] == tile
+        e.set_betas(np.linspace(0, 100, 200, endpoint=False))
+        e.run(200)
+        outs[tile] = (e.costs()[1].copy(), e.trees_packed(best=True).copy())
+        e.close()
+    for tile in (8, 16, 32):
+        assert (outs[tile][0] == outs[4][0]).all() and (outs[tile][1] == outs[4][1]).all()
+    e = Engine()
+    e.set_network(lb, ni).set_mode()
+    e.generate_chains(seeds)
+    assert e.config()['tile'] == 32          # a small batch: maximum parallelism
+    e.close()

@@ -25,6 +25,7 @@ namespace tnb {
 #if defined(TNB_EMU)
 struct Rt {
   std::string err;
+  int n_sms = 148;
   bool init(int) { return true; }
   void* alloc(size_t b) { return std::calloc(std::max<size_t>(b, 1), 1); }
   void free_(void* p) { std::free(p); }
@@ -38,7 +39,7 @@ struct Rt {
 #else
 struct Rt {
   std::string err;
-  int device = 0;
+  int device = 0, n_sms = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ok(cudaError_t e, const char* what) {
@@ -58,6 +59,7 @@ struct Rt {
       return false;
     }
     device = dev;
+    n_sms = prop.multiProcessorCount;
     if (!ok(cudaSetDevice(dev), "cudaSetDevice")) return false;
     if (!ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
     if (!ok(cudaEventCreate(&ev0), "cudaEventCreate") || !ok(cudaEventCreate(&ev1), "cudaEventCreate")) return false;
@@ -399,14 +401,19 @@ struct tnb_engine {
 
 namespace tnb {
 
-static int pick_tile(int W, int& wpl, bool hyper) {
+// Lanes per chain.  The memory layout does not depend on it (word w of an index set belongs to lane w), so it is
+// chosen per batch: sharing a warp between chains saves instructions but costs divergence and parallelism, and the
+// measurements reduce to one rule -- take the widest tile whose batch still fits one wave of
+// resident warps (28 per SM); if even the narrowest tile does not fit, take the narrowest.
+static int pick_tile(int W, int& wpl, bool hyper, long long n_chains, int n_sms) {
   wpl = 1;
   int tile = 32;
-  if (hyper) { wpl = (W + 31) / 32; return 32; }
-  if (W <= 4) tile = 4;
-  else if (W <= 8) tile = 8;
-  else if (W <= 32) tile = 32;  // measured: 16-lane tiles lose more to intra-warp divergence than they gain
-  else { tile = 32; wpl = (W + 31) / 32; }
+  if (hyper || W > 32) { wpl = (W + 31) / 32; return 32; }
+  const int narrowest = W <= 4 ? 4 : W <= 8 ? 8 : W <= 16 ? 16 : 32;
+  const long long capacity = 28ll * (n_sms > 0 ? n_sms : 148);
+  tile = narrowest;
+  for (int t = 32; t >= narrowest; t >>= 1)
+    if ((n_chains * t + 31) / 32 <= capacity) { tile = t; break; }
   if (const char* f = std::getenv("TNB_TILE")) {
     const int t = std::atoi(f);
     if ((t == 4 || t == 8 || t == 16 || t == 32) && t * 1 >= (W <= 32 ? W : 32)) tile = t;
@@ -454,6 +461,7 @@ static bool alloc_to(Rt& rt, T*& p, size_t count) {
 
 static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_best, bool with_slicer) {
   Rt& rt = e->rt;
+  if (&cs == &e->cs) e->tile = pick_tile(e->W, e->wpl, e->hyper, n_chains, rt.n_sms);
   cs.n_chains = n_chains;
   const size_t nc = size_t(n_chains), ni = size_t(std::max(e->n_int, 1));
   // layout: interleaved node records while the whole batch fits L2, split beyond
@@ -635,7 +643,7 @@ static bool refresh_hyper(tnb_engine* e) {
     hc[size_t(i)] = uint16_t(c < 0 ? 0 : c);
     e->hyper |= c >= 2;
   }
-  e->tile = pick_tile(e->W, e->wpl, e->hyper);
+  e->tile = pick_tile(e->W, e->wpl, e->hyper, 0, e->rt.n_sms);
   e->stride = 16 + 4 * e->Ws * (e->hyper ? 2 : 1);
   if (!e->rt.h2d(e->d_hcount0, hc.data(), hc.size() * sizeof(uint16_t)) || !e->rt.sync()) return e->rtfail();
   return true;
