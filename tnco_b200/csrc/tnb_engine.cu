@@ -385,6 +385,7 @@ struct tnb_engine {
   std::vector<uint64_t> h_seeds;
   // schedule
   double* d_betas = nullptr;
+  float* d_inv_betas = nullptr;
   int64_t n_betas = 0;
   // MT19937 feeding
   std::vector<Mt19937> mts;
@@ -440,7 +441,7 @@ static void fill_params(const tnb_engine* e, const ChainSet& cs, Params& P) {
   P.n_prop = cs.n_prop; P.n_acc = cs.n_acc; P.n_wrej = cs.n_wrej;
   P.stream = cs.stream; P.cursor = cs.cursor; P.stream_len = cs.stream_len; P.reserve = sweep_reserve(e);
   P.overrun = cs.overrun;
-  P.betas = e->d_betas; P.n_betas = e->n_betas; P.until = 0;
+  P.betas = e->d_betas; P.inv_betas = e->d_inv_betas; P.n_betas = e->n_betas; P.until = 0;
   P.nbig = cs.nbig; P.posbuf = cs.posbuf; P.cp2 = cs.cp2;
   P.slices_given = 0; P.out_seq = cs.out_seq; P.out_maxw = cs.out_maxw;
   P.kw = cs.kw; P.sz = cs.sz; P.word = cs.word; P.wkey = cs.wkey;
@@ -679,6 +680,7 @@ void tnb_destroy(tnb_engine* e) {
   e->rt.free_(e->d_leader);
   e->rt.free_(e->d_gw);
   e->rt.free_(e->d_betas);
+  e->rt.free_(e->d_inv_betas);
   e->rt.free_(e->d_flush);
   e->rt.destroy();
   delete e;
@@ -900,9 +902,14 @@ int tnb_set_betas(tnb_engine* e, const double* betas, int64_t n) {
   if (!e) return -1;
   if (!betas || n < 1) return e->fail("tnb_set_betas: invalid arguments"), -1;
   e->rt.free_(e->d_betas);
-  e->d_betas = nullptr;
-  if (!alloc_to(e->rt, e->d_betas, size_t(n))) return e->rtfail(), -3;
-  if (!e->rt.h2d(e->d_betas, betas, size_t(n) * sizeof(double)) || !e->rt.sync()) return e->rtfail(), -3;
+  e->rt.free_(e->d_inv_betas);
+  e->d_betas = nullptr; e->d_inv_betas = nullptr;
+  std::vector<float> inv(static_cast<size_t>(n));
+  for (int64_t i = 0; i < n; ++i) inv[size_t(i)] = betas[i] > 0.0 ? 1.f / float(betas[i]) : 3.0e38f;
+  if (!alloc_to(e->rt, e->d_betas, size_t(n)) || !alloc_to(e->rt, e->d_inv_betas, size_t(n))) return e->rtfail(), -3;
+  if (!e->rt.h2d(e->d_betas, betas, size_t(n) * sizeof(double)) ||
+      !e->rt.h2d(e->d_inv_betas, inv.data(), size_t(n) * sizeof(float)) || !e->rt.sync())
+    return e->rtfail(), -3;
   e->n_betas = n;
   return 0;
 }

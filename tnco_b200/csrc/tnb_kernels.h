@@ -66,6 +66,7 @@ struct Params {
   int* overrun;                 // [n_chains]
   // schedule
   const double* betas;
+  const float* inv_betas;  // 1/beta, or 3e38 for beta <= 0 (accept everything: (1+x)^-beta >= 1)
   long long n_betas, until;
   // scratch for the slicer
   uint16_t* nbig;   // [n_chains][Ws*32]
@@ -1212,7 +1213,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   keep_in_register(c.par);
   // PC: keep the reference's partial-cost cache (parity modes).  The production kernel drops it: the walk then
   // needs no partial costs of D/E/C, no two 16-byte stores per level and half the fp64 adds; its total is a
-  // running sum re-based on sum_ccost() every 16 sweeps.
+  // running sum re-based on sum_ccost() every 64 sweeps.
   constexpr bool PC = !Rng::kFast;
   // FS: production re-slicer (get_slices_fast); the walk then also maintains kw[] and sz[]
   constexpr bool FS = FINITE && Rng::kFast;
@@ -1328,14 +1329,18 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         if (rng.overrun()) break;
       }
       if (s >= P.until || !rng.can_start(P)) break;
-      beta = P.betas[s < P.n_betas ? s : P.n_betas - 1];
-      // 1/beta for the threshold form of the acceptance test; beta <= 0 accepts everything ((1+x)^-beta >= 1)
-      inv_beta_f = beta > 0.0 ? 1.f / float(beta) : 3.0e38f;
-      const int leaf = int(rng.leaf_word(t) % uint32_t(n));  // optimizer.hpp:103
+      {
+        const long long sb = s < P.n_betas ? s : P.n_betas - 1;
+        if (Rng::kFast) inv_beta_f = P.inv_betas[sb];  // 1/beta (host-computed) for the threshold acceptance test
+        else beta = P.betas[sb];
+      }
+      // leaf = prng() % n_leaves (optimizer.hpp:103); the production RNG maps its word with a multiply-high instead
+      const uint32_t lw = rng.leaf_word(t);
+      const int leaf = Rng::kFast ? int(mulhi32(lw, uint32_t(n))) : int(lw % uint32_t(n));
       B = c.par[leaf];
       if (PC) {
         total = c.pcv[root];                             // :112
-      } else if (rebase || (s & 15) == 0) {
+      } else if (rebase || (s & 63) == 0) {
         total = sum_ccost(c);
         rebase = false;
       }
