@@ -96,3 +96,7 @@ def test_emu_replay_dims(emu, name):
 
 def test_emu_packed_trees_and_cache(emu):
     G.test_packed_tree_readback_and_cached_engine()
+
+
+def test_emu_minima_exact_on_slow_ramp(emu):
+    G.test_minima_stay_exact_when_chains_wander_at_small_beta()

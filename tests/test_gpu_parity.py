@@ -532,3 +532,31 @@ def test_tile_shape_follows_the_batch_size():
     e.generate_chains(seeds)
     assert e.config()['tile'] == 32          # a small batch: maximum parallelism
     e.close()
+
+
+def test_minima_stay_exact_when_chains_wander_at_small_beta():
+    """Regression: on a slow beta ramp the chains first wander up to costs around 2^100 and come back; the running
+    total of the production kernel then carries the rounding of the large terms and once produced totals of the
+    wrong sign that were recorded as unbeatable minima.  Minima must stay positive and equal to the exact cost of
+    the recorded best tree."""
+    from tnco_b200 import networks
+    from tnco_b200.engine import Engine, pack_leaf_bits
+    ts, ni = networks.grid_rqc(6, 6, 12)
+    lb = pack_leaf_bits(ts, ni)
+    seeds = np.arange(96, dtype=np.uint64) + 1
+    e = Engine()
+    e.set_network(lb, ni).set_mode()
+    e.generate_chains(seeds)
+    n = 1000000
+    e.set_betas(np.array([k * (100.0 / n) for k in range(4000)]))   # the first 4000 sweeps of a 10^6-sweep ramp
+    peak = 0.0
+    for upto in (500, 1500, 4000):
+        e.run(upto)
+        t, m = e.costs()
+        peak = max(peak, float(np.log2(t.max())))
+        assert (m > 0).all() and (t > 0).all()
+        bP, bA, bB = e.trees(True)
+        bseq, _, _ = e.eval_cost(bP, bA, bB)
+        assert np.allclose(np.log2(bseq), np.log2(m), atol=1e-9)
+    assert peak > 70          # the scenario really occurred: totals far above what fp64 sums exactly
+    e.close()

@@ -1177,6 +1177,15 @@ TNB_D void chain_init(const Params& P, int chain) {
 
 // ------------------------------------------------------------------------------------------ sweeps
 TNB_D TNB_INLINE float exp2_fast(float x) { return exp2f(x); }  // ex2.approx under -ftz on the device
+TNB_D TNB_INLINE int exp_of(double x) {  // biased binary exponent
+#if defined(TNB_EMU)
+  unsigned long long u;
+  std::memcpy(&u, &x, 8);
+  return int((u >> 52) & 0x7ffu);
+#else
+  return (__double2hiint(x) >> 20) & 0x7ff;
+#endif
+}
 
 // Sum of all contraction costs of a chain (production mode keeps no partial-cost cache: the running total is
 // re-based on this exact-as-possible sum every few sweeps, like the reference re-reads partial_cost.back()
@@ -1225,7 +1234,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   long long s = P.sweep_idx[chain];
   double min_total = P.min_total[chain];
   bool rebase = true;
-  unsigned long long n_prop = 0, n_acc = 0, n_wrej = 0;  // folded from the 32-bit per-sweep counters below
+  // 32-bit counters, folded into the 64-bit ones in memory every 256 sweeps (keeps six registers free)
   uint32_t q_prop = 0, q_acc = 0, q_wrej = 0;
   uint32_t S[WPL];
 #pragma unroll
@@ -1246,11 +1255,16 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   for (int k = 0; k < WPL; ++k) b0[k] = b1[k] = bC[k] = bA[k] = hA[k] = hB[k] = 0u;
   double pc0 = 0.0, pc1 = 0.0, pcC = 0.0, ccA = 0.0, ccB = 0.0, total = 0.0, root_pc = 0.0, beta = 0.0;
   float inv_beta_f = 0.f;
+  int kmax = 0;  // largest (biased) exponent the running total had since it was last re-summed
 
   // Two copies of the loop body for the unconstrained kernels: the rotation of the loop-carried registers (a fifth
   // of a level's instructions were MOVs) then happens by renaming.  (The finite-width kernel, with the re-slicer in
   // its boundary branch, loses a third of its speed to the doubled body.)
   constexpr int kUnroll = FINITE ? 1 : 2;
+  if (!PC && s < P.until) {  // the running total starts from the exact sum of the contraction costs
+    total = sum_ccost(c);
+    kmax = exp_of(total);
+  }
   uint32_t iteration = 0;
 #pragma unroll kUnroll
   while (true) {
@@ -1271,6 +1285,8 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
 #pragma unroll
               for (int k = 0; k < WPL; ++k) diff |= S2[k] != S[k];
               if (t.any(diff)) {  // same slices -> same costs: nothing to decide
+                total = sum_ccost(c);  // the decision compares exact sums
+                kmax = exp_of(total);
                 if (DIM2 && !HYPER && P.n_inds <= 1000) {
                   int* dz = reinterpret_cast<int*>(P.wkey + size_t(chain) * P.Npad);
                   const int shift0 = mark_slice_diff(c, S, S2, dz, P.word + size_t(chain) * P.Npad);
@@ -1317,15 +1333,34 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
             }
           }
         }
-        if (!PC) root_pc = total;
+        if (!PC) {
+          // The running total is accurate only while nothing much larger than it has passed through it: a chain
+          // that wandered up to 2^110 at small beta and came back carries the rounding of the large terms (absolute
+          // error ~ 2^(kmax-52) per addition), up to a total of the wrong sign -- which would then be recorded as a
+          // minimum that nothing can beat.  kmax is the largest exponent the total had since it was last re-summed;
+          // re-sum whenever the total fell more than 2^10 below it, when it is not positive, and every 64 sweeps
+          // regardless: the relative error of the total, and of min_total, stays below ~1e-10.  (The reference sums
+          // positive partial costs and has no cancellation at all.  This is the only re-summation inside the loop:
+          // more inlined copies of sum_ccost in the unrolled body cost more than they save.)
+          const int et = exp_of(total);
+          if (!(total > 0.0) || kmax - et > 10 || ((s + 1) & 63) == 0) {
+            total = sum_ccost(c);
+            kmax = exp_of(total);
+          }
+          root_pc = total;
+        }
         if (root_pc < min_total) {  // infinite_memory/optimizer.hpp:197-201
           min_total = root_pc;
           snapshot_best(c, S, FINITE);
         }
         ++s;
         in_sweep = false;
-        n_prop += q_prop; n_acc += q_acc; n_wrej += q_wrej;
-        q_prop = q_acc = q_wrej = 0;
+        if ((s & 255) == 0) {
+          P.n_prop[chain] += q_prop;
+          P.n_acc[chain] += q_acc;
+          if (FINITE) P.n_wrej[chain] += q_wrej;
+          q_prop = q_acc = q_wrej = 0;
+        }
         if (rng.overrun()) break;
       }
       if (s >= P.until || !rng.can_start(P)) break;
@@ -1338,12 +1373,8 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       const uint32_t lw = rng.leaf_word(t);
       const int leaf = Rng::kFast ? int(mulhi32(lw, uint32_t(n))) : int(lw % uint32_t(n));
       B = c.par[leaf];
-      if (PC) {
-        total = c.pcv[root];                             // :112
-      } else if (rebase || (s & 63) == 0) {
-        total = sum_ccost(c);
-        rebase = false;
-      }
+      if (PC) total = c.pcv[root];                       // :112
+      rebase = false;
       root_pc = total;
       const uint32_t cw = c.ch(B);
       p0 = int(cw & 0xffffu);
@@ -1464,6 +1495,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         nB = c.cost_of(int(kpack >> 16));      // cost(D | C [| slices])
       }
       delta = (nB - ccB) + (nA - ccA);       // :158, this association order
+
       if (Rng::kFast && f_prob == kProbMH) {
         // same rule as prob/mh.hpp:45-59, solved for the move: u <= (1 + delta/total)^-beta
         //   <=>  delta <= (2^(-log2(u)/beta) - 1) * total.
@@ -1514,6 +1546,10 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       ccB = nB;
       ccA = nA;
       total += delta;
+      if (!PC) {  // largest exponent of the running total since it was last re-summed (see the sweep boundary)
+        const int e_now = exp_of(total);
+        kmax = e_now > kmax ? e_now : kmax;
+      }
       ++q_acc;
       if (FS) {
         kwp[B] = int16_t(ku);
@@ -1591,9 +1627,9 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   P.sweep_idx[chain] = s;
   P.min_total[chain] = min_total;
   P.total[chain] = PC ? c.pcv[root] : (rebase ? P.total[chain] : total);
-  P.n_prop[chain] += n_prop;
-  P.n_acc[chain] += n_acc;
-  P.n_wrej[chain] += n_wrej;
+  P.n_prop[chain] += q_prop;
+  P.n_acc[chain] += q_acc;
+  P.n_wrej[chain] += q_wrej;
 }
 
 }  // namespace tnb
