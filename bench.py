@@ -294,7 +294,7 @@ def run_ours(args):
         opt = Optimizer(method='sa', seed=1000 + i, max_width=mw)
         tdist.barrier()
         t0 = time.perf_counter()
-        tn, res = opt.optimize(rows, betas=(0, 100), n_steps=S, n_runs=C * world)
+        tn, res = opt.optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=S, n_runs=C * world)
         dt = tdist.all_reduce_max(time.perf_counter() - t0)
         if i >= args.e2e_warmup:
             e2e_props += tdist.all_reduce_sum(opt.last_stats['proposals'])
@@ -331,7 +331,7 @@ def run_ours(args):
                             state_bytes_per_chain=cfg['state_bytes_per_chain'], parallelism=f'chains sharded x{world}'),
                 clocks=clk.summary(),
                 e2e=dict(value=e2e_props / max(e2e_s, 1e-9), unit='proposals/s', h2d_bytes_per_step=h2d,
-                         d2h_bytes_per_step=d2h, api="Optimizer(method='sa').optimize(rows, betas=(0,100), n_steps, n_runs)",
+                         d2h_bytes_per_step=d2h, api="Optimizer(method='sa').optimize(rows, betas=(0,100), fuse=False, n_steps, n_runs)",
                          last_step_ms=e2e_parts),
                 gpu_launches=launches,
                 roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,

@@ -23,7 +23,7 @@ for rep in range(3):
     pr = cProfile.Profile()
     t0 = time.perf_counter()
     pr.enable()
-    tn, res = opt.optimize(rows, betas=(0, 100), n_steps=n_steps, n_runs=n_runs)
+    tn, res = opt.optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=n_steps, n_runs=n_runs)
     pr.disable()
     dt = time.perf_counter() - t0
     st = opt.last_stats

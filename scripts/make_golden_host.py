@@ -1,0 +1,82 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/host_fuse.json from the UNMODIFIED reference Python layer (/root/reference/tnco), imported
+here with the stand-ins of scripts/ref_shims for the packages this image lacks.  Build container only; the
+fixture is committed so machines without /root/reference can check tnco_b200's host-side pre-processing
+(`fuse`, structure-only `contract`, `load_tn(..., fuse=...)`) against outputs of the real reference.
+
+Index names are strings 'i<k>'.  With several hyper-indices on one merged tensor the reference orders them by
+frozenset iteration, i.e. by the per-process string hash; PYTHONHASHSEED is pinned to 0 while generating and
+the test compares such index tuples as sets.
+"""
+import json
+import os
+import sys
+import warnings
+
+if os.environ.get('PYTHONHASHSEED') != '0':
+    os.environ['PYTHONHASHSEED'] = '0'
+    os.execv(sys.executable, [sys.executable] + sys.argv)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, 'scripts', 'ref_shims'), '/root/reference', os.path.join(ROOT, 'oracle', '_ref'),
+                ROOT, os.path.join(ROOT, 'tests')]
+
+import tnco.app.app as ref_app  # noqa: E402
+import tnco.utils.tn as ref_tn  # noqa: E402
+from helpers import hyper_network, regular_network  # noqa: E402
+from tnco.app.tn import Tensor as RefTensor  # noqa: E402
+from tnco.app.tn import TensorNetwork as RefTN  # noqa: E402
+
+from tnco_b200 import networks  # noqa: E402
+
+
+def name(ts):
+    return [['i%d' % x for x in xs] for xs in ts]
+
+
+def cases():
+    # name, ts_inds, output_inds (None: dangling), dims (int or per-index list), max_width, seed
+    ts, ni = regular_network(24, 1)
+    yield 'reg24_w4', name(ts), None, 2, 4, 0
+    yield 'reg24_w6', name(ts), None, 2, 6, 5
+    ts, ni = regular_network(64, 2)
+    yield 'reg64_w4', name(ts), None, 2, 4, 1
+    yield 'reg64_w7_d3', name(ts), None, 3, 7, 2
+    yield 'reg64_mixed', name(ts), None, {('i%d' % k): (2, 4, 8)[k % 3] for k in range(ni)}, 5, 3
+    ts, ni = networks.grid_rqc(4, 4, 8)
+    yield 'grid4x4_w4', name(ts), None, 2, 4, 4
+    yield 'grid4x4_w8', name(ts), None, 2, 8, 6
+    ts, ni, out = hyper_network(32, 3)
+    yield 'hyper32_w4', name(ts), ['i%d' % x for x in out], 2, 4, 7
+    ts, ni, out = hyper_network(64, 5, n_hyper=10, n_open=5)
+    yield 'hyper64_w5', name(ts), ['i%d' % x for x in out], 2, 5, 8
+    ts, ni = networks.grid_rqc(6, 6, 12)
+    yield 'c2_w4', name(ts), None, 2, 4, 9
+
+
+def main():
+    out = {}
+    warnings.simplefilter('ignore')
+    for nm, ts, outs, dims, mw, seed in cases():
+        path, fused = ref_tn.fuse(ts, dims, max_width=mw, output_inds=outs, seed=seed, return_fused_inds=True)
+        c_ts, c_out = ref_tn.contract(path, ts, outs, dims=dims)
+        all_inds = list(dict.fromkeys(x for xs in ts for x in xs))
+        d = dims if isinstance(dims, dict) else {x: dims for x in all_inds}
+        tn = RefTN((RefTensor(xs, [d[x] for x in xs], tags=dict(name=k)) for k, xs in enumerate(ts)),
+                   output_inds=outs)
+        ltn = ref_app.load_tn(tn, fuse=mw, seed=seed)
+        out[nm] = dict(ts_inds=ts, output_inds=outs, dims=dims, max_width=mw, seed=seed,
+                       path=[list(p) for p in path], fused_inds=[list(x) for x in fused],
+                       contracted_ts_inds=[list(x) for x in c_ts], contracted_output_inds=sorted(c_out),
+                       load_tn=dict(ts_inds=[list(x) for x in ltn.ts_inds], ts_dims=[list(t.dims) for t in ltn],
+                                    output_inds=sorted(ltn.output_inds), ts_tags=list(ltn.ts_tags),
+                                    fuse_path=[list(p) for p in ltn.tags['fuse_path']]))
+        print(nm, len(ts), '->', len(c_ts), 'tensors,', len(path), 'merges')
+    # the reference's own doctest (tnco/utils/tn.py:636-641)
+    assert ref_tn.fuse([['i', 'j'], ['j', 'k'], ['k', 'l']], 2, max_width=2, seed=42) == [(0, 1), (0, 1)]
+    with open(os.path.join(ROOT, 'tests', 'golden', 'host_fuse.json'), 'w') as f:
+        json.dump(out, f, separators=(',', ':'))
+
+
+if __name__ == '__main__':
+    main()

@@ -78,11 +78,11 @@ def test_argument_errors(backend):
     rows = index_rows(ts, ni)
     opt = Optimizer(seed=1)
     with pytest.raises(ValueError):
-        opt.optimize(rows, betas=(0, 100))
+        opt.optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False)
     with pytest.raises(ValueError):
-        opt.optimize(rows, betas=(1, 1), n_steps=10)
+        opt.optimize(rows, betas=(1, 1), fuse=False, decompose_hyper_inds=False, n_steps=10)
     with pytest.raises(ValueError):
-        opt.optimize(rows, betas=(0, 100), n_steps=-1)
+        opt.optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=-1)
     with pytest.raises(TypeError):
         opt.optimize(object(), betas=(0, 100), n_steps=10)
 
@@ -93,7 +93,7 @@ def test_optimize_tn(backend, max_width):
     ts, ni = regular_network(30, 5)
     rows = index_rows(ts, ni)
     opt = Optimizer(seed=7, max_width=max_width)
-    tn, res = opt.optimize(rows, betas=(0, 100), n_steps=100, n_runs=4)
+    tn, res = opt.optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=100, n_runs=4)
     assert len(tn) == 30 and len(res) == 4
     # sorted by cost (test_app.py:229,278-279)
     assert [r.cost for r in res] == sorted(r.cost for r in res)
@@ -113,12 +113,35 @@ def test_optimize_tn(backend, max_width):
         if max_width is not None:
             assert frozenset(js['slices']) == r.slices
     # same seed => same results (tests/test_determinism.sh)
-    tn2, res2 = Optimizer(seed=7, max_width=max_width).optimize(rows, betas=(0, 100), n_steps=100, n_runs=4)
+    tn2, res2 = Optimizer(seed=7, max_width=max_width).optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=100, n_runs=4)
     assert [r.path for r in res] == [r.path for r in res2] and [r.cost for r in res] == [r.cost for r in res2]
-    out = Optimizer(seed=7, max_width=max_width, output_format='json').optimize(rows, betas=(0, 100), n_steps=20,
+    out = Optimizer(seed=7, max_width=max_width, output_format='json').optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=20,
                                                                                  n_runs=2)
     js = json.loads(out)
     assert len(js['res']) == 2 and len(js['tn']['tensors']) == 30
+
+
+@pytest.mark.parametrize('max_width', [None, 8])
+def test_optimize_with_default_load_tn_options(backend, max_width):
+    """Default arguments as a user of the reference calls it: load_tn pre-merges tensors (fuse=4, app.py:156) and the
+    results refer to the returned, fused network; 'fuse_path' maps it back (app.py:410-414)."""
+    import warnings
+
+    from tnco_b200.app import Optimizer, load_tn
+    ts, ni = regular_network(40, 6)
+    rows = index_rows(ts, ni)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        tn, res = Optimizer(seed=11, max_width=max_width).optimize(rows, betas=(0, 100), n_steps=100, n_runs=3)
+        want = load_tn(rows, seed=11)
+    assert tn.ts_inds == want.ts_inds and tn.tags['fuse_path'] == want.tags['fuse_path']
+    assert len(tn) == 40 - len(tn.tags['fuse_path']) < 40
+    assert all(len(t.inds) <= 4 for t in tn)
+    for r in res:
+        assert len(r.path) == len(tn) - 1
+        sl = r.slices if max_width is not None else frozenset()
+        c = replay_cost(r.path, tn.ts_inds, sl, max_width)
+        assert abs(math.log2(c) - math.log2(float(r.cost))) < 1e-4
 
 
 def test_disconnected_components(backend):
@@ -131,7 +154,7 @@ def test_disconnected_components(backend):
     random.Random(0).shuffle(order)
     ts = [ts[i] for i in order]
     rows = index_rows(ts, n1 + n2 + 1)
-    tn, res = Optimizer(seed=2).optimize(rows, betas=(0, 50), n_steps=50, n_runs=3)
+    tn, res = Optimizer(seed=2).optimize(rows, betas=(0, 50), fuse=False, decompose_hyper_inds=False, n_steps=50, n_runs=3)
     for r in res:
         assert len(r.disconnected_paths) == 3 and len(r.path) == len(ts) - 1
         assert sorted(len(p) for p in r.disconnected_paths) == [0, 7, 11]
@@ -164,7 +187,7 @@ def test_mt19937_rng_reproduces_reference_runs(backend):
     ts, ni = regular_network(24, 9)
     rows = index_rows(ts, ni)
     opt = Optimizer(seed=11, rng='mt19937', tree_builder='host')  # same initial trees as random_trees below
-    tn, res = opt.optimize(rows, betas=(0, 100), n_steps=200, n_runs=3)
+    tn, res = opt.optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=200, n_runs=3)
     seeds = random.Random(11).choices(range(2**32), k=3)
     inds = list(dict.fromkeys(x for xs in tn.ts_inds for x in xs))
     pos = {x: k for k, x in enumerate(inds)}
@@ -194,7 +217,7 @@ def test_hyper_index_network_through_the_app(backend, max_width):
     rows = index_rows(ts, ni)
     for x in out:
         rows[x].append('*')
-    tn, res = Optimizer(seed=5, max_width=max_width).optimize(rows, betas=(0, 100), n_steps=150, n_runs=6)
+    tn, res = Optimizer(seed=5, max_width=max_width).optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=150, n_runs=6)
     assert len(res) == 6 and [r.cost for r in res] == sorted(r.cost for r in res)
     for r in res:
         hc = dict(get_hyper_count(tn.ts_inds))
@@ -231,7 +254,7 @@ def test_per_index_dims_through_the_app(backend, max_width):
     rows = index_rows(ts, ni)
     for i, d in enumerate(dims):
         rows[i][0] = d
-    tn, res = Optimizer(seed=3, max_width=max_width).optimize(rows, betas=(0, 100), n_steps=150, n_runs=5)
+    tn, res = Optimizer(seed=3, max_width=max_width).optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=150, n_runs=5)
     assert [r.cost for r in res] == sorted(r.cost for r in res)
     for r in res:
         slices = frozenset(r.slices) if max_width is not None else frozenset()
@@ -249,4 +272,4 @@ def test_per_index_dims_through_the_app(backend, max_width):
         assert abs(math.log2(total) - math.log2(float(r.cost))) < 1e-4
     with pytest.raises(NotImplementedError, match='power'):
         rows[0][0] = 3
-        Optimizer(seed=3).optimize(rows, betas=(0, 100), n_steps=5, n_runs=1)
+        Optimizer(seed=3).optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=5, n_runs=1)

@@ -35,7 +35,7 @@ for t, xs in enumerate(ts):
     for x in xs:
         rows[x].append('t%d' % t)
 opt = Optimizer(seed=9, max_width={mw}, sync_every=20)
-tn, res = opt.optimize(rows, betas=(0, 100), n_steps=60, n_runs=6)
+tn, res = opt.optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=60, n_runs=6)
 out = dict(rank=rank, world=world, best=best, payload=payload.tolist(), owner=owner, gathered=rows_all.ravel().tolist(),
            costs=[str(r.cost) for r in res], paths=[r.path for r in res],
            slices=[sorted(r.slices) for r in res] if {mw} is not None else None,

@@ -172,13 +172,82 @@ def test_beta_ramp_and_seeds_follow_the_reference_driver():
 
 def test_load_tn_subset():
     from tnco_b200.app import TensorNetwork, load_tn
-    tn = load_tn([[2, 'a', 'b'], [2, 'b', 'c'], [3, 'c', '*']])
+    tn = load_tn([[2, 'a', 'b'], [2, 'b', 'c'], [3, 'c', '*']], fuse=False)
     assert len(tn) == 3 and tn.output_inds == frozenset({2}) and dict(tn.dims) == {0: 2, 1: 2, 2: 3}
     assert [t.tags['name'] for t in tn] == ['a', 'b', 'c']
-    tn2 = load_tn('# comment\n2 a b\n2  b c\n3 c *\n')
+    tn2 = load_tn('# comment\n2 a b\n2  b c\n3 c *\n', fuse=False)
     assert tn2.ts_inds == tn.ts_inds and isinstance(tn2, TensorNetwork)
-    assert load_tn(tn) is tn
+    assert load_tn(tn, fuse=False) is tn
     with pytest.raises(TypeError):
         load_tn(42)
-    with pytest.raises(NotImplementedError):
-        load_tn([[2, 'a', 'b']], fuse=4)
+    with pytest.raises(TypeError):
+        load_tn(tn, no_such_option=1)
+    # sparse indices switch fusing off, with the reference's warning (tnco/app/app.py:322-326)
+    with pytest.warns(UserWarning, match='sparse indices'):
+        tn3 = load_tn([[2, 'a', 'b', '/'], [2, 'b', 'c']])
+    assert len(tn3) == 3 and tn3.sparse_inds == frozenset({0})
+
+
+def _golden_fuse():
+    import json
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'host_fuse.json')) as f:
+        return json.load(f)
+
+
+def _same_inds(got, want, hyper):
+    """Index tuples of merged tensors; with hyper-indices the reference orders several of them by string hash."""
+    got, want = [tuple(x) for x in got], [tuple(x) for x in want]
+    if not hyper:
+        return got == want
+    return len(got) == len(want) and all(len(g) == len(w) and set(g) == set(w) for g, w in zip(got, want))
+
+
+@pytest.mark.parametrize('name', sorted(_golden_fuse()))
+def test_fuse_contract_load_tn_match_the_reference(name):
+    """tests/golden/host_fuse.json holds outputs of the unmodified reference (scripts/make_golden_host.py):
+    tnco.utils.tn.fuse / contract and tnco.app.load_tn(fuse=...) for the same seed."""
+    import warnings
+
+    from tnco_b200.app import Tensor, TensorNetwork, load_tn
+    from tnco_b200.tn import contract, fuse
+    g = _golden_fuse()[name]
+    hyper = g['output_inds'] is not None
+    path, fused = fuse(g['ts_inds'], g['dims'], max_width=g['max_width'], output_inds=g['output_inds'],
+                       seed=g['seed'], return_fused_inds=True)
+    assert [list(p) for p in path] == g['path']
+    assert _same_inds(fused, g['fused_inds'], hyper)
+    c_ts, c_out = contract(path, g['ts_inds'], g['output_inds'], dims=g['dims'])
+    assert _same_inds(c_ts, g['contracted_ts_inds'], hyper) and sorted(c_out) == g['contracted_output_inds']
+    inds = list(dict.fromkeys(x for xs in g['ts_inds'] for x in xs))
+    d = g['dims'] if isinstance(g['dims'], dict) else {x: g['dims'] for x in inds}
+    tn = TensorNetwork((Tensor(xs, [d[x] for x in xs], tags=dict(name=k)) for k, xs in enumerate(g['ts_inds'])),
+                       output_inds=g['output_inds'])
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ltn = load_tn(tn, fuse=g['max_width'], seed=g['seed'])
+    want = g['load_tn']
+    assert _same_inds(ltn.ts_inds, want['ts_inds'], hyper)
+    assert sorted(ltn.output_inds) == want['output_inds']
+    assert [list(p) for p in ltn.tags['fuse_path']] == want['fuse_path']
+    assert list(ltn.ts_tags) == want['ts_tags']
+    if not hyper:
+        assert [list(t.dims) for t in ltn] == want['ts_dims']
+
+
+def test_fuse_known_answers_and_errors():
+    from tnco_b200.tn import contract, fuse
+    # the reference's doctests (tnco/utils/tn.py:636-641, 939-948)
+    assert fuse([['i', 'j'], ['j', 'k'], ['k', 'l']], {'i': 2, 'j': 2, 'k': 2, 'l': 2}, max_width=2, seed=42) == \
+        [(0, 1), (0, 1)]
+    assert contract([(0, 1)], [['i', 'j'], ['j', 'k']], dims=2)[0] == [('i', 'k')]
+    assert fuse([['i', 'j'], ['j', 'k']], 2, max_width=4, exclude_inds=['j'], seed=0) == []
+    with pytest.raises(ValueError):
+        fuse([['i', 'j'], ['j', 'k']], 2, max_width=4, exclude_inds=['z'])
+    with pytest.raises(ValueError):
+        fuse([['i', 'j'], ['j', 'k'], ['j']], 2, max_width=4)          # hyper-index without output_inds
+    with pytest.raises(ValueError):
+        fuse([['i', 'j'], ['j', 'k']], {'i': 2}, max_width=4)
+    with pytest.raises(ValueError):
+        contract([(0, 0)], [['i', 'j'], ['j', 'k']], dims=2)
+    with pytest.raises(ValueError):
+        contract([(0, 1)], [['i', 'j'], ['j', 'k']])

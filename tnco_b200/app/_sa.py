@@ -144,8 +144,6 @@ def _comp_slices(pc, r):
 
 def optimize(opt, results_cls, tn, betas, n_steps, n_runs, n_projs, update_slices, timeout, finite,
              load_tn_options):
-    load_tn_options.setdefault('fuse', False)
-    load_tn_options.setdefault('decompose_hyper_inds', False)
     tn = opt._load_tn(tn, **load_tn_options)
     if tn.sparse_inds or n_projs is not None:
         raise NotImplementedError('tnco_b200: sparse indices / n_projs are not supported yet.')

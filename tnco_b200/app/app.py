@@ -2,8 +2,8 @@
 
 Mirrors tnco/app/app.py: ``BaseOptimizer`` (:715-795, same dataclass fields, plus engine knobs appended with
 defaults), ``BaseContractionResults`` (:64-94), ``dump_results`` (:573-712) and the structure-only subset of
-``load_tn`` (:154-570: TensorNetwork objects, lists / strings of indices).  Circuit front-ends, fusing and
-hyper-index decomposition are out of scope.
+``load_tn`` (:154-570: TensorNetwork objects, lists / strings of indices, index-level ``fuse``).  Circuit front-ends
+and hyper-index decomposition (both need tensor data) are out of scope.
 """
 from __future__ import annotations
 
@@ -18,8 +18,11 @@ from decimal import Decimal
 from pathlib import Path
 from random import Random
 from typing import Any
+from warnings import warn
 
 from ..tn import Tensor, TensorNetwork, read_inds
+from ..tn import contract as tn_contract
+from ..tn import fuse as tn_fuse
 
 __all__ = ['BaseOptimizer', 'BaseContractionResults', 'load_tn', 'dump_results', 'JSONEncoder']
 
@@ -118,23 +121,45 @@ def cost_to_decimal(x: float) -> Decimal:
 
 
 def load_tn(obj: Any, *, output_index_token: str = '*', sparse_index_token: str = '/', **options) -> TensorNetwork:
-    """Structure-only ``load_tn``: TensorNetwork, list of ``(dim, tensor names...)`` rows, or the same as text.
+    """Structure-only ``load_tn`` (tnco/app/app.py:154-570): TensorNetwork, list of ``(dim, tensor names...)`` rows
+    (one row per index), or the same as text.  As in the reference, tensors are pre-merged (``fuse=4``: while the
+    merged tensor has width <= 4) unless ``fuse=False``; ``decompose_hyper_inds`` needs arrays and is a no-op here.
 
-    >>> tn = load_tn([[2, 'i', 'j'], [2, 'j', 'k']])
+    >>> tn = load_tn([[2, 'i', 'j'], [2, 'j', 'k']], fuse=False)
     >>> len(tn)
     3
+    >>> load_tn([[2, 'i', 'j'], [2, 'j', 'k']], fuse=4, decompose_hyper_inds=False, seed=0).tags['fuse_path']
+    [(0, 1), (0, 1)]
     """
-    fuse = options.pop('fuse', False)
-    decompose = options.pop('decompose_hyper_inds', False)
-    for k in ('simplify_circuit', 'initial_state', 'final_state', 'atol', 'dtype', 'backend', 'seed', 'verbose'):
-        options.pop(k, None)
-    if options:
-        raise TypeError('Got unexpected keyword arguments: {}'.format(sorted(options)))
-    if fuse not in (False, None, 0) or decompose not in (False, None):
-        raise NotImplementedError("tnco_b200 does not pre-process tensors: pass fuse=False, "
-                                  "decompose_hyper_inds=False (numeric front-end is out of scope).")
     if isinstance(obj, TensorNetwork):
-        return obj
+        fuse = options.pop('fuse', 4)
+        decompose = options.pop('decompose_hyper_inds', True)
+        seed = options.pop('seed', None)
+        for k in ('simplify_circuit', 'initial_state', 'final_state', 'atol', 'dtype', 'backend', 'verbose'):
+            options.pop(k, None)
+        if options:
+            raise TypeError('Got unexpected keyword arguments: {}'.format(sorted(options)))
+        ts_inds, dims, tags, ts_tags = list(obj.ts_inds), obj.dims, dict(obj.tags), list(obj.ts_tags)
+        output_inds, sparse_inds = obj.output_inds, obj.sparse_inds
+        if sparse_inds:  # app.py:322-326
+            warn('The decomposition of hyper-indices and the fusion of indices is not yet supported if there are '
+                 'sparse indices')
+            decompose = fuse = False
+        if decompose:  # app.py:330-335: needs the arrays, which a structure-only network never has
+            warn('Cannot decompose hyper-indices if not all arrays are provided.')
+        if fuse is not None and fuse > 0:  # app.py:373-414
+            path = tn_fuse(ts_inds, dims, max_width=fuse, output_inds=output_inds, seed=seed)
+            ts_inds, output_inds = tn_contract(path, ts_inds, output_inds, dims=dims)
+            for px, py in map(sorted, path):
+                ty, tx = ts_tags.pop(py), ts_tags.pop(px)
+                ts_tags.append((tx or None) if not ty else ty if not tx else dict(x=tx, y=ty))
+            if 'fuse_path' in tags:
+                raise ValueError("'TensorNetwork' has already the tag 'fuse_path'.")
+            tags['fuse_path'] = path
+        else:
+            return obj
+        return TensorNetwork((Tensor(xs, [dims[x] for x in xs], tags=t) for xs, t in zip(ts_inds, ts_tags)),
+                             output_inds=output_inds, sparse_inds=sparse_inds, tags=tags)
     if isinstance(obj, str):
         rows = []
         for line in obj.splitlines():
@@ -145,7 +170,7 @@ def load_tn(obj: Any, *, output_index_token: str = '*', sparse_index_token: str 
                 raise TypeError("'obj' is not recognized.")
             d, *xs = line.split()
             rows.append((int(d), *xs))
-        return load_tn(rows, output_index_token=output_index_token, sparse_index_token=sparse_index_token)
+        return load_tn(rows, output_index_token=output_index_token, sparse_index_token=sparse_index_token, **options)
 
     def is_int(x):
         try:
@@ -162,9 +187,9 @@ def load_tn(obj: Any, *, output_index_token: str = '*', sparse_index_token: str 
         tensor_map, dims, output_inds, sparse_inds = read_inds(dict(enumerate(rows)),
                                                                output_index_token=output_index_token,
                                                                sparse_index_token=sparse_index_token)
-        return TensorNetwork((Tensor(xs, [dims[x] for x in xs], tags=dict(name=name))
-                              for name, xs in tensor_map.items()),
-                             output_inds=output_inds, sparse_inds=sparse_inds)
+        return load_tn(TensorNetwork((Tensor(xs, [dims[x] for x in xs], tags=dict(name=name))
+                                      for name, xs in tensor_map.items()),
+                                     output_inds=output_inds, sparse_inds=sparse_inds), **options)
     raise TypeError("'obj' is not recognized.")
 
 

@@ -6,12 +6,16 @@ Mirrors the parts of the reference that ``Optimizer.optimize`` touches:
   get_hyper_count                 tnco/utils/tn.py:572-595
   get_connected_components        tnco/utils/tn.py:61-106
   merge_contraction_paths         tnco/utils/tn.py:334-401
-Numeric pre-processing (fuse, hyper-index decomposition, circuit loading) is out of scope.
+  fuse                            tnco/utils/tn.py:598-824   (index-level pre-merge of small tensors, load_tn's default)
+  contract (structure only)       tnco/utils/tn.py:903-1075, tnco/utils/tensor.py:214-243
+Numeric pre-processing (arrays, hyper-index decomposition, circuit loading) is out of scope.
 """
 from __future__ import annotations
 
 import json
+import math
 from collections import Counter, defaultdict
+from random import Random
 from dataclasses import dataclass
 from types import MappingProxyType
 from typing import Any, Iterable
@@ -207,3 +211,132 @@ def merge_contraction_paths(n_tensors: int, paths, *, autocomplete: bool = True)
     if autocomplete:
         merged += [(0, 1)] * (len(merged_pos) - 1)
     return merged
+
+
+def _unique(xs):
+    """Order-preserving de-duplication (the reference's OrderedFrozenSet / unique_everseen)."""
+    return tuple(dict.fromkeys(xs))
+
+
+def _dims_dict(dims, all_inds):
+    try:
+        d = int(dims)
+    except (TypeError, ValueError):
+        return dict(dims)
+    return {x: d for x in all_inds}
+
+
+def fuse(ts_inds, dims, max_width, output_inds=None, *, exclude_inds=(), seed=None, return_fused_inds=False,
+         verbose=False):
+    """Random pre-merge of index-sharing tensors while the merged tensor stays within ``max_width``
+    (tnco/utils/tn.py:598-824).  Same draws from ``Random(seed)`` in the same order over the same containers, so
+    the returned path equals the reference's for the same seed (tests/golden/host_fuse.json).
+
+    >>> fuse([['i', 'j'], ['j', 'k'], ['k', 'l']], 2, max_width=2, seed=42)
+    [(0, 1), (0, 1)]
+    """
+    rng = Random(seed)
+    ts = dict(enumerate(map(tuple, ts_inds)))
+    all_inds = _unique(x for xs in ts.values() for x in xs)
+    exclude_inds = frozenset(exclude_inds)
+    if not exclude_inds.issubset(all_inds):
+        raise ValueError("'exclude_inds' contains indices not in 'ts_inds'.")
+    dims = _dims_dict(dims, all_inds)
+    if not set(all_inds).issubset(dims):
+        raise ValueError("'dims' is missing some indices.")
+    hyper_count = get_hyper_count(ts.values())
+    if output_inds is None:
+        if any(v > 1 for v in hyper_count.values()):
+            raise ValueError("'output_inds' must be provided if 'ts_inds' has hyper-indices.")
+        output_inds = (x for x, v in hyper_count.items() if v == 0)
+    output_inds = frozenset(output_inds)
+    if not output_inds.issubset(all_inds):
+        raise ValueError("'output_inds' is not consistent with 'ts_inds'.")
+    # index -> tensors holding it; the draws below iterate these sets, so they are built and updated with the very
+    # set operations of the reference (tn.py:690-697, 789-791) -- a set's iteration order depends on its history
+    index2tensors = {}
+    for t, xs in ts.items():
+        for x in xs:
+            index2tensors.setdefault(x, []).append(t)
+    index2tensors = {x: set(v) for x, v in index2tensors.items()}
+    dangling = frozenset(x for x, v in hyper_count.items() if v == 0)
+    avail = [x for x in all_inds if x not in exclude_inds and x not in dangling]
+    t_idx = len(ts)
+    merged = []
+    while avail:
+        index = avail.pop(rng.randrange(len(avail)))
+        if not hyper_count.get(index):
+            continue
+        px, py = rng.sample(tuple(index2tensors[index]), k=2)
+        tx, ty = ts[px], ts[py]
+        sx, sy = frozenset(tx), frozenset(ty)
+        if (sx | sy) & exclude_inds:
+            continue
+        shared = sx & sy
+        hyper = frozenset(x for x in shared if hyper_count[x] > 1)
+        keep = (sx ^ sy) | hyper | (output_inds & (sx | sy))
+        tz = _unique([x for x in tx if x in keep] + [y for y in ty if y in keep])
+        if sum(map(math.log2, map(dims.get, tz))) > max_width:
+            continue
+        for x in shared:
+            hyper_count[x] -= 1
+        for x in tz:
+            index2tensors[x] -= {px, py}
+            index2tensors[x] |= {t_idx}
+        for x in shared - hyper - output_inds:
+            del index2tensors[x]
+        del ts[px]
+        del ts[py]
+        ts[t_idx] = tz
+        t_idx += 1
+        if hyper_count.get(index):
+            avail.append(index)
+        merged.append((px, py, tz))
+    # SSA ids -> linear (einsum-style) positions
+    path, fused_inds, positions = [], [], list(range(t_idx))
+    for px, py, tz in merged:
+        px, py = sorted((px, py))
+        py = positions.index(py)
+        del positions[py]
+        px = positions.index(px)
+        del positions[px]
+        path.append((px, py))
+        fused_inds.append(tz)
+    return (path, fused_inds) if return_fused_inds else path
+
+
+def contract(path, ts_inds, output_inds=None, *, dims=None):
+    """Index bookkeeping of a linear contraction path (tnco/utils/tn.py:903-1075 with ``arrays=None``): returns
+    ``(ts_inds, output_inds)`` after the path.  Result indices are ordered as ``tensordot`` orders them
+    (tnco/utils/tensor.py:229-243): hyper-indices first, then x's own, then y's own.
+
+    >>> contract([(0, 1)], [['i', 'j'], ['j', 'k']], dims=2)
+    ([('i', 'k')], frozenset({'i', 'k'}))
+    """
+    if dims is None:
+        raise ValueError("Either 'dims' or 'arrays' must be provided.")
+    ts = list(map(tuple, ts_inds))
+    try:
+        int(dims)
+    except (TypeError, ValueError):
+        if not frozenset(dims).issuperset(x for xs in ts for x in xs):
+            raise ValueError("'ts_inds' has indices not in 'dims'.")
+    hyper_count = get_hyper_count(ts)
+    if output_inds is None:
+        if any(v > 1 for v in hyper_count.values()):
+            raise ValueError("'output_inds' must be provided if 'ts_inds' has hyper-indices.")
+        output_inds = (x for x, v in hyper_count.items() if v == 0)
+    output_inds = frozenset(output_inds)
+    if not output_inds.issubset(x for xs in ts for x in xs):
+        raise ValueError("'output_inds' is not consistent with 'ts_inds'.")
+    for x, y in map(sorted, path):
+        if x == y:
+            raise ValueError("'path' is not valid.")
+        ys = ts.pop(y)
+        xs = ts.pop(x)
+        shared = frozenset(xs) & frozenset(ys)
+        hyper = frozenset(i for i in shared if hyper_count[i] > 1) | (output_inds & shared)
+        for i in shared:
+            hyper_count[i] -= 1
+        ts.append(_unique([*hyper, *(i for i in xs if i not in shared), *(i for i in ys if i not in shared)]))
+    return ts, output_inds.intersection(x for xs in ts for x in xs)
