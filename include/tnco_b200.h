@@ -108,6 +108,15 @@ int tnb_set_output_inds(tnb_engine* e, const uint32_t* output_bits);
 /* 1 if the current network + output indices have hyper-indices */
 int tnb_is_hyper(tnb_engine* e);
 
+/* Sparse-index cost model (SimpleCostModelSparseInds: include/tnco/optimize/infinite_memory/cost_model/
+ * simple_sparse_inds.hpp:38-86 and finite_width/cost_model/simple_sparse_inds.hpp:38-157; what
+ * tnco.app's optimize(..., n_projs=) selects when the network has sparse indices):
+ *   cost  = get_cost(inds - sparse) * min(get_cost(inds & sparse), n_projs)
+ *   width = get_width(inds - sparse) + min(get_width(inds & sparse), log2(n_projs))      (float32)
+ * sparse_bits [W32] or NULL to return to the simple model; n_projs > 0.  Call after tnb_set_network; drops the
+ * chains.  With max_width the stream kernels serve it (TNB_RNG_MT19937 / TNB_RNG_REPLAY). */
+int tnb_set_sparse_inds(tnb_engine* e, const uint32_t* sparse_bits, uint64_t n_projs);
+
 /* max_width < 0 or +inf: unconstrained (infinite_memory optimizer).  Otherwise the memory-constrained
  * optimizer with float32 width arithmetic (tnco/app/app.py:757) and the greedy slicer, re-slicing on
  * sweeps s with s % update_slices_every == 0 (tnco/app/finite_width/sa.py:228). */

@@ -99,6 +99,8 @@ struct ora_chain {
   uint64_t dim;       /* uniform dim when dims == NULL */
   uint64_t* dims;     /* per-index dims or NULL */
   float max_width;    /* width_type = float32 (tnco/app/app.py:757) */
+  uint32_t* sparse;   /* [W] sparse indices (SimpleCostModelSparseInds) or NULL */
+  uint64_t n_projs;
   int32_t *par, *c0, *c1;
   uint32_t *bits, *hyper; /* [N][W] */
   double *cc, *pc;        /* contraction_cost, partial_cost */
@@ -119,7 +121,7 @@ static inline int popc_w(const uint32_t* a, int W) {
 }
 
 /* infinite_memory/cost_model/simple.hpp:38-54 get_cost(inds, dims) */
-static double cost_of(const ora_chain* c, const uint32_t* u) {
+static double cost_plain(const ora_chain* c, const uint32_t* u) {
   if (!c->dims) return pow((double)c->dim, (double)popc_w(u, c->W));
   double r = 1.0;
   for (int w = 0; w < c->W; ++w) {
@@ -133,7 +135,18 @@ static double cost_of(const ora_chain* c, const uint32_t* u) {
   return r;
 }
 
-/* contraction_cost(in1,in2,out,dims[,slices]) = get_cost(in1|in2[|slices]) (simple.hpp:66-83; fw :114-136) */
+/* infinite_memory/cost_model/simple_sparse_inds.hpp:38-49:
+ *   get_cost(inds - sparse) * min(get_cost(inds & sparse), n_projs),  min(x, y) = x < y ? x : y in cost_type */
+static double cost_of(const ora_chain* c, const uint32_t* u) {
+  if (!c->sparse) return cost_plain(c, u);
+  uint32_t d[c->W], s[c->W];
+  for (int i = 0; i < c->W; ++i) { d[i] = u[i] & ~c->sparse[i]; s[i] = u[i] & c->sparse[i]; }
+  const double x = cost_plain(c, s), y = (double)c->n_projs;
+  return cost_plain(c, d) * (x < y ? x : y);
+}
+
+/* contraction_cost(in1,in2,out,dims[,slices]) = get_cost(in1|in2[|slices]) (simple.hpp:66-83; fw :114-136;
+ * sparse: simple_sparse_inds.hpp:69-86, fw :136-157) */
 static double ccost_of(const ora_chain* c, const uint32_t* a, const uint32_t* b, const uint32_t* s) {
   uint32_t u[c->W];
   for (int i = 0; i < c->W; ++i) u[i] = a[i] | b[i] | (s ? s[i] : 0u);
@@ -141,7 +154,7 @@ static double ccost_of(const ora_chain* c, const uint32_t* a, const uint32_t* b,
 }
 
 /* finite_width/cost_model/simple.hpp:39-58 get_width<float> */
-static float width_of(const ora_chain* c, const uint32_t* u) {
+static float width_plain(const ora_chain* c, const uint32_t* u) {
   if (!c->dims) return (float)(log2((double)c->dim) * (double)popc_w(u, c->W));
   float wd = 0.0f;
   for (int w = 0; w < c->W; ++w) {
@@ -153,6 +166,17 @@ static float width_of(const ora_chain* c, const uint32_t* u) {
     }
   }
   return wd;
+}
+
+/* min(x, y) of finite_width/cost_model/simple_sparse_inds.hpp:43-45: x float, y = log2(n_projs) double */
+static float min_w(float x, double y) { return (double)x < y ? x : (float)y; }
+
+/* finite_width/cost_model/simple_sparse_inds.hpp:38-49 get_width<float> */
+static float width_of(const ora_chain* c, const uint32_t* u) {
+  if (!c->sparse) return width_plain(c, u);
+  uint32_t d[c->W], s[c->W];
+  for (int i = 0; i < c->W; ++i) { d[i] = u[i] & ~c->sparse[i]; s[i] = u[i] & c->sparse[i]; }
+  return width_plain(c, d) + min_w(width_plain(c, s), log2((double)c->n_projs));
 }
 
 /* utils.hpp:35-52 traverse: post-order, children[0] subtree first; writes node ids to `order` */
@@ -269,7 +293,16 @@ static void get_slices(ora_chain* c, uint32_t* out) {
       /* get_delta_width: (1 - 2*test(pos)) * log2(dim) as float, added in float (simple.hpp:60-76) */
       const double l2 = log2((double)(c->dims ? c->dims[p] : c->dim));
       const int tst = (xs[p >> 5] >> (p & 31)) & 1;
-      sw += (float)((double)(1 - 2 * tst) * l2);
+      if (c->sparse && ((c->sparse[p >> 5] >> (p & 31)) & 1)) {
+        /* sparse index (simple_sparse_inds.hpp:51-77): min(width(new & sparse), L) - min(width(old & sparse), L) */
+        uint32_t so[W], sn[W];
+        for (int w = 0; w < W; ++w) so[w] = sn[w] = xs[w] & c->sparse[w];
+        sn[p >> 5] ^= 1u << (p & 31);
+        const double L = log2((double)c->n_projs);
+        sw += min_w(width_plain(c, sn), L) - min_w(width_plain(c, so), L);
+      } else {
+        sw += (float)((double)(1 - 2 * tst) * l2);
+      }
       xs[p >> 5] &= ~(1u << (p & 31));
       if (sw <= c->max_width) break;
     }
@@ -290,11 +323,28 @@ static void copy_min(ora_chain* c) {
 ora_chain* ora_create(int n, int n_inds, const int32_t* parent, const int32_t* child0, const int32_t* child1,
                       const uint32_t* node_bits, uint64_t dim, const uint64_t* dims, int finite,
                       float max_width, uint32_t seed, int dsi, int* err) {
+  return ora_create_sparse(n, n_inds, parent, child0, child1, node_bits, dim, dims, finite, max_width, seed, dsi,
+                           NULL, 0, err);
+}
+
+ora_chain* ora_create_sparse(int n, int n_inds, const int32_t* parent, const int32_t* child0,
+                             const int32_t* child1, const uint32_t* node_bits, uint64_t dim, const uint64_t* dims,
+                             int finite, float max_width, uint32_t seed, int dsi, const uint32_t* sparse_bits,
+                             uint64_t n_projs, int* err) {
   if (err) *err = 0;
+  if (sparse_bits && n_projs == 0) { /* "'n_projs' must be a positive number." (simple_sparse_inds.hpp:64-67) */
+    if (err) *err = 3;
+    return NULL;
+  }
   ora_chain* c = (ora_chain*)calloc(1, sizeof(ora_chain));
   const int N = 2 * n - 1, W = (n_inds + 31) / 32;
   c->n = n; c->N = N; c->n_inds = n_inds; c->W = W;
   c->finite = finite; c->dsi = dsi; c->dim = dim; c->max_width = max_width;
+  if (sparse_bits) {
+    c->sparse = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)W);
+    memcpy(c->sparse, sparse_bits, sizeof(uint32_t) * (size_t)W);
+    c->n_projs = n_projs;
+  }
   if (dims) {
     c->dims = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)W * 32);
     memset(c->dims, 0, sizeof(uint64_t) * (size_t)W * 32);
@@ -339,7 +389,7 @@ ora_chain* ora_create(int n, int n_inds, const int32_t* parent, const int32_t* c
 
 void ora_destroy(ora_chain* c) {
   if (!c) return;
-  free(c->dims); free(c->par); free(c->c0); free(c->c1); free(c->mpar); free(c->mc0); free(c->mc1);
+  free(c->sparse); free(c->dims); free(c->par); free(c->c0); free(c->c1); free(c->mpar); free(c->mc0); free(c->mc1);
   free(c->bits); free(c->hyper); free(c->mbits); free(c->cc); free(c->pc); free(c->width);
   free(c->slices); free(c->mslices);
   free(c);

@@ -36,6 +36,13 @@ CASES = [
     ('dims64_inf', 64, 13, 1500, None, False, 0, 10),
     ('dims64_fw45', 64, 14, 1200, 0.45, False, 0, 10),
     ('dimshyper48_fw50', 48, 15, 1000, 0.5, True, 0, 10),
+    # sparse-index cost model (SimpleCostModelSparseInds): two more fields, number of sparse indices and n_projs
+    ('sparse64_inf', 64, 16, 1500, None, False, 2, 10, 12, 8),
+    ('sparse64_d3_inf', 64, 17, 1200, None, False, 3, 10, 10, 5),
+    ('sparse100_fw30', 100, 18, 1200, 0.3, False, 2, 10, 12, 16),
+    ('sparse64_d3_fw30', 64, 19, 1000, 0.3, False, 3, 10, 10, 2),
+    ('sparsedims64_fw40', 64, 20, 1000, 0.4, False, 0, 10, 10, 6),
+    ('sparsehyper64_fw40', 64, 21, 1000, 0.4, True, 2, 10, 8, 4),
 ]
 
 
@@ -47,7 +54,7 @@ def main():
     assert ref_core() is not None, 'build oracle/_ref first (make -C oracle ref)'
     os.makedirs(GOLDEN, exist_ok=True)
     only = set(sys.argv[1:])
-    for name, n, seed, n_sweeps, frac, hyper, dim, every in CASES:
+    for name, n, seed, n_sweeps, frac, hyper, dim, every, *sparse in CASES:
         if only and name not in only:
             continue
         if hyper:
@@ -68,7 +75,17 @@ def main():
                 l2 = np.log2(dims.astype(float))
                 w0 = max(sum(l2[i] for i in range(ni) if (int(row[i >> 5]) >> (i & 31)) & 1) for row in bits)
                 mw = float(int(w0 * frac))
-        rc = RefChain(p, a, b, bits, ni, dim=dim if dims is None else 2, dims=dims, max_width=mw, seed=seed)
+        sp_inds, sp_bits, n_projs = np.zeros(0, np.int32), None, 0
+        if sparse:
+            # open indices first (the usual case: sparse output states), the rest drawn at random
+            rest = [i for i in np.random.default_rng(seed + 7).permutation(ni).tolist() if i not in out]
+            sp_inds = np.array(sorted((list(out) + rest)[:sparse[0]]), np.int32)
+            sp_bits = np.zeros((ni + 31) // 32, np.uint32)
+            for i in sp_inds.tolist():
+                sp_bits[i >> 5] |= np.uint32(1 << (i & 31))
+            n_projs = sparse[1]
+        rc = RefChain(p, a, b, bits, ni, dim=dim if dims is None else 2, dims=dims, max_width=mw, seed=seed,
+                      sparse_bits=sp_bits, n_projs=n_projs)
         cps = sorted(set([0, 1, 2, 10, 11, n_sweeps // 3, n_sweeps // 2, n_sweeps - 1]))
         rec = dict(parent=[], child0=[], child1=[], log2_total=[], log2_min=[], prng_crc=[], slices=[],
                    min_slices=[])
@@ -93,6 +110,7 @@ def main():
         np.savez_compressed(
             os.path.join(GOLDEN, name + '.npz'), ts_inds=ts_arr, n_inds=ni, output_inds=np.array(out, np.int32),
             parent=p, child0=a, child1=b, bits=bits, dim=dim, dims=np.zeros(0, np.uint64) if dims is None else dims, max_width=np.float64(-1 if mw is None else mw),
+            sparse_inds=sp_inds, n_projs=n_projs,
             seed=seed, n_sweeps=n_sweeps, beta0=0.0, beta1=100.0, every=every, checkpoints=np.array(cps),
             init_log2_total=init_log2, init_slices=init_slices,
             cp_parent=np.array(rec['parent']), cp_child0=np.array(rec['child0']),

@@ -140,7 +140,7 @@ class RefChain:
     """Drives the compiled reference exactly as examples/BaseOptimization.ipynb does (raw tnco_core)."""
 
     def __init__(self, parent, c0, c1, bits, n_inds, *, dim=2, dims=None, max_width=None, seed=0,
-                 disable_shared_inds=False):
+                 disable_shared_inds=False, sparse_bits=None, n_projs=None):
         tc = ref_core()
         self.tc = tc
         nodes = [
@@ -152,7 +152,17 @@ class RefChain:
         self.n_inds = n_inds
         self.W = (n_inds + 31) // 32
         self.finite = max_width is not None
-        if self.finite:
+        sp = None if sparse_bits is None else tc.Bitset(positions(sparse_bits), n_inds)
+        if self.finite and sp is not None:
+            cm = tc.optimize.finite_width.cost_model.SimpleCostModelSparseInds_float64_float32(
+                float(max_width), sp, int(n_projs))
+            self.opt = tc.optimize.finite_width.greedy.Optimizer_float64_float32(
+                ctree, cm, seed=int(seed), disable_shared_inds=disable_shared_inds)
+        elif sp is not None:
+            cm = tc.optimize.infinite_memory.cost_model.SimpleCostModelSparseInds_float64(sp, int(n_projs))
+            self.opt = tc.optimize.infinite_memory.Optimizer_float64(
+                ctree, cm, seed=int(seed), disable_shared_inds=disable_shared_inds)
+        elif self.finite:
             cm = tc.optimize.finite_width.cost_model.SimpleCostModel_float64_float32(float(max_width))
             self.opt = tc.optimize.finite_width.greedy.Optimizer_float64_float32(
                 ctree, cm, seed=int(seed), disable_shared_inds=disable_shared_inds)
@@ -207,3 +217,13 @@ class RefChain:
 
     def prng_state_str(self):
         return self.opt.prng_state.strip()
+
+
+def golden_sparse(g):
+    """(sparse_bits [W32] | None, n_projs | None) of a golden fixture (sparse-index cost model cases)."""
+    if 'sparse_inds' not in g.files or int(g['n_projs']) == 0:
+        return None, None
+    b = np.zeros((int(g['n_inds']) + 31) // 32, np.uint32)
+    for i in g['sparse_inds'].tolist():
+        b[i >> 5] |= np.uint32(1 << (i & 31))
+    return b, int(g['n_projs'])

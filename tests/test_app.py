@@ -144,6 +144,52 @@ def test_optimize_with_default_load_tn_options(backend, max_width):
         assert abs(math.log2(c) - math.log2(float(r.cost))) < 1e-4
 
 
+def replay_cost_sparse(path, ts_inds, sparse, n_projs, slices=frozenset()):
+    """replay_cost under the sparse-index model: 2^|dense| * min(2^|sparse|, n_projs) per step
+    (tnco/optimize/infinite_memory/cost_model.py:47-57)."""
+    ts = [frozenset(x) for x in ts_inds]
+    total = 0
+    for x, y in path:
+        x, y = sorted((x, y))
+        ty = ts.pop(y)
+        tx = ts.pop(x)
+        u = tx | ty | slices
+        total += 2**len(u - sparse) * min(2**len(u & sparse), n_projs)
+        ts.append(tx ^ ty)
+    return total
+
+
+@pytest.mark.parametrize('max_width', [None, 9])
+def test_optimize_with_sparse_inds(backend, max_width):
+    """optimize(..., n_projs=) on a network with sparse indices ('/' rows of load_tn, tnco/app/app.py:219-236):
+    costs follow SimpleCostModelSparseInds; argument rules of tnco/optimize/infinite_memory/cost_model.py:79-89."""
+    import warnings
+
+    from tnco_b200.app import Optimizer
+    ts, ni = regular_network(30, 8)
+    rows = index_rows(ts, ni)
+    sparse = frozenset(range(0, ni, 6))
+    for i in sparse:
+        rows[i].append('/')
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')  # "fusion ... not yet supported if there are sparse indices"
+        tn, res = Optimizer(seed=4, max_width=max_width).optimize(rows, betas=(0, 100), n_steps=120, n_runs=4,
+                                                                    n_projs=4)
+        assert tn.sparse_inds == sparse and len(tn) == 30
+        for r in res:
+            sl = r.slices if max_width is not None else frozenset()
+            c = replay_cost_sparse(r.path, tn.ts_inds, sparse, 4, sl)
+            assert abs(math.log2(c) - math.log2(float(r.cost))) < 1e-4
+        # n_projs large enough never caps: the plain cost model's numbers
+        tn2, res2 = Optimizer(seed=4).optimize(rows, betas=(0, 100), n_steps=50, n_runs=2, n_projs=2**40)
+        for r in res2:
+            assert abs(math.log2(replay_cost(r.path, tn2.ts_inds)) - math.log2(float(r.cost))) < 1e-4
+        with pytest.raises(ValueError, match='n_projs'):
+            Optimizer(seed=4).optimize(rows, betas=(0, 100), n_steps=10)
+        with pytest.raises(ValueError, match='n_projs'):
+            Optimizer(seed=4).optimize(rows, betas=(0, 100), n_steps=10, n_projs=0)
+
+
 def test_disconnected_components(backend):
     """n_cc disconnected paths, single-tensor components skipped with cost 0 (sa.py:179-183, test_app.py:272-275)."""
     from tnco_b200.app import Optimizer

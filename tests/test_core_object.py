@@ -83,8 +83,8 @@ def test_partial_path_over_a_component(backend):
     assert ct.path() == [(0, 2), (2, 3)]
 
 
-@pytest.mark.parametrize('max_width_frac', [None, 0.5])
-def test_optimizer_lockstep_with_oracle(backend, max_width_frac):
+@pytest.mark.parametrize('max_width_frac,n_projs', [(None, None), (0.5, None), (None, 6), (0.5, 4)])
+def test_optimizer_lockstep_with_oracle(backend, max_width_frac, n_projs):
     from tnco_b200.ctree import ContractionTree
     from tnco_b200.optimize import finite_width, infinite_memory
     from tnco_b200.optimize.finite_width.cost_model import SimpleCostModel as FWModel
@@ -100,12 +100,19 @@ def test_optimizer_lockstep_with_oracle(backend, max_width_frac):
         for x in xs:
             nb[z, order[x] >> 5] |= np.uint32(1 << (order[x] & 31))
     mw = None
+    # sparse-index cost model (SimpleCostModel(sparse_inds=, n_projs=)): every fifth index is sparse
+    sparse = [x for x in ct._inds_order if order[x] % 5 == 0] if n_projs else None
+    sp = None
+    if sparse:
+        sp = np.zeros((ni + 31) // 32, np.uint32)
+        for x in sparse:
+            sp[order[x] >> 5] |= np.uint32(1 << (order[x] & 31))
     if max_width_frac is not None:
         mw = float(int(max(len(xs) for xs in ct.inds) * max_width_frac))
-        opt = finite_width.Optimizer(ct, FWModel(mw), seed=77)
+        opt = finite_width.Optimizer(ct, FWModel(mw, sparse_inds=sparse, n_projs=n_projs), seed=77)
     else:
-        opt = infinite_memory.Optimizer(ct, SimpleCostModel(), seed=77)
-    oc = so.Chain(P, A, B, nb, ni, max_width=mw, seed=77)
+        opt = infinite_memory.Optimizer(ct, SimpleCostModel(sparse_inds=sparse, n_projs=n_projs), seed=77)
+    oc = so.Chain(P, A, B, nb, ni, max_width=mw, seed=77, sparse_bits=sp, n_projs=n_projs)
     assert opt.log2_total_cost == oc.log2_total_cost
     assert opt.prng_state == oc.prng_state_str()
     rnd = random.Random(1)

@@ -100,3 +100,13 @@ def test_emu_packed_trees_and_cache(emu):
 
 def test_emu_minima_exact_on_slow_ramp(emu):
     G.test_minima_stay_exact_when_chains_wander_at_small_beta()
+
+
+@pytest.mark.parametrize('dim', [2, 3])
+def test_emu_sparse_philox(emu, dim):
+    G.test_philox_sparse_index_chains_are_valid(dim)
+
+
+@pytest.mark.parametrize('name', ['sparse64_inf', 'sparse100_fw30', 'sparsehyper64_fw40'])
+def test_emu_replay_sparse(emu, name):
+    G.test_replay_of_recorded_draw_stream_is_bit_exact(name)

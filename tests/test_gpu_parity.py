@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import GOLDEN, random_tree, regular_network
+from helpers import GOLDEN, golden_sparse, random_tree, regular_network
 from oracle import sa_oracle as so
 
 pytestmark = pytest.mark.gpu
@@ -30,8 +30,10 @@ def _engine(g, rng, tile=None, every=None):
     n = (g['parent'].shape[0] + 1) // 2
     e = Engine()
     dims = g['dims'] if 'dims' in g.files and len(g['dims']) else None   # per-index dims fixtures (dim == 0)
+    sp, n_projs = golden_sparse(g)
     e.set_network(g['bits'][:n], int(g['n_inds']), dim=int(g['dim']) or 2, dims=dims,
-                  output_bits=pack_index_set(g['output_inds'].tolist(), int(g['n_inds'])))
+                  output_bits=pack_index_set(g['output_inds'].tolist(), int(g['n_inds'])), sparse_bits=sp,
+                  n_projs=n_projs)
     assert e.hyper == bool(len(g['output_inds']))
     e.set_mode(max_width=mw, update_slices_every=int(g['every']) if every is None else every, rng=rng)
     e.set_chains(g['parent'][None], g['child0'][None], g['child1'][None], [int(g['seed'])])
@@ -84,7 +86,8 @@ def test_every_tile_shape_matches_golden(name, tile):
 
 
 @pytest.mark.parametrize('name', ['reg64_inf', 'reg100_fw30', 'reg300_inf', 'hyper64_inf', 'hyper64_fw40',
-                                  'dims64_fw45', 'dimshyper48_fw50'])
+                                  'dims64_fw45', 'dimshyper48_fw50', 'sparse64_inf', 'sparse100_fw30',
+                                  'sparsehyper64_fw40'])
 def test_replay_of_recorded_draw_stream_is_bit_exact(name):
     """north_star: replaying a reference-recorded proposal / uniform-draw sequence yields identical trees.
     The stream is recorded by the oracle (itself pinned to the reference) while it runs the same sweeps."""
@@ -94,8 +97,9 @@ def test_replay_of_recorded_draw_stream_is_bit_exact(name):
     mw = None if mw < 0 else mw
     n_sweeps = 400
     dims = g['dims'] if 'dims' in g.files and len(g['dims']) else None
+    sp, n_projs = golden_sparse(g)
     oc = so.Chain(g['parent'], g['child0'], g['child1'], g['bits'], int(g['n_inds']), dim=int(g['dim']) or 2,
-                  dims=dims, max_width=mw, seed=int(g['seed']))
+                  dims=dims, max_width=mw, seed=int(g['seed']), sparse_bits=sp, n_projs=n_projs)
     # the constructor's slicer draws precede the recording; re-create the full stream from the seed instead
     betas = [100.0 * s / n_sweeps for s in range(n_sweeps)]
     oc.run(betas, update_slices_every=int(g['every']))
@@ -183,6 +187,61 @@ def test_philox_chains_are_valid_and_deterministic():
     assert (outs[0][0] == outs[1][0]).all() and (outs[0][2] == outs[1][2]).all()
     assert len(set(outs[0][1].tolist())) > 8
     assert np.log2(outs[0][1]).mean() < np.log2(seq).mean() + 1e-9
+
+
+@pytest.mark.parametrize('dim', [2, 3])
+def test_philox_sparse_index_chains_are_valid(dim):
+    """Sparse-index cost model under the production RNG (table-cost kernels): the cached totals equal an independent
+    evaluation by the oracle's SimpleCostModelSparseInds restatement, and differ from the plain model's."""
+    from helpers import leaf_bits
+    from tnco_b200.engine import RNG_MT19937, Engine, EngineError, pack_index_set
+    ts, ni = regular_network(100, 9)
+    lb = leaf_bits(ts, ni)
+    sparse = np.random.default_rng(3).choice(ni, size=15, replace=False).tolist()
+    sp = pack_index_set(sparse, ni)
+    seeds = np.arange(48, dtype=np.uint64) + 5
+    outs = []
+    for rep in range(2):
+        e = Engine()
+        e.set_network(lb, ni, dim=dim, sparse_bits=sp, n_projs=8).set_mode().generate_chains(seeds)
+        e.set_betas(np.linspace(0, 100, 400, endpoint=False))
+        t0, _ = e.costs()
+        e.run(400)
+        t, m = e.costs()
+        P, A, B = e.trees()
+        seq, pc, _ = e.eval_cost(P, A, B)
+        assert np.allclose(np.log2(pc), np.log2(t), atol=1e-9) and (m <= t).all()
+        assert np.log2(m).mean() < np.log2(t0).mean() - 1
+        for c in (0, 11, 47):
+            oc = so.Chain(P[c], A[c], B[c], e.bits(c), ni, dim=dim, sparse_bits=sp, n_projs=8)
+            assert abs(np.log2(oc.total_cost) - np.log2(t[c])) < 1e-9
+            assert so.Chain(P[c], A[c], B[c], e.bits(c), ni, dim=dim).total_cost >= oc.total_cost
+        if rep == 0:  # same initial trees under the plain model cost more: the cap is active
+            e2 = Engine()
+            e2.set_network(lb, ni, dim=dim).set_mode().generate_chains(seeds)
+            p0 = e2.costs()[0]
+            assert (p0 >= t0).all() and (p0 > t0).any()
+            e2.close()
+        outs.append((t.copy(), P.copy()))
+        e.close()
+    assert (outs[0][0] == outs[1][0]).all() and (outs[0][1] == outs[1][1]).all()
+    # with max_width the sparse width model runs on the stream kernels only
+    e = Engine()
+    e.set_network(lb, ni, dim=dim, sparse_bits=sp, n_projs=8).set_mode(max_width=12 * np.log2(dim))
+    with pytest.raises((EngineError, ValueError), match='MT19937'):
+        e.generate_chains(seeds[:4])
+        e.costs()
+    e.close()
+    e = Engine()
+    e.set_network(lb, ni, dim=dim, sparse_bits=sp, n_projs=8).set_mode(max_width=12 * np.log2(dim), rng=RNG_MT19937)
+    e.generate_chains(seeds[:4]).set_betas(np.linspace(0, 100, 200, endpoint=False))
+    e.run(200)
+    t, m = e.costs()
+    P, A, B = e.trees()
+    _, pc, mw = e.eval_cost(P, A, B, slices=e.slices())
+    assert np.allclose(np.log2(pc), np.log2(t), atol=1e-9) and (mw <= np.float32(12 * np.log2(dim)) + 1e-6).all()
+    with pytest.raises((EngineError, ValueError), match='n_projs'):
+        Engine().set_network(lb, ni, sparse_bits=sp, n_projs=0)
 
 
 def _check_tree_valid(P, A, B, n):

@@ -14,6 +14,7 @@ import numpy as np
 from .. import dist
 from ..engine import (RNG_MT19937, RNG_PHILOX, cached_engine, TREES_GREEDY, TREES_RANDOM, merge_paths, pack_index_set,
                       pack_leaf_bits, random_trees, tree_to_path, unpack_bits)
+from ..optimize.infinite_memory.cost_model import check_sparse
 from ..tn import get_connected_components
 from .app import cost_to_decimal
 
@@ -39,7 +40,7 @@ def expand_betas(betas, n_steps):
     return b
 
 
-def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, deadline, stats):
+def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, deadline, stats, n_projs=None):
     """All runs of one connected component.  Returns per run: min cost (float), best tree -> path over all
     tensors of tn, slices (index names)."""
     all_ts, all_dims, outs = tn.ts_inds, tn.dims, tn.output_inds   # (properties that rebuild their value: read once)
@@ -53,6 +54,13 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
                                   'of two >= 2 (or all dimensions are equal).')
     lb = pack_leaf_bits([[pos[x] for x in xs] for xs in ts], len(inds))
     out_bits = pack_index_set([pos[x] for x in inds if x in outs], len(inds))
+    # sparse-index cost model (tnco/app/infinite_memory/sa.py:158-161): every component gets the network's sparse
+    # indices (those it holds) and the same n_projs
+    sparse = [pos[x] for x in inds if x in tn.sparse_inds] if tn.sparse_inds else []
+    sp_bits = pack_index_set(sparse, len(inds)) if tn.sparse_inds else None
+    rng_kind = RNG_MT19937 if opt.rng == 'mt19937' else RNG_PHILOX
+    if sp_bits is not None and finite:
+        rng_kind = RNG_MT19937  # sparse widths are served by the stream kernels (include/tnco_b200.h)
     n_runs = len(seeds)
     lo, hi = dist.shard(n_runs) if opt.distributed else (0, n_runs)
     my_seeds = np.asarray(seeds[lo:hi], np.uint64)
@@ -61,9 +69,9 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
     t_eng = time.perf_counter()
     eng = cached_engine(dist.local_device(opt.device))
     try:
-        eng.set_network(lb, len(inds), dim=dims[0], dims=None if uniform else dims, output_bits=out_bits)
-        eng.set_mode(max_width=opt.max_width if finite else None, update_slices_every=update_slices,
-                     rng=RNG_MT19937 if opt.rng == 'mt19937' else RNG_PHILOX)
+        eng.set_network(lb, len(inds), dim=dims[0], dims=None if uniform else dims, output_bits=out_bits,
+                        sparse_bits=sp_bits, n_projs=n_projs)
+        eng.set_mode(max_width=opt.max_width if finite else None, update_slices_every=update_slices, rng=rng_kind)
         t0 = time.perf_counter()
         if opt.tree_builder == 'device' and not eng.hyper:
             eng.generate_chains(my_seeds, chain_id0=lo, method=method)
@@ -145,8 +153,7 @@ def _comp_slices(pc, r):
 def optimize(opt, results_cls, tn, betas, n_steps, n_runs, n_projs, update_slices, timeout, finite,
              load_tn_options):
     tn = opt._load_tn(tn, **load_tn_options)
-    if tn.sparse_inds or n_projs is not None:
-        raise NotImplementedError('tnco_b200: sparse indices / n_projs are not supported yet.')
+    check_sparse(tn.sparse_inds, n_projs)  # the cost model's argument rules (sa.py:158-161 builds it first)
     betas = expand_betas(betas, n_steps)
     if int(n_runs) != n_runs or n_runs < 1:
         raise ValueError("'n_runs' must be a positive number.")
@@ -163,7 +170,8 @@ def optimize(opt, results_cls, tn, betas, n_steps, n_runs, n_projs, update_slice
             per_comp.append(None)
             continue
         per_comp.append(run_component(opt, comp, tn, None, seeds, betas, finite=finite,
-                                      update_slices=update_slices, deadline=deadline, stats=stats))
+                                      update_slices=update_slices, deadline=deadline, stats=stats,
+                                      n_projs=n_projs))
     runtime = time.perf_counter() - t_start
     R = int(n_runs)
     live = [pc for pc in per_comp if pc is not None]

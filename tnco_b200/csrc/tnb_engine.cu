@@ -357,6 +357,9 @@ struct tnb_engine {
   bool grouped = false;
   std::vector<int> voff, vw;
   uint32_t* d_leader = nullptr;  // [Ws] first virtual bit of every index
+  // sparse-index cost model (tnb_set_sparse_inds): sparse indices in the virtual index space, or none
+  uint32_t* d_sparse = nullptr;  // [Ws + tail]
+  uint64_t n_projs = 0;
   uint8_t* d_gw = nullptr;       // [Ws*32] log2(dim) at the leader positions
 
   // caller's index space <-> virtual index space (rows of Wu / W words)
@@ -432,7 +435,11 @@ static unsigned long long sweep_reserve(const tnb_engine* e) {
 static void fill_params(const tnb_engine* e, const ChainSet& cs, Params& P) {
   std::memset(&P, 0, sizeof(P));
   P.n = e->n; P.N = e->N; P.n_int = e->n_int; P.n_inds = e->n_inds; P.W = e->W; P.Ws = e->Ws;
-  P.leaf_bits = e->d_leaf_bits; P.pow_tab = e->d_pow_tab; P.dim2 = e->dim == 2; P.log2d = e->log2d;
+  P.leaf_bits = e->d_leaf_bits; P.pow_tab = e->d_pow_tab; P.log2d = e->log2d;
+  P.sparse = e->d_sparse;  // costs of a network with sparse indices come from the table kernels
+  P.dim2 = e->dim == 2 && !e->d_sparse;
+  P.n_projs = double(e->n_projs);
+  P.log2_n_projs = e->n_projs ? std::log2(double(e->n_projs)) : 0.0;
   P.finite = e->finite; P.every = e->every; P.dsi = e->dsi; P.prob_kind = e->prob_kind; P.max_width = e->max_width;
   P.n_chains = cs.n_chains; P.Npad = e->Npad;
   P.par = cs.par; P.hdr = cs.rec; P.bitsb = cs.bitsb; P.hstride = cs.hstride; P.bstride = cs.bstride; P.pc = cs.pc; P.bpar = cs.bpar; P.bch = cs.bch;
@@ -606,6 +613,9 @@ static bool ensure_init(tnb_engine* e) {
   if (e->initialized) return true;
   if (e->cs.n_chains == 0) return e->fail("no chains: call tnb_set_chains first");
   if (e->rng_kind == TNB_RNG_REPLAY && !e->cs.stream) return e->fail("TNB_RNG_REPLAY needs tnb_set_stream");
+  if (e->d_sparse && e->finite && e->rng_kind == TNB_RNG_PHILOX)
+    return e->fail("sparse indices with max_width run on the stream kernels: use TNB_RNG_MT19937 (the production "
+                   "re-slicer does not know the sparse-index width model)");
   if (e->rng_kind == TNB_RNG_MT19937) {
     ChainSet& cs = e->cs;
     const unsigned long long res = sweep_reserve(e);
@@ -679,6 +689,7 @@ void tnb_destroy(tnb_engine* e) {
   e->rt.free_(e->d_hcount0);
   e->rt.free_(e->d_leader);
   e->rt.free_(e->d_gw);
+  e->rt.free_(e->d_sparse);
   e->rt.free_(e->d_betas);
   e->rt.free_(e->d_inv_betas);
   e->rt.free_(e->d_flush);
@@ -760,8 +771,9 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds_u, const uint32_t* l
     leader[size_t(k) >> 5] |= 1u << (k & 31);
     gw[size_t(k)] = uint8_t(vw[size_t(i)]);
   }
-  void* old[] = {e->d_leaf_bits, e->d_pow_tab, e->d_net_own, e->d_hcount0, e->d_leader, e->d_gw};
+  void* old[] = {e->d_leaf_bits, e->d_pow_tab, e->d_net_own, e->d_hcount0, e->d_leader, e->d_gw, e->d_sparse};
   for (void* q : old) e->rt.free_(q);
+  e->d_sparse = nullptr; e->n_projs = 0;  // a new network starts with the simple cost model
   e->d_leaf_bits = nullptr; e->d_pow_tab = nullptr; e->d_net_own = nullptr; e->d_hcount0 = nullptr;
   e->d_leader = nullptr; e->d_gw = nullptr;
   if (!alloc_to(e->rt, e->d_net_own, own.size()) || !e->rt.h2d(e->d_net_own, own.data(), own.size() * sizeof(int16_t)) ||
@@ -795,6 +807,26 @@ int tnb_set_output_inds(tnb_engine* e, const uint32_t* output_bits) {
 }
 
 int tnb_is_hyper(tnb_engine* e) { return e && e->hyper ? 1 : 0; }
+
+int tnb_set_sparse_inds(tnb_engine* e, const uint32_t* sparse_bits, uint64_t n_projs) {
+  if (!e) return -1;
+  if (e->n == 0) return e->fail("tnb_set_sparse_inds: call tnb_set_network first"), -1;
+  if (sparse_bits && n_projs == 0) return e->fail("'n_projs' must be a positive number."), -1;
+  e->cs.release(e->rt);
+  e->initialized = false;
+  e->rt.free_(e->d_sparse);
+  e->d_sparse = nullptr;
+  e->n_projs = 0;
+  if (!sparse_bits) return 0;
+  std::vector<uint32_t> u(sparse_bits, sparse_bits + e->Wu), v(size_t(e->Ws) + kTailWords, 0u);
+  if (e->n_inds_u & 31) u[size_t(e->Wu) - 1] &= (1u << (e->n_inds_u & 31)) - 1u;
+  e->expand_row(u.data(), v.data());
+  if (!alloc_to(e->rt, e->d_sparse, v.size()) || !e->rt.h2d(e->d_sparse, v.data(), v.size() * sizeof(uint32_t)) ||
+      !e->rt.sync())
+    return e->rtfail(), -3;
+  e->n_projs = n_projs;
+  return 0;
+}
 
 int tnb_set_mode(tnb_engine* e, double max_width, int update_slices_every, int disable_shared_inds, int prob_kind,
                  int rng_kind, int layout) {

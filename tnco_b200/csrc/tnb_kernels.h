@@ -24,6 +24,12 @@ struct Params {
   const double* pow_tab;            // [n_inds+1] dim^k (host std::pow), unused when dim2
   int dim2;
   double log2d;
+  // sparse-index cost model (infinite_memory/cost_model/simple_sparse_inds.hpp:38-49, finite_width/...:38-77):
+  //   cost = get_cost(inds - sparse) * min(get_cost(inds & sparse), n_projs), width likewise with log2(n_projs).
+  // Served by the table-cost kernels only (the host clears dim2 for such networks); nullptr = simple cost model.
+  const uint32_t* sparse;  // [Ws]
+  double n_projs;          // (double)n_projs
+  double log2_n_projs;     // log2(n_projs)
   // mode
   int finite, every, dsi, prob_kind;
   float max_width;
@@ -332,6 +338,19 @@ struct ChainView {
     return ldg(P.pow_tab + k);
   }
   TNB_D TNB_INLINE float width_of(int k) const { return float(P.log2d * double(k)); }  // fw simple.hpp:47
+  // sparse-index model: k = popcount of the whole set, ks = popcount of its sparse part
+  TNB_D TNB_INLINE double cost_sp(int k, int ks) const {
+    const double x = cost_of(ks), y = P.n_projs;
+    return cost_of(k - ks) * (x < y ? x : y);
+  }
+  TNB_D TNB_INLINE float width_sp(int k, int ks) const {  // float + min(float, double) -> float, as the reference
+    const float ws = width_of(ks);
+    return width_of(k - ks) + (double(ws) < P.log2_n_projs ? ws : float(P.log2_n_projs));
+  }
+  TNB_D TNB_INLINE void load_sparse(uint32_t (&o)[WPL]) const {
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) o[k] = lane_ok[k] ? ldg(P.sparse + t.tl + k * TILE) : 0u;
+  }
   // stackless post-order over the CURRENT topology, children[0] subtree first (utils.hpp:35-52)
   TNB_D int po_first() const {
     int x = P.N - 1;
@@ -380,20 +399,32 @@ struct ScratchSink {
 
 template <int TILE, int WPL, bool WIDTHS, class Sink>
 TNB_D void cost_pass(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL], const Sink& dst, double& seq,
-                     uint32_t& maxk) {
+                     double& maxw) {
   const Params& P = c.P;
   seq = 0.0;
-  maxk = 0;
+  uint32_t maxk = 0;
+  float maxw_sp = 0.f;
+  const bool sparse = P.sparse != nullptr;
+  uint32_t SP[WPL];
+#pragma unroll
+  for (int i = 0; i < WPL; ++i) SP[i] = 0u;
+  if (sparse) c.load_sparse(SP);
   for (int z = c.po_first(); z >= 0; z = c.po_next(z)) {
     uint32_t kw_ = 0;
     if (WIDTHS) {  // sliced popcount of the node's own index set (widest node)
       uint32_t x[WPL];
       c.load_bits(z, x);
 #pragma unroll
-      for (int i = 0; i < WPL; ++i) kw_ += uint32_t(popc32(x[i] & ~S[i]));
+      for (int i = 0; i < WPL; ++i) kw_ += uint32_t(popc32(x[i] & ~S[i])) | (uint32_t(popc32(x[i] & ~S[i] & SP[i])) << 16);
+      if (sparse) {
+        kw_ = c.t.sum(kw_);
+        const float w = c.width_sp(int(kw_ & 0xffffu), int(kw_ >> 16));
+        maxw_sp = w > maxw_sp ? w : maxw_sp;
+        kw_ = 0;
+      }
     }
     if (z < P.n) {
-      if (WIDTHS) {
+      if (WIDTHS && !sparse) {
         kw_ = c.t.sum(kw_);
         maxk = kw_ > maxk ? kw_ : maxk;
       }
@@ -405,17 +436,26 @@ TNB_D void cost_pass(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL], co
     c.load_bits(a, xa);
     c.load_bits(b, xb);
     uint32_t kk = c.t.sum(popc_or3<WPL>(xa, xb, S) | (kw_ << 16));
-    if (WIDTHS) {
+    if (WIDTHS && !sparse) {
       const uint32_t k = kk >> 16;
       maxk = k > maxk ? k : maxk;
       kk &= 0xffffu;
     }
-    const double cost = c.cost_of(int(kk));
+    double cost;
+    if (sparse) {
+      uint32_t ks = 0;
+#pragma unroll
+      for (int i = 0; i < WPL; ++i) ks += uint32_t(popc32((xa[i] | xb[i] | S[i]) & SP[i]));
+      cost = c.cost_sp(int(kk), int(c.t.sum(ks)));
+    } else {
+      cost = c.cost_of(int(kk));
+    }
     const double pa = dst.pc(a);
     const double pb = dst.pc(b);
     dst.put(z, cost, cost + pa + pb);
     seq += cost;
   }
+  maxw = sparse ? double(maxw_sp) : P.log2d * double(maxk);
 }
 
 // Index sets (and, with HYPER, hyper rows) of all internal nodes from the topology, in post-order -- what
@@ -487,15 +527,20 @@ TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2
     if (w < P.W)
       for (int b = 0; b < 32; ++b) nbig[w * 32 + b] = 0;
   }
+  const bool sparse = P.sparse != nullptr;
+  uint32_t SP[WPL];
+#pragma unroll
+  for (int i = 0; i < WPL; ++i) SP[i] = 0u;
+  if (sparse) c.load_sparse(SP);
   // n_big_tensors (:41-47): every node, leaves included
   for (int z = 0; z < P.N; ++z) {
     uint32_t x[WPL];
     c.load_bits(z, x);
     uint32_t k = 0;
 #pragma unroll
-    for (int i = 0; i < WPL; ++i) k += popc32(x[i]);
+    for (int i = 0; i < WPL; ++i) k += uint32_t(popc32(x[i])) | (uint32_t(popc32(x[i] & SP[i])) << 16);
     k = t.sum(k);
-    if (c.width_of(int(k)) > P.max_width) {
+    if ((sparse ? c.width_sp(int(k & 0xffffu), int(k >> 16)) : c.width_of(int(k))) > P.max_width) {
 #pragma unroll
       for (int i = 0; i < WPL; ++i) {
         const int w = t.tl + i * TILE;
@@ -511,19 +556,23 @@ TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2
   for (int z = c.po_first(); z >= 0; z = c.po_next(z)) {
     uint32_t x[WPL];
     c.load_bits(z, x);
-    uint32_t k = 0, ks = 0;
+    uint32_t k = 0, ks = 0, kp = 0;  // kp: sparse parts of the whole and of the sliced set
 #pragma unroll
     for (int i = 0; i < WPL; ++i) {
       k += popc32(x[i]);
+      kp += uint32_t(popc32(x[i] & SP[i]));
       x[i] &= ~S2[i];
       ks += popc32(x[i]);
+      kp += uint32_t(popc32(x[i] & SP[i])) << 16;
     }
     k = t.sum(k | (ks << 16));
     ks = k >> 16;
     k &= 0xffffu;
-    if (!(c.width_of(int(k)) > P.max_width)) continue;
-    float sw = c.width_of(int(ks));
+    if (sparse) kp = t.sum(kp);
+    if (!((sparse ? c.width_sp(int(k), int(kp & 0xffffu)) : c.width_of(int(k))) > P.max_width)) continue;
+    float sw = sparse ? c.width_sp(int(ks), int(kp >> 16)) : c.width_of(int(ks));
     if (!(sw > P.max_width)) continue;
+    int kss = int(kp >> 16);  // sparse indices still unsliced on this node
     // ascending positions of the still unsliced indices of this node (group leaders when dims differ per index)
     uint32_t np = 0;
 #pragma unroll
@@ -592,7 +641,17 @@ TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2
     uint32_t m = 0;
     const float dw = float(-P.log2d);  // get_delta_width for a present index (fw simple.hpp:60-76)
     while (m < np) {
-      sw += P.grouped ? -float(int(P.gw[pos[m]])) : dw;
+      const int idx = pos[m];
+      if (sparse && ((P.sparse[idx >> 5] >> (idx & 31)) & 1u)) {
+        // get_delta_width of a sparse index (fw simple_sparse_inds.hpp:51-77): difference of the capped widths
+        const int g = P.grouped ? int(P.gw[idx]) : 1;
+        const float wo = c.width_of(kss), wn = c.width_of(kss - g);
+        const float L = float(P.log2_n_projs);
+        sw += (double(wn) < P.log2_n_projs ? wn : L) - (double(wo) < P.log2_n_projs ? wo : L);
+        kss -= g;
+      } else {
+        sw += P.grouped ? -float(int(P.gw[idx])) : dw;
+      }
       ++m;
       if (sw <= P.max_width) break;
     }
@@ -1164,13 +1223,13 @@ TNB_D void chain_init(const Params& P, int chain) {
     }
   }
   double seq;
-  uint32_t maxk;
-  cost_pass<TILE, WPL, true>(c, S, CacheSink<TILE, WPL>{c}, seq, maxk);
+  double maxw;
+  cost_pass<TILE, WPL, true>(c, S, CacheSink<TILE, WPL>{c}, seq, maxw);
   const double rootpc = c.pcv[P.N - 1];
   P.total[chain] = rootpc;
   P.min_total[chain] = seq;  // get_cost(min_ctree) sums in traversal order (infinite_memory/utils.hpp:102-116)
   if (P.out_seq) P.out_seq[chain] = seq;
-  if (P.out_maxw) P.out_maxw[chain] = P.log2d * double(maxk);
+  if (P.out_maxw) P.out_maxw[chain] = maxw;
   if (FINITE && P.kw && (!Rng::kFast || P.slices_given)) build_kw_sz(c);
   if (P.bpar) snapshot_best(c, S, FINITE);
 }
@@ -1314,8 +1373,8 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
             } else {
               get_slices_dev(c, rng, S2);
               double seq;
-              uint32_t maxk;
-              cost_pass<TILE, WPL, false>(c, S2, ScratchSink{cp2, n}, seq, maxk);
+              double maxw;
+              cost_pass<TILE, WPL, false>(c, S2, ScratchSink{cp2, n}, seq, maxw);
               const double r2 = cp2[P.n_int - 1].y;
               if (r2 < (PC ? root_pc : total)) {
                 t.sync();
@@ -1460,6 +1519,21 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       if (FINITE) ks += uint32_t(popc32(nb[k] & ~S[k]));
       if (FS) ks += uint32_t(popc32(nb[k])) << 16;  // unsliced popcount of the new B rides in the same reduction
     }
+    // sparse-index cost model (table-cost kernels only): the sparse parts of the same three sets
+    const bool sparse = !DIM2 && P.sparse != nullptr;
+    uint32_t kspack = 0, kss = 0;
+    if (sparse) {
+      uint32_t SP[WPL];
+      c.load_sparse(SP);
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) {
+        kspack += uint32_t(popc32((nb[k] | bE[k] | S[k]) & SP[k])) |
+                  (uint32_t(popc32((bD[k] | bC[k] | S[k]) & SP[k])) << 16);
+        if (FINITE) kss += uint32_t(popc32(nb[k] & ~S[k] & SP[k]));
+      }
+      kspack = t.sum_c(kspack);
+      if (FINITE) kss = t.sum_c(kss);
+    }
     const double pcD = pick0 ? pc0 : pc1;
     double pcE = pick0 ? pc1 : pc0;
     const int szD = pick0 ? sz0 : sz1;
@@ -1472,7 +1546,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         ku = ks >> 16;
         ks &= 0xffffu;
       }
-      gate = c.width_of(int(ks)) <= P.max_width;
+      gate = (sparse ? c.width_sp(int(ks), int(kss)) : c.width_of(int(ks))) <= P.max_width;
       if (!gate) ++q_wrej;
     }
     // header of the parent after next (Ann was requested at the top of this level)
@@ -1490,6 +1564,9 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         const uint32_t ka = kpack & 0xffffu, kb = kpack >> 16;
         nA = bits_to_f64((unsigned long long)(1023u + (ka > 1024u ? 1024u : ka)) << 52);
         nB = bits_to_f64((unsigned long long)(1023u + (kb > 1024u ? 1024u : kb)) << 52);
+      } else if (sparse) {
+        nA = c.cost_sp(int(kpack & 0xffffu), int(kspack & 0xffffu));
+        nB = c.cost_sp(int(kpack >> 16), int(kspack >> 16));
       } else {
         nA = c.cost_of(int(kpack & 0xffffu));  // cost(new_B | E [| slices])
         nB = c.cost_of(int(kpack >> 16));      // cost(D | C [| slices])

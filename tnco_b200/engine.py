@@ -184,7 +184,7 @@ class Engine:
                 raise ValueError(msg)
             raise EngineError(msg)
 
-    def set_network(self, leaf_bits, n_inds, dim=2, dims=None, output_bits=None):
+    def set_network(self, leaf_bits, n_inds, dim=2, dims=None, output_bits=None, sparse_bits=None, n_projs=None):
         lb = _c(leaf_bits, np.uint32)
         self.n, self.n_inds = lb.shape[0], int(n_inds)
         self.N, self.W = 2 * self.n - 1, (self.n_inds + 31) // 32
@@ -198,6 +198,21 @@ class Engine:
             if ob.shape != (self.W,):
                 raise ValueError('output_bits must be [ceil(n_inds/32)]')
             self._chk(self._L.tnb_set_output_inds(self._h, _ptr(ob, C.c_uint32)))
+        if sparse_bits is not None:
+            self.set_sparse_inds(sparse_bits, n_projs)
+        return self
+
+    def set_sparse_inds(self, sparse_bits, n_projs):
+        """Sparse-index cost model (SimpleCostModelSparseInds); ``sparse_bits=None`` returns to the simple one."""
+        if sparse_bits is None:
+            self._chk(self._L.tnb_set_sparse_inds(self._h, None, 0))
+            return self
+        sb = _c(sparse_bits, np.uint32).reshape(-1)
+        if sb.shape != (self.W,):
+            raise ValueError('sparse_bits must be [ceil(n_inds/32)]')
+        if n_projs is None or int(n_projs) != n_projs or n_projs < 1:
+            raise ValueError("'n_projs' must be a positive number.")
+        self._chk(self._L.tnb_set_sparse_inds(self._h, _ptr(sb, C.c_uint32), int(n_projs)))
         return self
 
     @property

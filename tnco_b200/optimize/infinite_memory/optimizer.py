@@ -43,10 +43,15 @@ class Optimizer:
         if not uniform and any(d < 2 or d & (d - 1) for d in dims):
             raise NotImplementedError('tnco_b200: per-index dimensions must all be powers of two >= 2.')
         lb, ni = ctree.leaf_bits()
-        self._e = Engine(device)
         pos = {x: k for k, x in enumerate(ctree._inds_order)}
+        self._e = Engine(device)
+        sparse = getattr(cmodel, 'sparse_inds', None)
+        if sparse and not frozenset(sparse).issubset(pos):  # tnco/optimize/infinite_memory/cost_model.py:190-194
+            raise ValueError("Sparse indices are not a subset of 'inds_order'.")
         self._e.set_network(lb, ni, dim=dims[0], dims=None if uniform else dims,
-                            output_bits=pack_index_set([pos[x] for x in ctree.output_inds()], ni))
+                            output_bits=pack_index_set([pos[x] for x in ctree.output_inds()], ni),
+                            sparse_bits=pack_index_set([pos[x] for x in sparse], ni) if sparse else None,
+                            n_projs=getattr(cmodel, 'n_projs', None))
         self._e.set_mode(max_width=getattr(cmodel, 'max_width', None) if self._finite else None,
                          update_slices_every=1, disable_shared_inds=self._dsi, rng=RNG_MT19937)
         p, a, b = ctree.arrays()
