@@ -88,6 +88,8 @@ void tnb_mt19937_stream(uint32_t seed, uint64_t n, uint32_t* out);
 /* Internal state of std::mt19937(seed) after n_draws outputs: the 624 words and the position that
  * libstdc++'s operator<< prints (reference Optimizer.prng_state, optimize/optimizer.hpp:191-195). */
 void tnb_mt19937_state(uint32_t seed, uint64_t n_draws, uint32_t* state624, int32_t* pos);
+/* advance a std::mt19937 state (624 words + position) by n_draws outputs, in place */
+void tnb_mt19937_advance(uint32_t* state624, int32_t* pos, uint64_t n_draws);
 
 /* ---------------------------------------------------------------- engine */
 
@@ -141,6 +143,18 @@ int tnb_set_chains(tnb_engine* e, int n_chains, const int32_t* parent, const int
  * hyper-index-free network; seed -> tree is deterministic).  method: TNB_TREES_GREEDY / TNB_TREES_RANDOM.
  * Fails with "not connected" if some chain runs out of index-sharing pairs. */
 int tnb_generate_chains(tnb_engine* e, int n_chains, const uint64_t* seeds, uint64_t chain_id0, int method);
+
+/* Resume chains from a saved state instead of constructing them afresh: what pickling a reference core object
+ * restores through its constructor (tnco/optimize/infinite_memory/optimizer.py:234-247 and
+ * finite_width/optimizer.py:330-346: seed = prng_state string, _min_ctree, _slices, _min_slices; C++ side
+ * include/tnco/optimize/optimizer.hpp:57-72, finite_width/greedy/optimizer.hpp:72-101).  Call right after
+ * tnb_set_chains (which gives the current trees); every argument may be NULL:
+ *   mt_state     [n_chains][625]  std::mt19937 state, 624 words + position (TNB_RNG_MT19937 mode)
+ *   slices       [n_chains][W32]  current slices: the constructor's slicer is not run
+ *   best_*       [n_chains][2*n_leaves-1] saved min_ctree;  best_slices [n_chains][W32] saved min_slices
+ * min_total_cost becomes get_cost(min_ctree[, min_slices]), as in the reference constructors. */
+int tnb_set_resume(tnb_engine* e, const uint32_t* mt_state, const uint32_t* slices, const int32_t* best_parent,
+                   const int32_t* best_child0, const int32_t* best_child1, const uint32_t* best_slices);
 
 /* TNB_RNG_REPLAY: raw draw stream per chain, words [n_chains][len]; cursors reset to 0. */
 int tnb_set_stream(tnb_engine* e, const uint32_t* words, uint64_t len);

@@ -146,6 +146,66 @@ def test_optimizer_lockstep_with_oracle(backend, max_width_frac, n_projs):
     assert [cur.inds[t] for t in range(26)] == [ct.inds[t] for t in range(26)]
 
 
+@pytest.mark.parametrize('max_width_frac', [None, 0.5])
+def test_pickle_and_resume_from_prng_state(backend, max_width_frac):
+    """Core objects pickle through their constructor like the reference's (__reduce__: ctree, cmodel, prng_state
+    string, min_ctree [, slices, min_slices]; tnco/optimize/infinite_memory/optimizer.py:234-247,
+    finite_width/optimizer.py:330-346) -- and an object rebuilt from the ORACLE's state mid-run (tree, std::mt19937
+    state text, best tree, slices) continues in lock step with it."""
+    import pickle
+
+    from tnco_b200.ctree import ContractionTree
+    from tnco_b200.optimize import finite_width, infinite_memory
+    from tnco_b200.optimize.finite_width.cost_model import SimpleCostModel as FWModel
+    from tnco_b200.optimize.infinite_memory.cost_model import SimpleCostModel
+    from tnco_b200.optimize.prob import MetropolisHastings
+    ts, ni = regular_network(26, 4)
+    p, a, b, bits = random_tree(ts, ni, 5)
+    ct = ContractionTree(tree_to_linear_path(a, b), ts, 2, check_shared_inds=True)
+    P, A, B = ct.arrays()
+    order = {x: k for k, x in enumerate(ct._inds_order)}
+    names = ct._inds_order
+    nb = np.zeros((len(P), (ni + 31) // 32), np.uint32)
+    for z, xs in enumerate(ct.inds):
+        for x in xs:
+            nb[z, order[x] >> 5] |= np.uint32(1 << (order[x] & 31))
+    mw = None if max_width_frac is None else float(int(max(len(xs) for xs in ct.inds) * max_width_frac))
+    oc = so.Chain(P, A, B, nb, ni, max_width=mw, seed=31)
+    for s in range(60):
+        oc.update(0.5 * s)
+
+    def unpack(row):
+        return frozenset(names[i] for i in range(ni) if (row[i >> 5] >> (i & 31)) & 1)
+
+    leaves = [ct.inds[t] for t in range(26)]
+    cur = ContractionTree.from_arrays(*oc.tree(), leaves, 2)
+    best = ContractionTree.from_arrays(*oc.tree(True), leaves, 2)
+    if mw is None:
+        opt = infinite_memory.Optimizer(cur, SimpleCostModel(), seed=oc.prng_state_str(), _min_ctree=best)
+    else:
+        opt = finite_width.Optimizer(cur, FWModel(mw), seed=oc.prng_state_str(), _min_ctree=best,
+                                     _slices=unpack(oc.slices()), _min_slices=unpack(oc.slices(True)))
+    assert opt.prng_state == oc.prng_state_str()
+    assert opt.log2_total_cost == oc.log2_total_cost and opt.log2_min_total_cost == oc.log2_min_total_cost
+    for s in range(60, 100):
+        oc.update(0.5 * s)
+        opt.update(MetropolisHastings(0.5 * s))
+        if s == 80:  # a pickle round trip in the middle changes nothing
+            twin = pickle.loads(pickle.dumps(opt))
+            assert twin == opt and twin.prng_state == opt.prng_state
+            opt = twin
+    for x, y in zip(opt.ctree.arrays(), oc.tree()):
+        assert (x == y).all()
+    for x, y in zip(opt.min_ctree.arrays(), oc.tree(True)):
+        assert (x == y).all()
+    assert opt.log2_total_cost == oc.log2_total_cost and opt.log2_min_total_cost == oc.log2_min_total_cost
+    assert opt.prng_state == oc.prng_state_str()
+    if mw is not None:
+        assert opt.slices == unpack(oc.slices()) and opt.min_slices == unpack(oc.slices(True))
+    with pytest.raises(ValueError, match='mt19937'):
+        infinite_memory.Optimizer(cur, SimpleCostModel(), seed='1 2 3')
+
+
 def test_precision_too_low_and_bad_input(backend):
     from tnco_b200.engine import Engine
     ts, ni = regular_network(60, 1)

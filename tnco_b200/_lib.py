@@ -31,6 +31,7 @@ SIGNATURES = {
     'tnb_path_to_tree': (C.c_int, [C.c_int, i32p, i32p, i32p, i32p]),
     'tnb_mt19937_stream': (None, [C.c_uint32, C.c_uint64, u32p]),
     'tnb_mt19937_state': (None, [C.c_uint32, C.c_uint64, u32p, i32p]),
+    'tnb_mt19937_advance': (None, [u32p, i32p, C.c_uint64]),
     'tnb_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     'tnb_destroy': (None, [C.c_void_p]),
     'tnb_set_network': (C.c_int, [C.c_void_p, C.c_int, C.c_int, u32p, C.c_uint64, u64p]),
@@ -42,6 +43,7 @@ SIGNATURES = {
     'tnb_set_update_slices': (C.c_int, [C.c_void_p, C.c_int]),
     'tnb_set_chains': (C.c_int, [C.c_void_p, C.c_int, i32p, i32p, i32p, u64p, C.c_uint64]),
     'tnb_generate_chains': (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_uint64, C.c_int]),
+    'tnb_set_resume': (C.c_int, [C.c_void_p, u32p, u32p, i32p, i32p, i32p, u32p]),
     'tnb_set_stream': (C.c_int, [C.c_void_p, u32p, C.c_uint64]),
     'tnb_set_betas': (C.c_int, [C.c_void_p, f64p, C.c_int64]),
     'tnb_run': (C.c_int, [C.c_void_p, C.c_int64]),

@@ -394,6 +394,11 @@ struct tnb_engine {
   std::vector<Mt19937> mts;
   std::vector<uint32_t> h_stream;
   std::vector<uint64_t> words_base;  // draws consumed before the current stream window, per chain
+  // resume (tnb_set_resume): saved generator states, slices and best trees that replace what the constructors derive
+  std::vector<uint32_t> rs_mt;                  // [n_chains][625]
+  std::vector<uint32_t> rs_slices, rs_bslices;  // [n_chains][Wu], caller's index space
+  std::vector<int32_t> rs_bp, rs_ba, rs_bb;     // [n_chains][N]
+  void clear_resume() { rs_mt.clear(); rs_slices.clear(); rs_bslices.clear(); rs_bp.clear(); rs_ba.clear(); rs_bb.clear(); }
   void* d_flush = nullptr;
   // timing
   double kernel_ms = 0.0;
@@ -503,15 +508,14 @@ static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_be
 }
 
 // allocate a chain set and upload the packed topology
-static bool make_chains(tnb_engine* e, ChainSet& cs, int n_chains, const int32_t* parent, const int32_t* c0,
-                        const int32_t* c1, bool with_best, bool with_slicer) {
-  if (!alloc_chains(e, cs, n_chains, with_best, with_slicer)) return false;
-  Rt& rt = e->rt;
+// validate trees in the reference's node order and pack them: parents [n_chains][Npad] int16, children words
+// child0 | child1 << 16 per internal node [n_chains][max(n_int, 1)]
+static bool pack_trees(tnb_engine* e, int n_chains, const int32_t* parent, const int32_t* c0, const int32_t* c1,
+                       std::vector<int16_t>& hp, std::vector<uint32_t>& hc) {
   const size_t nc = size_t(n_chains), ni = size_t(std::max(e->n_int, 1));
-  // validate + pack
   const int N = e->N, n = e->n;
-  std::vector<int16_t> hp(nc * e->Npad, int16_t(-1));
-  std::vector<uint32_t> hc(nc * ni, 0u);
+  hp.assign(nc * e->Npad, int16_t(-1));
+  hc.assign(nc * ni, 0u);
   std::vector<int> seen(size_t(N), 0);
   for (int c = 0; c < n_chains; ++c) {
     const int32_t *p = parent + size_t(c) * N, *a = c0 + size_t(c) * N, *b = c1 + size_t(c) * N;
@@ -533,6 +537,17 @@ static bool make_chains(tnb_engine* e, ChainSet& cs, int n_chains, const int32_t
     for (int z = 0; z < N - 1; ++z)
       if (seen[z] != 1) return e->fail("invalid tree: every non-root node must be a child exactly once");
   }
+  return true;
+}
+
+static bool make_chains(tnb_engine* e, ChainSet& cs, int n_chains, const int32_t* parent, const int32_t* c0,
+                        const int32_t* c1, bool with_best, bool with_slicer) {
+  if (!alloc_chains(e, cs, n_chains, with_best, with_slicer)) return false;
+  Rt& rt = e->rt;
+  const size_t nc = size_t(n_chains);
+  std::vector<int16_t> hp;
+  std::vector<uint32_t> hc;
+  if (!pack_trees(e, n_chains, parent, c0, c1, hp, hc)) return false;
   // the compact children words travel through bch (the init kernel overwrites it with the first snapshot)
   if (!rt.h2d(cs.par, hp.data(), hp.size() * sizeof(int16_t)) || !rt.h2d(cs.bch, hc.data(), hc.size() * sizeof(uint32_t)) ||
       !ch_copy(rt, cs.bch, cs.rec, cs.hstride, nc * size_t(e->n_int), true))
@@ -628,13 +643,59 @@ static bool ensure_init(tnb_engine* e) {
     e->h_stream.assign(size_t(cs.n_chains) * L, 0u);
     e->mts.resize(size_t(cs.n_chains));
     e->words_base.assign(size_t(cs.n_chains), 0);
-    for (int c = 0; c < cs.n_chains; ++c) e->mts[size_t(c)].seed(uint32_t(e->h_seeds[size_t(c)]));
+    for (int c = 0; c < cs.n_chains; ++c) {
+      Mt19937& m = e->mts[size_t(c)];
+      if (e->rs_mt.empty()) {
+        m.seed(uint32_t(e->h_seeds[size_t(c)]));
+      } else {  // resume: `iss >> prng` (optimize/optimizer.hpp:68-72)
+        std::memcpy(m.x, &e->rs_mt[size_t(c) * 625], sizeof(m.x));
+        m.p = int(e->rs_mt[size_t(c) * 625 + 624]);
+      }
+    }
     if (!mt_refill(e, true)) return false;
   }
+  const size_t nc_ = size_t(e->cs.n_chains);
   Params P;
   fill_params(e, e->cs, P);
+  if (!e->rs_slices.empty() && e->finite) {  // `slices=` given: the constructor does not run the slicer (:80-88)
+    std::vector<uint32_t> hs(nc_ * e->Ws, 0u);
+    for (size_t c = 0; c < nc_; ++c) e->expand_row(&e->rs_slices[c * e->Wu], &hs[c * e->Ws]);
+    if (!e->rt.h2d(e->cs.slices, hs.data(), hs.size() * sizeof(uint32_t)) || !e->rt.sync()) return e->rtfail();
+    P.slices_given = 1;
+  }
   if (!launch(e->rt, P, e->tile, e->wpl, true, e->finite, stream_mode(e))) return e->rtfail();
   if (!e->rt.sync()) return e->rtfail();
+  if (!e->rs_bp.empty()) {
+    // saved min_ctree [+ min_slices]: min_total_cost = get_cost(min_ctree[, min_slices]) as the reference
+    // constructors compute it (infinite_memory/optimizer.hpp:72-75, finite_width/greedy/optimizer.hpp:99-101)
+    std::vector<int16_t> hp;
+    std::vector<uint32_t> hc;
+    if (!pack_trees(e, e->cs.n_chains, e->rs_bp.data(), e->rs_ba.data(), e->rs_bb.data(), hp, hc)) return false;
+    std::vector<double> seq(nc_);
+    const uint32_t* bs = !e->finite ? nullptr : !e->rs_bslices.empty() ? e->rs_bslices.data()
+                         : !e->rs_slices.empty() ? e->rs_slices.data() : nullptr;
+    std::vector<uint32_t> cur;
+    if (e->finite && !bs) {  // min_slices defaults to the constructor's slices (:89-90)
+      std::vector<uint32_t> v(nc_ * e->Ws);
+      if (!e->rt.d2h(v.data(), e->cs.slices, v.size() * sizeof(uint32_t))) return e->rtfail();
+      cur.assign(nc_ * e->Wu, 0u);
+      for (size_t c = 0; c < nc_; ++c) e->contract_row(&v[c * e->Ws], &cur[c * e->Wu]);
+      bs = cur.data();
+    }
+    if (tnb_eval_cost(e, e->cs.n_chains, e->rs_bp.data(), e->rs_ba.data(), e->rs_bb.data(), bs, seq.data(), nullptr,
+                      nullptr) != 0)
+      return false;
+    if (!e->rt.h2d(e->cs.bpar, hp.data(), hp.size() * sizeof(int16_t)) ||
+        !e->rt.h2d(e->cs.bch, hc.data(), hc.size() * sizeof(uint32_t)) ||
+        !e->rt.h2d(e->cs.min_total, seq.data(), seq.size() * sizeof(double)))
+      return e->rtfail();
+    if (e->finite) {
+      std::vector<uint32_t> hb(nc_ * e->Ws, 0u);
+      for (size_t c = 0; c < nc_; ++c) e->expand_row(bs + c * e->Wu, &hb[c * e->Ws]);
+      if (!e->rt.h2d(e->cs.bslices, hb.data(), hb.size() * sizeof(uint32_t))) return e->rtfail();
+    }
+    if (!e->rt.sync()) return e->rtfail();
+  }
   // "Precision is too low." (infinite_memory/optimizer.hpp:77-87)
   std::vector<double> tot(size_t(e->cs.n_chains));
   if (!e->rt.d2h(tot.data(), e->cs.total, tot.size() * sizeof(double))) return e->rtfail();
@@ -865,6 +926,7 @@ int tnb_set_chains(tnb_engine* e, int n_chains, const int32_t* parent, const int
   if (n_chains < 1 || !parent || !child0 || !child1 || !seeds) return e->fail("tnb_set_chains: invalid arguments"), -1;
   e->cs.release(e->rt);
   e->initialized = false;
+  e->clear_resume();
   e->chain_id0 = chain_id0;
   if (!make_chains(e, e->cs, n_chains, parent, child0, child1, true, true)) { e->cs.release(e->rt); return -2; }
   if (!check_shared(e, child0, child1, n_chains)) { e->cs.release(e->rt); return -2; }
@@ -884,6 +946,7 @@ int tnb_generate_chains(tnb_engine* e, int n_chains, const uint64_t* seeds, uint
   ChainSet& cs = e->cs;
   cs.release(e->rt);
   e->initialized = false;
+  e->clear_resume();
   e->chain_id0 = chain_id0;
   if (!alloc_chains(e, cs, n_chains, true, true) || !alloc_to(e->rt, cs.kpop, size_t(n_chains) * e->Npad) ||
       !alloc_to(e->rt, cs.tree_fail, size_t(n_chains)) || !alloc_to(e->rt, cs.escore, size_t(n_chains) * e->Ws * 32)) {
@@ -909,6 +972,34 @@ int tnb_generate_chains(tnb_engine* e, int n_chains, const uint64_t* seeds, uint
       }
   } else if (!e->rt.sync()) {
     return e->rtfail(), -3;
+  }
+  return 0;
+}
+
+int tnb_set_resume(tnb_engine* e, const uint32_t* mt_state, const uint32_t* slices, const int32_t* best_parent,
+                   const int32_t* best_child0, const int32_t* best_child1, const uint32_t* best_slices) {
+  if (!e) return -1;
+  if (e->cs.n_chains == 0) return e->fail("tnb_set_resume: call tnb_set_chains first"), -1;
+  if (e->initialized) return e->fail("tnb_set_resume: the chains are already constructed; call it right after "
+                                     "tnb_set_chains"), -1;
+  if (mt_state && e->rng_kind != TNB_RNG_MT19937)
+    return e->fail("tnb_set_resume: generator states belong to TNB_RNG_MT19937 mode"), -1;
+  if ((best_parent || best_child0 || best_child1) && !(best_parent && best_child0 && best_child1))
+    return e->fail("tnb_set_resume: invalid arguments"), -1;
+  if ((slices || best_slices) && !e->finite) return e->fail("tnb_set_resume: slices need a max_width"), -1;
+  const size_t nc = size_t(e->cs.n_chains);
+  e->clear_resume();
+  if (mt_state) {
+    for (size_t c = 0; c < nc; ++c)
+      if (mt_state[c * 625 + 624] > 624u) return e->fail("tnb_set_resume: invalid generator state"), -1;
+    e->rs_mt.assign(mt_state, mt_state + nc * 625);
+  }
+  if (slices) e->rs_slices.assign(slices, slices + nc * e->Wu);
+  if (best_slices) e->rs_bslices.assign(best_slices, best_slices + nc * e->Wu);
+  if (best_parent) {
+    e->rs_bp.assign(best_parent, best_parent + nc * e->N);
+    e->rs_ba.assign(best_child0, best_child0 + nc * e->N);
+    e->rs_bb.assign(best_child1, best_child1 + nc * e->N);
   }
   return 0;
 }

@@ -340,6 +340,15 @@ void tnb_mt19937_state(uint32_t seed, uint64_t n_draws, uint32_t* state624, int3
   *pos = m.p;
 }
 
+void tnb_mt19937_advance(uint32_t* state624, int32_t* pos, uint64_t n_draws) {
+  Mt19937 m;
+  std::memcpy(m.x, state624, sizeof(m.x));
+  m.p = *pos;
+  for (uint64_t i = 0; i < n_draws; ++i) (void)m.next();
+  std::memcpy(state624, m.x, sizeof(m.x));
+  *pos = m.p;
+}
+
 int tnb_random_trees(int n_leaves, int n_inds, const uint32_t* leaf_bits, int n_trees, const uint64_t* seeds,
                      int method, int n_threads, int32_t* parent, int32_t* child0, int32_t* child1) {
   return tnb_random_trees_out(n_leaves, n_inds, leaf_bits, nullptr, n_trees, seeds, method, n_threads, parent, child0,

@@ -129,6 +129,25 @@ def mt19937_state_str(seed, n_draws):
     return ' '.join(map(str, st.tolist())) + ' ' + str(pos.value)
 
 
+def parse_mt19937_state(text):
+    """libstdc++ text form of a std::mt19937 (624 words, then the position) -> uint32[625]."""
+    try:
+        w = [int(x) for x in str(text).split()]
+    except ValueError:
+        w = []
+    if len(w) != 625 or w[624] > 624 or any(x < 0 or x >= 2**32 for x in w):
+        raise ValueError("'seed' is not a valid std::mt19937 state.")
+    return np.array(w, np.uint32)
+
+
+def mt19937_advance_str(state625, n_draws):
+    """Text form of the generator `state625` after n_draws further outputs."""
+    st = np.array(state625[:624], np.uint32)
+    pos = C.c_int32(int(state625[624]))
+    _lib.lib().tnb_mt19937_advance(_ptr(st, C.c_uint32), C.byref(pos), int(n_draws))
+    return ' '.join(map(str, st.tolist())) + ' ' + str(pos.value)
+
+
 # ------------------------------------------------------------------------------------------ engine
 _ENGINES = {}
 
@@ -240,6 +259,20 @@ class Engine:
         self.n_chains = len(s)
         self._chk(self._L.tnb_set_chains(self._h, self.n_chains, _ptr(p, C.c_int32), _ptr(a, C.c_int32),
                                          _ptr(b, C.c_int32), _ptr(s, C.c_uint64), int(chain_id0)))
+        return self
+
+    def set_resume(self, mt_state=None, slices=None, best_trees=None, best_slices=None):
+        """Continue from a saved state (tnb_set_resume): call right after set_chains."""
+        ms = None if mt_state is None else _c(mt_state, np.uint32).reshape(self.n_chains, 625)
+        sl = None if slices is None else _c(slices, np.uint32).reshape(self.n_chains, self.W)
+        bs = None if best_slices is None else _c(best_slices, np.uint32).reshape(self.n_chains, self.W)
+        bp = ba = bb = None
+        if best_trees is not None:
+            bp, ba, bb = (np.atleast_2d(_c(x, np.int32)) for x in best_trees)
+            if bp.shape != (self.n_chains, self.N) or ba.shape != bp.shape or bb.shape != bp.shape:
+                raise ValueError('best trees must be [n_chains][2*n_leaves-1]')
+        self._chk(self._L.tnb_set_resume(self._h, _ptr(ms, C.c_uint32), _ptr(sl, C.c_uint32), _ptr(bp, C.c_int32),
+                                         _ptr(ba, C.c_int32), _ptr(bb, C.c_int32), _ptr(bs, C.c_uint32)))
         return self
 
     def generate_chains(self, seeds, chain_id0=0, method=TREES_GREEDY):

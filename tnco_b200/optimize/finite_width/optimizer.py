@@ -23,3 +23,14 @@ class Optimizer(_Base):
 
     slices = property(lambda s: s._slice_names(False))
     min_slices = property(lambda s: s._slice_names(True))
+    skip_slices = property(lambda s: frozenset())
+
+    @staticmethod
+    def __build__(*args):
+        ctree, cmodel, prng_state, disable_shared_inds, min_ctree, slices, min_slices, skip_slices = args
+        return Optimizer(ctree, cmodel, seed=prng_state, disable_shared_inds=disable_shared_inds,
+                         skip_slices=skip_slices, _min_ctree=min_ctree, _slices=slices, _min_slices=min_slices)
+
+    def __reduce__(self):
+        return self.__build__, (self.ctree, self.cmodel, self.prng_state, self.disable_shared_inds, self.min_ctree,
+                                self.slices, self.min_slices, self.skip_slices)

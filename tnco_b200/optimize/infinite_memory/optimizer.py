@@ -12,7 +12,8 @@ import numpy as np
 
 from ..._lib import RNG_MT19937
 from ...ctree import ContractionTree
-from ...engine import Engine, mt19937_state_str, pack_index_set, unpack_bits
+from ...engine import (Engine, mt19937_advance_str, mt19937_state_str, pack_index_set, parse_mt19937_state,
+                       unpack_bits)
 from ..prob import BaseProbability
 
 
@@ -31,11 +32,14 @@ class Optimizer:
         if kwargs.pop('skip_slices', None):
             raise NotImplementedError("tnco_b200: 'skip_slices' is not supported yet.")
         kwargs.pop('slice_update', None)
+        # what unpickling hands back (optimizer.py:234-247, finite_width/optimizer.py:330-346)
+        min_ctree = kwargs.pop('_min_ctree', None)
+        slices, min_slices = kwargs.pop('_slices', None), kwargs.pop('_min_slices', None)
         if kwargs:
             raise TypeError('Got unexpected keyword arguments.')
-        if isinstance(seed, str):
-            raise NotImplementedError('tnco_b200: resuming from a PRNG state string is not supported; pass the seed.')
-        self._seed = secrets.randbits(32) if seed is None else int(seed) % 2**32
+        # seed: an integer, or a std::mt19937 state string as `prng_state` returns it (optimize/optimizer.hpp:68-72)
+        self._state0 = parse_mt19937_state(seed) if isinstance(seed, str) else None
+        self._seed = 0 if self._state0 is not None else secrets.randbits(32) if seed is None else int(seed) % 2**32
         self._ctree0, self._cmodel = ctree, cmodel
         self._dsi, self._atol = bool(disable_shared_inds), atol
         dims = [int(ctree.dims[x]) for x in ctree._inds_order]
@@ -56,6 +60,13 @@ class Optimizer:
                          update_slices_every=1, disable_shared_inds=self._dsi, rng=RNG_MT19937)
         p, a, b = ctree.arrays()
         self._e.set_chains(p[None], a[None], b[None], [self._seed])
+        if self._state0 is not None or min_ctree is not None or slices is not None or min_slices is not None:
+            def bits(names):
+                return None if names is None else pack_index_set([pos[x] for x in names], ni)[None]
+            best = None if min_ctree is None else tuple(x[None] for x in min_ctree.arrays())
+            self._e.set_resume(mt_state=None if self._state0 is None else self._state0[None],
+                               slices=bits(slices) if self._finite else None, best_trees=best,
+                               best_slices=bits(min_slices) if self._finite else None)
         self._n_updates = 0
         self._e.costs()  # construct caches now: invalid input / "Precision is too low." raise here (ValueError)
 
@@ -90,7 +101,28 @@ class Optimizer:
 
     @property
     def prng_state(self) -> str:
-        return mt19937_state_str(self._seed, int(self._e.progress()['words'][0]))
+        words = int(self._e.progress()['words'][0])
+        if self._state0 is not None:
+            return mt19937_advance_str(self._state0, words)
+        return mt19937_state_str(self._seed, words)
+
+    # ---- pickling: rebuild through the constructor from the current state, like the reference
+    @staticmethod
+    def __build__(*args):
+        ctree, cmodel, prng_state, disable_shared_inds, min_ctree = args
+        return Optimizer(ctree, cmodel, seed=prng_state, disable_shared_inds=disable_shared_inds,
+                         _min_ctree=min_ctree)
+
+    def __reduce__(self):
+        return self.__build__, (self.ctree, self.cmodel, self.prng_state, self.disable_shared_inds, self.min_ctree)
+
+    def __eq__(self, other):
+        return isinstance(other, Optimizer) and self.__reduce__()[1] == other.__reduce__()[1]
+
+    __hash__ = None
+
+    def __repr__(self):
+        return 'Optimizer(ctree={}, cmodel={})'.format(self.ctree, self.cmodel)
 
     def is_valid(self, *, atol: float = 1e-5, return_message: bool = False):
         """Re-derive the cached totals from the trees (infinite_memory/optimizer.hpp:223-252)."""
