@@ -124,6 +124,9 @@ int tnb_set_sparse_inds(tnb_engine* e, const uint32_t* sparse_bits, uint64_t n_p
  * sweeps s with s % update_slices_every == 0 (tnco/app/finite_width/sa.py:228). */
 int tnb_set_mode(tnb_engine* e, double max_width, int update_slices_every, int disable_shared_inds,
                  int prob_kind, int rng_kind, int layout);
+/* TNB_RNG_PHILOX (production) runs what tnco.app runs: Metropolis-Hastings acceptance with shared-index moves.
+ * Greedy / always acceptance and disable_shared_inds -- the core objects' options -- need TNB_RNG_MT19937 or
+ * TNB_RNG_REPLAY; tnb_run and the chain constructors fail otherwise. */
 
 /* Change only the acceptance rule (the reference passes a prob object to every update()); chains are kept. */
 int tnb_set_prob(tnb_engine* e, int prob_kind);

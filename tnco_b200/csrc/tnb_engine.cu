@@ -624,10 +624,19 @@ static bool mt_refill(tnb_engine* e, bool first) {
   return e->rt.sync() || e->rtfail();
 }
 
+// Philox kernels are compiled for the app's mode (Metropolis-Hastings, shared-index moves)
+static bool mode_ok(tnb_engine* e) {
+  if (e->rng_kind == TNB_RNG_PHILOX && (e->dsi || e->prob_kind != TNB_PROB_MH))
+    return e->fail("TNB_RNG_PHILOX runs Metropolis-Hastings with shared-index moves only: greedy / always acceptance "
+                   "and disable_shared_inds need TNB_RNG_MT19937 or TNB_RNG_REPLAY (invalid mode)");
+  return true;
+}
+
 static bool ensure_init(tnb_engine* e) {
   if (e->initialized) return true;
   if (e->cs.n_chains == 0) return e->fail("no chains: call tnb_set_chains first");
   if (e->rng_kind == TNB_RNG_REPLAY && !e->cs.stream) return e->fail("TNB_RNG_REPLAY needs tnb_set_stream");
+  if (!mode_ok(e)) return false;
   if (e->d_sparse && e->finite && e->rng_kind == TNB_RNG_PHILOX)
     return e->fail("sparse indices with max_width run on the stream kernels: use TNB_RNG_MT19937 (the production "
                    "re-slicer does not know the sparse-index width model)");
@@ -1041,6 +1050,7 @@ int tnb_run(tnb_engine* e, int64_t until_sweep) {
   if (!e) return -1;
   if (!e->d_betas) return e->fail("tnb_run: call tnb_set_betas first"), -1;
   if (!ensure_init(e)) return -2;
+  if (!mode_ok(e)) return -1;  // tnb_set_prob may have changed the rule since the chains were built
   Params P;
   for (int guard = 0;; ++guard) {
     fill_params(e, e->cs, P);

@@ -1279,6 +1279,11 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   keep_in_register(c.rec);
   keep_in_register(c.rec_lane);
   keep_in_register(c.par);
+  if constexpr (WPL == 1) {  // "this lane owns a word": one live flag instead of S2R + AND + constant load + compare
+    uint32_t okf = c.lane_ok[0] ? 1u : 0u;
+    keep_in_register(okf);
+    c.lane_ok[0] = okf != 0u;
+  }
   // PC: keep the reference's partial-cost cache (parity modes).  The production kernel drops it: the walk then
   // needs no partial costs of D/E/C, no two 16-byte stores per level and half the fp64 adds; its total is a
   // running sum re-based on sum_ccost() every 64 sweeps.
@@ -1300,7 +1305,11 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   for (int k = 0; k < WPL; ++k) S[k] = 0u;
   if (FINITE) load_slices(c, S);
 
-  const int f_dsi = P.dsi, f_prob = P.prob_kind;
+  // The production (Philox) kernels run what the app runs -- Metropolis-Hastings with shared-index moves -- with the
+  // two mode flags folded at compile time (per level: two constant loads, two compares and the generic acceptance
+  // branch gone); other acceptance rules / disable_shared_inds belong to the core objects, i.e. the stream kernels
+  // (the host refuses them in Philox mode).
+  const int f_dsi = Rng::kFast ? 0 : P.dsi, f_prob = Rng::kFast ? kProbMH : P.prob_kind;
   bool in_sweep = false;
   int B = 0, A = -1, C = 0, p0 = 0, p1 = 0, a0 = 0, a1 = 0;
   // one level ahead (loop-carried): An = parent(A) and its header, loaded during the previous level

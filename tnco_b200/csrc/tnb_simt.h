@@ -40,6 +40,16 @@ TNB_D TNB_INLINE void keep_in_register(T*& p) {
   (void)p;
 #endif
 }
+// Same for a 32-bit value: the compiler otherwise re-derives cheap-looking values (lane id -> "does this lane own a
+// word of the bitset") from special registers and kernel parameters at every use -- four instructions and an S2R
+// latency each time instead of one compare against a live register.
+TNB_D TNB_INLINE void keep_in_register(uint32_t& v) {
+#if !defined(TNB_EMU)
+  asm volatile("" : "+r"(v));
+#else
+  (void)v;
+#endif
+}
 #if defined(TNB_EMU)
 #define TNB_NOINLINE
 #else
