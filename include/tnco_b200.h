@@ -119,6 +119,11 @@ int tnb_is_hyper(tnb_engine* e);
  * chains.  With max_width the stream kernels serve it (TNB_RNG_MT19937 / TNB_RNG_REPLAY). */
 int tnb_set_sparse_inds(tnb_engine* e, const uint32_t* sparse_bits, uint64_t n_projs);
 
+/* skip_slices of the finite-width core object (tnco/optimize/finite_width/optimizer.py:60,96-107;
+ * include/tnco/optimize/finite_width/greedy/utils.hpp:76-79): indices the greedy slicer never takes.  [W32] or NULL
+ * for none.  Stream kernels only (TNB_RNG_MT19937 / TNB_RNG_REPLAY); call after tnb_set_network; drops the chains. */
+int tnb_set_skip_slices(tnb_engine* e, const uint32_t* skip_bits);
+
 /* max_width < 0 or +inf: unconstrained (infinite_memory optimizer).  Otherwise the memory-constrained
  * optimizer with float32 width arithmetic (tnco/app/app.py:757) and the greedy slicer, re-slicing on
  * sweeps s with s % update_slices_every == 0 (tnco/app/finite_width/sa.py:228). */

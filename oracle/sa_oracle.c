@@ -99,6 +99,7 @@ struct ora_chain {
   uint64_t dim;       /* uniform dim when dims == NULL */
   uint64_t* dims;     /* per-index dims or NULL */
   float max_width;    /* width_type = float32 (tnco/app/app.py:757) */
+  uint32_t* skip;     /* [W] skip_slices: indices the slicer must not take, or NULL */
   uint32_t* sparse;   /* [W] sparse indices (SimpleCostModelSparseInds) or NULL */
   uint64_t n_projs;
   int32_t *par, *c0, *c1;
@@ -262,7 +263,7 @@ static void get_slices(ora_chain* c, uint32_t* out) {
     if (!(sw > c->max_width)) continue;
     int np = 0;
     for (int w = 0; w < W; ++w) {
-      uint32_t v = xs[w];
+      uint32_t v = xs[w] & ~(c->skip ? c->skip[w] : 0u); /* sliced_xs - skip_slices (:76-79) */
       while (v) {
         pos[np++] = w * 32 + __builtin_ctz(v);
         v &= v - 1;
@@ -331,6 +332,14 @@ ora_chain* ora_create_sparse(int n, int n_inds, const int32_t* parent, const int
                              const int32_t* child1, const uint32_t* node_bits, uint64_t dim, const uint64_t* dims,
                              int finite, float max_width, uint32_t seed, int dsi, const uint32_t* sparse_bits,
                              uint64_t n_projs, int* err) {
+  return ora_create_ex(n, n_inds, parent, child0, child1, node_bits, dim, dims, finite, max_width, seed, dsi,
+                       sparse_bits, n_projs, NULL, err);
+}
+
+ora_chain* ora_create_ex(int n, int n_inds, const int32_t* parent, const int32_t* child0, const int32_t* child1,
+                         const uint32_t* node_bits, uint64_t dim, const uint64_t* dims, int finite, float max_width,
+                         uint32_t seed, int dsi, const uint32_t* sparse_bits, uint64_t n_projs,
+                         const uint32_t* skip_bits, int* err) {
   if (err) *err = 0;
   if (sparse_bits && n_projs == 0) { /* "'n_projs' must be a positive number." (simple_sparse_inds.hpp:64-67) */
     if (err) *err = 3;
@@ -340,6 +349,10 @@ ora_chain* ora_create_sparse(int n, int n_inds, const int32_t* parent, const int
   const int N = 2 * n - 1, W = (n_inds + 31) / 32;
   c->n = n; c->N = N; c->n_inds = n_inds; c->W = W;
   c->finite = finite; c->dsi = dsi; c->dim = dim; c->max_width = max_width;
+  if (skip_bits) {
+    c->skip = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)W);
+    memcpy(c->skip, skip_bits, sizeof(uint32_t) * (size_t)W);
+  }
   if (sparse_bits) {
     c->sparse = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)W);
     memcpy(c->sparse, sparse_bits, sizeof(uint32_t) * (size_t)W);
@@ -389,7 +402,7 @@ ora_chain* ora_create_sparse(int n, int n_inds, const int32_t* parent, const int
 
 void ora_destroy(ora_chain* c) {
   if (!c) return;
-  free(c->sparse); free(c->dims); free(c->par); free(c->c0); free(c->c1); free(c->mpar); free(c->mc0); free(c->mc1);
+  free(c->skip); free(c->sparse); free(c->dims); free(c->par); free(c->c0); free(c->c1); free(c->mpar); free(c->mc0); free(c->mc1);
   free(c->bits); free(c->hyper); free(c->mbits); free(c->cc); free(c->pc); free(c->width);
   free(c->slices); free(c->mslices);
   free(c);

@@ -35,9 +35,9 @@ def lib():
         L = C.CDLL(_SO)
         i32p, u32p, u64p, f64p = (C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
                                   C.POINTER(C.c_double))
-        L.ora_create_sparse.restype = C.c_void_p
-        L.ora_create_sparse.argtypes = [C.c_int, C.c_int, i32p, i32p, i32p, u32p, C.c_uint64, u64p, C.c_int,
-                                        C.c_float, C.c_uint32, C.c_int, u32p, C.c_uint64, C.POINTER(C.c_int)]
+        L.ora_create_ex.restype = C.c_void_p
+        L.ora_create_ex.argtypes = [C.c_int, C.c_int, i32p, i32p, i32p, u32p, C.c_uint64, u64p, C.c_int,
+                                    C.c_float, C.c_uint32, C.c_int, u32p, C.c_uint64, u32p, C.POINTER(C.c_int)]
         L.ora_create.restype = C.c_void_p
         L.ora_create.argtypes = [C.c_int, C.c_int, i32p, i32p, i32p, u32p, C.c_uint64, u64p, C.c_int,
                                  C.c_float, C.c_uint32, C.c_int, C.POINTER(C.c_int)]
@@ -78,7 +78,7 @@ class Chain:
     """One SA chain == one reference ``Optimizer`` object (infinite_memory or finite_width.greedy)."""
 
     def __init__(self, parent, child0, child1, node_bits, n_inds, *, dim=2, dims=None, max_width=None,
-                 seed=0, disable_shared_inds=False, sparse_bits=None, n_projs=None):
+                 seed=0, disable_shared_inds=False, sparse_bits=None, n_projs=None, skip_bits=None):
         L = lib()
         self.parent0, c0, c1 = _i32(parent), _i32(child0), _i32(child1)
         self.N = len(self.parent0)
@@ -90,12 +90,13 @@ class Chain:
         err = C.c_int(0)
         self.finite = max_width is not None
         sp = None if sparse_bits is None else np.ascontiguousarray(sparse_bits, dtype=np.uint32).reshape(self.W)
-        self._h = L.ora_create_sparse(self.n, self.n_inds, _p(self.parent0, C.c_int32), _p(c0, C.c_int32),
+        sk = None if skip_bits is None else np.ascontiguousarray(skip_bits, dtype=np.uint32).reshape(self.W)
+        self._h = L.ora_create_ex(self.n, self.n_inds, _p(self.parent0, C.c_int32), _p(c0, C.c_int32),
                                       _p(c1, C.c_int32), _p(nb, C.c_uint32), int(dim),
                                       None if dims_a is None else _p(dims_a, C.c_uint64), int(self.finite),
                                       float(max_width if self.finite else 0.0), int(seed) & 0xFFFFFFFF,
                                       int(disable_shared_inds), None if sp is None else _p(sp, C.c_uint32),
-                                      int(n_projs or 0), C.byref(err))
+                                      int(n_projs or 0), None if sk is None else _p(sk, C.c_uint32), C.byref(err))
         if not self._h:
             raise ValueError('Precision is too low.' if err.value == 2 else
                              "'n_projs' must be a positive number." if err.value == 3 else 'invalid input')

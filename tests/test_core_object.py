@@ -206,6 +206,45 @@ def test_pickle_and_resume_from_prng_state(backend, max_width_frac):
         infinite_memory.Optimizer(cur, SimpleCostModel(), seed='1 2 3')
 
 
+def test_skip_slices_lockstep_with_oracle(backend):
+    """skip_slices (tnco/optimize/finite_width/optimizer.py:60,96-107): the slicer never takes those indices."""
+    from tnco_b200.ctree import ContractionTree
+    from tnco_b200.optimize import finite_width
+    from tnco_b200.optimize.finite_width.cost_model import SimpleCostModel as FWModel
+    from tnco_b200.optimize.prob import MetropolisHastings
+    ts, ni = regular_network(30, 14)
+    p, a, b, bits = random_tree(ts, ni, 15)
+    ct = ContractionTree(tree_to_linear_path(a, b), ts, 2, check_shared_inds=True)
+    P, A, B = ct.arrays()
+    order = {x: k for k, x in enumerate(ct._inds_order)}
+    names = ct._inds_order
+    nb = np.zeros((len(P), (ni + 31) // 32), np.uint32)
+    for z, xs in enumerate(ct.inds):
+        for x in xs:
+            nb[z, order[x] >> 5] |= np.uint32(1 << (order[x] & 31))
+    mw = float(int(max(len(xs) for xs in ct.inds) * 0.5))
+    skip = [x for x in names if order[x] % 7 == 0]
+    sk = np.zeros((ni + 31) // 32, np.uint32)
+    for x in skip:
+        sk[order[x] >> 5] |= np.uint32(1 << (order[x] & 31))
+    opt = finite_width.Optimizer(ct, FWModel(mw), seed=5, skip_slices=skip)
+    oc = so.Chain(P, A, B, nb, ni, max_width=mw, seed=5, skip_bits=sk)
+    assert opt.skip_slices == frozenset(skip)
+    seen = set()
+    for s in range(80):
+        opt.update(MetropolisHastings(float(s)))
+        oc.update(float(s))
+        cur = frozenset(names[i] for i in range(ni) if (oc.slices()[i >> 5] >> (i & 31)) & 1)
+        assert opt.slices == cur and not (cur & frozenset(skip))
+        seen |= cur
+    assert seen and opt.log2_total_cost == oc.log2_total_cost and opt.prng_state == oc.prng_state_str()
+    assert opt.is_valid()
+    with pytest.raises(ValueError, match='subset'):
+        finite_width.Optimizer(ct, FWModel(mw), seed=5, skip_slices=['nope'])
+    with pytest.raises(ValueError, match='Too many'):
+        finite_width.Optimizer(ct, FWModel(1.0), seed=5, skip_slices=list(names))
+
+
 def test_precision_too_low_and_bad_input(backend):
     from tnco_b200.engine import Engine
     ts, ni = regular_network(60, 1)

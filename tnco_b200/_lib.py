@@ -38,6 +38,7 @@ SIGNATURES = {
     'tnb_set_output_inds': (C.c_int, [C.c_void_p, u32p]),
     'tnb_is_hyper': (C.c_int, [C.c_void_p]),
     'tnb_set_sparse_inds': (C.c_int, [C.c_void_p, u32p, C.c_uint64]),
+    'tnb_set_skip_slices': (C.c_int, [C.c_void_p, u32p]),
     'tnb_set_mode': (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     'tnb_set_prob': (C.c_int, [C.c_void_p, C.c_int]),
     'tnb_set_update_slices': (C.c_int, [C.c_void_p, C.c_int]),

@@ -360,6 +360,7 @@ struct tnb_engine {
   // sparse-index cost model (tnb_set_sparse_inds): sparse indices in the virtual index space, or none
   uint32_t* d_sparse = nullptr;  // [Ws + tail]
   uint64_t n_projs = 0;
+  uint32_t* d_skip = nullptr;    // [Ws + tail] skip_slices (tnb_set_skip_slices)
   uint8_t* d_gw = nullptr;       // [Ws*32] log2(dim) at the leader positions
 
   // caller's index space <-> virtual index space (rows of Wu / W words)
@@ -441,6 +442,7 @@ static void fill_params(const tnb_engine* e, const ChainSet& cs, Params& P) {
   std::memset(&P, 0, sizeof(P));
   P.n = e->n; P.N = e->N; P.n_int = e->n_int; P.n_inds = e->n_inds; P.W = e->W; P.Ws = e->Ws;
   P.leaf_bits = e->d_leaf_bits; P.pow_tab = e->d_pow_tab; P.log2d = e->log2d;
+  P.skip = e->d_skip;
   P.sparse = e->d_sparse;  // costs of a network with sparse indices come from the table kernels
   P.dim2 = e->dim == 2 && !e->d_sparse;
   P.n_projs = double(e->n_projs);
@@ -629,6 +631,8 @@ static bool mode_ok(tnb_engine* e) {
   if (e->rng_kind == TNB_RNG_PHILOX && (e->dsi || e->prob_kind != TNB_PROB_MH))
     return e->fail("TNB_RNG_PHILOX runs Metropolis-Hastings with shared-index moves only: greedy / always acceptance "
                    "and disable_shared_inds need TNB_RNG_MT19937 or TNB_RNG_REPLAY (invalid mode)");
+  if (e->rng_kind == TNB_RNG_PHILOX && e->finite && e->d_skip)
+    return e->fail("skip_slices is served by the stream kernels: use TNB_RNG_MT19937 or TNB_RNG_REPLAY (invalid mode)");
   return true;
 }
 
@@ -760,6 +764,7 @@ void tnb_destroy(tnb_engine* e) {
   e->rt.free_(e->d_leader);
   e->rt.free_(e->d_gw);
   e->rt.free_(e->d_sparse);
+  e->rt.free_(e->d_skip);
   e->rt.free_(e->d_betas);
   e->rt.free_(e->d_inv_betas);
   e->rt.free_(e->d_flush);
@@ -841,9 +846,11 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds_u, const uint32_t* l
     leader[size_t(k) >> 5] |= 1u << (k & 31);
     gw[size_t(k)] = uint8_t(vw[size_t(i)]);
   }
-  void* old[] = {e->d_leaf_bits, e->d_pow_tab, e->d_net_own, e->d_hcount0, e->d_leader, e->d_gw, e->d_sparse};
+  void* old[] = {e->d_leaf_bits, e->d_pow_tab, e->d_net_own, e->d_hcount0, e->d_leader, e->d_gw, e->d_sparse,
+                 e->d_skip};
   for (void* q : old) e->rt.free_(q);
   e->d_sparse = nullptr; e->n_projs = 0;  // a new network starts with the simple cost model
+  e->d_skip = nullptr;
   e->d_leaf_bits = nullptr; e->d_pow_tab = nullptr; e->d_net_own = nullptr; e->d_hcount0 = nullptr;
   e->d_leader = nullptr; e->d_gw = nullptr;
   if (!alloc_to(e->rt, e->d_net_own, own.size()) || !e->rt.h2d(e->d_net_own, own.data(), own.size() * sizeof(int16_t)) ||
@@ -877,6 +884,23 @@ int tnb_set_output_inds(tnb_engine* e, const uint32_t* output_bits) {
 }
 
 int tnb_is_hyper(tnb_engine* e) { return e && e->hyper ? 1 : 0; }
+
+int tnb_set_skip_slices(tnb_engine* e, const uint32_t* skip_bits) {
+  if (!e) return -1;
+  if (e->n == 0) return e->fail("tnb_set_skip_slices: call tnb_set_network first"), -1;
+  e->cs.release(e->rt);
+  e->initialized = false;
+  e->rt.free_(e->d_skip);
+  e->d_skip = nullptr;
+  if (!skip_bits) return 0;
+  std::vector<uint32_t> u(skip_bits, skip_bits + e->Wu), v(size_t(e->Ws) + kTailWords, 0u);
+  if (e->n_inds_u & 31) u[size_t(e->Wu) - 1] &= (1u << (e->n_inds_u & 31)) - 1u;
+  e->expand_row(u.data(), v.data());
+  if (!alloc_to(e->rt, e->d_skip, v.size()) || !e->rt.h2d(e->d_skip, v.data(), v.size() * sizeof(uint32_t)) ||
+      !e->rt.sync())
+    return e->rtfail(), -3;
+  return 0;
+}
 
 int tnb_set_sparse_inds(tnb_engine* e, const uint32_t* sparse_bits, uint64_t n_projs) {
   if (!e) return -1;

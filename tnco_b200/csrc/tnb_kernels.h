@@ -29,6 +29,8 @@ struct Params {
   // Served by the table-cost kernels only (the host clears dim2 for such networks); nullptr = simple cost model.
   const uint32_t* sparse;  // [Ws]
   double n_projs;          // (double)n_projs
+  // skip_slices (finite_width/greedy/utils.hpp:76-79): indices the greedy slicer never takes; stream kernels only
+  const uint32_t* skip;    // [Ws] or nullptr
   double log2_n_projs;     // log2(n_projs)
   // mode
   int finite, every, dsi, prob_kind;
@@ -579,6 +581,7 @@ TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2
     for (int i = 0; i < WPL; ++i) {
       const int w = t.tl + i * TILE;
       uint32_t v = x[i];
+      if (P.skip) v &= w < P.W ? ~P.skip[w] : 0u;  // sliced_xs - skip_slices
       if (P.grouped) v &= w < P.W ? P.leader[w] : 0u;
       uint32_t tot;
       uint32_t off = np + t.excl_scan_sum(uint32_t(popc32(v)), tot);

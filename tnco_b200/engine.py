@@ -221,6 +221,14 @@ class Engine:
             self.set_sparse_inds(sparse_bits, n_projs)
         return self
 
+    def set_skip_slices(self, skip_bits):
+        """Indices the greedy slicer never takes (core-object ``skip_slices``); ``None`` clears."""
+        sb = None if skip_bits is None else _c(skip_bits, np.uint32).reshape(-1)
+        if sb is not None and sb.shape != (self.W,):
+            raise ValueError('skip_bits must be [ceil(n_inds/32)]')
+        self._chk(self._L.tnb_set_skip_slices(self._h, _ptr(sb, C.c_uint32)))
+        return self
+
     def set_sparse_inds(self, sparse_bits, n_projs):
         """Sparse-index cost model (SimpleCostModelSparseInds); ``sparse_bits=None`` returns to the simple one."""
         if sparse_bits is None:

@@ -23,7 +23,7 @@ class Optimizer(_Base):
 
     slices = property(lambda s: s._slice_names(False))
     min_slices = property(lambda s: s._slice_names(True))
-    skip_slices = property(lambda s: frozenset())
+    skip_slices = property(lambda s: s._skip_slices)
 
     @staticmethod
     def __build__(*args):

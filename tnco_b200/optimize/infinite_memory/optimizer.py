@@ -29,8 +29,7 @@ class Optimizer:
         if kwargs.pop('max_number_new_slices', 0):
             raise NotImplementedError("tnco_b200: 'max_number_new_slices' > 0 is not supported (the app never "
                                       "enables it, tnco/optimize/finite_width/optimizer.py:59).")
-        if kwargs.pop('skip_slices', None):
-            raise NotImplementedError("tnco_b200: 'skip_slices' is not supported yet.")
+        self._skip_slices = frozenset(kwargs.pop('skip_slices', None) or ())
         kwargs.pop('slice_update', None)
         # what unpickling hands back (optimizer.py:234-247, finite_width/optimizer.py:330-346)
         min_ctree = kwargs.pop('_min_ctree', None)
@@ -56,6 +55,13 @@ class Optimizer:
                             output_bits=pack_index_set([pos[x] for x in ctree.output_inds()], ni),
                             sparse_bits=pack_index_set([pos[x] for x in sparse], ni) if sparse else None,
                             n_projs=getattr(cmodel, 'n_projs', None))
+        if self._finite:  # tnco/optimize/finite_width/optimizer.py:96-107
+            if not self._skip_slices.issubset(pos):
+                raise ValueError("'skip_slices' must be a subset of available indices.")
+            if max(cmodel.width(frozenset(xs) & self._skip_slices, ctree.dims) for xs in ctree.inds) > cmodel.max_width:
+                raise ValueError("Too many indices in 'skip_slices'.")
+            if self._skip_slices:
+                self._e.set_skip_slices(pack_index_set([pos[x] for x in self._skip_slices], ni))
         self._e.set_mode(max_width=getattr(cmodel, 'max_width', None) if self._finite else None,
                          update_slices_every=1, disable_shared_inds=self._dsi, rng=RNG_MT19937)
         p, a, b = ctree.arrays()
