@@ -1316,7 +1316,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   bool in_sweep = false;
   int B = 0, A = -1, C = 0, p0 = 0, p1 = 0, a0 = 0, a1 = 0;
   // one level ahead (loop-carried): An = parent(A) and its header, loaded during the previous level
-  int An = -1;
+  int An = -1, Ann = -1;  // Ann = parent(An): two levels ahead, so that An's successor header can be requested early
   uint32_t awn = 0u;
   double ccAn = 0.0;
   uint32_t b0[WPL], b1[WPL], bC[WPL];
@@ -1478,9 +1478,11 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         if (FS) szC = szp[C];
         ccA = c.cc(A);
         An = c.par[A];
+        Ann = -1;
         if (An >= 0) {
           awn = c.ch(An);
           ccAn = c.cc(An);
+          Ann = c.par[An];
         }
       }
     } else {
@@ -1489,8 +1491,16 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     // get_ctree_nn (optimize/optimizer.hpp:86-172): A = parent(B), C = sibling(B), D/E = children of B
     // Inputs of the NEXT level, issued before this level's own work so that every load has (at least) the whole
     // level to land.  They depend only on the chain of ancestors, which no move below them modifies:
-    //   Ann = parent(An);  the sibling of A under An (from An's header, in registers) and its index set.
-    const int Ann = An >= 0 ? int(c.par[An]) : -1;
+    //   the sibling of A under An (from An's header, in registers) and its index set; the header of Ann = parent(An)
+    //   (Ann itself was requested a level ago: a load whose ADDRESS is still in flight stalls the warp at issue);
+    //   and Annn = parent(Ann) for the level after.
+    const int Annn = Ann >= 0 ? int(c.par[Ann]) : -1;
+    uint32_t awnn = 0u;
+    double ccAnn = 0.0;
+    if (Ann >= 0) {
+      awnn = c.ch(Ann);
+      ccAnn = c.cc(Ann);
+    }
     int Cn = 0;
     uint32_t bCn[WPL], bAn[WPL], hAn[WPL];
     double pcCn = 0.0;
@@ -1560,13 +1570,6 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       }
       gate = (sparse ? c.width_sp(int(ks), int(kss)) : c.width_of(int(ks))) <= P.max_width;
       if (!gate) ++q_wrej;
-    }
-    // header of the parent after next (Ann was requested at the top of this level)
-    uint32_t awnn = 0u;
-    double ccAnn = 0.0;
-    if (Ann >= 0) {
-      awnn = c.ch(Ann);
-      ccAnn = c.cc(Ann);
     }
     bool acc = false;
     double nA = 0.0, nB = 0.0, delta = 0.0;
@@ -1708,6 +1711,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       ccA = ccAn;
     }
     An = Ann;
+    Ann = Annn;
     awn = awnn;
     ccAn = ccAnn;
     }  // level
