@@ -126,23 +126,22 @@ template <int TILE>
 struct RngPhilox {
   static constexpr bool kFast = true;  // log-domain fp32 acceptance test (see chain_sweeps)
   uint32_t k0, k1, g0, g1;
-  unsigned long long base;  // event index of the vector held by lane 0 (lane tl holds vector base + tl)
-  uint32_t pos;             // events consumed since `base`; == TILE: the held vectors are used up
-  bool fresh;               // registers hold the vectors [base, base + TILE)
+  // Lane tl holds the vector of event base + tl; pos = events consumed since `base`.  pos == TILE means "the held
+  // vectors are used up (or were never generated)": one compare per event decides whether to refill.
+  unsigned long long base;
+  uint32_t pos;
   uint32_t r0, r1, r2;
-  uint32_t e0, esrc;
-  float rf, ef;  // -log2(u) of this lane's vector / of the current event
+  uint32_t rc;   // this lane's vector as the sweep's levels use it: float bits of -log2(u), D/E coin in the last bit
+  uint32_t e0;   // current event: word 0 (leaf draw) / the level word (coin | -log2(u))
   TNB_D void set_counter(unsigned long long v) {
-    base = v;
-    pos = 0;
-    fresh = false;
+    base = v - (unsigned long long)TILE;  // (wraps for v < TILE; base + pos == v either way)
+    pos = TILE;
   }
   TNB_D unsigned long long counter() const { return base + pos; }
   TNB_D void load(const Params& P, int chain) {
     const unsigned long long s = P.seeds[chain], g = P.chain_id0 + (unsigned long long)chain;
     k0 = uint32_t(s); k1 = uint32_t(s >> 32); g0 = uint32_t(g); g1 = uint32_t(g >> 32);
-    r0 = r1 = r2 = e0 = esrc = 0;
-    rf = ef = 0.f;
+    r0 = r1 = r2 = rc = e0 = 0;
     set_counter(P.rng_ctr[chain]);
   }
   TNB_D void store(const Params& P, int chain) const { P.rng_ctr[chain] = counter(); }
@@ -151,47 +150,60 @@ struct RngPhilox {
     const unsigned long long idx = base + (unsigned long long)t.tl;
     uint32_t r3;
     philox4x32_10(uint32_t(idx), uint32_t(idx >> 32), g0, g1, k0, k1, r0, r1, r2, r3);
-    // u = (r1 + 0.5) / 2^32 in (0,1);  -log2(u) = 32 - log2(r1 + 0.5), computed once per vector
+    // u = (r1 + 0.5) / 2^32 in (0,1);  -log2(u) = 32 - log2(r1 + 0.5), computed once per vector.  The D/E coin of
+    // the level (last bit of word 0) rides in the last mantissa bit of that float -- one shuffle per level instead
+    // of two; the bit moves the acceptance threshold by one fp32 ulp, far inside the 3e-6 of ex2.approx.
 #if defined(TNB_EMU)
-    rf = 32.f - log2f(float(r1) + 0.5f);
+    const float rf = 32.f - log2f(float(r1) + 0.5f);
+    uint32_t fb;
+    std::memcpy(&fb, &rf, 4);
 #else
-    rf = 32.f - __log2f(float(r1) + 0.5f);
+    const uint32_t fb = __float_as_uint(32.f - __log2f(float(r1) + 0.5f));
 #endif
-    fresh = true;
+    rc = (fb & ~1u) | (r0 & 1u);
   }
   // Sub-warp tiles: every TILE iterations of the sweep loop ALL tiles of the warp refill together (an iteration
   // consumes at most one event, so nobody runs dry in between).  Refilling lazily, tile by tile, made the 70
   // instructions of a refill run with 1/8 of the lanes active several times per iteration (C1: 13.5 of 32 lanes
   // active on average).  Event e always uses vector e, so results do not depend on when a refill happens.
   TNB_D TNB_INLINE void tick(const Tile<TILE>& t, uint32_t iteration) {
-    if (TILE < 32 && (iteration & uint32_t(TILE - 1)) == 0u && (pos != 0u || !fresh)) {
+    if (TILE < 32 && (iteration & uint32_t(TILE - 1)) == 0u && pos != 0u) {  // (pos == 0: just refilled, unused)
       base += pos;
       pos = 0;
       generate(t);
     }
   }
-  TNB_D TNB_INLINE void event(const Tile<TILE>& t) {
+  TNB_D TNB_INLINE void refill_if_used_up(const Tile<TILE>& t) {
     if (pos == TILE) {
       base += TILE;
       pos = 0;
-      fresh = false;
+      generate(t);
     }
-    if (!fresh) generate(t);
-    esrc = pos;
+  }
+  TNB_D TNB_INLINE uint32_t leaf_word(const Tile<TILE>& t) {  // sweep start: the whole word 0
+    refill_if_used_up(t);
     e0 = t.bcast_c(r0, int(pos));
-#if defined(TNB_EMU)
-    ef = rf;
-#else
-    ef = __uint_as_float(t.bcast_c(__float_as_uint(rf), int(pos)));
-#endif
+    ++pos;
+    return e0;
+  }
+  TNB_D TNB_INLINE void begin_level(const Tile<TILE>& t) {    // one level: coin and -log2(u) in one word
+    refill_if_used_up(t);
+    e0 = t.bcast_c(rc, int(pos));
     ++pos;
   }
-  TNB_D TNB_INLINE float neg_log2_u() const { return ef; }
-  TNB_D TNB_INLINE uint32_t leaf_word(const Tile<TILE>& t) { event(t); return e0; }
-  TNB_D TNB_INLINE void begin_level(const Tile<TILE>& t) { event(t); }
   TNB_D TNB_INLINE uint32_t coin_word(const Tile<TILE>&) { return e0; }
-  TNB_D TNB_INLINE double uniform(const Tile<TILE>& t) {  // exact path (greedy / always rules)
-    return uniform_from(t.bcast(r1, int(esrc)), t.bcast(r2, int(esrc)));
+  TNB_D TNB_INLINE float neg_log2_u() const {
+#if defined(TNB_EMU)
+    float f;
+    std::memcpy(&f, &e0, 4);
+    return f;
+#else
+    return __uint_as_float(e0);
+#endif
+  }
+  TNB_D TNB_INLINE double uniform(const Tile<TILE>& t) {  // exact path (not used by the production kernels)
+    const int src = int(pos) - 1;
+    return uniform_from(t.bcast(r1, src), t.bcast(r2, src));
   }
   // lane-local draw (slicer, executed by lane 0 only); re-synchronise with sync_from0 afterwards
   TNB_D uint32_t local_next() {
