@@ -119,6 +119,18 @@ TNB_D TNB_INLINE double uniform_from(uint32_t lo, uint32_t hi) {
   return u;
 }
 
+template <int TILE>
+TNB_D TNB_INLINE unsigned lane_in_tile_here(int tl) {
+#if defined(TNB_EMU)
+  return unsigned(tl);
+#else
+  (void)tl;
+  unsigned l;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+  return l & unsigned(TILE - 1);
+#endif
+}
+
 // Counter-based production RNG.  Vector index v counts "events" of the chain: one per sweep start (word 0
 // -> leaf) and one per level (word 0 -> D/E coin, words 1,2 -> uniform).  A tile generates TILE vectors at
 // a time, one per lane, and fetches them by shuffle, so the 10-round Philox costs 1/TILE per event.
@@ -147,7 +159,9 @@ struct RngPhilox {
   TNB_D void store(const Params& P, int chain) const { P.rng_ctr[chain] = counter(); }
   TNB_D bool can_start(const Params&) const { return true; }
   TNB_D void generate(const Tile<TILE>& t) {
-    const unsigned long long idx = base + (unsigned long long)t.tl;
+    // (lane id read here, opaquely: otherwise the compiler hoists the special-register read and its masking out of
+    //  this rarely taken branch into every iteration of the sweep loop)
+    const unsigned long long idx = base + (unsigned long long)lane_in_tile_here<TILE>(t.tl);
     uint32_t r3;
     philox4x32_10(uint32_t(idx), uint32_t(idx >> 32), g0, g1, k0, k1, r0, r1, r2, r3);
     // u = (r1 + 0.5) / 2^32 in (0,1);  -log2(u) = 32 - log2(r1 + 0.5), computed once per vector.  The D/E coin of
@@ -260,6 +274,11 @@ struct RngStream {
 };
 
 // ------------------------------------------------------------------------------------------ chain view
+// node id -> 64-bit factor of an address product: node * stride as a widening 32x32->64 multiply-add onto the base
+// pointer is ONE instruction (IMAD.WIDE.U32); a 32-bit product has wrap-around semantics and costs three
+// (IMAD, IADD3, IMAD.X) -- with about six such addresses per level.
+TNB_D TNB_INLINE unsigned long long w64(int x) { return (unsigned long long)unsigned(x); }
+
 template <int TILE, int WPL>
 struct ChainView {
   const Params& P;
@@ -296,10 +315,10 @@ struct ChainView {
       // full-warp tile: "leaf or internal" is warp-uniform, so two predicated loads behind a uniform branch (the
       // leaf one through the read-only path) beat a selected pointer: C2 @ 4096 chains 4.22e9 vs 4.06e9
       if (node < n) {
-        const uint32_t* src = leaf_lane + unsigned(node) * Ws;
+        const uint32_t* src = leaf_lane + w64(node) * Ws;
         o[0] = lane_ok[0] ? ldg(src) : 0u;
       } else {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(rec_lane + unsigned(node) * bstride);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(rec_lane + w64(node) * bstride);
         o[0] = lane_ok[0] ? *src : 0u;
       }
     } else {
@@ -309,7 +328,7 @@ struct ChainView {
       const bool leaf = node < n;
       const char* base = leaf ? reinterpret_cast<const char*>(leaf_lane) : const_cast<const char*>(rec_lane);
       const unsigned st = leaf ? 4u * Ws : bstride;
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(base + unsigned(node) * st);
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(base + w64(node) * st);
 #if !defined(TNB_EMU)
       __builtin_assume(__isGlobal(src));
 #endif
@@ -318,32 +337,32 @@ struct ChainView {
     }
   }
   TNB_D TNB_INLINE void store_bits(int node, const uint32_t (&v)[WPL]) const {
-    uint32_t* dst = reinterpret_cast<uint32_t*>(rec_lane + unsigned(node) * bstride);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(rec_lane + w64(node) * bstride);
 #pragma unroll
     for (int k = 0; k < WPL; ++k)
       if (lane_ok[k]) dst[k * TILE] = v[k];
   }
   TNB_D TNB_INLINE void load_hyp(int node, uint32_t (&o)[WPL]) const {  // internal nodes only
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(rec_lane + unsigned(node) * bstride + unsigned(P.hyp_off));
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(rec_lane + w64(node) * bstride + unsigned(P.hyp_off));
 #pragma unroll
     for (int k = 0; k < WPL; ++k) o[k] = lane_ok[k] ? src[k * TILE] : 0u;
   }
   TNB_D TNB_INLINE void store_hyp(int node, const uint32_t (&v)[WPL]) const {
-    uint32_t* dst = reinterpret_cast<uint32_t*>(rec_lane + unsigned(node) * bstride + unsigned(P.hyp_off));
+    uint32_t* dst = reinterpret_cast<uint32_t*>(rec_lane + w64(node) * bstride + unsigned(P.hyp_off));
 #pragma unroll
     for (int k = 0; k < WPL; ++k)
       if (lane_ok[k]) dst[k * TILE] = v[k];
   }
   // header fields of internal node z
-  TNB_D TNB_INLINE uint32_t& ch(int z) const { return *reinterpret_cast<uint32_t*>(rec + unsigned(z) * hstride); }
-  TNB_D TNB_INLINE double& cc(int z) const { return *reinterpret_cast<double*>(rec + unsigned(z) * hstride + 8); }
+  TNB_D TNB_INLINE uint32_t& ch(int z) const { return *reinterpret_cast<uint32_t*>(rec + w64(z) * hstride); }
+  TNB_D TNB_INLINE double& cc(int z) const { return *reinterpret_cast<double*>(rec + w64(z) * hstride + 8); }
   TNB_D TNB_INLINE void store_header(int z, uint32_t children, double cost) const {
 #if defined(TNB_EMU)
     ch(z) = children;
     cc(z) = cost;
 #else
     const unsigned long long cb = (unsigned long long)__double_as_longlong(cost);
-    *reinterpret_cast<uint4*>(rec + unsigned(z) * hstride) = make_uint4(children, 0u, uint32_t(cb), uint32_t(cb >> 32));
+    *reinterpret_cast<uint4*>(rec + w64(z) * hstride) = make_uint4(children, 0u, uint32_t(cb), uint32_t(cb >> 32));
 #endif
   }
   TNB_D TNB_INLINE double pc_of(int node) const { return node < n ? 0.0 : pcv[node]; }
