@@ -1534,6 +1534,8 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     }
     int Cn = 0;
     uint32_t bCn[WPL], bAn[WPL], hAn[WPL];
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) bCn[k] = bAn[k] = hAn[k] = 0u;
     double pcCn = 0.0;
     int szCn = 0;
     if (An >= 0) {
@@ -1723,7 +1725,8 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     ccB = ccA;
     B = A;
     A = An;
-    if (An >= 0) {  // rotate the pipeline: what was loaded for the next level becomes current
+    {  // rotate the pipeline: what was loaded for the next level becomes current.  (Unconditional: at the root,
+       // An < 0, the next iteration is a sweep boundary that reloads every one of these -- two branches less.)
       a0 = int(awn & 0xffffu);
       a1 = int(awn >> 16);
       C = Cn;
