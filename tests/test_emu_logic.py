@@ -110,3 +110,7 @@ def test_emu_sparse_philox(emu, dim):
 @pytest.mark.parametrize('name', ['sparse64_inf', 'sparse100_fw30', 'sparsehyper64_fw40'])
 def test_emu_replay_sparse(emu, name):
     G.test_replay_of_recorded_draw_stream_is_bit_exact(name)
+
+
+def test_emu_mode_and_resume_errors(emu):
+    G.test_mode_and_resume_argument_errors()

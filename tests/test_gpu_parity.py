@@ -244,6 +244,46 @@ def test_philox_sparse_index_chains_are_valid(dim):
         Engine().set_network(lb, ni, sparse_bits=sp, n_projs=0)
 
 
+def test_mode_and_resume_argument_errors():
+    """Philox kernels are compiled for the app's mode; core-object options and resume states have their own rules."""
+    from helpers import leaf_bits
+    from tnco_b200._lib import PROB_GREEDY
+    from tnco_b200.engine import RNG_MT19937, Engine, EngineError, random_trees
+    ts, ni = regular_network(20, 3)
+    lb = leaf_bits(ts, ni)
+    seeds = np.array([1, 2], np.uint64)
+    p, a, b = random_trees(lb, ni, seeds)
+    e = Engine()
+    e.set_network(lb, ni).set_mode(prob=PROB_GREEDY).set_chains(p, a, b, seeds).set_betas([1.0, 2.0])
+    with pytest.raises((EngineError, ValueError), match='Metropolis'):
+        e.run(2)
+    e.set_mode(disable_shared_inds=True).set_chains(p, a, b, seeds)
+    with pytest.raises((EngineError, ValueError), match='Metropolis'):
+        e.costs()
+    e.set_mode(max_width=6.0).set_skip_slices(np.ones((ni + 31) // 32, np.uint32)).set_chains(p, a, b, seeds)
+    with pytest.raises((EngineError, ValueError), match='skip_slices'):
+        e.costs()
+    # greedy acceptance on the stream kernels: costs never go up
+    e.set_skip_slices(None).set_mode(prob=PROB_GREEDY, rng=RNG_MT19937).set_chains(p, a, b, seeds).set_betas([0.0] * 30)
+    t0, _ = e.costs()
+    e.run(30)
+    assert (e.costs()[0] <= t0).all()
+    # resume states: only right after set_chains, generator states only in MT19937 mode, slices only with max_width
+    with pytest.raises((EngineError, ValueError), match='already constructed'):
+        e.set_resume(mt_state=np.zeros((2, 625), np.uint32))
+    e.set_chains(p, a, b, seeds)
+    with pytest.raises((EngineError, ValueError), match='max_width'):
+        e.set_resume(slices=np.zeros((2, (ni + 31) // 32), np.uint32))
+    bad = np.zeros((2, 625), np.uint32)
+    bad[:, 624] = 700
+    with pytest.raises((EngineError, ValueError), match='generator state'):
+        e.set_resume(mt_state=bad)
+    e.set_mode().set_chains(p, a, b, seeds)
+    with pytest.raises((EngineError, ValueError), match='MT19937'):
+        e.set_resume(mt_state=np.zeros((2, 625), np.uint32))
+    e.close()
+
+
 def _check_tree_valid(P, A, B, n):
     """Reference tree invariants (include/tnco/tree.hpp:57-139): leaves first, root last, consistent links."""
     N = 2 * n - 1
