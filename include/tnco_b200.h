@@ -116,12 +116,14 @@ int tnb_is_hyper(tnb_engine* e);
  *   cost  = get_cost(inds - sparse) * min(get_cost(inds & sparse), n_projs)
  *   width = get_width(inds - sparse) + min(get_width(inds & sparse), log2(n_projs))      (float32)
  * sparse_bits [W32] or NULL to return to the simple model; n_projs > 0.  Call after tnb_set_network; drops the
- * chains.  With max_width the stream kernels serve it (TNB_RNG_MT19937 / TNB_RNG_REPLAY). */
+ * chains.  Served by the table-cost kernels; with max_width they re-slice with the reference's slicer verbatim. */
 int tnb_set_sparse_inds(tnb_engine* e, const uint32_t* sparse_bits, uint64_t n_projs);
 
 /* skip_slices of the finite-width core object (tnco/optimize/finite_width/optimizer.py:60,96-107;
  * include/tnco/optimize/finite_width/greedy/utils.hpp:76-79): indices the greedy slicer never takes.  [W32] or NULL
- * for none.  Stream kernels only (TNB_RNG_MT19937 / TNB_RNG_REPLAY); call after tnb_set_network; drops the chains. */
+ * for none.  Honoured by the reference's slicer (stream kernels, table-cost kernels), not by the production
+ * re-slicer of dimension-2 networks: use TNB_RNG_MT19937 / TNB_RNG_REPLAY there.  Call after tnb_set_network; drops
+ * the chains. */
 int tnb_set_skip_slices(tnb_engine* e, const uint32_t* skip_bits);
 
 /* max_width < 0 or +inf: unconstrained (infinite_memory optimizer).  Otherwise the memory-constrained

@@ -194,7 +194,7 @@ def test_philox_sparse_index_chains_are_valid(dim):
     """Sparse-index cost model under the production RNG (table-cost kernels): the cached totals equal an independent
     evaluation by the oracle's SimpleCostModelSparseInds restatement, and differ from the plain model's."""
     from helpers import leaf_bits
-    from tnco_b200.engine import RNG_MT19937, Engine, EngineError, pack_index_set
+    from tnco_b200.engine import RNG_MT19937, RNG_PHILOX, Engine, EngineError, pack_index_set
     ts, ni = regular_network(100, 9)
     lb = leaf_bits(ts, ni)
     sparse = np.random.default_rng(3).choice(ni, size=15, replace=False).tolist()
@@ -225,21 +225,23 @@ def test_philox_sparse_index_chains_are_valid(dim):
         outs.append((t.copy(), P.copy()))
         e.close()
     assert (outs[0][0] == outs[1][0]).all() and (outs[0][1] == outs[1][1]).all()
-    # with max_width the sparse width model runs on the stream kernels only
-    e = Engine()
-    e.set_network(lb, ni, dim=dim, sparse_bits=sp, n_projs=8).set_mode(max_width=12 * np.log2(dim))
-    with pytest.raises((EngineError, ValueError), match='MT19937'):
-        e.generate_chains(seeds[:4])
-        e.costs()
-    e.close()
-    e = Engine()
-    e.set_network(lb, ni, dim=dim, sparse_bits=sp, n_projs=8).set_mode(max_width=12 * np.log2(dim), rng=RNG_MT19937)
-    e.generate_chains(seeds[:4]).set_betas(np.linspace(0, 100, 200, endpoint=False))
-    e.run(200)
-    t, m = e.costs()
-    P, A, B = e.trees()
-    _, pc, mw = e.eval_cost(P, A, B, slices=e.slices())
-    assert np.allclose(np.log2(pc), np.log2(t), atol=1e-9) and (mw <= np.float32(12 * np.log2(dim)) + 1e-6).all()
+    # with max_width: the table-cost kernels re-slice with the reference's slicer, which knows the sparse width model
+    # (production RNG and MT19937 mode alike)
+    for rng in (RNG_PHILOX, RNG_MT19937):
+        e = Engine()
+        e.set_network(lb, ni, dim=dim, sparse_bits=sp, n_projs=8).set_mode(max_width=12 * np.log2(dim), rng=rng)
+        e.generate_chains(seeds[:6]).set_betas(np.linspace(0, 100, 200, endpoint=False))
+        t0, _ = e.costs()
+        e.run(200)
+        t, m = e.costs()
+        P, A, B = e.trees()
+        _, pc, mw = e.eval_cost(P, A, B, slices=e.slices())
+        assert np.allclose(np.log2(pc), np.log2(t), atol=1e-9) and (mw <= np.float32(12 * np.log2(dim)) + 1e-6).all()
+        bP, bA, bB = e.trees(True)
+        bseq, _, bmw = e.eval_cost(bP, bA, bB, slices=e.slices(True))
+        assert np.allclose(np.log2(bseq), np.log2(m), atol=1e-9) and (bmw <= np.float32(12 * np.log2(dim)) + 1e-6).all()
+        assert (m <= t).all() and np.log2(m).mean() < np.log2(t0).mean()
+        e.close()
     with pytest.raises((EngineError, ValueError), match='n_projs'):
         Engine().set_network(lb, ni, sparse_bits=sp, n_projs=0)
 

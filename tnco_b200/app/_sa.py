@@ -59,8 +59,6 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
     sparse = [pos[x] for x in inds if x in tn.sparse_inds] if tn.sparse_inds else []
     sp_bits = pack_index_set(sparse, len(inds)) if tn.sparse_inds else None
     rng_kind = RNG_MT19937 if opt.rng == 'mt19937' else RNG_PHILOX
-    if sp_bits is not None and finite:
-        rng_kind = RNG_MT19937  # sparse widths are served by the stream kernels (include/tnco_b200.h)
     n_runs = len(seeds)
     lo, hi = dist.shard(n_runs) if opt.distributed else (0, n_runs)
     my_seeds = np.asarray(seeds[lo:hi], np.uint64)

@@ -502,7 +502,10 @@ static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_be
          alloc_to(rt, cs.cp2, nc * ni);
   else if (ok && e->hyper)
     ok = alloc_to(rt, cs.nbig, nc * e->Ws * 32);  // hyper counters of build_sets
-  if (ok && with_slicer && e->finite)
+  // per-node popcounts / leaf counts for the production re-slicer: the kernels built for 2^popcount costs only
+  // (uniform dimension 2 or power-of-two groups, no sparse indices); the table-cost kernels re-slice with the
+  // reference's slicer verbatim
+  if (ok && with_slicer && e->finite && e->dim == 2 && !e->d_sparse)
     ok = alloc_to(rt, cs.kw, nc * e->Npad) && alloc_to(rt, cs.sz, nc * e->Npad) &&
          alloc_to(rt, cs.word, nc * e->Npad) && alloc_to(rt, cs.wkey, nc * e->Npad);
   if (!ok) return e->rtfail();
@@ -631,8 +634,9 @@ static bool mode_ok(tnb_engine* e) {
   if (e->rng_kind == TNB_RNG_PHILOX && (e->dsi || e->prob_kind != TNB_PROB_MH))
     return e->fail("TNB_RNG_PHILOX runs Metropolis-Hastings with shared-index moves only: greedy / always acceptance "
                    "and disable_shared_inds need TNB_RNG_MT19937 or TNB_RNG_REPLAY (invalid mode)");
-  if (e->rng_kind == TNB_RNG_PHILOX && e->finite && e->d_skip)
-    return e->fail("skip_slices is served by the stream kernels: use TNB_RNG_MT19937 or TNB_RNG_REPLAY (invalid mode)");
+  if (e->rng_kind == TNB_RNG_PHILOX && e->finite && e->d_skip && e->dim == 2 && !e->d_sparse)
+    return e->fail("skip_slices is not known to the production re-slicer: use TNB_RNG_MT19937 or TNB_RNG_REPLAY "
+                   "(invalid mode)");
   return true;
 }
 
@@ -641,9 +645,6 @@ static bool ensure_init(tnb_engine* e) {
   if (e->cs.n_chains == 0) return e->fail("no chains: call tnb_set_chains first");
   if (e->rng_kind == TNB_RNG_REPLAY && !e->cs.stream) return e->fail("TNB_RNG_REPLAY needs tnb_set_stream");
   if (!mode_ok(e)) return false;
-  if (e->d_sparse && e->finite && e->rng_kind == TNB_RNG_PHILOX)
-    return e->fail("sparse indices with max_width run on the stream kernels: use TNB_RNG_MT19937 (the production "
-                   "re-slicer does not know the sparse-index width model)");
   if (e->rng_kind == TNB_RNG_MT19937) {
     ChainSet& cs = e->cs;
     const unsigned long long res = sweep_reserve(e);

@@ -1322,8 +1322,10 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
   // needs no partial costs of D/E/C, no two 16-byte stores per level and half the fp64 adds; its total is a
   // running sum re-based on sum_ccost() every 64 sweeps.
   constexpr bool PC = !Rng::kFast;
-  // FS: production re-slicer (get_slices_fast); the walk then also maintains kw[] and sz[]
-  constexpr bool FS = FINITE && Rng::kFast;
+  // FS: production re-slicer (get_slices_fast); the walk then also maintains kw[] and sz[].  Only where a cost is
+  // 2^popcount (DIM2): the table-cost kernels -- other dimensions, sparse indices -- re-slice with the reference's
+  // slicer verbatim (get_slices_dev + a full cost pass), which knows every width model.
+  constexpr bool FS = FINITE && Rng::kFast && DIM2;
   int16_t* const kwp = FS ? P.kw + size_t(chain) * P.Npad : nullptr;
   int16_t* const szp = FS ? P.sz + size_t(chain) * P.Npad : nullptr;
   int sz0 = 0, sz1 = 0, szC = 0;
