@@ -43,6 +43,11 @@ CASES = [
     ('sparse64_d3_fw30', 64, 19, 1000, 0.3, False, 3, 10, 10, 2),
     ('sparsedims64_fw40', 64, 20, 1000, 0.4, False, 0, 10, 10, 6),
     ('sparsehyper64_fw40', 64, 21, 1000, 0.4, True, 2, 10, 8, 4),
+    # dim = -1: general per-index dimensions drawn from {2, 3, 5, 6, 7} (sequential products / float32 width sums)
+    ('gdims64_inf', 64, 22, 1200, None, False, -1, 10),
+    ('gdims64_fw40', 64, 23, 1000, 0.4, False, -1, 10),
+    ('gdimshyper48_fw50', 48, 24, 800, 0.5, True, -1, 10),
+    ('gdimssparse64_fw40', 64, 25, 800, 0.4, False, -1, 10, 10, 12),
 ]
 
 
@@ -66,6 +71,9 @@ def main():
         dims = None
         if dim == 0:
             dims = np.random.default_rng(seed).choice([2, 4, 8], size=ni).astype(np.uint64)
+        if dim == -1:
+            dims = np.random.default_rng(seed).choice([2, 3, 5, 6, 7], size=ni).astype(np.uint64)
+            dim = 0
         mw = None
         if frac is not None:
             if dims is None:

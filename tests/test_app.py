@@ -316,6 +316,17 @@ def test_per_index_dims_through_the_app(backend, max_width):
                 assert sum(math.log2(tn.dims[i]) for i in new - slices) <= max_width
             work.append(new)
         assert abs(math.log2(total) - math.log2(float(r.cost))) < 1e-4
-    with pytest.raises(NotImplementedError, match='power'):
-        rows[0][0] = 3
-        Optimizer(seed=3).optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=5, n_runs=1)
+    # any positive integer dimensions (sequential products like the reference's dims-vector cost model)
+    for i in range(0, ni, 3):
+        rows[i][0] = 3
+    tn, res = Optimizer(seed=3).optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=60,
+                                         n_runs=3)
+    for r in res:
+        work = [frozenset(x) for x in tn.ts_inds]
+        total = 0
+        for x, y in r.path:
+            x, y = sorted((x, y))
+            ty, tx = work.pop(y), work.pop(x)
+            total += math.prod(tn.dims[i] for i in tx | ty)
+            work.append(tx ^ ty)
+        assert abs(math.log2(total) - math.log2(float(r.cost))) < 1e-4

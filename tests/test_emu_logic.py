@@ -114,3 +114,8 @@ def test_emu_replay_sparse(emu, name):
 
 def test_emu_mode_and_resume_errors(emu):
     G.test_mode_and_resume_argument_errors()
+
+
+@pytest.mark.parametrize('n,max_width,sparse', [(60, None, False), (60, 16.0, False), (60, 16.0, True)])
+def test_emu_general_dims_philox(emu, n, max_width, sparse):
+    G.test_philox_general_per_index_dims(n, max_width, sparse)

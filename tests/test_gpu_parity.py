@@ -569,16 +569,56 @@ def test_philox_per_index_dims(n, max_width, hyper):
 
 
 def test_per_index_dims_must_be_powers_of_two():
+    """(Name kept for the emulation suite.)  Dimensions that are neither all equal nor all powers of two run the
+    reference's sequential product / sum loops: any positive integers are accepted; zero is not."""
     from helpers import leaf_bits
     from tnco_b200.engine import Engine
     ts, ni = regular_network(10, 1)
     dims = np.full(ni, 2, np.uint64)
     dims[3] = 3
     e = Engine()
-    with pytest.raises(ValueError, match='power of'):
-        e.set_network(leaf_bits(ts, ni), ni, dims=dims)
+    e.set_network(leaf_bits(ts, ni), ni, dims=dims)
     e.set_network(leaf_bits(ts, ni), ni, dims=np.full(ni, 3, np.uint64))   # uniform: any integer dimension
+    dims[3] = 0
+    with pytest.raises(ValueError, match='positive'):
+        e.set_network(leaf_bits(ts, ni), ni, dims=dims)
     e.close()
+
+
+@pytest.mark.parametrize('n,max_width,sparse', [(60, None, False), (60, 16.0, False), (60, 16.0, True)])
+def test_philox_general_per_index_dims(n, max_width, sparse):
+    """General per-index dimensions under the production RNG (table-cost kernels, sequential cost / width loops):
+    cached totals equal the oracle's dims-vector evaluation of the engine's own trees; sliced widths fit."""
+    from helpers import leaf_bits
+    from tnco_b200.engine import Engine, pack_index_set
+    ts, ni = regular_network(n, 41)
+    lb = leaf_bits(ts, ni)
+    dims = np.random.default_rng(6).choice([2, 3, 5, 6, 7], size=ni).astype(np.uint64)
+    sp = pack_index_set(list(range(0, ni, 7)), ni) if sparse else None
+    seeds = np.arange(24, dtype=np.uint64) + 3
+    outs = []
+    for rep in range(2):
+        e = Engine()
+        e.set_network(lb, ni, dims=dims, sparse_bits=sp, n_projs=9 if sparse else None).set_mode(max_width=max_width)
+        e.generate_chains(seeds).set_betas(np.linspace(0, 100, 250, endpoint=False))
+        t0, _ = e.costs()
+        e.run(250)
+        t, m = e.costs()
+        P, A, B = e.trees()
+        S = e.slices() if max_width is not None else None
+        seq, pc, mw = e.eval_cost(P, A, B, slices=S)
+        assert np.allclose(np.log2(pc), np.log2(t), atol=1e-9) and (m <= t).all()
+        if max_width is not None:
+            assert (mw <= np.float32(max_width) + 1e-5).all() and e.progress()['width_rejects'].sum() > 0
+        for c in (0, 7, 23):
+            oc = so.Chain(P[c], A[c], B[c], e.bits(c), ni, dims=dims, sparse_bits=sp, n_projs=9 if sparse else None,
+                          max_width=max_width)
+            if max_width is None:
+                assert abs(np.log2(oc.total_cost) - np.log2(t[c])) < 1e-9
+        outs.append((t.copy(), P.copy()))
+        e.close()
+    assert (outs[0][0] == outs[1][0]).all() and (outs[0][1] == outs[1][1]).all()
+    assert np.log2(outs[0][0]).mean() < np.log2(t0).mean()
 
 
 def test_packed_tree_readback_and_cached_engine():

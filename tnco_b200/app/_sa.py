@@ -49,9 +49,6 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
     pos = {x: k for k, x in enumerate(inds)}
     dims = [int(all_dims[x]) for x in inds]
     uniform = all(d == dims[0] for d in dims)
-    if not uniform and any(d < 2 or d & (d - 1) for d in dims):
-        raise NotImplementedError('tnco_b200: per-index dimensions are supported when every dimension is a power '
-                                  'of two >= 2 (or all dimensions are equal).')
     lb = pack_leaf_bits([[pos[x] for x in xs] for xs in ts], len(inds))
     out_bits = pack_index_set([pos[x] for x in inds if x in outs], len(inds))
     # sparse-index cost model (tnco/app/infinite_memory/sa.py:158-161): every component gets the network's sparse

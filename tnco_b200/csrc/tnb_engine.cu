@@ -361,6 +361,12 @@ struct tnb_engine {
   uint32_t* d_sparse = nullptr;  // [Ws + tail]
   uint64_t n_projs = 0;
   uint32_t* d_skip = nullptr;    // [Ws + tail] skip_slices (tnb_set_skip_slices)
+  // general per-index dimensions (not all equal, not all powers of two): the reference's sequential cost / width loops
+  bool generic = false;
+  double* d_gdims = nullptr;     // [Ws*32]
+  double* d_glog2 = nullptr;     // [Ws*32]
+  // costs are 2^popcount (uniform dimension 2 or power-of-two groups, simple cost model): DIM2 kernels, fast re-slicer
+  bool pow2_costs() const { return dim == 2 && !d_sparse && !generic; }
   uint8_t* d_gw = nullptr;       // [Ws*32] log2(dim) at the leader positions
 
   // caller's index space <-> virtual index space (rows of Wu / W words)
@@ -444,7 +450,9 @@ static void fill_params(const tnb_engine* e, const ChainSet& cs, Params& P) {
   P.leaf_bits = e->d_leaf_bits; P.pow_tab = e->d_pow_tab; P.log2d = e->log2d;
   P.skip = e->d_skip;
   P.sparse = e->d_sparse;  // costs of a network with sparse indices come from the table kernels
-  P.dim2 = e->dim == 2 && !e->d_sparse;
+  P.dim2 = e->pow2_costs();
+  P.gdims = e->generic ? e->d_gdims : nullptr;
+  P.glog2 = e->generic ? e->d_glog2 : nullptr;
   P.n_projs = double(e->n_projs);
   P.log2_n_projs = e->n_projs ? std::log2(double(e->n_projs)) : 0.0;
   P.finite = e->finite; P.every = e->every; P.dsi = e->dsi; P.prob_kind = e->prob_kind; P.max_width = e->max_width;
@@ -505,7 +513,7 @@ static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_be
   // per-node popcounts / leaf counts for the production re-slicer: the kernels built for 2^popcount costs only
   // (uniform dimension 2 or power-of-two groups, no sparse indices); the table-cost kernels re-slice with the
   // reference's slicer verbatim
-  if (ok && with_slicer && e->finite && e->dim == 2 && !e->d_sparse)
+  if (ok && with_slicer && e->finite && e->pow2_costs())
     ok = alloc_to(rt, cs.kw, nc * e->Npad) && alloc_to(rt, cs.sz, nc * e->Npad) &&
          alloc_to(rt, cs.word, nc * e->Npad) && alloc_to(rt, cs.wkey, nc * e->Npad);
   if (!ok) return e->rtfail();
@@ -634,7 +642,7 @@ static bool mode_ok(tnb_engine* e) {
   if (e->rng_kind == TNB_RNG_PHILOX && (e->dsi || e->prob_kind != TNB_PROB_MH))
     return e->fail("TNB_RNG_PHILOX runs Metropolis-Hastings with shared-index moves only: greedy / always acceptance "
                    "and disable_shared_inds need TNB_RNG_MT19937 or TNB_RNG_REPLAY (invalid mode)");
-  if (e->rng_kind == TNB_RNG_PHILOX && e->finite && e->d_skip && e->dim == 2 && !e->d_sparse)
+  if (e->rng_kind == TNB_RNG_PHILOX && e->finite && e->d_skip && e->pow2_costs())
     return e->fail("skip_slices is not known to the production re-slicer: use TNB_RNG_MT19937 or TNB_RNG_REPLAY "
                    "(invalid mode)");
   return true;
@@ -766,6 +774,8 @@ void tnb_destroy(tnb_engine* e) {
   e->rt.free_(e->d_gw);
   e->rt.free_(e->d_sparse);
   e->rt.free_(e->d_skip);
+  e->rt.free_(e->d_gdims);
+  e->rt.free_(e->d_glog2);
   e->rt.free_(e->d_betas);
   e->rt.free_(e->d_inv_betas);
   e->rt.free_(e->d_flush);
@@ -780,22 +790,25 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds_u, const uint32_t* l
   const int Wu = (n_inds_u + 31) / 32;
   // per-index dims: uniform -> scalar dim (include/tnco/ctree.hpp:80-89); powers of two -> virtual binary indices
   std::vector<int> vw(size_t(n_inds_u), 1), voff(size_t(n_inds_u), 0);
-  bool grouped = false;
+  bool grouped = false, generic = false;
   if (dims) {
-    bool uniform = true;
-    for (int i = 1; i < n_inds_u; ++i) uniform &= dims[i] == dims[0];
+    bool uniform = true, pow2 = true;
+    for (int i = 0; i < n_inds_u; ++i) {
+      const uint64_t d = dims[i];
+      if (d < 1) return e->fail("tnb_set_network: every dimension must be positive (invalid dims)"), -1;
+      uniform &= d == dims[0];
+      pow2 &= d >= 2 && (d & (d - 1)) == 0;
+    }
     if (uniform) {
       dim = dims[0];
-    } else {
-      for (int i = 0; i < n_inds_u; ++i) {
-        const uint64_t d = dims[i];
-        if (d < 2 || (d & (d - 1)) != 0)
-          return e->fail("tnb_set_network: per-index dims are not supported unless every dimension is a power of "
-                         "two >= 2 (index " + std::to_string(i) + " has dimension " + std::to_string(d) + ")"), -2;
-        vw[size_t(i)] = __builtin_ctzll(d);
-      }
+    } else if (pow2) {
+      for (int i = 0; i < n_inds_u; ++i) vw[size_t(i)] = __builtin_ctzll(dims[i]);
       grouped = true;
       dim = 2;
+    } else {
+      // anything else: one bit per index, costs / widths by the reference's sequential loops (table-cost kernels)
+      generic = true;
+      dim = 2;  // (only feeds the unused power table)
     }
   }
   if (dim < 1) return e->fail("tnb_set_network: dim must be positive"), -1;
@@ -815,6 +828,7 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds_u, const uint32_t* l
   e->initialized = false;
   e->n = n_leaves; e->N = 2 * n_leaves - 1; e->n_int = n_leaves - 1; e->n_inds = n_inds; e->W = W;
   e->n_inds_u = n_inds_u; e->Wu = Wu; e->grouped = grouped; e->vw = vw; e->voff = voff;
+  e->generic = generic;
   e->Ws = (W + 3) / 4 * 4;
   e->Npad = (e->N + 7) / 8 * 8;
   // everything below lives in the virtual index space
@@ -848,8 +862,9 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds_u, const uint32_t* l
     gw[size_t(k)] = uint8_t(vw[size_t(i)]);
   }
   void* old[] = {e->d_leaf_bits, e->d_pow_tab, e->d_net_own, e->d_hcount0, e->d_leader, e->d_gw, e->d_sparse,
-                 e->d_skip};
+                 e->d_skip, e->d_gdims, e->d_glog2};
   for (void* q : old) e->rt.free_(q);
+  e->d_gdims = nullptr; e->d_glog2 = nullptr;
   e->d_sparse = nullptr; e->n_projs = 0;  // a new network starts with the simple cost model
   e->d_skip = nullptr;
   e->d_leaf_bits = nullptr; e->d_pow_tab = nullptr; e->d_net_own = nullptr; e->d_hcount0 = nullptr;
@@ -860,6 +875,17 @@ int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds_u, const uint32_t* l
       !e->rt.h2d(e->d_gw, gw.data(), gw.size()))
     return e->rtfail(), -3;
   if (!refresh_hyper(e)) return -3;
+  if (generic) {
+    std::vector<double> gd(size_t(e->Ws) * 32, 1.0), gl(size_t(e->Ws) * 32, 0.0);
+    for (int i = 0; i < n_inds_u; ++i) {
+      gd[size_t(i)] = double(dims[i]);
+      gl[size_t(i)] = std::log2(double(dims[i]));
+    }
+    if (!alloc_to(e->rt, e->d_gdims, gd.size()) || !alloc_to(e->rt, e->d_glog2, gl.size()) ||
+        !e->rt.h2d(e->d_gdims, gd.data(), gd.size() * sizeof(double)) ||
+        !e->rt.h2d(e->d_glog2, gl.data(), gl.size() * sizeof(double)) || !e->rt.sync())
+      return e->rtfail(), -3;
+  }
   if (!alloc_to(e->rt, e->d_leaf_bits, padded.size() + kTailWords)) return e->rtfail(), -3;
   std::vector<double> tab(size_t(n_inds) + 1);
   for (int k = 0; k <= n_inds; ++k) tab[size_t(k)] = std::pow(double(dim), double(k));

@@ -29,6 +29,12 @@ struct Params {
   // Served by the table-cost kernels only (the host clears dim2 for such networks); nullptr = simple cost model.
   const uint32_t* sparse;  // [Ws]
   double n_projs;          // (double)n_projs
+  // General per-index dimensions (not all equal, not all powers of two): costs and widths are the reference's own
+  // sequential loops over the set bits in ascending index order (cost_model/simple.hpp:46-54, finite_width/
+  // cost_model/simple.hpp:47-58) -- fp64 products / float32 sums round per step, so the order is part of the
+  // result.  Table-cost kernels only; nullptr = off.
+  const double* gdims;     // [Ws*32] dimension of every index
+  const double* glog2;     // [Ws*32] log2 of it (host std::log2)
   // skip_slices (finite_width/greedy/utils.hpp:76-79): indices the greedy slicer never takes; stream kernels only
   const uint32_t* skip;    // [Ws] or nullptr
   double log2_n_projs;     // log2(n_projs)
@@ -380,6 +386,70 @@ struct ChainView {
     const float ws = width_of(ks);
     return width_of(k - ks) + (double(ws) < P.log2_n_projs ? ws : float(P.log2_n_projs));
   }
+  // ---- general per-index dimensions: every lane walks the whole set word by word (words fetched by shuffle from
+  // their owners), so the result is tile-uniform and the rounding order is the reference's.  CONV: called from the
+  // sweep loop (converged-lane shuffles).
+  // (out of line and not unrolled: a rare path that would otherwise be inlined into every table-cost kernel at a
+  //  dozen call sites)
+  template <bool CONV>
+  TNB_D TNB_NOINLINE double gcost(const uint32_t (&u)[WPL]) const {
+    double r = 1.0;
+#pragma unroll 1
+    for (int k = 0; k < WPL; ++k)
+#pragma unroll 1
+      for (int o = 0; o < TILE; ++o) {
+        const int w = k * TILE + o;
+        if (w >= P.W) break;
+        uint32_t v = CONV ? t.bcast_c(u[k], o) : t.bcast(u[k], o);
+        while (v) {
+          r *= ldg(P.gdims + w * 32 + ctz32(v));
+          v &= v - 1;
+        }
+      }
+    return r;
+  }
+  template <bool CONV>
+  TNB_D TNB_NOINLINE float gwidth(const uint32_t (&u)[WPL]) const {
+    float wd = 0.f;
+#pragma unroll 1
+    for (int k = 0; k < WPL; ++k)
+#pragma unroll 1
+      for (int o = 0; o < TILE; ++o) {
+        const int w = k * TILE + o;
+        if (w >= P.W) break;
+        uint32_t v = CONV ? t.bcast_c(u[k], o) : t.bcast(u[k], o);
+        while (v) {
+          wd = float(double(wd) + ldg(P.glog2 + w * 32 + ctz32(v)));  // width_ += log2(dims[pos]), width_ float
+          v &= v - 1;
+        }
+      }
+    return wd;
+  }
+  // the same under the active cost model (sparse indices or not); SP = this lane's words of the sparse mask or 0
+  template <bool CONV>
+  TNB_D TNB_NOINLINE double gcost_model(const uint32_t (&u)[WPL], const uint32_t (&SP)[WPL]) const {
+    if (P.sparse == nullptr) return gcost<CONV>(u);
+    uint32_t d[WPL], sp[WPL];
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      d[k] = u[k] & ~SP[k];
+      sp[k] = u[k] & SP[k];
+    }
+    const double x = gcost<CONV>(sp), y = P.n_projs;
+    return gcost<CONV>(d) * (x < y ? x : y);
+  }
+  TNB_D TNB_INLINE float cap_w(float ws) const { return double(ws) < P.log2_n_projs ? ws : float(P.log2_n_projs); }
+  template <bool CONV>
+  TNB_D TNB_NOINLINE float gwidth_model(const uint32_t (&u)[WPL], const uint32_t (&SP)[WPL]) const {
+    if (P.sparse == nullptr) return gwidth<CONV>(u);
+    uint32_t d[WPL], sp[WPL];
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      d[k] = u[k] & ~SP[k];
+      sp[k] = u[k] & SP[k];
+    }
+    return gwidth<CONV>(d) + cap_w(gwidth<CONV>(sp));
+  }
   TNB_D TNB_INLINE void load_sparse(uint32_t (&o)[WPL]) const {
 #pragma unroll
     for (int k = 0; k < WPL; ++k) o[k] = lane_ok[k] ? ldg(P.sparse + t.tl + k * TILE) : 0u;
@@ -438,12 +508,35 @@ TNB_D void cost_pass(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL], co
   uint32_t maxk = 0;
   float maxw_sp = 0.f;
   const bool sparse = P.sparse != nullptr;
+  const bool gen = P.gdims != nullptr;
   uint32_t SP[WPL];
 #pragma unroll
   for (int i = 0; i < WPL; ++i) SP[i] = 0u;
   if (sparse) c.load_sparse(SP);
   for (int z = c.po_first(); z >= 0; z = c.po_next(z)) {
     uint32_t kw_ = 0;
+    if (gen) {  // general per-index dimensions: the reference's sequential loops
+      if (WIDTHS) {
+        uint32_t x[WPL];
+        c.load_bits(z, x);
+#pragma unroll
+        for (int i = 0; i < WPL; ++i) x[i] &= ~S[i];
+        const float w = c.template gwidth_model<false>(x, SP);
+        maxw_sp = w > maxw_sp ? w : maxw_sp;
+      }
+      if (z < P.n) continue;
+      const uint32_t cw = c.ch(z);
+      const int a = int(cw & 0xffffu), b = int(cw >> 16);
+      uint32_t xa[WPL], xb[WPL];
+      c.load_bits(a, xa);
+      c.load_bits(b, xb);
+#pragma unroll
+      for (int i = 0; i < WPL; ++i) xa[i] |= xb[i] | S[i];
+      const double cost = c.template gcost_model<false>(xa, SP);
+      dst.put(z, cost, cost + dst.pc(a) + dst.pc(b));
+      seq += cost;
+      continue;
+    }
     if (WIDTHS) {  // sliced popcount of the node's own index set (widest node)
       uint32_t x[WPL];
       c.load_bits(z, x);
@@ -488,7 +581,7 @@ TNB_D void cost_pass(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL], co
     dst.put(z, cost, cost + pa + pb);
     seq += cost;
   }
-  maxw = sparse ? double(maxw_sp) : P.log2d * double(maxk);
+  maxw = (sparse || gen) ? double(maxw_sp) : P.log2d * double(maxk);
 }
 
 // Index sets (and, with HYPER, hyper rows) of all internal nodes from the topology, in post-order -- what
@@ -561,6 +654,7 @@ TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2
       for (int b = 0; b < 32; ++b) nbig[w * 32 + b] = 0;
   }
   const bool sparse = P.sparse != nullptr;
+  const bool gen = P.gdims != nullptr;
   uint32_t SP[WPL];
 #pragma unroll
   for (int i = 0; i < WPL; ++i) SP[i] = 0u;
@@ -573,7 +667,9 @@ TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2
 #pragma unroll
     for (int i = 0; i < WPL; ++i) k += uint32_t(popc32(x[i])) | (uint32_t(popc32(x[i] & SP[i])) << 16);
     k = t.sum(k);
-    if ((sparse ? c.width_sp(int(k & 0xffffu), int(k >> 16)) : c.width_of(int(k))) > P.max_width) {
+    const float wz = gen ? c.template gwidth_model<false>(x, SP)
+                         : sparse ? c.width_sp(int(k & 0xffffu), int(k >> 16)) : c.width_of(int(k));
+    if (wz > P.max_width) {
 #pragma unroll
       for (int i = 0; i < WPL; ++i) {
         const int w = t.tl + i * TILE;
@@ -590,6 +686,8 @@ TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2
     uint32_t x[WPL];
     c.load_bits(z, x);
     uint32_t k = 0, ks = 0, kp = 0;  // kp: sparse parts of the whole and of the sliced set
+    float wfull = 0.f;
+    if (gen) wfull = c.template gwidth_model<false>(x, SP);
 #pragma unroll
     for (int i = 0; i < WPL; ++i) {
       k += popc32(x[i]);
@@ -602,10 +700,15 @@ TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2
     ks = k >> 16;
     k &= 0xffffu;
     if (sparse) kp = t.sum(kp);
-    if (!((sparse ? c.width_sp(int(k), int(kp & 0xffffu)) : c.width_of(int(k))) > P.max_width)) continue;
-    float sw = sparse ? c.width_sp(int(ks), int(kp >> 16)) : c.width_of(int(ks));
+    if (!gen) wfull = sparse ? c.width_sp(int(k), int(kp & 0xffffu)) : c.width_of(int(k));
+    if (!(wfull > P.max_width)) continue;
+    float sw = gen ? c.template gwidth_model<false>(x, SP)
+                   : sparse ? c.width_sp(int(ks), int(kp >> 16)) : c.width_of(int(ks));
     if (!(sw > P.max_width)) continue;
     int kss = int(kp >> 16);  // sparse indices still unsliced on this node
+    uint32_t xsp[WPL];        // (general dims) the sparse part of the still unsliced set, kept in step with the picks
+#pragma unroll
+    for (int i = 0; i < WPL; ++i) xsp[i] = x[i] & SP[i];
     // ascending positions of the still unsliced indices of this node (group leaders when dims differ per index)
     uint32_t np = 0;
 #pragma unroll
@@ -663,7 +766,10 @@ TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2
         const uint16_t kb = nbig[key];
         const int gk = P.grouped ? int(P.gw[key]) : 0;
         int b = int(a) - 1;
-        while (b >= 0 && (kb > nbig[pos[b]] || (P.grouped && kb == nbig[pos[b]] && gk > int(P.gw[pos[b]])))) {
+        // (general dims: second key log2 dim as float, DimsCache<width_type>, :52-62)
+        const float lk = gen ? float(P.glog2[key]) : 0.f;
+        while (b >= 0 && (kb > nbig[pos[b]] || (P.grouped && kb == nbig[pos[b]] && gk > int(P.gw[pos[b]])) ||
+                          (gen && kb == nbig[pos[b]] && lk > float(P.glog2[pos[b]])))) {
           pos[b + 1] = pos[b];
           --b;
         }
@@ -676,7 +782,16 @@ TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2
     const float dw = float(-P.log2d);  // get_delta_width for a present index (fw simple.hpp:60-76)
     while (m < np) {
       const int idx = pos[m];
-      if (sparse && ((P.sparse[idx >> 5] >> (idx & 31)) & 1u)) {
+      if (gen) {
+        if (sparse && ((P.sparse[idx >> 5] >> (idx & 31)) & 1u)) {
+          const float wo = c.cap_w(c.template gwidth<false>(xsp));
+#pragma unroll
+          for (int i = 0; i < WPL; ++i) xsp[i] &= ~span_mask(idx, 1, t.tl + i * TILE);
+          sw += c.cap_w(c.template gwidth<false>(xsp)) - wo;
+        } else {
+          sw += float(-P.glog2[idx]);  // (1 - 2*test(pos)) * log2(dims[pos]) as float, :60-76
+        }
+      } else if (sparse && ((P.sparse[idx >> 5] >> (idx & 31)) & 1u)) {
         // get_delta_width of a sparse index (fw simple_sparse_inds.hpp:51-77): difference of the capped widths
         const int g = P.grouped ? int(P.gw[idx]) : 1;
         const float wo = c.width_of(kss), wn = c.width_of(kss - g);
@@ -1578,9 +1693,12 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     }
     // sparse-index cost model (table-cost kernels only): the sparse parts of the same three sets
     const bool sparse = !DIM2 && P.sparse != nullptr;
+    const bool gen = !DIM2 && P.gdims != nullptr;  // general per-index dimensions: sequential products / sums
     uint32_t kspack = 0, kss = 0;
+    uint32_t SP[WPL];
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) SP[k] = 0u;
     if (sparse) {
-      uint32_t SP[WPL];
       c.load_sparse(SP);
 #pragma unroll
       for (int k = 0; k < WPL; ++k) {
@@ -1603,7 +1721,14 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         ku = ks >> 16;
         ks &= 0xffffu;
       }
-      gate = (sparse ? c.width_sp(int(ks), int(kss)) : c.width_of(int(ks))) <= P.max_width;
+      if (gen) {
+        uint32_t xs[WPL];
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) xs[k] = nb[k] & ~S[k];
+        gate = c.template gwidth_model<true>(xs, SP) <= P.max_width;
+      } else {
+        gate = (sparse ? c.width_sp(int(ks), int(kss)) : c.width_of(int(ks))) <= P.max_width;
+      }
       if (!gate) ++q_wrej;
     }
     bool acc = false;
@@ -1614,6 +1739,15 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         const uint32_t ka = kpack & 0xffffu, kb = kpack >> 16;
         nA = bits_to_f64((unsigned long long)(1023u + (ka > 1024u ? 1024u : ka)) << 52);
         nB = bits_to_f64((unsigned long long)(1023u + (kb > 1024u ? 1024u : kb)) << 52);
+      } else if (gen) {
+        uint32_t uA[WPL], uB[WPL];
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) {
+          uA[k] = nb[k] | bE[k] | S[k];
+          uB[k] = bD[k] | bC[k] | S[k];
+        }
+        nA = c.template gcost_model<true>(uA, SP);
+        nB = c.template gcost_model<true>(uB, SP);
       } else if (sparse) {
         nA = c.cost_sp(int(kpack & 0xffffu), int(kspack & 0xffffu));
         nB = c.cost_sp(int(kpack >> 16), int(kspack >> 16));

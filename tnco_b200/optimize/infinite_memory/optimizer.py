@@ -43,8 +43,6 @@ class Optimizer:
         self._dsi, self._atol = bool(disable_shared_inds), atol
         dims = [int(ctree.dims[x]) for x in ctree._inds_order]
         uniform = len(set(dims)) == 1
-        if not uniform and any(d < 2 or d & (d - 1) for d in dims):
-            raise NotImplementedError('tnco_b200: per-index dimensions must all be powers of two >= 2.')
         lb, ni = ctree.leaf_bits()
         pos = {x: k for k, x in enumerate(ctree._inds_order)}
         self._e = Engine(device)
