@@ -98,7 +98,10 @@ void tnb_destroy(tnb_engine* e);
 
 /* Network = what ContractionTree carries besides the tree (include/tnco/ctree.hpp:32-40): per-leaf index
  * sets and dims.  leaf_bits [n_leaves][W32].  dims == NULL: every index has dimension `dim`
- * (ctree.hpp:80-89).  The network must be connected.  Output indices: tnb_set_output_inds. */
+ * (ctree.hpp:80-89).  dims [n_inds] otherwise: all equal = the same as `dim`; all powers of two = carried as groups
+ * of binary indices (costs stay 2^popcount); anything else = the reference's sequential product / width loops
+ * (include/tnco/optimize/infinite_memory/cost_model/simple.hpp:46-54), bit-identical and much slower.
+ * The network must be connected.  Output indices: tnb_set_output_inds. */
 int tnb_set_network(tnb_engine* e, int n_leaves, int n_inds, const uint32_t* leaf_bits, uint64_t dim,
                     const uint64_t* dims);
 
