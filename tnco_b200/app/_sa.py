@@ -5,6 +5,7 @@ engine run over all ``n_runs`` chains on the GPU."""
 from __future__ import annotations
 
 import functools as fts
+import gc
 import operator as op
 import time
 from sys import stderr
@@ -203,7 +204,16 @@ def optimize(opt, results_cls, tn, betas, n_steps, n_runs, n_projs, update_slice
             return fts.reduce(op.or_, field('disconnected_slices', r), frozenset())
         raise AttributeError(name)
 
-    results = [results_cls._from_source(field, r) for r in order.tolist()]
+    # One record per run, tens of thousands per call.  They are created with the cyclic collector paused: every few
+    # hundred container allocations would otherwise start a collection that walks all of them (and the previous
+    # call's, still alive in the caller) -- measured 64 ms instead of ~10 for 8 x 4096 records on the 8-GPU box.
+    gc_was_on = gc.isenabled()
+    gc.disable()
+    try:
+        results = [results_cls._from_source(field, r) for r in order.tolist()]
+    finally:
+        if gc_was_on:
+            gc.enable()
     stats['assemble_s'] = time.perf_counter() - t_start - runtime
     if opt.verbose == 1:
         print(' Done!', file=stderr, flush=True)
