@@ -67,7 +67,7 @@ class _LazyFields:
         """Record whose every field is ``source(field_name, key)``, evaluated and cached on first access (one
         shared callable instead of per-record closures: optimize() creates one record per run)."""
         o = object.__new__(cls)
-        object.__setattr__(o, '_src', (source, key))
+        o.__dict__['_src'] = (source, key)   # (not object.__setattr__: half the cost, times tens of thousands of records)
         return o
 
     def __setattr__(self, k, v):

@@ -82,6 +82,14 @@ def all_gather_rows(local, n_total):
     pad = np.zeros((mx,) + local.shape[1:], local.dtype)
     pad[:local.shape[0]] = local
     t = _tensor(pad)
+    if all(c == mx for c in counts):
+        # equal blocks (the usual case): gather into ONE tensor and read it back with one copy
+        out = torch.empty((size * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        try:
+            d.all_gather_into_tensor(out, t)
+            return out.cpu().numpy()
+        except (RuntimeError, NotImplementedError, AttributeError):
+            pass  # backend without the flat form: the list form below
     outs = [torch.empty_like(t) for _ in range(size)]
     d.all_gather(outs, t)
     return np.concatenate([o.cpu().numpy()[:c] for o, c in zip(outs, counts)], axis=0)
