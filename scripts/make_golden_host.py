@@ -76,6 +76,40 @@ def main():
     assert ref_tn.fuse([['i', 'j'], ['j', 'k'], ['k', 'l']], 2, max_width=2, seed=42) == [(0, 1), (0, 1)]
     with open(os.path.join(ROOT, 'tests', 'golden', 'host_fuse.json'), 'w') as f:
         json.dump(out, f, separators=(',', ':'))
+    wire_format()
+
+
+def wire_format():
+    """tests/golden/host_wire.json: the reference's JSON wire format (JSONEncoder of tnco/app/app.py:48-61 and
+    tnco/app/{infinite_memory,finite_width}/sa.py:36-60, TensorNetwork.to_json, dump_results) for fixed inputs."""
+    from decimal import Decimal
+
+    import tnco.app.finite_width.sa as rfw
+    import tnco.app.infinite_memory.sa as rim
+    kw = dict(cost='1.11685E+9', runtime_s=1.25, path=[[0, 1], [0, 2], [0, 1]], disconnected_costs=['1.11685E+9'],
+              disconnected_paths=[[[0, 1], [0, 2], [0, 1]]])
+    kw2 = dict(kw, disconnected_slices=[['a']], slices=['a'])
+
+    def build(cls, k):
+        k = dict(k, cost=Decimal(k['cost']), disconnected_costs=[Decimal(x) for x in k['disconnected_costs']],
+                 path=[tuple(x) for x in k['path']],
+                 disconnected_paths=[[tuple(x) for x in p] for p in k['disconnected_paths']])
+        if 'slices' in k:
+            k['slices'] = frozenset(k['slices'])
+            k['disconnected_slices'] = [frozenset(x) for x in k['disconnected_slices']]
+        return cls(**k)
+
+    r_im, r_fw = build(rim.ContractionResults, kw), build(rfw.ContractionResults, kw2)
+    rows = [[2, 'x', 'y'], [2, 'y', 'z'], [3, 'z', 'x', '*'], [4, 'x', '/']]
+    tns = {}
+    for name, rws, opts in (('plain', rows, dict(fuse=False)), ('fused', rows[:3], dict(fuse=4, seed=3))):
+        tn = ref_app.load_tn(rws, **opts)
+        tns[name] = dict(rows=rws, options=opts, tn_json=tn.to_json(), tags=tn.tags,
+                         dump_json=ref_app.dump_results(tn, [r_im, r_im], output_format='json'))
+    out = dict(rows=rows, im=dict(kwargs=kw, json=r_im.to_json(), repr=repr(r_im)),
+               fw=dict(kwargs=kw2, json=r_fw.to_json(), repr=repr(r_fw)), tn=tns)
+    with open(os.path.join(ROOT, 'tests', 'golden', 'host_wire.json'), 'w') as f:
+        json.dump(out, f, indent=1)
 
 
 if __name__ == '__main__':

@@ -251,3 +251,38 @@ def test_fuse_known_answers_and_errors():
         contract([(0, 0)], [['i', 'j'], ['j', 'k']], dims=2)
     with pytest.raises(ValueError):
         contract([(0, 1)], [['i', 'j'], ['j', 'k']])
+
+
+def test_json_wire_format_matches_the_reference():
+    """tests/golden/host_wire.json holds strings produced by the unmodified reference (scripts/make_golden_host.py):
+    ContractionResults.to_json / repr of both plugins, TensorNetwork.to_json, dump_results(output_format='json')
+    (tnco/app/app.py:48-61,573-712; tnco/app/infinite_memory/sa.py:36-60; tnco/app/finite_width/sa.py:36-70)."""
+    import json
+    import warnings
+    from decimal import Decimal
+
+    from tnco_b200.app import dump_results, load_tn
+    from tnco_b200.app.finite_width import sa as fw
+    from tnco_b200.app.infinite_memory import sa as im
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'host_wire.json')) as f:
+        g = json.load(f)
+
+    def build(cls, k):
+        k = dict(k, cost=Decimal(k['cost']), disconnected_costs=[Decimal(x) for x in k['disconnected_costs']],
+                 path=[tuple(x) for x in k['path']],
+                 disconnected_paths=[[tuple(x) for x in p] for p in k['disconnected_paths']])
+        if 'slices' in k:
+            k['slices'] = frozenset(k['slices'])
+            k['disconnected_slices'] = [frozenset(x) for x in k['disconnected_slices']]
+        return cls(**k)
+
+    r_im, r_fw = build(im.ContractionResults, g['im']['kwargs']), build(fw.ContractionResults, g['fw']['kwargs'])
+    assert r_im.to_json() == g['im']['json'] and repr(r_im) == g['im']['repr']
+    assert r_fw.to_json() == g['fw']['json'] and repr(r_fw) == g['fw']['repr']
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for case in g['tn'].values():
+            tn = load_tn(case['rows'], **case['options'])
+            assert tn.to_json() == case['tn_json']
+            assert json.loads(json.dumps(tn.tags)) == case['tags']
+            assert dump_results(tn, [r_im, r_im], output_format='json') == case['dump_json']
