@@ -77,6 +77,80 @@ def main():
     with open(os.path.join(ROOT, 'tests', 'golden', 'host_fuse.json'), 'w') as f:
         json.dump(out, f, separators=(',', ':'))
     wire_format()
+    ctree_and_paths()
+
+
+def ctree_and_paths():
+    """tests/golden/host_ctree.json: tnco.ctree.ContractionTree (path -> nodes + index sets with the hyper-count rule,
+    path(), max_width; tnco/ctree.py:69-251,350-388), get_connected_components and merge_contraction_paths
+    (tnco/utils/tn.py:61-106,334-401) of the reference on seeded random inputs."""
+    import random
+
+    from helpers import random_tree
+    from tnco.ctree import ContractionTree as RefCT
+
+    def linear_path(a, b):
+        n = (len(a) + 1) // 2
+        pos = list(range(n))
+        path = []
+        for z in range(n, 2 * n - 1):
+            x, y = sorted((pos.index(int(a[z])), pos.index(int(b[z]))))
+            path.append([x, y])
+            pos.pop(y)
+            pos.pop(x)
+            pos.append(z)
+        return path
+
+    trees = []
+    for n, seed, hyper in ((8, 1, False), (20, 2, False), (40, 3, False), (16, 4, True), (36, 5, True)):
+        if hyper:
+            ts, ni, outs = hyper_network(n, seed)
+        else:
+            ts, ni = regular_network(n, seed)
+            outs = []
+        p, a, b, bits = random_tree(ts, ni, seed + 10, outs)
+        path = linear_path(a, b)
+        dims = 2 if seed % 2 else {i: (2, 3, 4)[i % 3] for i in range(ni)}
+        ct = RefCT(path, ts, dims, output_inds=outs if hyper else None)
+        trees.append(dict(ts_inds=ts, dims=dims if isinstance(dims, int) else [dims[i] for i in range(ni)],
+                          output_inds=outs if hyper else None, path=path,
+                          parent=[-1 if nd.parent is None else nd.parent for nd in ct.nodes],
+                          children=[[-1 if c is None else c for c in nd.children] for nd in ct.nodes],
+                          inds=[sorted(xs) for xs in ct.inds], ref_path=[list(x) for x in ct.path()],
+                          max_width=ct.max_width(), n_inds=ct.n_inds, inds_order=list(ct._inds_order)))
+    rng = random.Random(7)
+    comps, merges = [], []
+    for _ in range(6):
+        n = rng.randrange(6, 30)
+        ts = [[rng.randrange(n) for _ in range(rng.randrange(1, 4))] for _ in range(n)]
+        comps.append(dict(ts_inds=ts, components=[list(c) for c in ref_tn.get_connected_components(ts)]))
+    for _ in range(6):
+        n = rng.randrange(5, 16)
+        order = list(range(n))
+        rng.shuffle(order)
+        k = rng.randrange(1, 4)
+        cuts = sorted(rng.sample(range(1, n), k - 1)) if k > 1 else []
+        groups = [sorted(order[i:j]) for i, j in zip([0] + cuts, cuts + [n])]
+        paths = []
+        for g in groups:   # a random linear path over all n tensors that contracts exactly the tensors of g
+            pos = list(range(n))
+            live = list(g)
+            path = []
+            while len(live) > 1:
+                x, y = rng.sample(live, 2)
+                ix, iy = sorted((pos.index(x), pos.index(y)))
+                path.append([ix, iy])
+                pos.pop(iy)
+                pos.pop(ix)
+                new = ('m', len(path), tuple(g))
+                pos.append(new)
+                live = [t for t in live if t not in (x, y)] + [new]
+            paths.append(path)
+        merges.append(dict(n=n, paths=paths, merged=[list(x) for x in ref_tn.merge_contraction_paths(n, paths)],
+                           merged_noauto=[list(x) for x in
+                                          ref_tn.merge_contraction_paths(n, paths, autocomplete=False)]))
+    with open(os.path.join(ROOT, 'tests', 'golden', 'host_ctree.json'), 'w') as f:
+        json.dump(dict(trees=trees, components=comps, merges=merges), f, separators=(',', ':'))
 
 
 def wire_format():

@@ -286,3 +286,37 @@ def test_json_wire_format_matches_the_reference():
             assert tn.to_json() == case['tn_json']
             assert json.loads(json.dumps(tn.tags)) == case['tags']
             assert dump_results(tn, [r_im, r_im], output_format='json') == case['dump_json']
+
+
+def test_ctree_components_and_path_merging_match_the_reference():
+    """tests/golden/host_ctree.json (scripts/make_golden_host.py, unmodified reference): ContractionTree built from a
+    linear path -- nodes, index sets under the hyper-count rule, path(), max_width (tnco/ctree.py:69-251,350-388) --
+    and get_connected_components / merge_contraction_paths (tnco/utils/tn.py:61-106,334-401)."""
+    import json
+
+    from tnco_b200.ctree import ContractionTree
+    from tnco_b200.tn import get_connected_components, merge_contraction_paths
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'host_ctree.json')) as f:
+        g = json.load(f)
+    for t in g['trees']:
+        dims = t['dims'] if isinstance(t['dims'], int) else {i: d for i, d in enumerate(t['dims'])}
+        ct = ContractionTree([tuple(x) for x in t['path']], t['ts_inds'], dims, output_inds=t['output_inds'])
+        P, A, B = ct.arrays()
+        assert P.tolist() == t['parent']
+        assert [[int(a), int(b)] for a, b in zip(A, B)] == t['children']
+        assert [sorted(xs) for xs in ct.inds] == t['inds']
+        assert [list(x) for x in ct.path()] == t['ref_path']
+        assert ct.max_width() == t['max_width'] and ct.n_inds == t['n_inds']
+        assert list(ct._inds_order) == t['inds_order']
+    for c in g['components']:
+        assert [list(x) for x in get_connected_components(c['ts_inds'])] == c['components']
+    for m in g['merges']:
+        paths = [[tuple(x) for x in p] for p in m['paths']]
+        assert [list(x) for x in merge_contraction_paths(m['n'], paths)] == m['merged']
+        assert [list(x) for x in merge_contraction_paths(m['n'], paths, autocomplete=False)] == m['merged_noauto']
+        # the C++ merge (tnb_merge_paths, Fenwick trees) gives the same
+        from tnco_b200.engine import merge_paths
+        lens = [len(p) for p in paths]
+        if sum(lens):
+            cat = np.array([x for p in paths for x in p], np.int32).reshape(1, -1, 2)
+            assert merge_paths(m['n'], lens, cat)[0].tolist() == m['merged']
