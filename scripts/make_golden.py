@@ -48,6 +48,12 @@ CASES = [
     ('gdims64_fw40', 64, 23, 1000, 0.4, False, -1, 10),
     ('gdimshyper48_fw50', 48, 24, 800, 0.5, True, -1, 10),
     ('gdimssparse64_fw40', 64, 25, 800, 0.4, False, -1, 10, 10, 12),
+    # BASELINE.json configs C2 / C3 / C4 themselves (tnco_b200.networks builds the same networks bench.py runs);
+    # n is taken from the network, and for C4 max_width_frac < 0 means the absolute max_width = -frac (32, as benchmarked)
+    ('c2_grid6x6d12_inf', 'grid_rqc(6, 6, 12)', 26, 1200, None, False, 2, 10),
+    ('c3_sycamore14_inf', 'sycamore(14)', 27, 800, None, False, 2, 10),
+    ('c4_sycamore20_fw32', 'sycamore(20)', 28, 800, -32.0, False, 2, 10),
+    ('c4_sycamore20_fw32_b', 'sycamore(20)', 29, 400, -32.0, False, 2, 3),
 ]
 
 
@@ -62,7 +68,11 @@ def main():
     for name, n, seed, n_sweeps, frac, hyper, dim, every, *sparse in CASES:
         if only and name not in only:
             continue
-        if hyper:
+        if isinstance(n, str):   # a benchmark network by its tnco_b200.networks constructor
+            from tnco_b200 import networks
+            ts, ni = eval('networks.' + n)
+            n, out = len(ts), []
+        elif hyper:
             ts, ni, out = hyper_network(n, seed)
         else:
             ts, ni = regular_network(n, seed)
@@ -75,7 +85,9 @@ def main():
             dims = np.random.default_rng(seed).choice([2, 3, 5, 6, 7], size=ni).astype(np.uint64)
             dim = 0
         mw = None
-        if frac is not None:
+        if frac is not None and frac < 0:
+            mw = -float(frac)
+        elif frac is not None:
             if dims is None:
                 w0 = max(sum(bin(int(v)).count('1') for v in row) for row in bits)
                 mw = float(int(w0 * frac)) * float(np.log2(dim))
