@@ -17,224 +17,37 @@
 #include <vector>
 
 #include "tnb_internal.h"
-#include "tnb_kernels.h"
+#include "tnb_launch.h"
 
 namespace tnb {
 
-// ------------------------------------------------------------------------------------------ runtime layer
-#if defined(TNB_EMU)
-struct Rt {
-  std::string err;
-  int n_sms = 148;
-  bool init(int) { return true; }
-  void* alloc(size_t b) { return std::calloc(std::max<size_t>(b, 1), 1); }
-  void free_(void* p) { std::free(p); }
-  bool h2d(void* d, const void* h, size_t b) { std::memcpy(d, h, b); return true; }
-  bool d2h(void* h, const void* d, size_t b) { std::memcpy(h, d, b); return true; }
-  bool zero(void* d, size_t b) { std::memset(d, 0, b); return true; }
-  bool fill_ff(void* d, size_t b) { std::memset(d, 0xff, b); return true; }
-  bool sync() { return true; }
-  void destroy() {}
-};
-#else
-struct Rt {
-  std::string err;
-  int device = 0, n_sms = 148;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool ok(cudaError_t e, const char* what) {
-    if (e == cudaSuccess) return true;
-    err = std::string(what) + ": " + cudaGetErrorString(e);
-    return false;
-  }
-  bool init(int dev) {
-    int count = 0;
-    if (!ok(cudaGetDeviceCount(&count), "cudaGetDeviceCount")) return false;
-    if (dev < 0 || dev >= count) { err = "no such CUDA device"; return false; }
-    cudaDeviceProp prop;
-    if (!ok(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties")) return false;
-    if (prop.major != 10) {
-      err = "tnco_b200 needs an sm_100 (Blackwell B200) device; found sm_" + std::to_string(prop.major) +
-            std::to_string(prop.minor) + " (there is no CPU or other-architecture fallback)";
-      return false;
-    }
-    device = dev;
-    n_sms = prop.multiProcessorCount;
-    if (!ok(cudaSetDevice(dev), "cudaSetDevice")) return false;
-    if (!ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
-    if (!ok(cudaEventCreate(&ev0), "cudaEventCreate") || !ok(cudaEventCreate(&ev1), "cudaEventCreate")) return false;
-    return true;
-  }
-  // Device allocations are recycled through an exact-size free list: cudaMalloc / cudaFree synchronise the device
-  // and were the most variable part (10-350 ms) of a back-to-back optimize() call that needs the same arrays again.
-  std::multimap<size_t, void*> pool;
-  std::unordered_map<void*, size_t> sizes;
-  size_t pooled = 0;
-  static constexpr size_t kPoolCap = size_t(16) << 30;
-  void* alloc(size_t b) {
-    b = std::max<size_t>(b, 16);
-    void* p = nullptr;
-    cudaSetDevice(device);
-    auto it = pool.find(b);
-    if (it != pool.end()) {
-      p = it->second;
-      pool.erase(it);
-      pooled -= b;
-    } else {
-      if (cudaMalloc(&p, b) != cudaSuccess) {  // out of memory: give the cached blocks back and retry once
-        cudaGetLastError();
-        trim();
-        if (!ok(cudaMalloc(&p, b), "cudaMalloc")) return nullptr;
-      }
-      sizes[p] = b;
-    }
-    cudaMemsetAsync(p, 0, b, stream);
-    return p;
-  }
-  void free_(void* p) {
-    if (!p) return;
-    auto it = sizes.find(p);
-    if (it == sizes.end()) { cudaFree(p); return; }
-    if (pooled + it->second > kPoolCap) {
-      cudaStreamSynchronize(stream);
-      cudaFree(p);
-      sizes.erase(it);
-      return;
-    }
-    pool.emplace(it->second, p);  // later kernels of this stream are ordered after the ones still using it
-    pooled += it->second;
-  }
-  void trim() {
-    cudaStreamSynchronize(stream);
-    for (auto& kv : pool) {
-      cudaFree(kv.second);
-      sizes.erase(kv.second);
-    }
-    pool.clear();
-    pooled = 0;
-  }
-  bool h2d(void* d, const void* h, size_t b) {
-    return b == 0 || ok(cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, stream), "cudaMemcpy H2D");
-  }
-  bool d2h(void* h, const void* d, size_t b) {
-    if (b == 0) return true;
-    return ok(cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, stream), "cudaMemcpy D2H") && sync();
-  }
-  bool zero(void* d, size_t b) { return b == 0 || ok(cudaMemsetAsync(d, 0, b, stream), "cudaMemset"); }
-  bool fill_ff(void* d, size_t b) { return b == 0 || ok(cudaMemsetAsync(d, 0xff, b, stream), "cudaMemset"); }
-  bool sync() { return ok(cudaStreamSynchronize(stream), "cudaStreamSynchronize"); }
-  void destroy() {
-    trim();
-    if (ev0) cudaEventDestroy(ev0);
-    if (ev1) cudaEventDestroy(ev1);
-    if (stream) cudaStreamDestroy(stream);
-  }
-};
+#if !defined(TNB_EMU)
+// one translation unit per tile shape (tnb_inst.cu)
+#define TNB_EXTERN_SHAPE(T, W)                                                            \
+  extern template bool launch_tw<T, W>(Rt&, const Params&, bool, bool, bool);             \
+  extern template bool launch_treegen_t<T, W>(Rt&, const Params&);
+TNB_EXTERN_SHAPE(4, 1)
+TNB_EXTERN_SHAPE(8, 1)
+TNB_EXTERN_SHAPE(16, 1)
+TNB_EXTERN_SHAPE(32, 1)
+TNB_EXTERN_SHAPE(32, 2)
+TNB_EXTERN_SHAPE(32, 3)
+TNB_EXTERN_SHAPE(32, 4)
+#undef TNB_EXTERN_SHAPE
 #endif
 
-// ------------------------------------------------------------------------------------------ kernels
-constexpr int kBlock = 128;
-constexpr size_t kTailWords = 256;  // padding words behind every array that load_bits reads rows from
-
 #if !defined(TNB_EMU)
-template <int TILE, int WPL, bool FINITE, class Rng>
-__global__ void __launch_bounds__(kBlock) sa_init_kernel(const __grid_constant__ Params P) {
-  const int chain = (blockIdx.x * kBlock + threadIdx.x) / TILE;
-  if (chain >= P.n_chains) return;
-  chain_init<TILE, WPL, FINITE, Rng>(P, chain);
-}
-// One warp per block: the hardware block scheduler then balances chains over the 148 SMs at warp granularity
-// (4096 chains of 16 lanes = 2048 blocks = 13.8 per SM, all resident in a single wave at <= 128 registers).
-constexpr int kSweepBlock = 32;
-// Production (Philox) kernels are held to 72 registers (no spills) so that 28 single-warp blocks fit on an SM:
-// 148 x 28 = 4144 resident chains at TILE = 32.  Parity kernels (fp64 pow, stream bookkeeping) keep 128.
-// MINB = single-warp blocks resident per SM the register allocation must allow (28 -> 72 registers).
-template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2, int MINB, bool HYPER>
-__global__ void __launch_bounds__(kSweepBlock, MINB) sa_sweep_kernel(const __grid_constant__ Params P) {
-  const int chain = (blockIdx.x * kSweepBlock + threadIdx.x) / TILE;
-  if (chain >= P.n_chains) return;
-  chain_sweeps<TILE, WPL, FINITE, Rng, DIM2, HYPER>(P, chain);
-}
-
 // children words between the compact [n_chains][n_int] array (upload / read-back form) and the node records
-__global__ void __launch_bounds__(256) ch_scatter_kernel(const uint32_t* src, char* rec, int stride, size_t count) {
+static __global__ void __launch_bounds__(256) ch_scatter_kernel(const uint32_t* src, char* rec, int stride, size_t count) {
   const size_t i = size_t(blockIdx.x) * 256 + threadIdx.x;
   if (i < count) *reinterpret_cast<uint32_t*>(rec + i * size_t(stride)) = src[i];
 }
-__global__ void __launch_bounds__(256) ch_gather_kernel(uint32_t* dst, const char* rec, int stride, size_t count) {
+static __global__ void __launch_bounds__(256) ch_gather_kernel(uint32_t* dst, const char* rec, int stride, size_t count) {
   const size_t i = size_t(blockIdx.x) * 256 + threadIdx.x;
   if (i < count) dst[i] = *reinterpret_cast<const uint32_t*>(rec + i * size_t(stride));
 }
 
-template <int TILE, int WPL>
-__global__ void __launch_bounds__(kBlock) sa_treegen_kernel(const __grid_constant__ Params P) {
-  const int chain = (blockIdx.x * kBlock + threadIdx.x) / TILE;
-  if (chain >= P.n_chains) return;
-  chain_treegen<TILE, WPL>(P, chain);
-}
 #endif
-
-template <int TILE, int WPL>
-static bool launch_treegen_t(Rt& rt, const Params& P) {
-#if defined(TNB_EMU)
-  (void)rt;
-  for (int c = 0; c < P.n_chains; ++c) chain_treegen<TILE, WPL>(P, c);
-  return true;
-#else
-  const long long threads = (long long)P.n_chains * TILE;
-  const int grid = int((threads + kBlock - 1) / kBlock);
-  if (grid == 0) return true;
-  sa_treegen_kernel<TILE, WPL><<<grid, kBlock, 0, rt.stream>>>(P);
-  return rt.ok(cudaGetLastError(), "sa_treegen_kernel launch");
-#endif
-}
-
-template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2, bool HYPER>
-static bool launch_h(Rt& rt, const Params& P, bool init) {
-#if defined(TNB_EMU)
-  (void)rt;
-  for (int c = 0; c < P.n_chains; ++c) {
-    if (init) chain_init<TILE, WPL, FINITE, Rng>(P, c);
-    else chain_sweeps<TILE, WPL, FINITE, Rng, DIM2, HYPER>(P, c);
-  }
-  return true;
-#else
-  const long long threads = (long long)P.n_chains * TILE;
-  const int blk = init ? kBlock : kSweepBlock;
-  const int grid = int((threads + blk - 1) / blk);
-  if (grid == 0) return true;
-  // occupancy class: production kernels 28 single-warp blocks per SM (<= 72 registers), parity kernels 16
-  constexpr int MINB = Rng::kFast ? 28 : 16;
-  if (init) sa_init_kernel<TILE, WPL, FINITE, Rng><<<grid, kBlock, 0, rt.stream>>>(P);
-  else sa_sweep_kernel<TILE, WPL, FINITE, Rng, DIM2, MINB, HYPER><<<grid, kSweepBlock, 0, rt.stream>>>(P);
-  return rt.ok(cudaGetLastError(), init ? "sa_init_kernel launch" : "sa_sweep_kernel launch");
-#endif
-}
-
-// HYPER kernels exist for full-warp tiles only (pick_tile gives hyper-index networks TILE = 32)
-template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2>
-static bool launch_t(Rt& rt, const Params& P, bool init) {
-  if constexpr (TILE == 32 || TILE == 1) {
-    if (P.hyper && !init) return launch_h<TILE, WPL, FINITE, Rng, DIM2, true>(rt, P, init);
-  } else {
-    if (P.hyper) { rt.err = "hyper-index networks need TILE = 32"; return false; }
-  }
-  return launch_h<TILE, WPL, FINITE, Rng, DIM2, false>(rt, P, init);
-}
-
-template <int TILE, int WPL>
-static bool launch_tw(Rt& rt, const Params& P, bool init, bool finite, bool stream_rng) {
-  // parity (stream) modes always take costs from the std::pow table; the production kernel builds 2^k directly
-  const bool d2 = P.dim2 != 0;
-  if (finite) {
-    if (stream_rng) return launch_t<TILE, WPL, true, RngStream<TILE>, false>(rt, P, init);
-    return d2 ? launch_t<TILE, WPL, true, RngPhilox<TILE>, true>(rt, P, init)
-              : launch_t<TILE, WPL, true, RngPhilox<TILE>, false>(rt, P, init);
-  }
-  if (stream_rng) return launch_t<TILE, WPL, false, RngStream<TILE>, false>(rt, P, init);
-  return d2 ? launch_t<TILE, WPL, false, RngPhilox<TILE>, true>(rt, P, init)
-            : launch_t<TILE, WPL, false, RngPhilox<TILE>, false>(rt, P, init);
-}
 
 static bool launch(Rt& rt, const Params& P, int tile, int wpl, bool init, bool finite, bool stream_rng) {
 #if defined(TNB_EMU)
