@@ -172,6 +172,29 @@ int tnb_set_resume(tnb_engine* e, const uint32_t* mt_state, const uint32_t* slic
 /* TNB_RNG_REPLAY: raw draw stream per chain, words [n_chains][len]; cursors reset to 0. */
 int tnb_set_stream(tnb_engine* e, const uint32_t* words, uint64_t len);
 
+/* Decision trace of the PRODUCTION kernels (TNB_RNG_PHILOX, 2^popcount costs, no hyper-indices), for parity tests:
+ * chains [0, n_chains) append one 32-byte record per sweep start, per proposal and per re-slice
+ *   struct { uint32_t w0, w1, w2, w3; double d0, d1; }
+ *   w0: bits 0-1 kind (0 sweep start, 1 proposal, 2 re-slice); proposal flags: bit 2 D is child slot 0 of B,
+ *       bit 3 width gate passed, bit 4 accepted, bit 5 a coin was drawn (both children of B intersect C);
+ *       bits 16-31 node B
+ *   w1: sweep start: the leaf's random word; proposal: float bits of -log2(u), coin in the last bit; re-slice: its number
+ *   w2: proposal: float bits of 1/beta          w3: sweep start: leaf; proposal: node A; re-slice: 1 = new slices kept
+ *   d0, d1: proposal: delta, running total before the move; sweep start: total, min_total; re-slice: cost under
+ *       the candidate slices, cost under the current ones
+ * so that a CPU restatement of the reference (include/tnco/optimize/infinite_memory/optimizer.hpp:90-201,
+ * finite_width/greedy/optimizer.hpp:117-390) can be driven through the very same decisions and must arrive at the
+ * same trees, index sets and contraction costs.  Call after tnb_set_chains / tnb_generate_chains; n_chains = 0
+ * switches the trace off.  cap_records / cap_reslices: capacity per chain (further events are counted, not stored). */
+int tnb_set_trace(tnb_engine* e, int n_chains, uint64_t cap_records, uint32_t cap_reslices);
+/* records [min(*n_records, cap_records)] x 32 bytes and the candidate slices of every re-slice
+ * [min(*n_reslices, cap_reslices)][W32] of one traced chain; any pointer may be NULL */
+int tnb_get_trace(tnb_engine* e, int chain, uint64_t* n_records, void* records, uint32_t* n_reslices,
+                  uint32_t* slices);
+/* contraction cost of every node of the CURRENT tree of one chain, [2*n_leaves-1] (0 for leaves):
+ * the reference's CostCache contraction_cost (include/tnco/optimize/infinite_memory/utils.hpp:32-56) */
+int tnb_get_node_costs(tnb_engine* e, int chain, double* ccost);
+
 /* Inverse temperatures, one per sweep (tnco/app/infinite_memory/sa.py:147-156,199-205). */
 int tnb_set_betas(tnb_engine* e, const double* betas, int64_t n);
 

@@ -14,6 +14,10 @@ typedef struct {
   int p;
   uint32_t* rec;
   uint64_t rec_cap, rec_n, drawn;
+  /* replay: draws come from a caller-supplied word stream instead of the generator (ora_set_replay) */
+  const uint32_t* rp;
+  uint64_t rp_n, rp_k;
+  int rp_over;
 } mt_t;
 
 static void mt_seed(mt_t* m, uint32_t s) { /* optimize/optimizer.hpp:75 prng.seed(size_t) -> s mod 2^32 */
@@ -22,6 +26,9 @@ static void mt_seed(mt_t* m, uint32_t s) { /* optimize/optimizer.hpp:75 prng.see
   m->p = 624;
   m->rec = NULL;
   m->rec_cap = m->rec_n = m->drawn = 0;
+  m->rp = NULL;
+  m->rp_n = m->rp_k = 0;
+  m->rp_over = 0;
 }
 
 static void mt_twist(mt_t* m) {
@@ -34,6 +41,11 @@ static void mt_twist(mt_t* m) {
 }
 
 static uint32_t mt_next(mt_t* m) {
+  if (m->rp) {
+    m->drawn++;
+    if (m->rp_k >= m->rp_n) { m->rp_over = 1; return 0u; }
+    return m->rp[m->rp_k++];
+  }
   if (m->p >= 624) mt_twist(m);
   uint32_t y = m->x[m->p++];
   y ^= y >> 11;
@@ -113,6 +125,14 @@ struct ora_chain {
   double min_total;
   mt_t mt;
   uint64_t proposals, accepts, sweeps, width_rejects;
+  /* test hooks */
+  ora_trace_rec* tr;          /* per-proposal trace (ora_trace) */
+  uint64_t tr_cap, tr_n;
+  const uint32_t* fs;         /* forced re-slices (ora_set_forced_slices): candidates [fs_n][W], keep flags */
+  const uint8_t* fs_keep;
+  uint64_t fs_n, fs_k;
+  double* rl;                 /* re-slice log: (cost under candidate, cost under current) pairs */
+  uint64_t rl_cap, rl_n;
 };
 
 static inline int popc_w(const uint32_t* a, int W) {
@@ -340,6 +360,14 @@ ora_chain* ora_create_ex(int n, int n_inds, const int32_t* parent, const int32_t
                          const uint32_t* node_bits, uint64_t dim, const uint64_t* dims, int finite, float max_width,
                          uint32_t seed, int dsi, const uint32_t* sparse_bits, uint64_t n_projs,
                          const uint32_t* skip_bits, int* err) {
+  return ora_create_ex2(n, n_inds, parent, child0, child1, node_bits, dim, dims, finite, max_width, seed, dsi,
+                        sparse_bits, n_projs, skip_bits, NULL, err);
+}
+
+ora_chain* ora_create_ex2(int n, int n_inds, const int32_t* parent, const int32_t* child0, const int32_t* child1,
+                          const uint32_t* node_bits, uint64_t dim, const uint64_t* dims, int finite, float max_width,
+                          uint32_t seed, int dsi, const uint32_t* sparse_bits, uint64_t n_projs,
+                          const uint32_t* skip_bits, const uint32_t* init_slices, int* err) {
   if (err) *err = 0;
   if (sparse_bits && n_projs == 0) { /* "'n_projs' must be a positive number." (simple_sparse_inds.hpp:64-67) */
     if (err) *err = 3;
@@ -385,7 +413,8 @@ ora_chain* ora_create_ex(int n, int n_inds, const int32_t* parent, const int32_t
   if (finite) {
     /* finite_width/greedy/optimizer.hpp:80-101: WidthCache -> slices (consumes prng) -> CostCache */
     for (int t = 0; t < N; ++t) c->width[t] = width_of(c, c->bits + (size_t)t * W);
-    get_slices(c, c->slices);
+    if (init_slices) memcpy(c->slices, init_slices, sizeof(uint32_t) * (size_t)W); /* `slices=` given (:80-88) */
+    else get_slices(c, c->slices);
   }
   build_cost_cache(c, finite ? c->slices : NULL, c->cc, c->pc);
   copy_min(c);
@@ -453,12 +482,24 @@ void ora_update(ora_chain* c, int kind, double beta, int update_slices) {
       gate = width_of(c, tmp) <= c->max_width;
       if (!gate) c->width_rejects++;
     }
+    ora_trace_rec* tr = NULL;
+    if (c->tr) {
+      if (c->tr_n < c->tr_cap) {
+        tr = c->tr + c->tr_n;
+        memset(tr, 0, sizeof *tr);
+        tr->B = B; tr->A = A; tr->pick0 = (uint8_t)(D == p0); tr->gate = (uint8_t)gate;
+        tr->coin = (uint8_t)(c->dsi || (i0 && i1)); tr->total = total;
+      }
+      c->tr_n++;
+    }
     if (gate) {
       const double nA = ccost_of(c, newB, BITS(E), S);    /* :152-155 */
       const double nB = ccost_of(c, BITS(D), BITS(C), S);
       const double delta = (nB - c->cc[B]) + (nA - c->cc[A]); /* :158 */
       const double u = mt_uniform(mt);
-      if (u <= prob_of(kind, beta, delta, total)) {        /* :162 */
+      const double pr = prob_of(kind, beta, delta, total);
+      if (tr) { tr->delta = delta; tr->u = u; tr->p = pr; tr->acc = (uint8_t)(u <= pr); }
+      if (u <= pr) {        /* :162 */
         /* tree.hpp:141-192 swap_with_nn(E): E <-> C, child slots preserved */
         if (c->c0[A] == C) c->c0[A] = E; else c->c1[A] = E;
         if (c->c0[B] == E) c->c0[B] = C; else c->c1[B] = C;
@@ -486,11 +527,28 @@ void ora_update(ora_chain* c, int kind, double beta, int update_slices) {
     for (int w = 0; w < W; ++w) any |= c->slices[w] != 0;
     if (any) {
       uint32_t ns[W];
-      get_slices(c, ns);
+      int forced = -1; /* test hook: candidate slices and the keep decision come from the caller */
+      if (c->fs) {
+        if (c->fs_k < c->fs_n) {
+          memcpy(ns, c->fs + (size_t)c->fs_k * W, sizeof(uint32_t) * (size_t)W);
+          forced = c->fs_keep[c->fs_k];
+        } else {
+          memcpy(ns, c->slices, sizeof(uint32_t) * (size_t)W);
+          forced = 0;
+          c->mt.rp_over = 1; /* ran out of forced re-slices: flag it like a stream overrun */
+        }
+        c->fs_k++;
+      } else {
+        get_slices(c, ns);
+      }
       double* cc2 = (double*)malloc(sizeof(double) * (size_t)N);
       double* pc2 = (double*)malloc(sizeof(double) * (size_t)N);
       build_cost_cache(c, ns, cc2, pc2);
-      if (pc2[N - 1] < c->pc[N - 1]) {
+      if (c->rl) {
+        if (c->rl_n < c->rl_cap) { c->rl[2 * c->rl_n] = pc2[N - 1]; c->rl[2 * c->rl_n + 1] = c->pc[N - 1]; }
+        c->rl_n++;
+      }
+      if (forced >= 0 ? forced : (pc2[N - 1] < c->pc[N - 1])) {
         memcpy(c->slices, ns, sizeof(uint32_t) * (size_t)W);
         memcpy(c->cc, cc2, sizeof(double) * (size_t)N);
         memcpy(c->pc, pc2, sizeof(double) * (size_t)N);
@@ -541,6 +599,33 @@ void ora_counters(const ora_chain* c, uint64_t* p, uint64_t* a, uint64_t* s, uin
   if (w) *w = c->mt.drawn;
   if (wr) *wr = c->width_rejects;
 }
+void ora_set_replay(ora_chain* c, const uint32_t* words, uint64_t n) {
+  c->mt.rp = words;
+  c->mt.rp_n = n;
+  c->mt.rp_k = 0;
+  c->mt.rp_over = 0;
+}
+void ora_replay_state(const ora_chain* c, uint64_t* consumed, int* overrun) {
+  if (consumed) *consumed = c->mt.rp_k;
+  if (overrun) *overrun = c->mt.rp_over;
+}
+void ora_trace(ora_chain* c, ora_trace_rec* buf, uint64_t cap) {
+  c->tr = buf;
+  c->tr_cap = cap;
+  c->tr_n = 0;
+}
+uint64_t ora_traced(const ora_chain* c) { return c->tr_n; }
+void ora_set_forced_slices(ora_chain* c, const uint32_t* cand, const uint8_t* keep, uint64_t n, double* log2x,
+                           uint64_t log_cap) {
+  c->fs = cand;
+  c->fs_keep = keep;
+  c->fs_n = n;
+  c->fs_k = 0;
+  c->rl = log2x;
+  c->rl_cap = log_cap;
+  c->rl_n = 0;
+}
+uint64_t ora_forced_used(const ora_chain* c) { return c->fs_k; }
 void ora_record(ora_chain* c, uint32_t* buf, uint64_t cap) {
   c->mt.rec = buf;
   c->mt.rec_cap = cap;

@@ -38,6 +38,17 @@ def lib():
         L.ora_create_ex.restype = C.c_void_p
         L.ora_create_ex.argtypes = [C.c_int, C.c_int, i32p, i32p, i32p, u32p, C.c_uint64, u64p, C.c_int,
                                     C.c_float, C.c_uint32, C.c_int, u32p, C.c_uint64, u32p, C.POINTER(C.c_int)]
+        L.ora_create_ex2.restype = C.c_void_p
+        L.ora_create_ex2.argtypes = [C.c_int, C.c_int, i32p, i32p, i32p, u32p, C.c_uint64, u64p, C.c_int,
+                                     C.c_float, C.c_uint32, C.c_int, u32p, C.c_uint64, u32p, u32p, C.POINTER(C.c_int)]
+        L.ora_set_replay.argtypes = [C.c_void_p, u32p, C.c_uint64]
+        L.ora_replay_state.argtypes = [C.c_void_p, u64p, C.POINTER(C.c_int)]
+        L.ora_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.ora_traced.restype = C.c_uint64
+        L.ora_traced.argtypes = [C.c_void_p]
+        L.ora_set_forced_slices.argtypes = [C.c_void_p, u32p, C.POINTER(C.c_uint8), C.c_uint64, f64p, C.c_uint64]
+        L.ora_forced_used.restype = C.c_uint64
+        L.ora_forced_used.argtypes = [C.c_void_p]
         L.ora_create.restype = C.c_void_p
         L.ora_create.argtypes = [C.c_int, C.c_int, i32p, i32p, i32p, u32p, C.c_uint64, u64p, C.c_int,
                                  C.c_float, C.c_uint32, C.c_int, C.POINTER(C.c_int)]
@@ -78,7 +89,8 @@ class Chain:
     """One SA chain == one reference ``Optimizer`` object (infinite_memory or finite_width.greedy)."""
 
     def __init__(self, parent, child0, child1, node_bits, n_inds, *, dim=2, dims=None, max_width=None,
-                 seed=0, disable_shared_inds=False, sparse_bits=None, n_projs=None, skip_bits=None):
+                 seed=0, disable_shared_inds=False, sparse_bits=None, n_projs=None, skip_bits=None,
+                 init_slices=None):
         L = lib()
         self.parent0, c0, c1 = _i32(parent), _i32(child0), _i32(child1)
         self.N = len(self.parent0)
@@ -91,12 +103,14 @@ class Chain:
         self.finite = max_width is not None
         sp = None if sparse_bits is None else np.ascontiguousarray(sparse_bits, dtype=np.uint32).reshape(self.W)
         sk = None if skip_bits is None else np.ascontiguousarray(skip_bits, dtype=np.uint32).reshape(self.W)
-        self._h = L.ora_create_ex(self.n, self.n_inds, _p(self.parent0, C.c_int32), _p(c0, C.c_int32),
-                                      _p(c1, C.c_int32), _p(nb, C.c_uint32), int(dim),
-                                      None if dims_a is None else _p(dims_a, C.c_uint64), int(self.finite),
-                                      float(max_width if self.finite else 0.0), int(seed) & 0xFFFFFFFF,
-                                      int(disable_shared_inds), None if sp is None else _p(sp, C.c_uint32),
-                                      int(n_projs or 0), None if sk is None else _p(sk, C.c_uint32), C.byref(err))
+        isl = None if init_slices is None else np.ascontiguousarray(init_slices, dtype=np.uint32).reshape(self.W)
+        self._h = L.ora_create_ex2(self.n, self.n_inds, _p(self.parent0, C.c_int32), _p(c0, C.c_int32),
+                                       _p(c1, C.c_int32), _p(nb, C.c_uint32), int(dim),
+                                       None if dims_a is None else _p(dims_a, C.c_uint64), int(self.finite),
+                                       float(max_width if self.finite else 0.0), int(seed) & 0xFFFFFFFF,
+                                       int(disable_shared_inds), None if sp is None else _p(sp, C.c_uint32),
+                                       int(n_projs or 0), None if sk is None else _p(sk, C.c_uint32),
+                                       None if isl is None else _p(isl, C.c_uint32), C.byref(err))
         if not self._h:
             raise ValueError('Precision is too low.' if err.value == 2 else
                              "'n_projs' must be a positive number." if err.value == 3 else 'invalid input')
@@ -155,6 +169,44 @@ class Chain:
         lib().ora_counters(self._h, *[C.byref(x) for x in v])
         return dict(zip(('proposals', 'accepts', 'sweeps', 'words_drawn', 'width_rejects'),
                         (x.value for x in v)))
+
+    TRACE_DTYPE = np.dtype([('B', '<i4'), ('A', '<i4'), ('pick0', 'u1'), ('gate', 'u1'), ('acc', 'u1'), ('coin', 'u1'),
+                            ('pad', '<u4'), ('delta', '<f8'), ('total', '<f8'), ('u', '<f8'), ('p', '<f8')])
+
+    def set_replay(self, words):
+        """Feed every 32-bit draw from `words` (the reference's data-dependent draw order) instead of the generator."""
+        self._rp = np.ascontiguousarray(words, dtype=np.uint32)
+        lib().ora_set_replay(self._h, _p(self._rp, C.c_uint32), len(self._rp))
+
+    def replay_state(self):
+        k, o = C.c_uint64(0), C.c_int(0)
+        lib().ora_replay_state(self._h, C.byref(k), C.byref(o))
+        return k.value, bool(o.value)
+
+    def trace(self, cap):
+        self._tr = np.zeros(int(cap), self.TRACE_DTYPE)
+        assert self.TRACE_DTYPE.itemsize == 48
+        lib().ora_trace(self._h, self._tr.ctypes.data_as(C.c_void_p), int(cap))
+
+    def traced(self):
+        n = int(lib().ora_traced(self._h))
+        if n > len(self._tr):
+            raise RuntimeError('trace buffer overflow')
+        return self._tr[:n]
+
+    def set_forced_slices(self, candidates, keep):
+        """k-th re-slice: candidate slices candidates[k], kept iff keep[k]; see reslice_log()."""
+        self._fs = np.ascontiguousarray(candidates, dtype=np.uint32).reshape(-1, self.W)
+        self._fk = np.ascontiguousarray(keep, dtype=np.uint8).reshape(-1)
+        assert len(self._fs) == len(self._fk)
+        self._rl = np.zeros((max(len(self._fk), 1), 2), np.float64)
+        lib().ora_set_forced_slices(self._h, _p(self._fs, C.c_uint32), self._fk.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                    len(self._fk), _p(self._rl, C.c_double), len(self._rl))
+
+    def reslice_log(self):
+        """(re-slices consumed, [k][2] = reference criterion: cost under the candidate, cost under the current)."""
+        k = int(lib().ora_forced_used(self._h))
+        return k, self._rl[:min(k, len(self._rl))]
 
     def record(self, cap):
         self._rec = np.zeros(int(cap), np.uint32)

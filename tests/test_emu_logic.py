@@ -119,3 +119,17 @@ def test_emu_mode_and_resume_errors(emu):
 @pytest.mark.parametrize('n,max_width,sparse', [(60, None, False), (60, 16.0, False), (60, 16.0, True)])
 def test_emu_general_dims_philox(emu, n, max_width, sparse):
     G.test_philox_general_per_index_dims(n, max_width, sparse)
+
+
+@pytest.mark.parametrize('name,n_sweeps', [('C1', 1500), ('C2', 500), ('C4', 200), ('reg200_fw', 300)])
+def test_emu_production_kernel_replay(emu, name, n_sweeps):
+    """Same kernel source, one lane per chain: the recorded decisions replayed through the oracle (see
+    tests/test_gpu_philox_replay.py; the GPU run is the parity test proper)."""
+    import test_gpu_philox_replay as R
+    net, mw = R.NETS[name]
+    R.run_and_replay(net, mw, n_sweeps, chains=2)
+
+
+def test_emu_production_kernel_replay_low_beta(emu):
+    import test_gpu_philox_replay as R
+    R.test_production_kernel_replay_low_beta_and_every_sweep_reslice()

@@ -46,6 +46,9 @@ SIGNATURES = {
     'tnb_generate_chains': (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_uint64, C.c_int]),
     'tnb_set_resume': (C.c_int, [C.c_void_p, u32p, u32p, i32p, i32p, i32p, u32p]),
     'tnb_set_stream': (C.c_int, [C.c_void_p, u32p, C.c_uint64]),
+    'tnb_set_trace': (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint32]),
+    'tnb_get_trace': (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_void_p, u32p, u32p]),
+    'tnb_get_node_costs': (C.c_int, [C.c_void_p, C.c_int, f64p]),
     'tnb_set_betas': (C.c_int, [C.c_void_p, f64p, C.c_int64]),
     'tnb_run': (C.c_int, [C.c_void_p, C.c_int64]),
     'tnb_get_timing': (C.c_int, [C.c_void_p, f64p, i64p]),

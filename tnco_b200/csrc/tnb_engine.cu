@@ -134,10 +134,16 @@ struct ChainSet {
   double* escore = nullptr;
   uint32_t* stream = nullptr;
   unsigned long long stream_len = 0;
+  // decision trace (tnb_set_trace)
+  TraceRec* trace = nullptr;
+  unsigned long long *trace_n = nullptr, trace_cap = 0;
+  uint32_t *trace_S = nullptr, *trace_sn = nullptr, trace_scap = 0;
+  int trace_chains = 0;
 
   void release(Rt& rt) {
     void* ps[] = {par, bpar, rec, bits_alloc, bch, pc, slices, bslices, cp2, total, min_total, out_seq, out_maxw, seeds,
-                  rng_ctr, n_prop, n_acc, n_wrej, cursor, sweep_idx, overrun, nbig, posbuf, kpop, tree_fail, escore, stream, kw, sz, word, wkey};
+                  rng_ctr, n_prop, n_acc, n_wrej, cursor, sweep_idx, overrun, nbig, posbuf, kpop, tree_fail, escore, stream, kw, sz, word, wkey,
+                  trace, trace_n, trace_S, trace_sn};
     for (void* p : ps) rt.free_(p);
     *this = ChainSet();
   }
@@ -286,6 +292,8 @@ static void fill_params(const tnb_engine* e, const ChainSet& cs, Params& P) {
       if (float(e->log2d * double(k)) <= e->max_width) P.kthr = k;
   P.grouped = e->grouped; P.leader = e->d_leader; P.gw = e->d_gw;
   P.hyper = e->hyper; P.hyp_off = 4 * e->Ws; P.hcount0 = e->d_hcount0;
+  P.trace = cs.trace; P.trace_n = cs.trace_n; P.trace_cap = cs.trace_cap; P.trace_S = cs.trace_S; P.trace_sn = cs.trace_sn;
+  P.trace_scap = cs.trace_scap; P.trace_chains = cs.trace_chains;
   P.net_own = e->d_net_own; P.kpop = cs.kpop; P.escore = cs.escore; P.tree_fail = cs.tree_fail; P.tree_method = TNB_TREES_GREEDY;
 }
 
@@ -874,6 +882,61 @@ int tnb_set_resume(tnb_engine* e, const uint32_t* mt_state, const uint32_t* slic
     e->rs_ba.assign(best_child0, best_child0 + nc * e->N);
     e->rs_bb.assign(best_child1, best_child1 + nc * e->N);
   }
+  return 0;
+}
+
+int tnb_set_trace(tnb_engine* e, int n_chains, uint64_t cap_records, uint32_t cap_reslices) {
+  if (!e) return -1;
+  ChainSet& cs = e->cs;
+  if (cs.n_chains == 0) return e->fail("tnb_set_trace: call tnb_set_chains / tnb_generate_chains first"), -1;
+  if (n_chains < 0 || n_chains > cs.n_chains) return e->fail("tnb_set_trace: invalid arguments (chain count)"), -1;
+  if (n_chains > 0 && (e->rng_kind != TNB_RNG_PHILOX || !e->pow2_costs() || e->hyper))
+    return e->fail("tnb_set_trace: the decision trace is not supported outside the production kernels "
+                   "(TNB_RNG_PHILOX, 2^popcount costs, no hyper-indices)"), -1;
+  for (void* p : {(void*)cs.trace, (void*)cs.trace_n, (void*)cs.trace_S, (void*)cs.trace_sn}) e->rt.free_(p);
+  cs.trace = nullptr; cs.trace_n = nullptr; cs.trace_S = nullptr; cs.trace_sn = nullptr;
+  cs.trace_chains = 0; cs.trace_cap = 0; cs.trace_scap = 0;
+  if (n_chains == 0) return 0;
+  const size_t nc = size_t(n_chains);
+  if (!alloc_to(e->rt, cs.trace, nc * std::max<uint64_t>(cap_records, 1)) || !alloc_to(e->rt, cs.trace_n, nc) ||
+      !alloc_to(e->rt, cs.trace_S, nc * std::max<uint32_t>(cap_reslices, 1) * size_t(e->Ws)) ||
+      !alloc_to(e->rt, cs.trace_sn, nc) || !e->rt.sync())
+    return e->rtfail(), -3;
+  cs.trace_chains = n_chains; cs.trace_cap = cap_records; cs.trace_scap = cap_reslices;
+  return 0;
+}
+
+int tnb_get_trace(tnb_engine* e, int chain, uint64_t* n_records, void* records, uint32_t* n_reslices, uint32_t* slices) {
+  if (!e) return -1;
+  ChainSet& cs = e->cs;
+  if (chain < 0 || chain >= cs.trace_chains) return e->fail("tnb_get_trace: chain range"), -1;
+  unsigned long long n = 0;
+  uint32_t ns = 0;
+  if (!e->rt.d2h(&n, cs.trace_n + chain, sizeof n) || !e->rt.d2h(&ns, cs.trace_sn + chain, sizeof ns)) return e->rtfail(), -3;
+  if (n_records) *n_records = n;
+  if (n_reslices) *n_reslices = ns;
+  const size_t have = size_t(std::min<unsigned long long>(n, cs.trace_cap));
+  if (records && !e->rt.d2h(records, cs.trace + size_t(chain) * cs.trace_cap, have * sizeof(TraceRec))) return e->rtfail(), -3;
+  if (slices) {
+    const size_t hs = std::min<size_t>(ns, cs.trace_scap);
+    std::vector<uint32_t> v(hs * size_t(e->Ws));
+    if (!e->rt.d2h(v.data(), cs.trace_S + size_t(chain) * cs.trace_scap * size_t(e->Ws), v.size() * sizeof(uint32_t)))
+      return e->rtfail(), -3;
+    for (size_t k = 0; k < hs; ++k) e->contract_row(&v[k * size_t(e->Ws)], slices + k * size_t(e->Wu));
+  }
+  return 0;
+}
+
+int tnb_get_node_costs(tnb_engine* e, int chain, double* ccost) {
+  if (!e) return -1;
+  if (!ensure_init(e)) return -2;
+  if (chain < 0 || chain >= e->cs.n_chains || !ccost) return e->fail("tnb_get_node_costs: arguments"), -1;
+  for (int z = 0; z < e->n; ++z) ccost[z] = 0.0;
+  if (e->n_int == 0) return 0;
+  const size_t ni = size_t(e->n_int), hs = size_t(e->cs.hstride);
+  std::vector<char> hb(ni * hs);
+  if (!e->rt.d2h(hb.data(), e->cs.rec + size_t(chain) * ni * hs, (ni - 1) * hs + 16)) return e->rtfail(), -3;
+  for (size_t z = 0; z < ni; ++z) std::memcpy(&ccost[size_t(e->n) + z], &hb[z * hs + 8], sizeof(double));
   return 0;
 }
 

@@ -17,6 +17,18 @@ namespace tnb {
 
 constexpr int kProbMH = 0, kProbGreedy = 1, kProbAlways = 2;
 
+// One record of the decision trace (32 bytes).  w0: bits 0-1 kind (0 sweep start, 1 proposal, 2 re-slice),
+// proposal flags bit 2 pick0 (D = child slot 0), bit 3 width gate passed, bit 4 accepted, bit 5 coin drawn (both
+// children of B intersect C); bits 16-31 node B.  w1: the event's random word (sweep start: leaf word; proposal:
+// float bits of -log2(u) with the coin in the last bit; re-slice: its number).  w2: float bits of 1/beta.
+// w3: sweep start: leaf; proposal: node A; re-slice: 1 if the new slices were kept.  d0 / d1: proposal: delta and
+// the running total before the move; sweep start: total and min_total; re-slice: cost under the candidate slices
+// and under the current ones.
+struct TraceRec {
+  uint32_t w0, w1, w2, w3;
+  double d0, d1;
+};
+
 struct Params {
   // network
   int n, N, n_int, n_inds, W, Ws;  // leaves, nodes, internal nodes, indices, words per bitset, row stride
@@ -98,6 +110,14 @@ struct Params {
   double* escore;          // [n_chains][Ws*32] cached greedy score of every live edge
   int tree_method;         // TNB_TREES_GREEDY / TNB_TREES_RANDOM
   int* tree_fail;          // [n_chains] set when the network turned out to be disconnected
+  // decision trace of the production kernel (TRACE instantiations; tests replay it through the CPU oracle)
+  TraceRec* trace;                // [trace_chains][trace_cap]
+  unsigned long long* trace_n;    // [trace_chains] records produced (beyond trace_cap: counted, not stored)
+  unsigned long long trace_cap;
+  uint32_t* trace_S;              // [trace_chains][trace_scap][Ws] candidate slices of every re-slice
+  uint32_t* trace_sn;             // [trace_chains] re-slices produced
+  uint32_t trace_scap;
+  int trace_chains;               // chains [0, trace_chains) are traced
   // init / eval
   int slices_given;
   double* out_seq;   // [n_chains] cost summed in traversal order (get_cost)
@@ -212,6 +232,15 @@ struct RngPhilox {
     ++pos;
   }
   TNB_D TNB_INLINE uint32_t coin_word(const Tile<TILE>&) { return e0; }
+  static TNB_D TNB_INLINE uint32_t float_bits(float f) {
+#if defined(TNB_EMU)
+    uint32_t b;
+    std::memcpy(&b, &f, 4);
+    return b;
+#else
+    return __float_as_uint(f);
+#endif
+  }
   TNB_D TNB_INLINE float neg_log2_u() const {
 #if defined(TNB_EMU)
     float f;
@@ -1415,7 +1444,7 @@ TNB_D double sum_ccost(const ChainView<TILE, WPL>& c) {
 // walks.  The inputs of level k+1 (parent A', its children word and contraction cost, the sibling's index set
 // and partial cost) do not depend on the move at level k, so they are loaded during level k in three stages and
 // are in registers when level k+1 starts.
-template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2, bool HYPER = false>
+template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2, bool HYPER = false, bool TRACE = false>
 TNB_D void chain_sweeps(const Params& P, int chain) {
   ChainView<TILE, WPL> c(P, chain);
   const Tile<TILE>& t = c.t;
@@ -1484,6 +1513,26 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     total = sum_ccost(c);
     kmax = exp_of(total);
   }
+  // decision trace (tests): lane 0 of a traced chain appends 32-byte records
+  const bool tracing = TRACE && chain < P.trace_chains;
+  unsigned long long tr_n = tracing ? P.trace_n[chain] : 0ull;
+  uint32_t tr_sn = tracing ? P.trace_sn[chain] : 0u;
+  auto trace_put = [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, double d0, double d1) {
+    if (t.tl == 0 && tr_n < P.trace_cap) P.trace[size_t(chain) * P.trace_cap + tr_n] = TraceRec{w0, w1, w2, w3, d0, d1};
+    ++tr_n;
+  };
+  auto trace_slices = [&](const uint32_t (&S2)[WPL], bool kept, double r2, double r1) {
+    if (tr_sn < P.trace_scap) {
+      uint32_t* dst = P.trace_S + (size_t(chain) * P.trace_scap + tr_sn) * P.Ws;
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) {
+        const int w = t.tl + k * TILE;
+        if (w < P.W) dst[w] = S2[k];
+      }
+    }
+    trace_put(2u, tr_sn, 0u, kept ? 1u : 0u, r2, r1);
+    ++tr_sn;
+  };
   uint32_t iteration = 0;
 #pragma unroll kUnroll
   while (true) {
@@ -1503,6 +1552,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
               bool diff = false;
 #pragma unroll
               for (int k = 0; k < WPL; ++k) diff |= S2[k] != S[k];
+              if constexpr (TRACE) if (tracing && !t.any(diff)) trace_slices(S2, false, total, total);
               if (t.any(diff)) {  // same slices -> same costs: nothing to decide
                 total = sum_ccost(c);  // the decision compares exact sums
                 kmax = exp_of(total);
@@ -1510,6 +1560,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
                   int* dz = reinterpret_cast<int*>(P.wkey + size_t(chain) * P.Npad);
                   const int shift0 = mark_slice_diff(c, S, S2, dz, P.word + size_t(chain) * P.Npad);
                   const double r2 = sum_shifted<TILE, WPL, false>(c, dz, shift0);
+                  if constexpr (TRACE) if (tracing) trace_slices(S2, r2 < total, r2, total);
                   if (r2 < total) {
                     total = sum_shifted<TILE, WPL, true>(c, dz, shift0);
                     t.sync();
@@ -1519,6 +1570,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
                   }
                 } else {
                   const double r2 = recost_all<TILE, WPL, DIM2>(c, S2, cp2);
+                  if constexpr (TRACE) if (tracing) trace_slices(S2, r2 < total, r2, total);
                   if (r2 < total) {
                     t.sync();
                     for (int i = t.tl; i < P.n_int; i += TILE) c.cc(n + i) = cp2[i].x;
@@ -1591,6 +1643,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       // leaf = prng() % n_leaves (optimizer.hpp:103); the production RNG maps its word with a multiply-high instead
       const uint32_t lw = rng.leaf_word(t);
       const int leaf = Rng::kFast ? int(mulhi32(lw, uint32_t(n))) : int(lw % uint32_t(n));
+      if constexpr (TRACE) if (tracing) trace_put(0u, lw, 0u, uint32_t(leaf), total, min_total);
       B = c.par[leaf];
       if (PC) total = c.pcv[root];                       // :112
       rebase = false;
@@ -1780,6 +1833,12 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         acc = u <= p;
       }
     }
+    if constexpr (TRACE) if (tracing) {
+      uint32_t ib = 0u;
+      if constexpr (Rng::kFast) ib = Rng::float_bits(inv_beta_f);
+      trace_put(1u | (pick0 ? 4u : 0u) | (gate ? 8u : 0u) | (acc ? 16u : 0u) | ((i0 && i1) ? 32u : 0u) | (uint32_t(B) << 16),
+                rng.coin_word(t), ib, uint32_t(A), delta, total);
+    }
     uint32_t bB[WPL];
     if (acc) {
       // Tree::swap_with_nn(E): E <-> C, child slots preserved (tree.hpp:141-192)
@@ -1885,6 +1944,10 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     awn = awnn;
     ccAn = ccAnn;
     }  // level
+  }
+  if constexpr (TRACE) if (tracing) {
+    P.trace_n[chain] = tr_n;
+    P.trace_sn[chain] = tr_sn;
   }
   rng.store(P, chain);
   P.sweep_idx[chain] = s;

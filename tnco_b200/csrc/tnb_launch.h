@@ -25,11 +25,11 @@ constexpr int kSweepBlock = 32;
 // Production (Philox) kernels are held to 72 registers (no spills) so that 28 single-warp blocks fit on an SM:
 // 148 x 28 = 4144 resident chains at TILE = 32.  Parity kernels (fp64 pow, stream bookkeeping) keep 128.
 // MINB = single-warp blocks resident per SM the register allocation must allow (28 -> 72 registers).
-template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2, int MINB, bool HYPER>
+template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2, int MINB, bool HYPER, bool TRACE>
 __global__ void __launch_bounds__(kSweepBlock, MINB) sa_sweep_kernel(const __grid_constant__ Params P) {
   const int chain = (blockIdx.x * kSweepBlock + threadIdx.x) / TILE;
   if (chain >= P.n_chains) return;
-  chain_sweeps<TILE, WPL, FINITE, Rng, DIM2, HYPER>(P, chain);
+  chain_sweeps<TILE, WPL, FINITE, Rng, DIM2, HYPER, TRACE>(P, chain);
 }
 
 template <int TILE, int WPL>
@@ -55,13 +55,13 @@ bool launch_treegen_t(Rt& rt, const Params& P) {
 #endif
 }
 
-template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2, bool HYPER>
+template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2, bool HYPER, bool TRACE = false>
 static bool launch_h(Rt& rt, const Params& P, bool init) {
 #if defined(TNB_EMU)
   (void)rt;
   for (int c = 0; c < P.n_chains; ++c) {
     if (init) chain_init<TILE, WPL, FINITE, Rng>(P, c);
-    else chain_sweeps<TILE, WPL, FINITE, Rng, DIM2, HYPER>(P, c);
+    else chain_sweeps<TILE, WPL, FINITE, Rng, DIM2, HYPER, TRACE>(P, c);
   }
   return true;
 #else
@@ -72,7 +72,7 @@ static bool launch_h(Rt& rt, const Params& P, bool init) {
   // occupancy class: production kernels 28 single-warp blocks per SM (<= 72 registers), parity kernels 16
   constexpr int MINB = Rng::kFast ? 28 : 16;
   if (init) sa_init_kernel<TILE, WPL, FINITE, Rng><<<grid, kBlock, 0, rt.stream>>>(P);
-  else sa_sweep_kernel<TILE, WPL, FINITE, Rng, DIM2, MINB, HYPER><<<grid, kSweepBlock, 0, rt.stream>>>(P);
+  else sa_sweep_kernel<TILE, WPL, FINITE, Rng, DIM2, MINB, HYPER, TRACE><<<grid, kSweepBlock, 0, rt.stream>>>(P);
   return rt.ok(cudaGetLastError(), init ? "sa_init_kernel launch" : "sa_sweep_kernel launch");
 #endif
 }
@@ -84,6 +84,10 @@ static bool launch_t(Rt& rt, const Params& P, bool init) {
     if (P.hyper && !init) return launch_h<TILE, WPL, FINITE, Rng, DIM2, true>(rt, P, init);
   } else {
     if (P.hyper) { rt.err = "hyper-index networks need TILE = 32"; return false; }
+  }
+  // decision trace (tests): the production kernel proper -- Philox, 2^popcount costs, no hyper-indices
+  if constexpr (Rng::kFast && DIM2) {
+    if (P.trace && !init) return launch_h<TILE, WPL, FINITE, Rng, DIM2, false, true>(rt, P, init);
   }
   return launch_h<TILE, WPL, FINITE, Rng, DIM2, false>(rt, P, init);
 }

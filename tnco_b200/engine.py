@@ -298,6 +298,32 @@ class Engine:
         self._chk(self._L.tnb_set_stream(self._h, _ptr(w, C.c_uint32), w.shape[1]))
         return self
 
+    TRACE_DTYPE = np.dtype([('w0', '<u4'), ('w1', '<u4'), ('w2', '<u4'), ('w3', '<u4'), ('d0', '<f8'), ('d1', '<f8')])
+
+    def set_trace(self, n_chains, cap_records, cap_reslices=0):
+        """Record the decisions of chains [0, n_chains) of the production kernels (tnb_set_trace); 0 = off."""
+        self._trace_caps = (int(cap_records), int(cap_reslices))
+        self._chk(self._L.tnb_set_trace(self._h, int(n_chains), int(cap_records), int(cap_reslices)))
+        return self
+
+    def trace(self, chain):
+        """(records as a structured array of TRACE_DTYPE, candidate slices [n_reslices][W32]) of a traced chain."""
+        cap, scap = self._trace_caps
+        n, ns = C.c_uint64(0), C.c_uint32(0)
+        self._chk(self._L.tnb_get_trace(self._h, int(chain), C.byref(n), None, C.byref(ns), None))
+        if n.value > cap or ns.value > scap:
+            raise EngineError(f'trace overflow: {n.value} records / {ns.value} re-slices, capacity {cap} / {scap}')
+        rec = np.zeros(n.value, self.TRACE_DTYPE)
+        sl = np.zeros((ns.value, self.W), np.uint32)
+        self._chk(self._L.tnb_get_trace(self._h, int(chain), C.byref(n), rec.ctypes.data_as(C.c_void_p), C.byref(ns),
+                                        _ptr(sl, C.c_uint32)))
+        return rec, sl
+
+    def node_costs(self, chain):
+        o = np.empty(self.N, np.float64)
+        self._chk(self._L.tnb_get_node_costs(self._h, int(chain), _ptr(o, C.c_double)))
+        return o
+
     def set_betas(self, betas):
         b = _c(betas, np.float64).reshape(-1)
         self._chk(self._L.tnb_set_betas(self._h, _ptr(b, C.c_double), len(b)))
