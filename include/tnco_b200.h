@@ -202,6 +202,13 @@ int tnb_set_betas(tnb_engine* e, const double* betas, int64_t n);
  * In REPLAY mode a chain stops early when its stream cannot cover another sweep; see tnb_get_progress. */
 int tnb_run(tnb_engine* e, int64_t until_sweep);
 
+/* The same under a wall-clock budget: the reference's `timeout` (tnco/parallel.py:243-248 flips a stop flag that
+ * every run polls once per sweep, tnco/app/infinite_memory/sa.py:201, and each run returns its best so far).  Here the
+ * clock is checked between internal launches of K sweeps (K doubles from 16 while a launch takes under 50 ms), so the
+ * call returns within one launch of the deadline.  timeout_s < 0 or +inf: no limit.  *reached = sweep index every
+ * chain has reached (<= until_sweep); the chains stay valid and can be advanced further. */
+int tnb_run_timed(tnb_engine* e, int64_t until_sweep, double timeout_s, int64_t* reached);
+
 /* elapsed device time (ms, CUDA events on the engine's stream) and launch count of the sweep kernel
  * accumulated since the last call */
 int tnb_get_timing(tnb_engine* e, double* kernel_ms, int64_t* launches);

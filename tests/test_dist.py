@@ -26,20 +26,49 @@ if world > 1:
     dist.init_process_group('gloo')
 rank = tdist.world()[0]
 assert tdist.shard(10, 0, 3) == (0, 3) and tdist.shard(10, 2, 3) == (6, 10)
-# global_best: rank r offers cost 10-r with payload [r]*4
-best, payload, owner = tdist.global_best(10.0 - rank, np.full(4, rank, np.int32))
+# global_best: ONE packed-key min-reduction + ONE broadcast.  Rank r owns chains [2r, 2r+2) of 2*world and offers
+# cost 10-r for its chain 2r+1 with payload [r]*4
+tdist.set_shard_total(2 * world)
+best, payload, owner, chain = tdist.global_best(10.0 - rank, 2 * rank + 1, np.full(4, rank, np.int32))
+assert chain == 2 * (world - 1) + 1
+assert tdist.pack_key(3.0, 5) < tdist.pack_key(3.5, 1) and tdist.pack_key(3.0, 1) < tdist.pack_key(3.0, 5)
+assert tdist.pack_key(float('inf'), 0) > tdist.pack_key(1e300, 2**24 - 1)
 rows_all = tdist.all_gather_rows(np.arange(*tdist.shard(7)).reshape(-1, 1), 7)
 ts, ni = regular_network(20, 3)
 rows = [[2] for _ in range(ni)]
 for t, xs in enumerate(ts):
     for x in xs:
         rows[x].append('t%d' % t)
-opt = Optimizer(seed=9, max_width={mw}, sync_every=20)
+opt = Optimizer(seed=9, max_width={mw}, sync_every=20, gather_paths='all')
 tn, res = opt.optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=60, n_runs=6)
+# top-k gathering: costs of all runs everywhere, trees of the k best + this rank's own runs only
+opt_k = Optimizer(seed=9, max_width={mw}, gather_paths=2)
+_, res_k = opt_k.optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=60, n_runs=6)
+topk = dict(costs=[str(r.cost) for r in res_k], paths=[], missing=0)
+for r in res_k:
+    try:
+        topk['paths'].append(r.path)
+    except RuntimeError as ex:
+        assert 'another rank' in str(ex)
+        topk['paths'].append(None)
+        topk['missing'] += 1
+# fewer runs than ranks: the rank without runs must neither crash nor hang the collectives
+_, res_1 = Optimizer(seed=3, max_width={mw}).optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False,
+                                                     n_steps=30, n_runs=1)
+one = dict(cost=str(res_1[0].cost), path=res_1[0].path, n=len(res_1))
+# seed=None: every rank must end up with the same (fused) network and the same run seeds
+tn_n, res_n = Optimizer(seed=None, max_width={mw}).optimize(rows, betas=(0, 100), n_steps=20, n_runs=4)
+noseed = dict(n_tensors=len(tn_n), costs=[str(r.cost) for r in res_n], best_path=res_n[0].path)
+# timeout together with the periodic exchange: the stop decision is collective (no mismatched collectives / hang)
+opt_t = Optimizer(seed=5, max_width={mw}, sync_every=5)
+_, res_t = opt_t.optimize(rows, betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=200000, n_runs=4,
+                          timeout=0.5 + 0.4 * rank)
+timed = dict(n=len(res_t), exchanges=len(opt_t.last_stats.get('global_best_history', [])))
 out = dict(rank=rank, world=world, best=best, payload=payload.tolist(), owner=owner, gathered=rows_all.ravel().tolist(),
            costs=[str(r.cost) for r in res], paths=[r.path for r in res],
            slices=[sorted(r.slices) for r in res] if {mw} is not None else None,
-           local_sweeps=opt.last_stats['sweeps'], history=opt.last_stats.get('global_best_history'))
+           local_sweeps=opt.last_stats['sweeps'], history=opt.last_stats.get('global_best_history'),
+           topk=topk, one=one, noseed=noseed, timed=timed)
 open(os.path.join({outdir!r}, 'out_%d_%d.json' % (world, rank)), 'w').write(json.dumps(out))
 if world > 1:
     dist.destroy_process_group()
@@ -77,3 +106,15 @@ def test_two_ranks_over_gloo_match_single_process(mw, tmp_path):
         assert [h[0] for h in r['history']] == [20, 40, 60] and r['history'] == two[0]['history']
         assert all(a[1] >= b[1] for a, b in zip(r['history'], r['history'][1:]))
     assert two[0]['local_sweeps'] + two[1]['local_sweeps'] == single['local_sweeps'] == 6 * 60
+    # gather_paths=2: all costs on both ranks; the two best trees everywhere; the rest only where they ran
+    for r in two:
+        assert r['topk']['costs'] == single['costs']
+        assert r['topk']['paths'][:2] == single['paths'][:2]
+        assert all(p is None or p == q for p, q in zip(r['topk']['paths'], single['paths']))
+    assert single['topk']['missing'] == 0 and two[0]['topk']['missing'] + two[1]['topk']['missing'] == 4
+    # n_runs = 1 < world size
+    assert all(r['one'] == single['one'] for r in two) and single['one']['n'] == 1
+    # seed=None: ranks agree with each other (not with the single process, which drew its own seed)
+    assert two[0]['noseed'] == two[1]['noseed']
+    # collective stop
+    assert two[0]['timed']['exchanges'] == two[1]['timed']['exchanges'] >= 1 and two[0]['timed']['n'] == 4

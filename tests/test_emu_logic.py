@@ -133,3 +133,9 @@ def test_emu_production_kernel_replay(emu, name, n_sweeps):
 def test_emu_production_kernel_replay_low_beta(emu):
     import test_gpu_philox_replay as R
     R.test_production_kernel_replay_low_beta_and_every_sweep_reslice()
+
+
+@pytest.mark.parametrize('case,chains', [('c2_1e4', 96), ('c4_1e4', 64)])
+def test_emu_equal_sweep_distribution(emu, case, chains):
+    import test_gpu_statistics as S
+    S.test_equal_sweep_distribution_on_the_benchmarked_networks(case, chains)

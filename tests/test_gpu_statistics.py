@@ -50,3 +50,45 @@ def test_best_cost_distribution_is_no_worse_than_the_reference(n, max_width, n_s
     se = np.sqrt(ours.var() / len(ours) + ref.var() / len(ref))
     assert ours.mean() <= ref.mean() + 4 * se + 0.01 * abs(ref.mean()), (ours.mean(), ref.mean(), se)
     assert ours.mean() >= ref.mean() - 6 * se - 0.03 * abs(ref.mean()), (ours.mean(), ref.mean(), se)
+
+
+# ---- the benchmarked networks, at the benchmark's sweep count, against the UNMODIFIED reference core.
+# tests/golden/stat_*.json hold 256 reference runs each (scripts/make_golden_stats.py, oracle/_ref driven like core_).
+@pytest.mark.parametrize('case,chains', [('c1_1e4', 1024), ('c2_1e4', 1024), ('c3_1e4', 1024), ('c4_1e4', 1024),
+                                         ('c4_3e4', 768)])
+def test_equal_sweep_distribution_on_the_benchmarked_networks(case, chains):
+    import json
+    import os
+
+    from helpers import GOLDEN
+    from tnco_b200 import networks
+    from tnco_b200.engine import Engine, pack_leaf_bits, random_trees
+    fx = json.load(open(os.path.join(GOLDEN, f'stat_{case}.json')))
+    ref = np.array(fx['log2_min_total_cost'])
+    assert len(ref) >= 256 and fx['n_sweeps'] >= 10000
+    ts, ni = eval('networks.' + fx['network'])
+    lb = pack_leaf_bits(ts, ni)
+    seeds = np.arange(chains, dtype=np.uint64) + 100001
+    P, A, B = random_trees(lb, ni, seeds)          # same initial-tree generator as the reference arm
+    n_sweeps = fx['n_sweeps']
+    e = Engine()
+    e.set_network(lb, ni).set_mode(max_width=fx['max_width'], update_slices_every=fx['update_slices'])
+    e.set_chains(P, A, B, seeds)
+    e.set_betas([100.0 * s / n_sweeps for s in range(n_sweeps)])
+    e.run(n_sweeps)
+    t, m = e.costs()
+    # the returned minima are real: re-evaluate every best tree (+ slices) from scratch
+    bp, ba, bb = e.trees(best=True)
+    sl = e.slices(best=True) if fx['max_width'] is not None else None
+    seq, pc, mw = e.eval_cost(bp, ba, bb, slices=sl)
+    assert np.allclose(np.log2(pc), np.log2(m), atol=1e-9)
+    if fx['max_width'] is not None:
+        assert (mw <= fx['max_width']).all()
+    e.close()
+    ours = np.log2(m)
+    p_worse = stats.mannwhitneyu(ours, ref, alternative='greater').pvalue
+    se = np.sqrt(ours.var() / len(ours) + ref.var() / len(ref))
+    print(f'{case}: ours mean {ours.mean():.4f} min {ours.min():.4f} | reference mean {ref.mean():.4f} '
+          f'min {ref.min():.4f} | p(ours worse) {p_worse:.3g} | se {se:.4f}')
+    assert p_worse > 1e-3, (ours.mean(), ref.mean(), p_worse)
+    assert ours.mean() <= ref.mean() + 4 * se, (ours.mean(), ref.mean(), se)

@@ -51,6 +51,7 @@ SIGNATURES = {
     'tnb_get_node_costs': (C.c_int, [C.c_void_p, C.c_int, f64p]),
     'tnb_set_betas': (C.c_int, [C.c_void_p, f64p, C.c_int64]),
     'tnb_run': (C.c_int, [C.c_void_p, C.c_int64]),
+    'tnb_run_timed': (C.c_int, [C.c_void_p, C.c_int64, C.c_double, i64p]),
     'tnb_get_timing': (C.c_int, [C.c_void_p, f64p, i64p]),
     'tnb_get_costs': (C.c_int, [C.c_void_p, f64p, f64p]),
     'tnb_get_trees': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p]),

@@ -250,6 +250,9 @@ class BaseOptimizer:
     device: int | None = None  # CUDA device; default LOCAL_RANK or 0
     distributed: bool = True   # shard runs over torch.distributed ranks when a process group exists
     sync_every: int | None = None  # sweeps between min-reductions of the best cost over ranks (None: only at the end)
+    # torch.distributed: best trees stay on the rank that ran them; the k best of all ranks are gathered everywhere
+    # (costs of ALL runs always are).  'all' gathers every tree on every rank, like the reference's single process.
+    gather_paths: Any = 64
 
     def optimize(self, *args, **kwargs):
         raise NotImplementedError()
@@ -274,6 +277,8 @@ class BaseOptimizer:
             raise ValueError("'init_trees' must be 'greedy' or 'random'.")
         if self.tree_builder not in ('device', 'host'):
             raise ValueError("'tree_builder' must be 'device' or 'host'.")
+        if self.gather_paths != 'all' and (not isinstance(self.gather_paths, int) or self.gather_paths < 1):
+            raise ValueError("'gather_paths' must be a positive number or 'all'.")
         self._dump_results(None, None, check_only=True)
 
     def __getstate__(self):

@@ -1018,6 +1018,42 @@ int tnb_run(tnb_engine* e, int64_t until_sweep) {
   return 0;
 }
 
+int tnb_run_timed(tnb_engine* e, int64_t until_sweep, double timeout_s, int64_t* reached) {
+  if (!e) return -1;
+  if (!e->d_betas) return e->fail("tnb_run_timed: call tnb_set_betas first"), -1;
+  if (!ensure_init(e)) return -2;
+  const size_t nc = size_t(e->cs.n_chains);
+  std::vector<long long> sw(nc);
+  auto min_sweep = [&](long long& out) {
+    if (!e->rt.d2h(sw.data(), e->cs.sweep_idx, nc * sizeof(long long))) return false;
+    out = *std::min_element(sw.begin(), sw.end());
+    return true;
+  };
+  long long done = 0;
+  if (!min_sweep(done)) return e->rtfail(), -3;
+  const bool limited = !(timeout_s < 0.0) && !std::isinf(timeout_s) && !std::isnan(timeout_s);
+  if (!limited) {
+    const int rc = tnb_run(e, until_sweep);
+    if (rc == 0 && !min_sweep(done)) return e->rtfail(), -3;
+    if (reached) *reached = done;
+    return rc;
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
+  long long chunk = 16;
+  while (done < until_sweep && elapsed() < timeout_s) {
+    const double t1 = elapsed();
+    const long long target = std::min<long long>(until_sweep, done + chunk);
+    const int rc = tnb_run(e, target);
+    if (rc != 0) return rc;
+    if (!min_sweep(done)) return e->rtfail(), -3;
+    if (done < target) break;  // REPLAY mode: a stream ran dry
+    if (elapsed() - t1 < 0.05) chunk *= 2;
+  }
+  if (reached) *reached = done;
+  return 0;
+}
+
 int tnb_get_timing(tnb_engine* e, double* kernel_ms, int64_t* launches) {
   if (!e) return -1;
   if (kernel_ms) *kernel_ms = e->kernel_ms;

@@ -329,8 +329,16 @@ class Engine:
         self._chk(self._L.tnb_set_betas(self._h, _ptr(b, C.c_double), len(b)))
         return self
 
-    def run(self, until_sweep):
-        self._chk(self._L.tnb_run(self._h, int(until_sweep)))
+    def run(self, until_sweep, timeout_s=None):
+        """Advance every chain to sweep `until_sweep`; with `timeout_s` the engine stops between its internal launches
+        once the wall clock passes it (``self.reached`` = the sweep index actually reached)."""
+        if timeout_s is None:
+            self._chk(self._L.tnb_run(self._h, int(until_sweep)))
+            self.reached = int(until_sweep)
+            return self
+        r = C.c_int64(0)
+        self._chk(self._L.tnb_run_timed(self._h, int(until_sweep), float(timeout_s), C.byref(r)))
+        self.reached = r.value
         return self
 
     def timing(self):
