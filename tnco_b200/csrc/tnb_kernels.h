@@ -110,7 +110,7 @@ struct Params {
   double* escore;          // [n_chains][Ws*32] cached greedy score of every live edge
   int tree_method;         // TNB_TREES_GREEDY / TNB_TREES_RANDOM
   int* tree_fail;          // [n_chains] set when the network turned out to be disconnected
-  // decision trace of the production kernel (TRACE instantiations; tests replay it through the CPU oracle)
+  // decision trace of the production kernel (TRACE instantiations; tests replay it through a CPU restatement of the reference)
   TraceRec* trace;                // [trace_chains][trace_cap]
   unsigned long long* trace_n;    // [trace_chains] records produced (beyond trace_cap: counted, not stored)
   unsigned long long trace_cap;
