@@ -240,12 +240,66 @@ def run_reference_arm(args):
                 e2e=dict(value=value, unit='proposals/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 best_log2_flops=min(o['best_log2'] for o in timed))
     if args.anneal_budget > 0:   # BASELINE metric part (ii) for this arm: one anneal filling the wall-clock budget
-        sys.path.insert(0, os.path.join(ROOT, 'scripts'))
-        from anneal60 import cpu_arm
         ts, ni, lb = workload()
         c = cpu_arm(lb, ni, WORKLOADS[_SEL['name']]['max_width'], args.anneal_budget)
         line['best_log2_at_60s'] = dict(budget_s=args.anneal_budget, cpu_reference=c['best_log2_flops'], cpu_detail=c)
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ fixed wall clock, CPU arm
+def _cpu_worker(args):
+    P, A, B, nb, ni, seed, n_sweeps, mw, every, budget = args
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from helpers import RefChain
+    rc = RefChain(P, A, B, nb, ni, seed=seed, max_width=mw)
+    opt, mh = rc.opt, rc.mh
+    t0 = time.perf_counter()
+    done = 0
+    for n in range(n_sweeps):
+        mh.beta = n * (100.0 / n_sweeps)
+        if mw is None:
+            opt.update(mh)
+        else:
+            opt.update(mh, update_slices=(n % every == 0))
+        done = n + 1
+        if (n & 255) == 0 and time.perf_counter() - t0 > budget:  # the reference's timeout flag (parallel.py:243-248)
+            break
+    return time.perf_counter() - t0, done, opt.log2_min_total_cost
+
+
+def cpu_arm(lb, ni, mw, budget, every=10):
+    from joblib import Parallel, delayed
+    from tnco_b200.engine import random_trees
+    cores = os.cpu_count() or 1
+    seeds = np.arange(cores, dtype=np.uint64) + 1
+    P, A, B = random_trees(lb, ni, seeds)
+    n = lb.shape[0]
+    nbs = []
+    for k in range(cores):
+        nb = np.zeros((2 * n - 1, lb.shape[1]), np.uint32)
+        nb[:n] = lb
+        for z in range(n, 2 * n - 1):
+            nb[z] = nb[A[k][z]] ^ nb[B[k][z]]
+        nbs.append(nb)
+    with Parallel(n_jobs=cores, backend='loky') as par:
+        cal = par(delayed(_cpu_worker)((P[k], A[k], B[k], nbs[k], ni, int(seeds[k]), 3000, mw, every, 1e9))
+                  for k in range(cores))
+        rate = 3000 / max(c[0] for c in cal)   # sweeps/s of the slowest run with every core busy
+        # second pass: a whole beta ramp of ~5 s (sweeps get cheaper as the trees improve, a short ramp underestimates)
+        n2 = max(3000, int(rate * 5.0))
+        cal = par(delayed(_cpu_worker)((P[k], A[k], B[k], nbs[k], ni, int(seeds[k]), n2, mw, every, 1e9))
+                  for k in range(cores))
+        rate = n2 / max(c[0] for c in cal)
+        n_sweeps = max(1000, int(rate * budget * 0.97))
+        t0 = time.perf_counter()
+        res = par(delayed(_cpu_worker)((P[k], A[k], B[k], nbs[k], ni, int(seeds[k]), n_sweeps, mw, every, budget))
+                  for k in range(cores))
+        wall = time.perf_counter() - t0
+    return dict(cores=cores, runs=cores, n_sweeps=n_sweeps, sweeps_done=[r[1] for r in res], wall_s=round(wall, 2),
+                in_loop_s=round(max(r[0] for r in res), 2), best_log2_flops=min(r[2] for r in res),
+                mean_best_log2_flops=float(np.mean([r[2] for r in res])))
+
 
 
 # ------------------------------------------------------------------------------------------ roofline
@@ -451,8 +505,6 @@ def anneal_gpu(name, dev, rank, world, chains, budget):
 
 
 def anneal_cpu(name, budget):
-    sys.path.insert(0, os.path.join(ROOT, 'scripts'))
-    from anneal60 import cpu_arm
     ts, ni, lb = workload(name)
     return cpu_arm(lb, ni, WORKLOADS[name]['max_width'], budget)
 

@@ -43,6 +43,9 @@ typedef struct tnb_engine tnb_engine;
 #define TNB_LAYOUT_AUTO 0        /* INTERLEAVED while the whole batch fits L2 (<= 96 MiB), SPLIT beyond */
 #define TNB_LAYOUT_INTERLEAVED 1 /* one record {children, cost, index set} per tree node */
 #define TNB_LAYOUT_SPLIT 2       /* node headers and index sets in separate arrays (headers stay L2-resident) */
+#define TNB_LAYOUT_SMEM 3        /* chain state (parents + node records) resident in SHARED MEMORY for the whole launch:
+                                    small networks, unconstrained production kernels; falls back to INTERLEAVED when
+                                    a warp's chains do not fit 200 KB or the mode has no such kernel */
 
 #define TNB_TREES_GREEDY 0 /* random tie-broken greedy merges (stand-in for opt_einsum 'greedy', tnco/utils/tn.py:225) */
 #define TNB_TREES_RANDOM 1 /* uniformly random merges of index-sharing pairs */
@@ -140,6 +143,13 @@ int tnb_set_mode(tnb_engine* e, double max_width, int update_slices_every, int d
 
 /* Change only the acceptance rule (the reference passes a prob object to every update()); chains are kept. */
 int tnb_set_prob(tnb_engine* e, int prob_kind);
+
+/* max_number_new_slices of the finite-width core object (tnco/optimize/finite_width/optimizer.py:59,
+ * include/tnco/optimize/finite_width/greedy/optimizer.hpp:226-321): a move whose new tensor exceeds max_width may slice
+ * up to that many random indices of it; if it fits then, the whole cost cache is rebuilt under the new slices and the
+ * move is put to the acceptance rule.  0 (default -- what tnco.app uses) disables it.  Stream modes only
+ * (TNB_RNG_MT19937 / TNB_RNG_REPLAY); chains are kept. */
+int tnb_set_new_slices(tnb_engine* e, int max_number_new_slices);
 
 /* Change only the re-slicing period (update(prob, update_slices) of the finite-width core object); chains kept. */
 int tnb_set_update_slices(tnb_engine* e, int update_slices_every);

@@ -125,6 +125,8 @@ struct ora_chain {
   double min_total;
   mt_t mt;
   uint64_t proposals, accepts, sweeps, width_rejects;
+  int max_new_slices;         /* max_number_new_slices (finite_width/greedy/optimizer.hpp:77,226-321) */
+  uint64_t new_slice_moves, new_slice_accepts;
   /* test hooks */
   ora_trace_rec* tr;          /* per-proposal trace (ora_trace) */
   uint64_t tr_cap, tr_n;
@@ -518,8 +520,70 @@ void ora_update(ora_chain* c, int kind, double beta, int update_slices) {
         c->accepts++;
       }
     }
-    c->pc[B] = c->pc[D] + c->pc[E] + c->cc[B]; /* :185-188 */
-    c->pc[A] = c->pc[B] + c->pc[C] + c->cc[A];
+    int skip_prop = 0;
+    if (!gate && c->max_new_slices > 0) { /* finite_width/greedy/optimizer.hpp:226-321: random new slices */
+      uint32_t ns[W];
+      memcpy(ns, S, sizeof(uint32_t) * (size_t)W);
+      int32_t* pos = (int32_t*)malloc(sizeof(int32_t) * (size_t)W * 32);
+      int n_pos = 0, n_new = 0;
+      for (int w = 0; w < W; ++w) { /* (new_inds_B - slices [- skip_slices]).positions(), ascending */
+        uint32_t v = newB[w] & ~S[w] & ~(c->skip ? c->skip[w] : 0u);
+        while (v) { pos[n_pos++] = w * 32 + __builtin_ctz(v); v &= v - 1; }
+      }
+      float nsw = width_of(c, tmp); /* new_sliced_width_B (tmp = newB & ~S) */
+      while (n_new < c->max_new_slices && nsw > c->max_width && n_pos > 0) {
+        const uint32_t r = mt_next(mt) % (uint32_t)n_pos; /* :246 */
+        const int32_t t_ = pos[r]; pos[r] = pos[n_pos - 1]; pos[n_pos - 1] = t_;
+        const int p = pos[n_pos - 1];
+        ns[p >> 5] |= 1u << (p & 31);
+        /* new_sliced_width_B -= log2_dims[...] in width_type, DimsCache<width_type> (:256-266) */
+        nsw -= (float)log2((double)(c->dims ? c->dims[p] : c->dim));
+        --n_pos; ++n_new;
+      }
+      free(pos);
+      if (nsw <= c->max_width) { /* :283-318 */
+        c->new_slice_moves++;
+        uint32_t oldB[W];
+        memcpy(oldB, BITS(B), sizeof(uint32_t) * (size_t)W);
+        memcpy(BITS(B), newB, sizeof(uint32_t) * (size_t)W);
+        /* swap_with_nn(E): E <-> C */
+        if (c->c0[A] == C) c->c0[A] = E; else c->c1[A] = E;
+        if (c->c0[B] == E) c->c0[B] = C; else c->c1[B] = C;
+        c->par[C] = B;
+        c->par[E] = A;
+        double* cc2 = (double*)malloc(sizeof(double) * (size_t)N);
+        double* pc2 = (double*)malloc(sizeof(double) * (size_t)N);
+        build_cost_cache(c, ns, cc2, pc2);
+        const double delta = pc2[N - 1] - total;
+        const double u = mt_uniform(mt);
+        if (u <= prob_of(kind, beta, delta, total)) {
+          memcpy(c->cc, cc2, sizeof(double) * (size_t)N);
+          memcpy(c->pc, pc2, sizeof(double) * (size_t)N);
+          for (int w = 0; w < W; ++w) { /* pos_C / pos_E are NOT renamed in this branch (:300-302) */
+            HYP(A)[w] = BITS(A)[w] & BITS(B)[w] & BITS(E)[w];
+            HYP(B)[w] = BITS(B)[w] & BITS(D)[w] & BITS(C)[w];
+          }
+          c->width[B] = new_width_B;
+          total = c->pc[N - 1];
+          memcpy(c->slices, ns, sizeof(uint32_t) * (size_t)W);
+          skip_prop = 1;
+          c->accepts++;
+          c->new_slice_accepts++;
+        } else { /* swap back: swap_with_nn(pos_C) */
+          if (c->c0[A] == E) c->c0[A] = C; else c->c1[A] = C;
+          if (c->c0[B] == C) c->c0[B] = E; else c->c1[B] = E;
+          c->par[C] = A;
+          c->par[E] = B;
+          memcpy(BITS(B), oldB, sizeof(uint32_t) * (size_t)W);
+        }
+        free(cc2);
+        free(pc2);
+      }
+    }
+    if (!skip_prop) {
+      c->pc[B] = c->pc[D] + c->pc[E] + c->cc[B]; /* :185-188 */
+      c->pc[A] = c->pc[B] + c->pc[C] + c->cc[A];
+    }
     B = A;
   }
   if (c->finite && update_slices) { /* finite_width/greedy/optimizer.hpp:360-376 */
@@ -598,6 +662,11 @@ void ora_counters(const ora_chain* c, uint64_t* p, uint64_t* a, uint64_t* s, uin
   if (s) *s = c->sweeps;
   if (w) *w = c->mt.drawn;
   if (wr) *wr = c->width_rejects;
+}
+void ora_set_max_new_slices(ora_chain* c, int max_number_new_slices) { c->max_new_slices = max_number_new_slices; }
+void ora_new_slice_counters(const ora_chain* c, uint64_t* moves, uint64_t* accepts) {
+  if (moves) *moves = c->new_slice_moves;
+  if (accepts) *accepts = c->new_slice_accepts;
 }
 void ora_set_replay(ora_chain* c, const uint32_t* words, uint64_t n) {
   c->mt.rp = words;

@@ -49,6 +49,8 @@ def lib():
         L.ora_set_forced_slices.argtypes = [C.c_void_p, u32p, C.POINTER(C.c_uint8), C.c_uint64, f64p, C.c_uint64]
         L.ora_forced_used.restype = C.c_uint64
         L.ora_forced_used.argtypes = [C.c_void_p]
+        L.ora_set_max_new_slices.argtypes = [C.c_void_p, C.c_int]
+        L.ora_new_slice_counters.argtypes = [C.c_void_p, u64p, u64p]
         L.ora_create.restype = C.c_void_p
         L.ora_create.argtypes = [C.c_int, C.c_int, i32p, i32p, i32p, u32p, C.c_uint64, u64p, C.c_int,
                                  C.c_float, C.c_uint32, C.c_int, C.POINTER(C.c_int)]
@@ -90,7 +92,7 @@ class Chain:
 
     def __init__(self, parent, child0, child1, node_bits, n_inds, *, dim=2, dims=None, max_width=None,
                  seed=0, disable_shared_inds=False, sparse_bits=None, n_projs=None, skip_bits=None,
-                 init_slices=None):
+                 init_slices=None, max_number_new_slices=0):
         L = lib()
         self.parent0, c0, c1 = _i32(parent), _i32(child0), _i32(child1)
         self.N = len(self.parent0)
@@ -115,6 +117,13 @@ class Chain:
             raise ValueError('Precision is too low.' if err.value == 2 else
                              "'n_projs' must be a positive number." if err.value == 3 else 'invalid input')
         self._rec = None
+        if max_number_new_slices:
+            L.ora_set_max_new_slices(self._h, int(max_number_new_slices))
+
+    def new_slice_counters(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        lib().ora_new_slice_counters(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def __del__(self):
         if getattr(self, '_h', None):

@@ -22,58 +22,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 
-def _cpu_worker(args):
-    P, A, B, nb, ni, seed, n_sweeps, mw, every, budget = args
-    sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, 'tests'))
-    from helpers import RefChain
-    rc = RefChain(P, A, B, nb, ni, seed=seed, max_width=mw)
-    opt, mh = rc.opt, rc.mh
-    t0 = time.perf_counter()
-    done = 0
-    for n in range(n_sweeps):
-        mh.beta = n * (100.0 / n_sweeps)
-        if mw is None:
-            opt.update(mh)
-        else:
-            opt.update(mh, update_slices=(n % every == 0))
-        done = n + 1
-        if (n & 255) == 0 and time.perf_counter() - t0 > budget:  # the reference's timeout flag (parallel.py:243-248)
-            break
-    return time.perf_counter() - t0, done, opt.log2_min_total_cost
-
-
-def cpu_arm(lb, ni, mw, budget, every=10):
-    from joblib import Parallel, delayed
-    from tnco_b200.engine import random_trees
-    cores = os.cpu_count() or 1
-    seeds = np.arange(cores, dtype=np.uint64) + 1
-    P, A, B = random_trees(lb, ni, seeds)
-    n = lb.shape[0]
-    nbs = []
-    for k in range(cores):
-        nb = np.zeros((2 * n - 1, lb.shape[1]), np.uint32)
-        nb[:n] = lb
-        for z in range(n, 2 * n - 1):
-            nb[z] = nb[A[k][z]] ^ nb[B[k][z]]
-        nbs.append(nb)
-    with Parallel(n_jobs=cores, backend='loky') as par:
-        cal = par(delayed(_cpu_worker)((P[k], A[k], B[k], nbs[k], ni, int(seeds[k]), 3000, mw, every, 1e9))
-                  for k in range(cores))
-        rate = 3000 / max(c[0] for c in cal)   # sweeps/s of the slowest run with every core busy
-        # second pass: a whole beta ramp of ~5 s (sweeps get cheaper as the trees improve, a short ramp underestimates)
-        n2 = max(3000, int(rate * 5.0))
-        cal = par(delayed(_cpu_worker)((P[k], A[k], B[k], nbs[k], ni, int(seeds[k]), n2, mw, every, 1e9))
-                  for k in range(cores))
-        rate = n2 / max(c[0] for c in cal)
-        n_sweeps = max(1000, int(rate * budget * 0.97))
-        t0 = time.perf_counter()
-        res = par(delayed(_cpu_worker)((P[k], A[k], B[k], nbs[k], ni, int(seeds[k]), n_sweeps, mw, every, budget))
-                  for k in range(cores))
-        wall = time.perf_counter() - t0
-    return dict(cores=cores, runs=cores, n_sweeps=n_sweeps, sweeps_done=[r[1] for r in res], wall_s=round(wall, 2),
-                in_loop_s=round(max(r[0] for r in res), 2), best_log2_flops=min(r[2] for r in res),
-                mean_best_log2_flops=float(np.mean([r[2] for r in res])))
+from bench import _cpu_worker, cpu_arm  # noqa: E402,F401  (defined there: bench.py times the same arm)
 
 
 def gpu_arm(lb, ni, mw, budget, n_chains, every=10):

@@ -56,6 +56,15 @@ def probe(cfg, n_chains, n_sweeps, max_width=None, tile=None, trees='greedy', la
 if __name__ == '__main__':
     which = sys.argv[1:] or ['C1', 'C2', 'C3', 'C4', 'C5']
     for cfg in which:
+        if cfg == 'SMEM':   # shared-memory-resident layout (3) against the in-place layout (1), small networks
+            for tile in (4, 8, 16, 32):
+                for layout in (1, 3):
+                    probe('C1', 32768, 2000, tile=tile, layout=layout)
+            for tile in (16, 32):
+                for layout in (1, 3):
+                    probe('C2', 4096, 2000, tile=tile, layout=layout)
+            for layout in (1, 3):
+                probe('C2', 16384, 1000, tile=16, layout=layout)
         if cfg == 'C1':
             probe('C1', 32768, 2000)
             probe('C1', 32768, 2000, tile=32)

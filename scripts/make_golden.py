@@ -48,6 +48,12 @@ CASES = [
     ('gdims64_fw40', 64, 23, 1000, 0.4, False, -1, 10),
     ('gdimshyper48_fw50', 48, 24, 800, 0.5, True, -1, 10),
     ('gdimssparse64_fw40', 64, 25, 800, 0.4, False, -1, 10, 10, 12),
+    # max_number_new_slices > 0 (finite_width/greedy/optimizer.hpp:226-321): three extra fields (0 sparse, 0, max_new)
+    ('reg64_fw50_ns1', 64, 30, 800, 0.5, False, 2, 10, 0, 0, 1),
+    ('reg100_fw30_ns4', 100, 31, 800, 0.3, False, 2, 10, 0, 0, 4),
+    ('hyper64_fw40_ns2', 64, 32, 700, 0.4, True, 2, 10, 0, 0, 2),
+    ('dims64_fw45_ns3', 64, 33, 700, 0.45, False, 0, 10, 0, 0, 3),
+    ('gdims64_fw40_ns2', 64, 34, 600, 0.4, False, -1, 10, 0, 0, 2),
     # BASELINE.json configs C2 / C3 / C4 themselves (tnco_b200.networks builds the same networks bench.py runs);
     # n is taken from the network, and for C4 max_width_frac < 0 means the absolute max_width = -frac (32, as benchmarked)
     ('c2_grid6x6d12_inf', 'grid_rqc(6, 6, 12)', 26, 1200, None, False, 2, 10),
@@ -96,6 +102,9 @@ def main():
                 w0 = max(sum(l2[i] for i in range(ni) if (int(row[i >> 5]) >> (i & 31)) & 1) for row in bits)
                 mw = float(int(w0 * frac))
         sp_inds, sp_bits, n_projs = np.zeros(0, np.int32), None, 0
+        max_new = sparse[2] if len(sparse) > 2 else 0
+        if sparse and not sparse[0]:
+            sparse = []
         if sparse:
             # open indices first (the usual case: sparse output states), the rest drawn at random
             rest = [i for i in np.random.default_rng(seed + 7).permutation(ni).tolist() if i not in out]
@@ -105,7 +114,7 @@ def main():
                 sp_bits[i >> 5] |= np.uint32(1 << (i & 31))
             n_projs = sparse[1]
         rc = RefChain(p, a, b, bits, ni, dim=dim if dims is None else 2, dims=dims, max_width=mw, seed=seed,
-                      sparse_bits=sp_bits, n_projs=n_projs)
+                      sparse_bits=sp_bits, n_projs=n_projs, max_number_new_slices=max_new)
         cps = sorted(set([0, 1, 2, 10, 11, n_sweeps // 3, n_sweeps // 2, n_sweeps - 1]))
         rec = dict(parent=[], child0=[], child1=[], log2_total=[], log2_min=[], prng_crc=[], slices=[],
                    min_slices=[])
@@ -130,7 +139,7 @@ def main():
         np.savez_compressed(
             os.path.join(GOLDEN, name + '.npz'), ts_inds=ts_arr, n_inds=ni, output_inds=np.array(out, np.int32),
             parent=p, child0=a, child1=b, bits=bits, dim=dim, dims=np.zeros(0, np.uint64) if dims is None else dims, max_width=np.float64(-1 if mw is None else mw),
-            sparse_inds=sp_inds, n_projs=n_projs,
+            sparse_inds=sp_inds, n_projs=n_projs, max_new=max_new,
             seed=seed, n_sweeps=n_sweeps, beta0=0.0, beta1=100.0, every=every, checkpoints=np.array(cps),
             init_log2_total=init_log2, init_slices=init_slices,
             cp_parent=np.array(rec['parent']), cp_child0=np.array(rec['child0']),

@@ -140,7 +140,7 @@ class RefChain:
     """Drives the compiled reference exactly as examples/BaseOptimization.ipynb does (raw tnco_core)."""
 
     def __init__(self, parent, c0, c1, bits, n_inds, *, dim=2, dims=None, max_width=None, seed=0,
-                 disable_shared_inds=False, sparse_bits=None, n_projs=None, skip_bits=None):
+                 disable_shared_inds=False, sparse_bits=None, n_projs=None, skip_bits=None, max_number_new_slices=0):
         tc = ref_core()
         self.tc = tc
         nodes = [
@@ -158,6 +158,7 @@ class RefChain:
                 float(max_width), sp, int(n_projs))
             self.opt = tc.optimize.finite_width.greedy.Optimizer_float64_float32(
                 ctree, cm, seed=int(seed), disable_shared_inds=disable_shared_inds,
+                max_number_new_slices=int(max_number_new_slices),
                 skip_slices=None if skip_bits is None else tc.Bitset(positions(skip_bits), n_inds))
         elif sp is not None:
             cm = tc.optimize.infinite_memory.cost_model.SimpleCostModelSparseInds_float64(sp, int(n_projs))
@@ -167,6 +168,7 @@ class RefChain:
             cm = tc.optimize.finite_width.cost_model.SimpleCostModel_float64_float32(float(max_width))
             self.opt = tc.optimize.finite_width.greedy.Optimizer_float64_float32(
                 ctree, cm, seed=int(seed), disable_shared_inds=disable_shared_inds,
+                max_number_new_slices=int(max_number_new_slices),
                 skip_slices=None if skip_bits is None else tc.Bitset(positions(skip_bits), n_inds))
         else:
             cm = tc.optimize.infinite_memory.cost_model.SimpleCostModel_float64()

@@ -245,6 +245,46 @@ def test_skip_slices_lockstep_with_oracle(backend):
         finite_width.Optimizer(ct, FWModel(1.0), seed=5, skip_slices=list(names))
 
 
+@pytest.mark.parametrize('max_new', [1, 4])
+def test_new_slice_move_lockstep_with_oracle(backend, max_new):
+    """max_number_new_slices > 0 (tnco/optimize/finite_width/optimizer.py:59,122; finite_width/greedy/optimizer.hpp:
+    226-321): too-wide moves may add random slices.  Same draws, same trees, same slices as the reference's restatement
+    (which is in lock step with the compiled reference, tests/test_oracle.py)."""
+    from tnco_b200.ctree import ContractionTree
+    from tnco_b200.optimize import finite_width, infinite_memory
+    from tnco_b200.optimize.finite_width.cost_model import SimpleCostModel as FWModel
+    from tnco_b200.optimize.infinite_memory.cost_model import SimpleCostModel
+    from tnco_b200.optimize.prob import MetropolisHastings
+    ts, ni = regular_network(40, 24)
+    p, a, b, bits = random_tree(ts, ni, 25)
+    ct = ContractionTree(tree_to_linear_path(a, b), ts, 2, check_shared_inds=True)
+    P, A, B = ct.arrays()
+    order = {x: k for k, x in enumerate(ct._inds_order)}
+    names = ct._inds_order
+    nb = np.zeros((len(P), (ni + 31) // 32), np.uint32)
+    for z, xs in enumerate(ct.inds):
+        for x in xs:
+            nb[z, order[x] >> 5] |= np.uint32(1 << (order[x] & 31))
+    mw = float(int(max(len(xs) for xs in ct.inds) * 0.45))
+    opt = finite_width.Optimizer(ct, FWModel(mw), seed=8, max_number_new_slices=max_new)
+    oc = so.Chain(P, A, B, nb, ni, max_width=mw, seed=8, max_number_new_slices=max_new)
+    for s in range(150):
+        beta = 0.1 * s
+        opt.update(MetropolisHastings(beta), update_slices=(s % 5 == 0))
+        oc.update(beta, update_slices=(s % 5 == 0))
+        if s % 10 == 0 or s > 140:
+            cur = frozenset(names[i] for i in range(ni) if (oc.slices()[i >> 5] >> (i & 31)) & 1)
+            assert opt.slices == cur, s
+            assert opt.log2_total_cost == oc.log2_total_cost and opt.prng_state == oc.prng_state_str(), s
+    assert oc.new_slice_counters()[1] > 0
+    assert opt.is_valid() and opt.log2_min_total_cost == oc.log2_min_total_cost
+    oa, ob = oc.tree()[1:], None
+    tp, ta, tb = opt.ctree.arrays()
+    assert (ta == oc.tree()[1]).all() and (tb == oc.tree()[2]).all()
+    with pytest.raises(TypeError):
+        infinite_memory.Optimizer(ct, SimpleCostModel(), seed=1, max_number_new_slices=2)
+
+
 def test_precision_too_low_and_bad_input(backend):
     from tnco_b200.engine import Engine
     ts, ni = regular_network(60, 1)

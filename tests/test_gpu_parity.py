@@ -36,6 +36,8 @@ def _engine(g, rng, tile=None, every=None):
                   n_projs=n_projs)
     assert e.hyper == bool(len(g['output_inds']))
     e.set_mode(max_width=mw, update_slices_every=int(g['every']) if every is None else every, rng=rng)
+    if 'max_new' in g.files and int(g['max_new']):
+        e.set_new_slices(int(g['max_new']))
     e.set_chains(g['parent'][None], g['child0'][None], g['child1'][None], [int(g['seed'])])
     os.environ.pop('TNB_TILE', None)
     return e, mw
@@ -87,7 +89,7 @@ def test_every_tile_shape_matches_golden(name, tile):
 
 @pytest.mark.parametrize('name', ['reg64_inf', 'reg100_fw30', 'reg300_inf', 'hyper64_inf', 'hyper64_fw40',
                                   'dims64_fw45', 'dimshyper48_fw50', 'sparse64_inf', 'sparse100_fw30',
-                                  'sparsehyper64_fw40'])
+                                  'sparsehyper64_fw40', 'reg100_fw30_ns4', 'hyper64_fw40_ns2', 'gdims64_fw40_ns2'])
 def test_replay_of_recorded_draw_stream_is_bit_exact(name):
     """north_star: replaying a reference-recorded proposal / uniform-draw sequence yields identical trees.
     The stream is recorded by the oracle (itself pinned to the reference) while it runs the same sweeps."""
@@ -99,7 +101,8 @@ def test_replay_of_recorded_draw_stream_is_bit_exact(name):
     dims = g['dims'] if 'dims' in g.files and len(g['dims']) else None
     sp, n_projs = golden_sparse(g)
     oc = so.Chain(g['parent'], g['child0'], g['child1'], g['bits'], int(g['n_inds']), dim=int(g['dim']) or 2,
-                  dims=dims, max_width=mw, seed=int(g['seed']), sparse_bits=sp, n_projs=n_projs)
+                  dims=dims, max_width=mw, seed=int(g['seed']), sparse_bits=sp, n_projs=n_projs,
+                  max_number_new_slices=int(g['max_new']) if 'max_new' in g.files else 0)
     # the constructor's slicer draws precede the recording; re-create the full stream from the seed instead
     betas = [100.0 * s / n_sweeps for s in range(n_sweeps)]
     oc.run(betas, update_slices_every=int(g['every']))
@@ -435,6 +438,41 @@ def test_split_layout_gives_identical_results(max_width):
     for k in (1, 2):
         assert all((x == y).all() for x, y in zip(a[k], b[k]))
     assert (a[3] == b[3]).all() and (a[4] == b[4]).all() and (a[5] == b[5]).all()
+
+
+@pytest.mark.parametrize('n,tile', [(64, 4), (64, 8), (64, 32), (180, 16), (180, 32), (300, 32)])
+def test_shared_memory_resident_layout_gives_identical_results(n, tile):
+    """TNB_LAYOUT_SMEM (chain state resident in shared memory for the whole launch, north_star item 4) runs the same
+    chains as the in-place layouts: same seeds -> identical trees, costs, best trees, index sets, counters -- over two
+    launches (state goes home to global memory in between)."""
+    from helpers import leaf_bits
+    from tnco_b200._lib import LAYOUT_INTERLEAVED, LAYOUT_SMEM
+    from tnco_b200.engine import Engine
+    ts, ni = regular_network(n, 70 + n)
+    lb = leaf_bits(ts, ni)
+    seeds = np.arange(70, dtype=np.uint64) + 9
+    outs = []
+    for layout in (LAYOUT_INTERLEAVED, LAYOUT_SMEM):
+        os.environ['TNB_TILE'] = str(tile)
+        try:
+            e = Engine()
+            e.set_network(lb, ni).set_mode(layout=layout)
+            e.generate_chains(seeds)
+        finally:
+            os.environ.pop('TNB_TILE', None)
+        cfg = e.config()
+        assert cfg['layout'] == layout and cfg['tile'] == tile, cfg
+        e.set_betas(np.linspace(0, 100, 400, endpoint=False))
+        e.run(150)
+        e.run(400)
+        outs.append((e.costs(), e.trees(), e.trees(True), e.bits(7), e.bits(69), e.progress()['proposals'],
+                     e.progress()['accepts']))
+        e.close()
+    a, b = outs
+    assert (a[0][0] == b[0][0]).all() and (a[0][1] == b[0][1]).all()
+    for k in (1, 2):
+        assert all((x == y).all() for x, y in zip(a[k], b[k]))
+    assert all((a[k] == b[k]).all() for k in (3, 4, 5, 6))
 
 
 def _hyper_case(n, seed):

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libtnco_b200.so')
 
 PROB_MH, PROB_GREEDY, PROB_ALWAYS = 0, 1, 2
 RNG_PHILOX, RNG_MT19937, RNG_REPLAY = 0, 1, 2
-LAYOUT_AUTO, LAYOUT_INTERLEAVED, LAYOUT_SPLIT = 0, 1, 2
+LAYOUT_AUTO, LAYOUT_INTERLEAVED, LAYOUT_SPLIT, LAYOUT_SMEM = 0, 1, 2, 3
 TREES_GREEDY, TREES_RANDOM = 0, 1
 
 i32p, u32p, u64p, i64p, f64p = (C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
@@ -41,6 +41,7 @@ SIGNATURES = {
     'tnb_set_skip_slices': (C.c_int, [C.c_void_p, u32p]),
     'tnb_set_mode': (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     'tnb_set_prob': (C.c_int, [C.c_void_p, C.c_int]),
+    'tnb_set_new_slices': (C.c_int, [C.c_void_p, C.c_int]),
     'tnb_set_update_slices': (C.c_int, [C.c_void_p, C.c_int]),
     'tnb_set_chains': (C.c_int, [C.c_void_p, C.c_int, i32p, i32p, i32p, u64p, C.c_uint64]),
     'tnb_generate_chains': (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_uint64, C.c_int]),

@@ -207,6 +207,7 @@ struct tnb_engine {
   bool finite = false;
   float max_width = 0.f;
   int every = 0, dsi = 0, prob_kind = TNB_PROB_MH, rng_kind = TNB_RNG_PHILOX, layout = TNB_LAYOUT_AUTO;
+  int max_new = 0;  // max_number_new_slices (tnb_set_new_slices)
   // chains
   ChainSet cs;
   bool initialized = false;
@@ -260,6 +261,7 @@ static unsigned long long sweep_reserve(const tnb_engine* e) {
   // worst case draws of one sweep: leaf + (coin + 2) per level, depth <= n-1; plus slicer head-room
   unsigned long long r = 1ull + 3ull * (unsigned long long)(e->n > 1 ? e->n - 1 : 1);
   if (e->finite) r += 8ull * (unsigned long long)e->n_inds + 64ull;
+  if (e->finite && e->max_new > 0) r += (unsigned long long)e->max_new * (unsigned long long)(e->n > 1 ? e->n - 1 : 1);
   return r;
 }
 
@@ -274,6 +276,7 @@ static void fill_params(const tnb_engine* e, const ChainSet& cs, Params& P) {
   P.glog2 = e->generic ? e->d_glog2 : nullptr;
   P.n_projs = double(e->n_projs);
   P.log2_n_projs = e->n_projs ? std::log2(double(e->n_projs)) : 0.0;
+  P.max_new = e->max_new;
   P.finite = e->finite; P.every = e->every; P.dsi = e->dsi; P.prob_kind = e->prob_kind; P.max_width = e->max_width;
   P.n_chains = cs.n_chains; P.Npad = e->Npad;
   P.par = cs.par; P.hdr = cs.rec; P.bitsb = cs.bitsb; P.hstride = cs.hstride; P.bstride = cs.bstride; P.pc = cs.pc; P.bpar = cs.bpar; P.bch = cs.bch;
@@ -292,6 +295,13 @@ static void fill_params(const tnb_engine* e, const ChainSet& cs, Params& P) {
       if (float(e->log2d * double(k)) <= e->max_width) P.kthr = k;
   P.grouped = e->grouped; P.leader = e->d_leader; P.gw = e->d_gw;
   P.hyper = e->hyper; P.hyp_off = 4 * e->Ws; P.hcount0 = e->d_hcount0;
+  // shared-memory-resident chains (TNB_LAYOUT_SMEM): unconstrained production kernels whose state fits the SM
+  P.smem_chain_bytes = 0;
+  if (e->layout == TNB_LAYOUT_SMEM && !e->finite && e->rng_kind == TNB_RNG_PHILOX && e->pow2_costs() && !e->hyper &&
+      e->wpl == 1 && !cs.bits_alloc) {
+    const size_t b = smem_chain_bytes(e->Npad, e->n_int, e->stride);
+    if (b * size_t(32 / e->tile) <= size_t(200) << 10) P.smem_chain_bytes = int(b);
+  }
   P.trace = cs.trace; P.trace_n = cs.trace_n; P.trace_cap = cs.trace_cap; P.trace_S = cs.trace_S; P.trace_sn = cs.trace_sn;
   P.trace_scap = cs.trace_scap; P.trace_chains = cs.trace_chains;
   P.net_own = e->d_net_own; P.kpop = cs.kpop; P.escore = cs.escore; P.tree_fail = cs.tree_fail; P.tree_method = TNB_TREES_GREEDY;
@@ -311,7 +321,7 @@ static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_be
   // layout: interleaved node records while the whole batch fits L2, split beyond
   const size_t state = nc * ni * size_t(e->stride);
   bool split = state > (size_t(96) << 20);
-  if (e->layout == TNB_LAYOUT_INTERLEAVED) split = false;
+  if (e->layout == TNB_LAYOUT_INTERLEAVED || e->layout == TNB_LAYOUT_SMEM) split = false;
   if (e->layout == TNB_LAYOUT_SPLIT) split = true;
   cs.hstride = split ? 16 : e->stride;
   cs.bstride = split ? 4 * e->Ws * (e->hyper ? 2 : 1) : e->stride;
@@ -463,6 +473,9 @@ static bool mode_ok(tnb_engine* e) {
   if (e->rng_kind == TNB_RNG_PHILOX && (e->dsi || e->prob_kind != TNB_PROB_MH))
     return e->fail("TNB_RNG_PHILOX runs Metropolis-Hastings with shared-index moves only: greedy / always acceptance "
                    "and disable_shared_inds need TNB_RNG_MT19937 or TNB_RNG_REPLAY (invalid mode)");
+  if (e->rng_kind == TNB_RNG_PHILOX && e->finite && e->max_new > 0)
+    return e->fail("max_number_new_slices > 0 is a core-object option: use TNB_RNG_MT19937 or TNB_RNG_REPLAY "
+                   "(invalid mode)");
   if (e->rng_kind == TNB_RNG_PHILOX && e->finite && e->d_skip && e->pow2_costs())
     return e->fail("skip_slices is not known to the production re-slicer: use TNB_RNG_MT19937 or TNB_RNG_REPLAY "
                    "(invalid mode)");
@@ -773,7 +786,7 @@ int tnb_set_sparse_inds(tnb_engine* e, const uint32_t* sparse_bits, uint64_t n_p
 int tnb_set_mode(tnb_engine* e, double max_width, int update_slices_every, int disable_shared_inds, int prob_kind,
                  int rng_kind, int layout) {
   if (!e) return -1;
-  if (prob_kind < 0 || prob_kind > 2 || rng_kind < 0 || rng_kind > 2 || layout < 0 || layout > 2)
+  if (prob_kind < 0 || prob_kind > 2 || rng_kind < 0 || rng_kind > 2 || layout < 0 || layout > 3)
     return e->fail("tnb_set_mode: invalid arguments"), -1;
   e->finite = !(max_width < 0.0) && !std::isinf(max_width) && !std::isnan(max_width);
   e->max_width = e->finite ? float(max_width) : 0.f;
@@ -791,6 +804,13 @@ int tnb_set_prob(tnb_engine* e, int prob_kind) {
   if (!e) return -1;
   if (prob_kind < 0 || prob_kind > 2) return e->fail("tnb_set_prob: invalid arguments"), -1;
   e->prob_kind = prob_kind;
+  return 0;
+}
+
+int tnb_set_new_slices(tnb_engine* e, int max_number_new_slices) {
+  if (!e) return -1;
+  if (max_number_new_slices < 0) return e->fail("tnb_set_new_slices: invalid arguments"), -1;
+  e->max_new = max_number_new_slices;
   return 0;
 }
 
@@ -1225,7 +1245,14 @@ int tnb_get_config(tnb_engine* e, int* tile, int* words_per_lane, int* layout, i
   if (!e) return -1;
   if (tile) *tile = e->tile;
   if (words_per_lane) *words_per_lane = e->wpl;
-  if (layout) *layout = e->cs.n_chains ? (e->cs.bits_alloc ? TNB_LAYOUT_SPLIT : TNB_LAYOUT_INTERLEAVED) : e->layout;
+  if (layout) {
+    *layout = e->cs.n_chains ? (e->cs.bits_alloc ? TNB_LAYOUT_SPLIT : TNB_LAYOUT_INTERLEAVED) : e->layout;
+    if (e->cs.n_chains) {
+      Params P;
+      fill_params(e, e->cs, P);
+      if (P.smem_chain_bytes > 0) *layout = TNB_LAYOUT_SMEM;
+    }
+  }
   if (state_bytes_per_chain)
     *state_bytes_per_chain = int(size_t(e->n_int) * size_t(e->stride) + size_t(e->Npad) * 2);
   return 0;

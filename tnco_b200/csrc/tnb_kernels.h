@@ -53,6 +53,7 @@ struct Params {
   // mode
   int finite, every, dsi, prob_kind;
   float max_width;
+  int max_new;  // max_number_new_slices (finite_width/greedy/optimizer.hpp:226-321); stream kernels only, 0 = off
   // chains
   int n_chains, Npad;
   // hyper-indices (an index on 3+ tensors, or on 2 and open): HYPER kernels keep, next to every internal node's
@@ -94,6 +95,8 @@ struct Params {
   const double* betas;
   const float* inv_betas;  // 1/beta, or 3e38 for beta <= 0 (accept everything: (1+x)^-beta >= 1)
   long long n_betas, until;
+  // shared-memory-resident chains (TNB_LAYOUT_SMEM): bytes per chain, 0 = state is walked in global memory
+  int smem_chain_bytes;
   // scratch for the slicer
   uint16_t* nbig;   // [n_chains][Ws*32]
   int16_t* posbuf;  // [n_chains][Ws*32]
@@ -330,6 +333,7 @@ struct ChainView {
   char* rec_lane;             // this lane's first word of z's index set at rec_lane + z*bstride (+ 4*k*TILE)
   double* pcv;                // pcv[z] = partial cost of internal node z (parity modes)
   bool lane_ok[WPL];
+  bool smem = false;          // rec / rec_lane / par point into shared memory (chain_sweeps<..., SMEM>)
 
   TNB_D ChainView(const Params& P_, int chain_) : P(P_), chain(chain_) {
     n = P.n;
@@ -361,6 +365,18 @@ struct ChainView {
       // select and predicated loads (C1 +7 %, C5 +10 % against the branching form).  An unconditional load of the
       // whole tile of words plus a mask is shorter still but drags extra sectors through L1 (C2 -5 %).
       const bool leaf = node < n;
+      if (smem) {  // leaves in global memory (read-only path), internal nodes in shared memory: two predicated loads
+        const uint32_t* gl = leaf_lane + w64(node) * Ws;
+        const uint32_t* sh = reinterpret_cast<const uint32_t*>(rec_lane + w64(node) * bstride);
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) {
+          uint32_t v = 0u;
+          if (lane_ok[k] && leaf) v = ldg(gl + k * TILE);
+          if (lane_ok[k] && !leaf) v = sh[k * TILE];
+          o[k] = v;
+        }
+        return;
+      }
       const char* base = leaf ? reinterpret_cast<const char*>(leaf_lane) : const_cast<const char*>(rec_lane);
       const unsigned st = leaf ? 4u * Ws : bstride;
       const uint32_t* src = reinterpret_cast<const uint32_t*>(base + w64(node) * st);
@@ -1444,8 +1460,14 @@ TNB_D double sum_ccost(const ChainView<TILE, WPL>& c) {
 // walks.  The inputs of level k+1 (parent A', its children word and contraction cost, the sibling's index set
 // and partial cost) do not depend on the move at level k, so they are loaded during level k in three stages and
 // are in registers when level k+1 starts.
-template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2, bool HYPER = false, bool TRACE = false>
-TNB_D void chain_sweeps(const Params& P, int chain) {
+// Shared-memory-resident chain state (small networks, north_star item 4): bytes one chain occupies -- its parent
+// array and its node records {header, index set} in the interleaved layout.
+TNB_HD inline size_t smem_chain_bytes(int Npad, int n_int, int stride) {
+  return (size_t(Npad) * 2 + 15) / 16 * 16 + size_t(n_int) * size_t(stride);
+}
+
+template <int TILE, int WPL, bool FINITE, class Rng, bool DIM2, bool HYPER = false, bool TRACE = false, bool SMEM = false>
+TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
   ChainView<TILE, WPL> c(P, chain);
   const Tile<TILE>& t = c.t;
   const int n = P.n, root = P.N - 1;
@@ -1453,10 +1475,31 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     P.sweep_idx[chain] = P.until;
     return;
   }
+  // SMEM: the chain's topology and node records live in shared memory for the whole launch (copied in here, copied
+  // back at the end); the walk then never leaves the SM except for leaf index sets (read-only path) and snapshots.
+  int16_t* g_par = c.par;
+  char* g_rec = c.rec + w64(n) * c.hstride;  // record of internal node n, i.e. the chain's first
+  const size_t par_bytes = (size_t(P.Npad) * 2 + 15) / 16 * 16;
+  if constexpr (SMEM) {
+#if !defined(TNB_EMU)
+    uint32_t* sp = reinterpret_cast<uint32_t*>(smem_tile);
+    const uint32_t* gp = reinterpret_cast<const uint32_t*>(g_par);
+    for (int i = t.tl; i < P.Npad / 2; i += TILE) sp[i] = gp[i];
+    uint32_t* sr = reinterpret_cast<uint32_t*>(smem_tile + par_bytes);
+    const uint32_t* gr = reinterpret_cast<const uint32_t*>(g_rec);
+    const int words = P.n_int * (P.hstride / 4);
+    for (int i = t.tl; i < words; i += TILE) sr[i] = gr[i];
+    t.sync();
+    c.par = reinterpret_cast<int16_t*>(smem_tile);
+    c.rec = smem_tile + par_bytes - w64(n) * c.hstride;
+    c.rec_lane = c.rec + 16 + 4 * t.tl;
+    c.smem = true;
+#endif
+  }
   // the per-chain bases stay in registers (otherwise they are re-derived from the kernel parameters at every use)
-  keep_in_register(c.rec);
-  keep_in_register(c.rec_lane);
-  keep_in_register(c.par);
+  keep_in_register<SMEM>(c.rec);
+  keep_in_register<SMEM>(c.rec_lane);
+  keep_in_register<SMEM>(c.par);
   if constexpr (WPL == 1) {  // "this lane owns a word": one live flag instead of S2R + AND + constant load + compare
     uint32_t okf = c.lane_ok[0] ? 1u : 0u;
     keep_in_register(okf);
@@ -1768,6 +1811,7 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     int szE = pick0 ? sz1 : sz0;
     ++q_prop;
     bool gate = true;
+    float swB = 0.f;  // new_sliced_width_B
     if (FINITE) {  // finite_width/greedy/optimizer.hpp:176-188
       ks = t.sum_c(ks);
       if (FS) {
@@ -1778,10 +1822,11 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
         uint32_t xs[WPL];
 #pragma unroll
         for (int k = 0; k < WPL; ++k) xs[k] = nb[k] & ~S[k];
-        gate = c.template gwidth_model<true>(xs, SP) <= P.max_width;
+        swB = c.template gwidth_model<true>(xs, SP);
       } else {
-        gate = (sparse ? c.width_sp(int(ks), int(kss)) : c.width_of(int(ks))) <= P.max_width;
+        swB = sparse ? c.width_sp(int(ks), int(kss)) : c.width_of(int(ks));
       }
+      gate = swB <= P.max_width;
       if (!gate) ++q_wrej;
     }
     bool acc = false;
@@ -1839,6 +1884,153 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
       trace_put(1u | (pick0 ? 4u : 0u) | (gate ? 8u : 0u) | (acc ? 16u : 0u) | ((i0 && i1) ? 32u : 0u) | (uint32_t(B) << 16),
                 rng.coin_word(t), ib, uint32_t(A), delta, total);
     }
+    // ---- random new slices (finite_width/greedy/optimizer.hpp:226-321; core-object option, stream kernels only):
+    // the new tensor is too wide -> slice up to max_new random indices of it; if it fits then, swap, rebuild the whole
+    // cost cache under the new slices and put the move to the acceptance rule with delta = new total - total.
+    bool ns_taken = false;
+    if constexpr (FINITE && !Rng::kFast) {
+      if (!gate && P.max_new > 0) {
+        int16_t* pos = P.posbuf + size_t(chain) * P.Ws * 32;
+        uint32_t np = 0;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) {  // (new_inds_B - slices [- skip_slices]).positions(), ascending (:233-238)
+          const int w = t.tl + k * TILE;
+          uint32_t v = nb[k] & ~S[k];
+          if (P.skip) v &= w < P.W ? ~P.skip[w] : 0u;
+          if (P.grouped) v &= w < P.W ? P.leader[w] : 0u;
+          uint32_t tot;
+          uint32_t off = np + t.excl_scan_sum(uint32_t(popc32(v)), tot);
+          while (v) {
+            pos[off++] = int16_t(w * 32 + ctz32(v));
+            v &= v - 1;
+          }
+          np += tot;
+        }
+        t.sync();
+        uint32_t n_new = 0;
+        float nsw = swB;
+        if (t.tl == 0) {
+          uint32_t n_pos = np;
+          while (n_new < uint32_t(P.max_new) && nsw > P.max_width && n_pos > 0u) {
+            const uint32_t r = rng.local_next() % n_pos;  // :246
+            const int16_t tmp = pos[r];
+            pos[r] = pos[n_pos - 1];
+            pos[n_pos - 1] = tmp;
+            const int idx = pos[n_pos - 1];
+            // new_sliced_width_B -= log2_dims[...] in width_type (DimsCache<width_type>, :256-266)
+            nsw -= gen ? float(P.glog2[idx]) : P.grouped ? float(int(P.gw[idx])) : float(P.log2d);
+            --n_pos;
+            ++n_new;
+          }
+        }
+        rng.sync_from0(t);
+        n_new = t.bcast(n_new, 0);
+        const bool fits = t.bcast(nsw <= P.max_width ? 1u : 0u, 0) != 0u;
+        t.sync();
+        if (fits) {
+          uint32_t S2[WPL];
+#pragma unroll
+          for (int k = 0; k < WPL; ++k) S2[k] = S[k];
+          for (uint32_t j = np - n_new; j < np; ++j) {
+            const int idx = pos[j];
+            const int g = P.grouped ? int(P.gw[idx]) : 1;
+#pragma unroll
+            for (int k = 0; k < WPL; ++k) S2[k] |= span_mask(idx, g, t.tl + k * TILE);
+          }
+          // tentative swap_with_nn(E) in memory: the cost pass walks the tree as stored
+          const int na0 = bslot0 ? a0 : E, na1 = bslot0 ? E : a1;
+          const int np0 = pick0 ? p0 : C, np1 = pick0 ? C : p1;
+          c.ch(A) = uint32_t(na0) | (uint32_t(na1) << 16);
+          c.ch(B) = uint32_t(np0) | (uint32_t(np1) << 16);
+          c.par[C] = int16_t(B);
+          c.par[E] = int16_t(A);
+          c.store_bits(B, nb);
+          t.sync();
+          dbl2* cp2 = P.cp2 + size_t(chain) * P.n_int;
+          double seq2, maxw2;
+          cost_pass<TILE, WPL, false>(c, S2, ScratchSink{cp2, n}, seq2, maxw2);
+          t.sync();
+          const double r2 = cp2[P.n_int - 1].y;
+          const double d2 = r2 - total;
+          const double u2 = rng.uniform(t);
+          double p2;
+          if (f_prob == kProbMH) p2 = d2 <= 0.0 ? 1.0 : (total == 0.0 ? 0.0 : pow(1.0 + d2 / total, -beta));
+          else if (f_prob == kProbGreedy) p2 = d2 <= 0.0 ? 1.0 : 0.0;
+          else p2 = 1.0;
+          if (u2 <= p2) {  // :290-312 (pos_C / pos_E keep their names in this branch)
+            t.sync();
+            for (int i = t.tl; i < P.n_int; i += TILE) {
+              c.cc(n + i) = cp2[i].x;
+              c.pcv[n + i] = cp2[i].y;
+            }
+            t.sync();
+            if (HYPER) {
+#pragma unroll
+              for (int k = 0; k < WPL; ++k) {
+                hA[k] = bA[k] & nb[k] & bE[k];
+                hB[k] = nb[k] & bD[k] & bC[k];
+              }
+              c.store_hyp(A, hA);
+              c.store_hyp(B, hB);
+            }
+#pragma unroll
+            for (int k = 0; k < WPL; ++k) S[k] = S2[k];
+            store_slices(c, S);
+            total = r2;
+            root_pc = r2;
+            ++q_acc;
+            ns_taken = true;
+          } else {  // swap back (swap_with_nn(pos_C), :314-317)
+            c.ch(A) = uint32_t(a0) | (uint32_t(a1) << 16);
+            c.ch(B) = uint32_t(p0) | (uint32_t(p1) << 16);
+            c.par[C] = int16_t(A);
+            c.par[E] = int16_t(B);
+            uint32_t ob[WPL];
+#pragma unroll
+            for (int k = 0; k < WPL; ++k) ob[k] = HYPER ? ((bD[k] ^ bE[k]) | hB[k]) : (bD[k] ^ bE[k]);
+            c.store_bits(B, ob);
+            t.sync();
+          }
+        }
+      }
+    }
+    if (ns_taken) {
+      // The whole cost cache was replaced (skip_cost_propagation, :311): nothing carried in registers for the levels
+      // above is valid any more.  Re-enter the walk at B <- A from memory, like a sweep start does.
+      if constexpr (FINITE && !Rng::kFast) {
+        B = A;
+        const uint32_t cw = c.ch(B);
+        p0 = int(cw & 0xffffu);
+        p1 = int(cw >> 16);
+        c.load_bits(p0, b0);
+        c.load_bits(p1, b1);
+        pc0 = c.pc_of(p0);
+        pc1 = c.pc_of(p1);
+        ccB = c.cc(B);
+        if (HYPER) c.load_hyp(B, hB);
+        A = c.par[B];
+        if (A >= 0) {
+          const uint32_t aw = c.ch(A);
+          a0 = int(aw & 0xffffu);
+          a1 = int(aw >> 16);
+          C = (a0 == B) ? a1 : a0;
+          c.load_bits(C, bC);
+          if (HYPER) {
+            c.load_bits(A, bA);
+            c.load_hyp(A, hA);
+          }
+          pcC = c.pc_of(C);
+          ccA = c.cc(A);
+          An = c.par[A];
+          Ann = -1;
+          if (An >= 0) {
+            awn = c.ch(An);
+            ccAn = c.cc(An);
+            Ann = c.par[An];
+          }
+        }
+      }
+    } else {
     uint32_t bB[WPL];
     if (acc) {
       // Tree::swap_with_nn(E): E <-> C, child slots preserved (tree.hpp:141-192)
@@ -1943,11 +2135,24 @@ TNB_D void chain_sweeps(const Params& P, int chain) {
     Ann = Annn;
     awn = awnn;
     ccAn = ccAnn;
+    }  // (no new-slice move taken)
     }  // level
   }
   if constexpr (TRACE) if (tracing) {
     P.trace_n[chain] = tr_n;
     P.trace_sn[chain] = tr_sn;
+  }
+  if constexpr (SMEM) {  // state back to its home in global memory
+#if !defined(TNB_EMU)
+    t.sync();
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(smem_tile);
+    uint32_t* gp = reinterpret_cast<uint32_t*>(g_par);
+    for (int i = t.tl; i < P.Npad / 2; i += TILE) gp[i] = sp[i];
+    const uint32_t* sr = reinterpret_cast<const uint32_t*>(smem_tile + par_bytes);
+    uint32_t* gr = reinterpret_cast<uint32_t*>(g_rec);
+    const int words = P.n_int * (P.hstride / 4);
+    for (int i = t.tl; i < words; i += TILE) gr[i] = sr[i];
+#endif
   }
   rng.store(P, chain);
   P.sweep_idx[chain] = s;

@@ -31,6 +31,14 @@ __global__ void __launch_bounds__(kSweepBlock, MINB) sa_sweep_kernel(const __gri
   if (chain >= P.n_chains) return;
   chain_sweeps<TILE, WPL, FINITE, Rng, DIM2, HYPER, TRACE>(P, chain);
 }
+// Shared-memory-resident variant: every tile of the block's warp owns P.smem_chain_bytes of dynamic shared memory.
+template <int TILE, class Rng, int MINB>
+__global__ void __launch_bounds__(kSweepBlock, MINB) sa_sweep_smem_kernel(const __grid_constant__ Params P) {
+  extern __shared__ __align__(16) char smem_all[];
+  const int chain = (blockIdx.x * kSweepBlock + threadIdx.x) / TILE;
+  if (chain >= P.n_chains) return;
+  chain_sweeps<TILE, 1, false, Rng, true, false, false, true>(P, chain, smem_all + size_t(threadIdx.x / TILE) * P.smem_chain_bytes);
+}
 
 template <int TILE, int WPL>
 __global__ void __launch_bounds__(kBlock) sa_treegen_kernel(const __grid_constant__ Params P) {
@@ -85,6 +93,22 @@ static bool launch_t(Rt& rt, const Params& P, bool init) {
   } else {
     if (P.hyper) { rt.err = "hyper-index networks need TILE = 32"; return false; }
   }
+#if !defined(TNB_EMU)
+  // shared-memory-resident chains: unconstrained production kernel, one word per lane
+  if constexpr (Rng::kFast && DIM2 && !FINITE && WPL == 1) {
+    if (P.smem_chain_bytes > 0 && !init && !P.trace) {
+      const long long threads = (long long)P.n_chains * TILE;
+      const int grid = int((threads + kSweepBlock - 1) / kSweepBlock);
+      if (grid == 0) return true;
+      const size_t bytes = size_t(kSweepBlock / TILE) * size_t(P.smem_chain_bytes);
+      auto kern = sa_sweep_smem_kernel<TILE, Rng, 28>;
+      if (!rt.ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)), "smem size"))
+        return false;
+      kern<<<grid, kSweepBlock, bytes, rt.stream>>>(P);
+      return rt.ok(cudaGetLastError(), "sa_sweep_smem_kernel launch");
+    }
+  }
+#endif
   // decision trace (tests): the production kernel proper -- Philox, 2^popcount costs, no hyper-indices
   if constexpr (Rng::kFast && DIM2) {
     if (P.trace && !init) return launch_h<TILE, WPL, FINITE, Rng, DIM2, false, true>(rt, P, init);

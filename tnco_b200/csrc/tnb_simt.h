@@ -31,11 +31,13 @@ namespace tnb {
 
 // Make a value opaque to the optimiser (it then stays in its register instead of being re-derived from kernel
 // parameters at every use; the per-chain base pointers of the sweep loop are kept this way).
-template <class T>
+template <bool SHARED = false, class T>
 TNB_D TNB_INLINE void keep_in_register(T*& p) {
 #if !defined(TNB_EMU)
   asm volatile("" : "+l"(p));
-  __builtin_assume(__isGlobal(p));  // the asm hides the address space: keep LDG/STG instead of generic LD/ST
+  // the asm hides the address space: keep LDG/STG (or LDS/STS) instead of generic LD/ST
+  if (SHARED) __builtin_assume(__isShared(p));
+  else __builtin_assume(__isGlobal(p));
 #else
   (void)p;
 #endif

@@ -255,6 +255,11 @@ class Engine:
                                        int(prob), int(rng), int(layout)))
         return self
 
+    def set_new_slices(self, max_number_new_slices):
+        """max_number_new_slices of the finite-width core object (stream modes only); 0 = off."""
+        self._chk(self._L.tnb_set_new_slices(self._h, int(max_number_new_slices)))
+        return self
+
     def set_prob(self, prob):
         self._chk(self._L.tnb_set_prob(self._h, int(prob)))
         return self

@@ -26,9 +26,11 @@ class Optimizer:
 
     def __init__(self, ctree: ContractionTree, cmodel, *, seed=None, disable_shared_inds: bool = False,
                  atol: float = 1e-5, device: int = 0, **kwargs):
-        if kwargs.pop('max_number_new_slices', 0):
-            raise NotImplementedError("tnco_b200: 'max_number_new_slices' > 0 is not supported (the app never "
-                                      "enables it, tnco/optimize/finite_width/optimizer.py:59).")
+        # finite-width core object only (tnco/optimize/finite_width/optimizer.py:59,122-123)
+        self._max_new = int(kwargs.pop('max_number_new_slices', 0) or 0)
+        if self._max_new < 0 or (self._max_new and not self._finite):
+            raise TypeError('Got unexpected keyword arguments.' if not self._finite else
+                            "'max_number_new_slices' must be a non-negative number.")
         self._skip_slices = frozenset(kwargs.pop('skip_slices', None) or ())
         kwargs.pop('slice_update', None)
         # what unpickling hands back (optimizer.py:234-247, finite_width/optimizer.py:330-346)
@@ -62,6 +64,8 @@ class Optimizer:
                 self._e.set_skip_slices(pack_index_set([pos[x] for x in self._skip_slices], ni))
         self._e.set_mode(max_width=getattr(cmodel, 'max_width', None) if self._finite else None,
                          update_slices_every=1, disable_shared_inds=self._dsi, rng=RNG_MT19937)
+        if self._max_new:
+            self._e.set_new_slices(self._max_new)
         p, a, b = ctree.arrays()
         self._e.set_chains(p[None], a[None], b[None], [self._seed])
         if self._state0 is not None or min_ctree is not None or slices is not None or min_slices is not None:
