@@ -254,6 +254,39 @@ int tnb_flush_l2(tnb_engine* e);
 /* the layout / tile shape the engine picked: lanes per chain, words per lane, TNB_LAYOUT_* , state bytes per chain */
 int tnb_get_config(tnb_engine* e, int* tile, int* words_per_lane, int* layout, int* state_bytes_per_chain);
 
+/* ---------------------------------------------------------------- several GPUs of one box behind one handle
+ * For hosts that are not Python (the Python layer runs one process per GPU and exchanges over NCCL,
+ * tnco_b200/dist.py).  What the reference does with one loky process per run (tnco/parallel.py:330-341) is done here
+ * with one engine + one host thread per device: chains are sharded contiguously (chain i -> device floor(i*G/n)),
+ * seeds and Philox counters use GLOBAL chain ids, so results do not depend on the number of devices.  The one
+ * exchange step -- minimum over all chains + the winner's tree -- is tnb_group_get_best; inside one
+ * process it is a host-side minimum over values tnb_get_costs has already brought back (nothing for NCCL to reduce).
+ * `devices` may name the same device more than once (two engines on one GPU).  Per-device engines are reachable
+ * through tnb_group_engine for everything not fanned out below (sparse indices, read-back of single chains, ...). */
+typedef struct tnb_group tnb_group;
+int tnb_group_create(tnb_group** g, const int* devices, int n_dev);
+void tnb_group_destroy(tnb_group* g);
+int tnb_group_size(const tnb_group* g);
+tnb_engine* tnb_group_engine(tnb_group* g, int k);
+const char* tnb_group_last_error(const tnb_group* g);
+/* tnb_set_network (+ tnb_set_output_inds when output_bits != NULL), tnb_set_mode, tnb_set_betas on every device */
+int tnb_group_set_network(tnb_group* g, int n_leaves, int n_inds, const uint32_t* leaf_bits, uint64_t dim,
+                          const uint64_t* dims, const uint32_t* output_bits);
+int tnb_group_set_mode(tnb_group* g, double max_width, int update_slices_every, int disable_shared_inds,
+                       int prob_kind, int rng_kind, int layout);
+int tnb_group_set_betas(tnb_group* g, const double* betas, int64_t n);
+/* n_chains runs over all devices (>= one per device), seeds [n_chains]; trees are built on the devices */
+int tnb_group_generate_chains(tnb_group* g, int n_chains, const uint64_t* seeds, int method);
+/* all devices concurrently, each under the same wall-clock budget (tnb_run_timed); *reached = min over devices */
+int tnb_group_run(tnb_group* g, int64_t until_sweep, double timeout_s, int64_t* reached);
+/* [n_chains] in global chain order */
+int tnb_group_get_costs(tnb_group* g, double* total, double* min_total);
+int tnb_group_get_counters(tnb_group* g, uint64_t* proposals, uint64_t* accepts, uint64_t* sweeps);
+/* the exchange step: best min_total_cost over all chains of all devices, its global chain id, its tree
+ * ([2*n_leaves-1] each) and slices ([W32], finite width only); any pointer may be NULL */
+int tnb_group_get_best(tnb_group* g, double* cost, int64_t* chain, int32_t* parent, int32_t* child0,
+                       int32_t* child1, uint32_t* slices);
+
 #ifdef __cplusplus
 }
 #endif

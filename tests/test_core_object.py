@@ -304,7 +304,7 @@ def test_precision_too_low_and_bad_input(backend):
     bad[-1] = bad[-2]
     with pytest.raises(ValueError):
         e2.set_chains(p[None], bad[None], b[None], [1])
-    # hyper-index (an index on three tensors): accepted, runs the HYPER kernels; trees must come from the host
+    # hyper-index (an index on three tensors): accepted, runs the HYPER kernels; trees from the host or the device
     lb = bits[:10].copy()
     lb[0, 0] |= 1
     lb[1, 0] |= 1
@@ -312,5 +312,5 @@ def test_precision_too_low_and_bad_input(backend):
     e3 = Engine()
     e3.set_network(lb, ni).set_mode()
     assert e3.hyper and not e2.hyper
-    with pytest.raises(ValueError, match='hyper'):
-        e3.generate_chains([1, 2])
+    e3.generate_chains([1, 2])
+    assert (e3.costs()[0] > 0).all()

@@ -139,3 +139,8 @@ def test_emu_production_kernel_replay_low_beta(emu):
 def test_emu_equal_sweep_distribution(emu, case, chains):
     import test_gpu_statistics as S
     S.test_equal_sweep_distribution_on_the_benchmarked_networks(case, chains)
+
+
+@pytest.mark.parametrize('n,method', [(12, 0), (48, 0), (48, 1)])
+def test_emu_generated_trees_hyper(emu, n, method):
+    G.test_device_generated_trees_for_hyper_index_networks(n, method)

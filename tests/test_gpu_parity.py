@@ -402,6 +402,45 @@ def test_device_generated_trees_are_valid(n, method):
         e.close()
 
 
+@pytest.mark.parametrize('n,method', [(12, 0), (48, 0), (48, 1), (90, 0)])
+def test_device_generated_trees_for_hyper_index_networks(n, method):
+    """tnb_generate_chains on networks WITH hyper-indices and open indices: valid trees whose contractions share an
+    index under the hyper-count rule (the validating entry point tnb_set_chains re-derives it on the host and accepts
+    them, and its index sets equal the oracle-side construction), deterministic, and better than random for greedy."""
+    from tnco_b200.engine import Engine, random_trees
+    ts, ni, out, lb, ob = _hyper_case(n, 500 + n)
+    seeds = np.arange(20, dtype=np.uint64) * 5 + 2
+    outs = []
+    for rep in range(2):
+        e = Engine()
+        e.set_network(lb, ni, output_bits=ob).set_mode()
+        assert e.hyper
+        e.generate_chains(seeds, method=method)
+        P, A, B = e.trees()
+        t, m = e.costs()
+        for c in range(len(seeds)):
+            _check_tree_valid(P[c], A[c], B[c], n)
+        e2 = Engine()
+        e2.set_network(lb, ni, output_bits=ob).set_mode()
+        e2.set_chains(P, A, B, seeds)       # host-side check_shared_inds + hyper-count rule
+        assert (e2.costs()[0] == t).all() and (e2.bits(3) == e.bits(3)).all()
+        e2.close()
+        e.set_betas(np.linspace(0, 100, 60, endpoint=False))
+        e.run(60)
+        assert (e.costs()[1] <= t).all()
+        outs.append((P.copy(), t.copy()))
+        e.close()
+    assert (outs[0][0] == outs[1][0]).all()
+    assert len({tuple(r) for r in outs[0][0].tolist()}) > (3 if n < 20 else 10)
+    if method == 0 and n >= 48:
+        hp, ha, hb = random_trees(lb, ni, seeds, method=1, output_bits=ob)
+        e = Engine()
+        e.set_network(lb, ni, output_bits=ob).set_mode()
+        e.set_chains(hp, ha, hb, seeds)
+        assert np.log2(outs[0][1]).mean() < np.log2(e.costs()[0]).mean()
+        e.close()
+
+
 def test_device_generated_trees_reject_disconnected_network():
     from helpers import leaf_bits
     from tnco_b200.engine import Engine

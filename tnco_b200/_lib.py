@@ -64,6 +64,19 @@ SIGNATURES = {
     'tnb_eval_cost': (C.c_int, [C.c_void_p, C.c_int, i32p, i32p, i32p, u32p, f64p, f64p, f64p]),
     'tnb_flush_l2': (C.c_int, [C.c_void_p]),
     'tnb_get_config': (C.c_int, [C.c_void_p, intp, intp, intp, intp]),
+    'tnb_group_create': (C.c_int, [C.POINTER(C.c_void_p), intp, C.c_int]),
+    'tnb_group_destroy': (None, [C.c_void_p]),
+    'tnb_group_size': (C.c_int, [C.c_void_p]),
+    'tnb_group_engine': (C.c_void_p, [C.c_void_p, C.c_int]),
+    'tnb_group_last_error': (C.c_char_p, [C.c_void_p]),
+    'tnb_group_set_network': (C.c_int, [C.c_void_p, C.c_int, C.c_int, u32p, C.c_uint64, u64p, u32p]),
+    'tnb_group_set_mode': (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    'tnb_group_set_betas': (C.c_int, [C.c_void_p, f64p, C.c_int64]),
+    'tnb_group_generate_chains': (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_int]),
+    'tnb_group_run': (C.c_int, [C.c_void_p, C.c_int64, C.c_double, i64p]),
+    'tnb_group_get_costs': (C.c_int, [C.c_void_p, f64p, f64p]),
+    'tnb_group_get_counters': (C.c_int, [C.c_void_p, u64p, u64p, u64p]),
+    'tnb_group_get_best': (C.c_int, [C.c_void_p, f64p, i64p, i32p, i32p, i32p, u32p]),
 }
 
 _LIB = None

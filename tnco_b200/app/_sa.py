@@ -82,9 +82,15 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
                             sparse_bits=sp_bits, n_projs=n_projs)
             eng.set_mode(max_width=opt.max_width if finite else None, update_slices_every=update_slices, rng=rng_kind)
             t0 = time.perf_counter()
-            if opt.tree_builder == 'device' and not eng.hyper:
-                eng.generate_chains(my_seeds, chain_id0=lo, method=method)
-            else:  # host C++ threads; the only builder for networks with hyper-indices
+            built = False
+            if opt.tree_builder == 'device':
+                try:
+                    eng.generate_chains(my_seeds, chain_id0=lo, method=method)
+                    built = True
+                except ValueError as ex:   # (hyper-index networks with very few indices per tensor)
+                    if 'not supported' not in str(ex):
+                        raise
+            if not built:  # host C++ threads
                 P, A, B = random_trees(lb, len(inds), my_seeds, method=method, output_bits=out_bits)
                 eng.set_chains(P, A, B, my_seeds, chain_id0=lo)
             stats['tree_gen_s'] += time.perf_counter() - t0

@@ -841,9 +841,9 @@ int tnb_generate_chains(tnb_engine* e, int n_chains, const uint64_t* seeds, uint
   if (e->n == 0) return e->fail("tnb_generate_chains: call tnb_set_network first"), -1;
   if (n_chains < 1 || !seeds || (method != TNB_TREES_GREEDY && method != TNB_TREES_RANDOM))
     return e->fail("tnb_generate_chains: invalid arguments"), -1;
-  if (e->hyper)
-    return e->fail("tnb_generate_chains: device tree construction is not supported for hyper-index networks "
-                   "(use tnb_random_trees_out + tnb_set_chains)"), -2;
+  if (e->hyper && e->n > 4 * e->Ws * 32)
+    return e->fail("tnb_generate_chains: device tree construction is not supported for hyper-index networks with more "
+                   "than 128 tensors per 32 indices (use tnb_random_trees_out + tnb_set_chains)"), -2;
   ChainSet& cs = e->cs;
   cs.release(e->rt);
   e->initialized = false;
@@ -1255,6 +1255,174 @@ int tnb_get_config(tnb_engine* e, int* tile, int* words_per_lane, int* layout, i
   }
   if (state_bytes_per_chain)
     *state_bytes_per_chain = int(size_t(e->n_int) * size_t(e->stride) + size_t(e->Npad) * 2);
+  return 0;
+}
+
+// ============================================================================================ device groups
+// Several GPUs of one box behind one handle, for hosts that are not Python (the Python layer runs one process per
+// GPU instead, tnco_b200/dist.py).  Chains are sharded contiguously (chain i -> device floor(i*G/n)),
+// seeds and Philox counters use GLOBAL chain ids, so results do not depend on G.  Every fan-out call runs one host
+// thread per device.  The exchange step (minimum over devices + the winner's tree) happens on the host: inside one
+// process the per-device minima are G doubles that tnb_get_costs has already brought back, so there is nothing for
+// NCCL to do here; across processes it is NCCL (dist.py).
+}  // extern "C"
+
+#include <thread>
+
+struct tnb_group {
+  std::vector<tnb_engine*> eng;
+  std::vector<int> lo, hi;  // chain range of every device
+  int n_chains = 0;
+  std::string err;
+};
+
+namespace tnb {
+template <class F>
+static int group_fan(tnb_group* g, F f) {
+  const size_t G = g->eng.size();
+  std::vector<int> rc(G, 0);
+  std::vector<std::thread> th;
+  for (size_t k = 0; k < G; ++k)
+    th.emplace_back([&, k] {
+#if !defined(TNB_EMU)
+      cudaSetDevice(g->eng[k]->rt.device);
+#endif
+      rc[k] = f(int(k), g->eng[k]);
+    });
+  for (auto& t : th) t.join();
+  for (size_t k = 0; k < G; ++k)
+    if (rc[k] != 0) {
+      g->err = "device " + std::to_string(k) + ": " + g->eng[k]->err;
+      return rc[k];
+    }
+  return 0;
+}
+}  // namespace tnb
+
+extern "C" {
+
+int tnb_group_create(tnb_group** out, const int* devices, int n_dev) {
+  if (!out || !devices || n_dev < 1) { set_global_error("tnb_group_create: invalid arguments"); return -1; }
+  *out = nullptr;
+  tnb_group* g = new tnb_group();
+  for (int k = 0; k < n_dev; ++k) {
+    tnb_engine* e = nullptr;
+    const int rc = tnb_create(&e, devices[k]);
+    if (rc != 0) {
+      for (tnb_engine* x : g->eng) tnb_destroy(x);
+      delete g;
+      return rc;  // message in tnb_last_error(NULL)
+    }
+    g->eng.push_back(e);
+  }
+  *out = g;
+  return 0;
+}
+
+void tnb_group_destroy(tnb_group* g) {
+  if (!g) return;
+  for (tnb_engine* e : g->eng) {
+#if !defined(TNB_EMU)
+    cudaSetDevice(e->rt.device);
+#endif
+    tnb_destroy(e);
+  }
+  delete g;
+}
+
+int tnb_group_size(const tnb_group* g) { return g ? int(g->eng.size()) : 0; }
+tnb_engine* tnb_group_engine(tnb_group* g, int k) { return g && k >= 0 && k < int(g->eng.size()) ? g->eng[size_t(k)] : nullptr; }
+const char* tnb_group_last_error(const tnb_group* g) { return g ? g->err.c_str() : global_error(); }
+
+int tnb_group_set_network(tnb_group* g, int n_leaves, int n_inds, const uint32_t* leaf_bits, uint64_t dim,
+                          const uint64_t* dims, const uint32_t* output_bits) {
+  if (!g) return -1;
+  return group_fan(g, [&](int, tnb_engine* e) {
+    const int rc = tnb_set_network(e, n_leaves, n_inds, leaf_bits, dim, dims);
+    return rc != 0 || !output_bits ? rc : tnb_set_output_inds(e, output_bits);
+  });
+}
+
+int tnb_group_set_mode(tnb_group* g, double max_width, int update_slices_every, int disable_shared_inds, int prob_kind,
+                       int rng_kind, int layout) {
+  if (!g) return -1;
+  return group_fan(g, [&](int, tnb_engine* e) {
+    return tnb_set_mode(e, max_width, update_slices_every, disable_shared_inds, prob_kind, rng_kind, layout);
+  });
+}
+
+int tnb_group_set_betas(tnb_group* g, const double* betas, int64_t n) {
+  if (!g) return -1;
+  return group_fan(g, [&](int, tnb_engine* e) { return tnb_set_betas(e, betas, n); });
+}
+
+int tnb_group_generate_chains(tnb_group* g, int n_chains, const uint64_t* seeds, int method) {
+  if (!g) return -1;
+  const int G = int(g->eng.size());
+  if (n_chains < G || !seeds) { g->err = "tnb_group_generate_chains: need at least one chain per device"; return -1; }
+  g->lo.assign(size_t(G), 0);
+  g->hi.assign(size_t(G), 0);
+  for (int k = 0; k < G; ++k) {
+    g->lo[size_t(k)] = int((long long)n_chains * k / G);
+    g->hi[size_t(k)] = int((long long)n_chains * (k + 1) / G);
+  }
+  g->n_chains = n_chains;
+  return group_fan(g, [&](int k, tnb_engine* e) {
+    const int lo = g->lo[size_t(k)], hi = g->hi[size_t(k)];
+    return tnb_generate_chains(e, hi - lo, seeds + lo, uint64_t(lo), method);
+  });
+}
+
+int tnb_group_run(tnb_group* g, int64_t until_sweep, double timeout_s, int64_t* reached) {
+  if (!g) return -1;
+  std::vector<int64_t> r(g->eng.size(), 0);
+  const int rc = group_fan(g, [&](int k, tnb_engine* e) { return tnb_run_timed(e, until_sweep, timeout_s, &r[size_t(k)]); });
+  if (reached) *reached = *std::min_element(r.begin(), r.end());
+  return rc;
+}
+
+int tnb_group_get_costs(tnb_group* g, double* total, double* min_total) {
+  if (!g) return -1;
+  return group_fan(g, [&](int k, tnb_engine* e) {
+    const int lo = g->lo[size_t(k)];
+    return tnb_get_costs(e, total ? total + lo : nullptr, min_total ? min_total + lo : nullptr);
+  });
+}
+
+int tnb_group_get_counters(tnb_group* g, uint64_t* proposals, uint64_t* accepts, uint64_t* sweeps) {
+  if (!g) return -1;
+  const size_t G = g->eng.size();
+  std::vector<uint64_t> p(G, 0), a(G, 0), s(G, 0);
+  const int rc = group_fan(g, [&](int k, tnb_engine* e) { return tnb_get_counters(e, &p[size_t(k)], &a[size_t(k)], &s[size_t(k)]); });
+  uint64_t sp = 0, sa = 0, ss = 0;
+  for (size_t k = 0; k < G; ++k) { sp += p[k]; sa += a[k]; ss += s[k]; }
+  if (proposals) *proposals = sp;
+  if (accepts) *accepts = sa;
+  if (sweeps) *sweeps = ss;
+  return rc;
+}
+
+int tnb_group_get_best(tnb_group* g, double* cost, int64_t* chain, int32_t* parent, int32_t* child0, int32_t* child1,
+                       uint32_t* slices) {
+  if (!g || g->n_chains == 0) return -1;
+  std::vector<double> m(size_t(g->n_chains));
+  int rc = tnb_group_get_costs(g, nullptr, m.data());
+  if (rc != 0) return rc;
+  // strict minimum, ties to the smaller global chain id: the packed-key order of the multi-process exchange
+  int best = 0;
+  for (int i = 1; i < g->n_chains; ++i)
+    if (m[size_t(i)] < m[size_t(best)]) best = i;
+  int k = 0;
+  while (!(g->lo[size_t(k)] <= best && best < g->hi[size_t(k)])) ++k;
+  tnb_engine* e = g->eng[size_t(k)];
+#if !defined(TNB_EMU)
+  cudaSetDevice(e->rt.device);
+#endif
+  const int local = best - g->lo[size_t(k)];
+  if (parent && child0 && child1 && (rc = tnb_get_trees(e, 1, local, 1, parent, child0, child1)) != 0) { g->err = e->err; return rc; }
+  if (slices && e->finite && (rc = tnb_get_slices(e, 1, local, 1, slices)) != 0) { g->err = e->err; return rc; }
+  if (cost) *cost = m[size_t(best)];
+  if (chain) *chain = best;
   return 0;
 }
 

@@ -1251,8 +1251,130 @@ TNB_D void store_slices(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL])
 // (index set = XOR), and re-points the owners of the surviving indices.  GREEDY scores an edge like opt_einsum's
 // greedy, size(out) - size(a) - size(b), ties broken by a per-(seed, step, edge) hash; RANDOM uses the hash only.
 // Every merge is along a shared index, so check_shared_inds holds by construction.
+// The same for networks WITH hyper-indices (an index on 3+ tensors, or on 2 and open): there is no "edge = index with
+// two owners" any more, so every step scores all pairs of live clusters that share an index (strided over the lanes;
+// O(n^2 W / TILE) per step -- these networks are small), with the index set of a contraction given by the hyper-count
+// rule of tnco/ctree.py:169-189: a shared index survives while other tensors (or the output) still hold it.
+template <int TILE, int WPL>
+TNB_D void chain_treegen_hyper(const Params& P, int chain) {
+  ChainView<TILE, WPL> c(P, chain);
+  const Tile<TILE>& t = c.t;
+  const int n = P.n, W = P.W;
+  uint16_t* cnt = P.nbig + size_t(chain) * P.Ws * 32;  // remaining hyper count of every index
+  int16_t* kpop = P.kpop + size_t(chain) * P.Npad;
+  int16_t* live = reinterpret_cast<int16_t*>(P.escore + size_t(chain) * P.Ws * 32);  // live clusters (4*Ws*32 slots)
+  const unsigned long long seed = P.seeds[chain];
+  const uint32_t s0 = mix32(uint32_t(seed) ^ 0x9e3779b9u), s1 = mix32(uint32_t(seed >> 32) + 0x7f4a7c15u);
+#pragma unroll
+  for (int k = 0; k < WPL; ++k) {
+    const int w = t.tl + k * TILE;
+    if (w < W)
+      for (int b = 0; b < 32; ++b) cnt[w * 32 + b] = P.hcount0[w * 32 + b];
+  }
+  for (int x = t.tl; x < P.N; x += TILE) {
+    int k = 0;
+    if (x < n)
+      for (int w = 0; w < W; ++w) k += popc32(P.leaf_bits[size_t(x) * P.Ws + w]);
+    kpop[x] = int16_t(k);
+    c.par[x] = int16_t(-1);
+    if (x < n) live[x] = int16_t(x);
+  }
+  t.sync();
+  auto row = [&](int x) -> const uint32_t* {
+    return x < n ? P.leaf_bits + size_t(x) * P.Ws
+                 : reinterpret_cast<const uint32_t*>(c.rec_lane - 4 * t.tl + unsigned(x) * c.bstride);
+  };
+  auto pow2 = [](int k) { return bits_to_f64((unsigned long long)(1023 + (k > 1000 ? 1000 : k)) << 52); };
+  int nl = n;
+  for (int step = 0; step < n - 1; ++step) {
+    const int z = n + step;
+    double best = 1.0e308;
+    uint32_t best_tie = 0xffffffffu;
+    int best_i = -1, best_j = -1;
+    const uint32_t hs = mix32(s0 + uint32_t(step) * 0x632be5abu);
+    for (int i = 0; i + 1 < nl; ++i) {
+      const int a = live[i];
+      const uint32_t* ra = row(a);
+      for (int j = i + 1 + t.tl; j < nl; j += TILE) {
+        const int b = live[j];
+        const uint32_t* rb = row(b);
+        int ko = 0;
+        bool shared = false;
+        for (int w = 0; w < W; ++w) {
+          const uint32_t xa = ra[w], xb = rb[w];
+          ko += popc32(xa ^ xb);
+          uint32_t v = xa & xb;
+          shared |= v != 0u;
+          while (v) {  // a shared index stays on the result while somebody else still holds it
+            ko += int(cnt[w * 32 + ctz32(v)]) - 1 > 0 ? 1 : 0;
+            v &= v - 1;
+          }
+        }
+        if (!shared) continue;
+        const double sc = P.tree_method != 0 ? 0.0 : pow2(ko) - pow2(kpop[a]) - pow2(kpop[b]);
+        const uint32_t tie = mix32(hs ^ (uint32_t(a) * 0x9e3779b1u) ^ (uint32_t(b) * 0x85ebca77u) ^ s1);
+        if (sc < best || (sc == best && tie < best_tie)) {
+          best = sc;
+          best_tie = tie;
+          best_i = i;
+          best_j = j;
+        }
+      }
+    }
+#if !defined(TNB_EMU)
+#pragma unroll
+    for (int d = TILE / 2; d > 0; d >>= 1) {
+      const unsigned m = TILE == 32 ? 0xffffffffu : t.mask;
+      const double os = __shfl_xor_sync(m, best, d, TILE);
+      const uint32_t ot = __shfl_xor_sync(m, best_tie, d, TILE);
+      const int oi = __shfl_xor_sync(m, best_i, d, TILE), oj = __shfl_xor_sync(m, best_j, d, TILE);
+      const bool take = oi >= 0 && (best_i < 0 || os < best || (os == best && (ot < best_tie ||
+                        (ot == best_tie && (oi < best_i || (oi == best_i && oj < best_j))))));
+      if (take) { best = os; best_tie = ot; best_i = oi; best_j = oj; }
+    }
+#endif
+    if (best_i < 0) {  // no two live clusters share an index: the network is disconnected
+      P.tree_fail[chain] = 1;
+      return;
+    }
+    int a = live[best_i], b = live[best_j];
+    if (best_tie & 1u) { const int tmp = a; a = b; b = tmp; }
+    uint32_t xa[WPL], xb[WPL], xz[WPL];
+    c.load_bits(a, xa);
+    c.load_bits(b, xb);
+    uint32_t k = 0;
+#pragma unroll
+    for (int q = 0; q < WPL; ++q) {
+      const int w = t.tl + q * TILE;
+      uint32_t keep = 0u, v = xa[q] & xb[q];
+      while (v) {
+        const int bit = ctz32(v);
+        v &= v - 1;
+        if (--cnt[w * 32 + bit] > 0) keep |= 1u << bit;
+      }
+      xz[q] = (xa[q] ^ xb[q]) | keep;
+      k += uint32_t(popc32(xz[q]));
+    }
+    c.store_bits(z, xz);
+    k = t.sum(k);
+    t.sync();  // everybody has read live[best_i], live[best_j]
+    kpop[z] = int16_t(k);
+    c.par[a] = int16_t(z);
+    c.par[b] = int16_t(z);
+    c.ch(z) = uint32_t(a) | (uint32_t(b) << 16);
+    live[best_i] = int16_t(z);  // (best_i < best_j <= nl - 1)
+    live[best_j] = live[nl - 1];
+    --nl;
+    t.sync();
+  }
+}
+
 template <int TILE, int WPL>
 TNB_D void chain_treegen(const Params& P, int chain) {
+  if (P.hyper) {
+    chain_treegen_hyper<TILE, WPL>(P, chain);
+    return;
+  }
   ChainView<TILE, WPL> c(P, chain);
   const Tile<TILE>& t = c.t;
   const int n = P.n, N = P.N, W = P.W;
