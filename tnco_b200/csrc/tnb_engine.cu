@@ -128,8 +128,8 @@ struct ChainSet {
   long long* sweep_idx = nullptr;
   int* overrun = nullptr;
   uint16_t* nbig = nullptr;
-  int16_t *posbuf = nullptr, *kpop = nullptr, *kw = nullptr, *sz = nullptr, *word = nullptr;
-  uint32_t* wkey = nullptr;
+  int16_t *posbuf = nullptr, *kpop = nullptr, *word = nullptr;
+  uint32_t *wkey = nullptr, *kwsz = nullptr;
   int* tree_fail = nullptr;
   double* escore = nullptr;
   uint32_t* stream = nullptr;
@@ -142,7 +142,7 @@ struct ChainSet {
 
   void release(Rt& rt) {
     void* ps[] = {par, bpar, rec, bits_alloc, bch, pc, slices, bslices, cp2, total, min_total, out_seq, out_maxw, seeds,
-                  rng_ctr, n_prop, n_acc, n_wrej, cursor, sweep_idx, overrun, nbig, posbuf, kpop, tree_fail, escore, stream, kw, sz, word, wkey,
+                  rng_ctr, n_prop, n_acc, n_wrej, cursor, sweep_idx, overrun, nbig, posbuf, kpop, tree_fail, escore, stream, kwsz, word, wkey,
                   trace, trace_n, trace_S, trace_sn};
     for (void* p : ps) rt.free_(p);
     *this = ChainSet();
@@ -288,7 +288,7 @@ static void fill_params(const tnb_engine* e, const ChainSet& cs, Params& P) {
   P.betas = e->d_betas; P.inv_betas = e->d_inv_betas; P.n_betas = e->n_betas; P.until = 0;
   P.nbig = cs.nbig; P.posbuf = cs.posbuf; P.cp2 = cs.cp2;
   P.slices_given = 0; P.out_seq = cs.out_seq; P.out_maxw = cs.out_maxw;
-  P.kw = cs.kw; P.sz = cs.sz; P.word = cs.word; P.wkey = cs.wkey;
+  P.kwsz = cs.kwsz; P.word = cs.word; P.wkey = cs.wkey;
   P.kthr = 0;
   if (e->finite)
     for (int k = 0; k <= e->n_inds; ++k)
@@ -345,7 +345,7 @@ static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_be
   // (uniform dimension 2 or power-of-two groups, no sparse indices); the table-cost kernels re-slice with the
   // reference's slicer verbatim
   if (ok && with_slicer && e->finite && e->pow2_costs())
-    ok = alloc_to(rt, cs.kw, nc * e->Npad) && alloc_to(rt, cs.sz, nc * e->Npad) &&
+    ok = alloc_to(rt, cs.kwsz, nc * e->Npad) &&
          alloc_to(rt, cs.word, nc * e->Npad) && alloc_to(rt, cs.wkey, nc * e->Npad);
   if (!ok) return e->rtfail();
   return true;

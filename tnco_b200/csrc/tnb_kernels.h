@@ -102,8 +102,8 @@ struct Params {
   int16_t* posbuf;  // [n_chains][Ws*32]
   dbl2* cp2;        // [n_chains][n_int]
   // production re-slicer (finite width, Philox): per-node popcount / leaf count kept in step with the tree
-  int16_t* kw;      // [n_chains][Npad] popcount of every node's index set (unsliced width / log2 d)
-  int16_t* sz;      // [n_chains][Npad] leaves below every node
+  uint32_t* kwsz;   // [n_chains][Npad] per node: popcount of its index set (unsliced width / log2 d) in the low half,
+                    //                   leaves below it in the high half -- one word, one load / store for both
   uint32_t* wkey;   // [n_chains][Npad] scratch: (post-order rank << 16 | node) of the wide nodes
   int16_t* word;    // [n_chains][Npad] scratch: wide nodes, then wide nodes in post-order
   int kthr;         // largest popcount whose width still fits max_width
@@ -386,6 +386,17 @@ struct ChainView {
 #pragma unroll
       for (int k = 0; k < WPL; ++k) o[k] = lane_ok[k] ? src[k * TILE] : 0u;
     }
+  }
+  // L2 prefetch of a node's whole index set (first and last byte: a row may straddle two lines)
+  TNB_D TNB_INLINE void prefetch_row(int node) const {
+#if !defined(TNB_EMU)
+    const char* p = node < n ? reinterpret_cast<const char*>(leaf_lane - t.tl) + w64(node) * (4u * Ws)
+                             : rec_lane - 4 * t.tl + w64(node) * bstride;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 4 * (P.W - 1)));
+#else
+    (void)node;
+#endif
   }
   TNB_D TNB_INLINE void store_bits(int node, const uint32_t (&v)[WPL]) const {
     uint32_t* dst = reinterpret_cast<uint32_t*>(rec_lane + w64(node) * bstride);
@@ -873,8 +884,7 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, Rng& rng,
   const Params& P = c.P;
   const Tile<TILE>& t = c.t;
   constexpr int NB = 8;
-  const int16_t* kw = P.kw + size_t(c.chain) * P.Npad;
-  const int16_t* sz = P.sz + size_t(c.chain) * P.Npad;
+  const uint32_t* kwsz = P.kwsz + size_t(c.chain) * P.Npad;
   uint32_t* wkey = P.wkey + size_t(c.chain) * P.Npad;
   int16_t* word = P.word + size_t(c.chain) * P.Npad;
   uint32_t cnt[WPL][NB];
@@ -886,15 +896,27 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, Rng& rng,
   }
   // (1) wide nodes (leaves included, :41-47): list them and count, per index, how many contain it
   int nw = 0;
-  for (int base = 0; base < P.N; base += TILE) {
-    const int z = base + t.tl;
-    const bool wide = z < P.N && int(kw[z]) > P.kthr;
-    const uint32_t m = t.ballot(wide);
-    if (wide) word[nw + popc32(m & ((1u << t.tl) - 1u))] = int16_t(z);
-    nw += popc32(m);
+  for (int base = 0; base < P.N; base += 4 * TILE) {  // four independent loads in flight per round trip
+    int kv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int z = base + u * TILE + t.tl;
+      kv[u] = z < P.N ? int(kwsz[z] & 0xffffu) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool wide = kv[u] > P.kthr;
+      const uint32_t m = t.ballot(wide);
+      if (wide) word[nw + popc32(m & ((1u << t.tl) - 1u))] = int16_t(base + u * TILE + t.tl);
+      nw += popc32(m);
+    }
   }
   if (nw == 0) return;
   t.sync();
+  // The rows of the wide nodes are read twice below, one after the other (counting, then selection in post-order):
+  // ask for all of them now, one row per lane, so that the sequential passes find them in L2 instead of paying one
+  // HBM round trip per row.
+  for (int j = t.tl; j < nw; j += TILE) c.prefetch_row(word[j]);
   {
     uint32_t xn[WPL];
     c.load_bits(word[0], xn);
@@ -920,13 +942,13 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, Rng& rng,
   // (2) post-order rank of every wide node, one node per lane
   for (int j = t.tl; j < nw; j += TILE) {
     const int z = word[j];
-    uint32_t post = 2u * uint32_t(sz[z]) - 2u;
+    uint32_t post = 2u * (kwsz[z] >> 16) - 2u;
     int y = z;
     while (true) {
       const int p = c.par[y];
       if (p < 0) break;
       const int l = int(c.ch(p) & 0xffffu);
-      if (l != y) post += 2u * uint32_t(sz[l]) - 1u;
+      if (l != y) post += 2u * (kwsz[l] >> 16) - 1u;
       y = p;
     }
     wkey[j] = (post << 16) | uint32_t(z);
@@ -1115,7 +1137,7 @@ TNB_D TNB_NOINLINE int mark_slice_diff(const ChainView<TILE, WPL>& c, const uint
   // has the larger leaf count), and meet in the node that contracts idx; every node entered on the way has idx in
   // one of its children.  Only par[] and sz[] are read: small arrays that stay in L2 even when the index sets
   // live in HBM (testing the bit of idx in every node's index set cost one HBM round trip per step).
-  const int16_t* sz = P.sz + size_t(c.chain) * P.Npad;
+  const uint32_t* kwsz = P.kwsz + size_t(c.chain) * P.Npad;
   for (int j = t.tl; j < int(nd); j += TILE) {
     const int e = uint16_t(list[j]);
     const int idx = e & 0x7fff, sgn = (e & 0x8000) ? 1 : -1;
@@ -1139,11 +1161,11 @@ TNB_D TNB_NOINLINE int mark_slice_diff(const ChainView<TILE, WPL>& c, const uint
     while (a != b) {
       if (sa <= sb) {
         a = c.par[a];
-        sa = sz[a];
+        sa = int(kwsz[a] >> 16);
         if (a != b) mark(a);
       } else {
         b = c.par[b];
-        sb = sz[b];
+        sb = int(kwsz[b] >> 16);
         if (a != b) mark(b);
       }
     }
@@ -1183,20 +1205,19 @@ TNB_D double sum_shifted(const ChainView<TILE, WPL>& c, const int* dz, int shift
 template <int TILE, int WPL>
 TNB_D void build_kw_sz(const ChainView<TILE, WPL>& c) {
   const Params& P = c.P;
-  int16_t* kw = P.kw + size_t(c.chain) * P.Npad;
-  int16_t* sz = P.sz + size_t(c.chain) * P.Npad;
+  uint32_t* kwsz = P.kwsz + size_t(c.chain) * P.Npad;
   for (int z = c.po_first(); z >= 0; z = c.po_next(z)) {
     uint32_t x[WPL];
     c.load_bits(z, x);
     uint32_t k = 0;
 #pragma unroll
     for (int i = 0; i < WPL; ++i) k += uint32_t(popc32(x[i]));
-    kw[z] = int16_t(c.t.sum(k));
+    k = c.t.sum(k);
     if (z < P.n) {
-      sz[z] = 1;
+      kwsz[z] = k | (1u << 16);
     } else {
       const uint32_t w = c.ch(z);
-      sz[z] = int16_t(sz[w & 0xffffu] + sz[w >> 16]);
+      kwsz[z] = k | (((kwsz[w & 0xffffu] >> 16) + (kwsz[w >> 16] >> 16)) << 16);
     }
   }
 }
@@ -1525,7 +1546,7 @@ TNB_D void chain_init(const Params& P, int chain) {
       Rng rng;
       rng.load(P, chain);
       if constexpr (Rng::kFast) {
-        if (P.kw) {  // production: the same greedy rule through the fast slicer
+        if (P.kwsz) {  // production: the same greedy rule through the fast slicer
           build_kw_sz(c);
           get_slices_fast(c, rng, S);
         } else {
@@ -1546,7 +1567,7 @@ TNB_D void chain_init(const Params& P, int chain) {
   P.min_total[chain] = seq;  // get_cost(min_ctree) sums in traversal order (infinite_memory/utils.hpp:102-116)
   if (P.out_seq) P.out_seq[chain] = seq;
   if (P.out_maxw) P.out_maxw[chain] = maxw;
-  if (FINITE && P.kw && (!Rng::kFast || P.slices_given)) build_kw_sz(c);
+  if (FINITE && P.kwsz && (!Rng::kFast || P.slices_given)) build_kw_sz(c);
   if (P.bpar) snapshot_best(c, S, FINITE);
 }
 
@@ -1635,8 +1656,10 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
   // 2^popcount (DIM2): the table-cost kernels -- other dimensions, sparse indices -- re-slice with the reference's
   // slicer verbatim (get_slices_dev + a full cost pass), which knows every width model.
   constexpr bool FS = FINITE && Rng::kFast && DIM2;
-  int16_t* const kwp = FS ? P.kw + size_t(chain) * P.Npad : nullptr;
-  int16_t* const szp = FS ? P.sz + size_t(chain) * P.Npad : nullptr;
+  // popcount | leaf count << 16 of every node; the per-chain base is pinned like the others (re-derived from the
+  // kernel parameters it cost ten instructions per 2-byte access)
+  uint32_t* kws = FS ? P.kwsz + size_t(chain) * P.Npad : nullptr;
+  if constexpr (FS) keep_in_register(kws);
   int sz0 = 0, sz1 = 0, szC = 0;
   Rng rng;
   rng.load(P, chain);
@@ -1823,8 +1846,8 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
         pc1 = c.pc_of(p1);
       }
       if (FS) {
-        sz0 = szp[p0];
-        sz1 = szp[p1];
+        sz0 = int(kws[p0] >> 16);
+        sz1 = int(kws[p1] >> 16);
       }
       ccB = c.cc(B);
       if (HYPER) c.load_hyp(B, hB);
@@ -1841,7 +1864,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
           c.load_hyp(A, hA);
         }
         if (PC) pcC = c.pc_of(C);
-        if (FS) szC = szp[C];
+        if (FS) szC = int(kws[C] >> 16);
         ccA = c.cc(A);
         An = c.par[A];
         Ann = -1;
@@ -1882,7 +1905,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
         c.load_hyp(An, hAn);
       }
       if (PC) pcCn = c.pc_of(Cn);
-      if (FS) szCn = szp[Cn];
+      if (FS) szCn = int(kws[Cn] >> 16);
     }
     const bool bslot0 = (a0 == B);
     bool l0 = false, l1 = false;
@@ -1945,10 +1968,12 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
 #pragma unroll
         for (int k = 0; k < WPL; ++k) xs[k] = nb[k] & ~S[k];
         swB = c.template gwidth_model<true>(xs, SP);
-      } else {
+      } else if (!FS) {
         swB = sparse ? c.width_sp(int(ks), int(kss)) : c.width_of(int(ks));
       }
-      gate = swB <= P.max_width;
+      // (2^popcount kernels: width = log2(d) * popcount is monotone in the popcount, and kthr is the largest popcount
+      //  whose float32 width still fits -- the same decision without the fp64 product on the dependent path)
+      gate = FS ? int(ks) <= P.kthr : swB <= P.max_width;
       if (!gate) ++q_wrej;
     }
     bool acc = false;
@@ -2186,8 +2211,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
       }
       ++q_acc;
       if (FS) {
-        kwp[B] = int16_t(ku);
-        szp[B] = int16_t(szD + szC);
+        kws[B] = ku | (uint32_t(szD + szC) << 16);
       }
       {
         const int ti = C; C = E; E = ti;
