@@ -76,5 +76,7 @@ if __name__ == '__main__':
             probe('C3', 8192, 1000)
         if cfg == 'C4':
             probe('C4', 4096, 500, max_width=32)
+        if cfg.startswith('C4x'):   # C4 with another chain count, e.g. C4x3552
+            probe('C4', int(cfg[3:]), 500, max_width=32)
         if cfg == 'C5':
             probe('C5', 4096, 500)

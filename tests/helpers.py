@@ -231,3 +231,25 @@ def golden_sparse(g):
     for i in g['sparse_inds'].tolist():
         b[i >> 5] |= np.uint32(1 << (i & 31))
     return b, int(g['n_projs'])
+
+
+def py_merge_paths(n_tensors, paths):
+    """Checker for merge_contraction_paths: replay every component path on its own position list while keeping one
+    shared list of what is left in the merged network; a contraction's merged positions are where its two operands
+    sit in the shared list.  Trailing (0, 1) steps join the components."""
+    shared = [('t', k) for k in range(n_tensors)]
+    out = []
+    for c, path in enumerate(paths):
+        own = [('t', k) for k in range(n_tensors)]
+        for step, (x, y) in enumerate(path):
+            lo, hi = min(x, y), max(x, y)
+            b = own.pop(hi)
+            a = own.pop(lo)
+            new = ('c', c, step)
+            own.append(new)
+            ia, ib = shared.index(a), shared.index(b)
+            out.append((min(ia, ib), max(ia, ib)))
+            for k in sorted((ia, ib), reverse=True):
+                shared.pop(k)
+            shared.append(new)
+    return out + [(0, 1)] * (len(shared) - 1)

@@ -113,6 +113,7 @@ def test_tree_to_path_matches_reference_algorithm():
 
 
 def test_merge_paths_matches_reference_algorithm():
+    from helpers import py_merge_paths
     from tnco_b200.engine import merge_paths
     from tnco_b200.tn import merge_contraction_paths
     assert merge_contraction_paths(4, [[(0, 1)], [(2, 3)]]) == [(0, 1), (0, 1), (0, 1)]  # tn.py:357-360
@@ -137,7 +138,8 @@ def test_merge_paths_matches_reference_algorithm():
                 pos.append(new)
                 mine = [m for m in mine if m not in (x, y)] + [new]
             paths.append(path)
-        want = merge_contraction_paths(nt, paths)
+        want = py_merge_paths(nt, paths)
+        assert merge_contraction_paths(nt, paths) == want
         lens = [len(p) for p in paths]
         cat = np.array([[q for p in paths for q in p]], np.int32).reshape(1, sum(lens), 2)
         got = merge_paths(nt, lens, cat)

@@ -129,7 +129,7 @@ def load_tn(obj: Any, *, output_index_token: str = '*', sparse_index_token: str 
     >>> len(tn)
     3
     >>> load_tn([[2, 'i', 'j'], [2, 'j', 'k']], fuse=4, decompose_hyper_inds=False, seed=0).tags['fuse_path']
-    [(0, 1), (0, 1)]
+    [(1, 2), (0, 1)]
     """
     if isinstance(obj, TensorNetwork):
         fuse = options.pop('fuse', 4)

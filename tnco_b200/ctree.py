@@ -99,6 +99,7 @@ class ContractionTree:
             sets[z] = frozenset(iz)
         self._parent, self._c0, self._c1 = parent, c0, c1
         self._inds = tuple(sets)
+        self._leaves = tuple(tuple(v) for v in leaves)   # ordered leaf index tuples: they fix the index bit positions
         self._inds_order = _unique(x for xs in ([tuple(v) for v in leaves] + [tuple(s) for s in sets[n:]]) for x in xs)
         try:
             self._dims = {x: int(dims[x]) for x in self._inds_order}

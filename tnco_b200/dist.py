@@ -87,6 +87,7 @@ def global_best(local_cost, local_chain_id, local_payload, payload_len=None):
     chain = best_key & ((1 << KEY_ID_BITS) - 1)
     n = int(payload_len if payload_len is not None else len(payload))
     owner = owner_of_chain(chain)
+    assert 0 <= owner < size, 'no rank owns the winning chain'  
     msg = np.zeros(n + 2, np.int32)
     if rank == owner:
         assert mine == best_key, 'the winning key must come from the rank that owns the chain'

@@ -95,8 +95,10 @@ class Optimizer:
     def _tree(self, best):
         p, a, b = self._e.trees(best=best, chain0=0, n=1)
         c = self._ctree0
-        return ContractionTree.from_arrays(p[0], a[0], b[0], [c.inds[t] for t in range(c.n_leaves)], c.dims,
-                                           output_inds=c.output_inds())
+        # (the ORDERED leaf tuples: rebuilding from the frozensets would let the index bit positions -- which feed the
+        #  slicer's tie-breaks -- depend on PYTHONHASHSEED for string indices, and a pickled object would resume
+        #  differently from the uninterrupted run)
+        return ContractionTree.from_arrays(p[0], a[0], b[0], list(c._leaves), c.dims, output_inds=c.output_inds())
 
     ctree = property(lambda s: s._tree(False))
     min_ctree = property(lambda s: s._tree(True))

@@ -186,31 +186,20 @@ def get_connected_components(ts_inds: Iterable[Iterable]) -> list[tuple[int, ...
 
 
 def merge_contraction_paths(n_tensors: int, paths, *, autocomplete: bool = True):
-    """Merge per-component linear paths (each expressed over all n_tensors tensors) into one path.
+    """Merge per-component linear paths (each expressed over all n_tensors tensors) into one path
+    (tnco/utils/tn.py:334-401).  Done by the C++ helper ``tnb_merge_paths`` (Fenwick trees instead of list searches).
 
     >>> merge_contraction_paths(4, [[(0, 1)], [(2, 3)]])
     [(0, 1), (0, 1), (0, 1)]
     """
-    merged_pos = list(range(n_tensors))
-    merged = []
-    for i, path in enumerate(paths):
-        pos = list(range(n_tensors))
-        for x, y in path:
-            x, y = sorted((x, y))
-            y = pos.pop(y)
-            x = pos.pop(x)
-            pos.append((i, len(pos)))
-            try:
-                mx, my = sorted((merged_pos.index(x), merged_pos.index(y)))
-            except ValueError as e:
-                raise ValueError("'paths' are not valid or not disconnected.") from e
-            merged.append((mx, my))
-            merged_pos.pop(my)
-            merged_pos.pop(mx)
-            merged_pos.append(pos[-1])
-    if autocomplete:
-        merged += [(0, 1)] * (len(merged_pos) - 1)
-    return merged
+    import numpy as np
+
+    from .engine import merge_paths
+    paths = [[tuple(q) for q in p] for p in paths]
+    lens = [len(p) for p in paths]
+    cat = np.array([q for p in paths for q in p], np.int32).reshape(1, sum(lens), 2)
+    out = merge_paths(n_tensors, lens, cat)[0]
+    return [tuple(x) for x in out[:len(out) if autocomplete else sum(lens)].tolist()]
 
 
 def _unique(xs):
@@ -310,8 +299,9 @@ def contract(path, ts_inds, output_inds=None, *, dims=None):
     ``(ts_inds, output_inds)`` after the path.  Result indices are ordered as ``tensordot`` orders them
     (tnco/utils/tensor.py:229-243): hyper-indices first, then x's own, then y's own.
 
-    >>> contract([(0, 1)], [['i', 'j'], ['j', 'k']], dims=2)
-    ([('i', 'k')], frozenset({'i', 'k'}))
+    >>> ts, out = contract([(0, 1)], [['i', 'j'], ['j', 'k']], dims=2)
+    >>> ts, sorted(out)
+    ([('i', 'k')], ['i', 'k'])
     """
     if dims is None:
         raise ValueError("Either 'dims' or 'arrays' must be provided.")
