@@ -28,9 +28,8 @@ def main(path):
     for name, c in out.items():
         k = c['counters']
         rd, wr = k.get('DRAM read', 0.0), k.get('DRAM write', 0.0)
-        scale = 1e9 if rd < 1e3 else 1e6 if rd < 1e6 else 1.0   # ncu prints GB / MB / bytes depending on the size
-        c['dram_bytes_per_launch'] = (rd + wr) * scale
-        c['dram_bytes_per_proposal'] = (rd + wr) * scale / c['proposals_per_launch']
+        c['dram_bytes_per_launch'] = rd + wr   # (scripts/ncu_summary.py prints bytes)
+        c['dram_bytes_per_proposal'] = (rd + wr) / c['proposals_per_launch']
         c['warp_instructions_per_proposal'] = k.get('warp instructions', 0.0) / c['proposals_per_launch']
         c['source'] = 'ncu --set full --clock-control none of the timed launch of `bench.py --workload %s --steps 1 --warmup 3`' % name
     print(json.dumps(out, indent=1))

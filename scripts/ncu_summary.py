@@ -8,8 +8,16 @@ import sys
 def raw(path):
     out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr, vals = rows[0], rows[2] if len(rows) > 2 else rows[1]
-    return dict(zip(hdr, vals))
+    hdr, units, vals = rows[0], rows[1], rows[2] if len(rows) > 2 else rows[1]
+    d = dict(zip(hdr, vals))
+    scale = {'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12, 'usecond': 1e3, 'msecond': 1e6, 'second': 1e9}
+    for k, u in zip(hdr, units):   # bytes and nanoseconds, whatever unit ncu chose to print
+        if u in scale and k in d:
+            try:
+                d[k] = repr(float(d[k].replace(',', '')) * scale[u])
+            except ValueError:
+                pass
+    return d
 
 
 def f(d, k):
