@@ -5,7 +5,7 @@ import subprocess
 import sys
 
 
-def main(path, per=None, top=40):
+def main(path, per=None, top=40, by=0):
     out = subprocess.run(['ncu', '-i', path, '--page', 'source', '--csv', '--print-source', 'cuda,sass'],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -30,10 +30,11 @@ def main(path, per=None, top=40):
     tot = sum(v for v, _ in agg.values()) or 1
     tots = sum(s for _, s in agg.values()) or 1
     print(f'total warp instructions {tot}, samples {tots}')
-    for (f, ln, src), (v, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    for (f, ln, src), (v, s) in sorted(agg.items(), key=lambda kv: -kv[1][by])[:top]:
         extra = f'{v / per:7.1f}/unit ' if per else ''
         print(f'{100 * v / tot:5.1f}% instr {extra}{100 * s / tots:5.1f}% stall  {f}:{ln:<4d} {src}')
 
 
 if __name__ == '__main__':
-    main(sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else None)
+    main(sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else None, int(sys.argv[3]) if len(sys.argv) > 3 else 40,
+         1 if len(sys.argv) > 4 and sys.argv[4] == 'stall' else 0)

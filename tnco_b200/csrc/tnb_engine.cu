@@ -241,9 +241,11 @@ namespace tnb {
 // chosen per batch: sharing a warp between chains saves instructions but costs divergence and parallelism, and the
 // measurements reduce to one rule -- take the widest tile whose batch still fits one wave of
 // resident warps (28 per SM); if even the narrowest tile does not fit, take the narrowest.
-static int pick_tile(int W, int& wpl, bool hyper, long long n_chains, int n_sms) {
+static int pick_tile(int W, int n_inds, int& wpl, bool hyper, long long n_chains, int n_sms) {
   wpl = 1;
   int tile = 32;
+  // (one-word-per-lane kernels pack popcounts into 10-bit fields: 1024 indices exactly take two words per lane)
+  if (n_inds >= 1024 && W <= 32) { wpl = 2; return 32; }
   if (hyper || W > 32) { wpl = (W + 31) / 32; return 32; }
   const int narrowest = W <= 4 ? 4 : W <= 8 ? 8 : W <= 16 ? 16 : 32;
   const long long capacity = 28ll * (n_sms > 0 ? n_sms : 148);
@@ -272,6 +274,8 @@ static void fill_params(const tnb_engine* e, const ChainSet& cs, Params& P) {
   P.skip = e->d_skip;
   P.sparse = e->d_sparse;  // costs of a network with sparse indices come from the table kernels
   P.dim2 = e->pow2_costs();
+  // 2^popcount production kernels keep the high word of every contraction cost at header +4 (Params::cost_hi)
+  P.cost_hi = e->rng_kind == TNB_RNG_PHILOX && e->pow2_costs();
   P.gdims = e->generic ? e->d_gdims : nullptr;
   P.glog2 = e->generic ? e->d_glog2 : nullptr;
   P.n_projs = double(e->n_projs);
@@ -315,7 +319,7 @@ static bool alloc_to(Rt& rt, T*& p, size_t count) {
 
 static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_best, bool with_slicer) {
   Rt& rt = e->rt;
-  if (&cs == &e->cs) e->tile = pick_tile(e->W, e->wpl, e->hyper, n_chains, rt.n_sms);
+  if (&cs == &e->cs) e->tile = pick_tile(e->W, e->n_inds, e->wpl, e->hyper, n_chains, rt.n_sms);
   cs.n_chains = n_chains;
   const size_t nc = size_t(n_chains), ni = size_t(std::max(e->n_int, 1));
   // layout: interleaved node records while the whole batch fits L2, split beyond
@@ -571,7 +575,7 @@ static bool refresh_hyper(tnb_engine* e) {
     hc[size_t(i)] = uint16_t(c < 0 ? 0 : c);
     e->hyper |= c >= 2;
   }
-  e->tile = pick_tile(e->W, e->wpl, e->hyper, 0, e->rt.n_sms);
+  e->tile = pick_tile(e->W, e->n_inds, e->wpl, e->hyper, 0, e->rt.n_sms);
   e->stride = 16 + 4 * e->Ws * (e->hyper ? 2 : 1);
   if (!e->rt.h2d(e->d_hcount0, hc.data(), hc.size() * sizeof(uint16_t)) || !e->rt.sync()) return e->rtfail();
   return true;
@@ -956,7 +960,17 @@ int tnb_get_node_costs(tnb_engine* e, int chain, double* ccost) {
   const size_t ni = size_t(e->n_int), hs = size_t(e->cs.hstride);
   std::vector<char> hb(ni * hs);
   if (!e->rt.d2h(hb.data(), e->cs.rec + size_t(chain) * ni * hs, (ni - 1) * hs + 16)) return e->rtfail(), -3;
-  for (size_t z = 0; z < ni; ++z) std::memcpy(&ccost[size_t(e->n) + z], &hb[z * hs + 8], sizeof(double));
+  const bool hi_only = e->rng_kind == TNB_RNG_PHILOX && e->pow2_costs();  // Params::cost_hi
+  for (size_t z = 0; z < ni; ++z) {
+    if (hi_only) {
+      uint32_t hi;
+      std::memcpy(&hi, &hb[z * hs + 4], 4);
+      const unsigned long long b = (unsigned long long)hi << 32;
+      std::memcpy(&ccost[size_t(e->n) + z], &b, sizeof(double));
+    } else {
+      std::memcpy(&ccost[size_t(e->n) + z], &hb[z * hs + 8], sizeof(double));
+    }
+  }
   return 0;
 }
 
@@ -998,6 +1012,7 @@ int tnb_run(tnb_engine* e, int64_t until_sweep) {
   if (!e->d_betas) return e->fail("tnb_run: call tnb_set_betas first"), -1;
   if (!ensure_init(e)) return -2;
   if (!mode_ok(e)) return -1;  // tnb_set_prob may have changed the rule since the chains were built
+  if (until_sweep >= (int64_t(1) << 31)) return e->fail("tnb_run: until_sweep must be below 2^31"), -1;
   Params P;
   for (int guard = 0;; ++guard) {
     fill_params(e, e->cs, P);

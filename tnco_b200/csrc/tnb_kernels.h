@@ -11,6 +11,8 @@
 // reads back its own stores.  Cross-lane reads exist only in the slicer scratch and are fenced by
 // Tile::sync().  Networks must be free of hyper-indices, hence inds(z) = inds(c0) ^ inds(c1).
 #pragma once
+#include <type_traits>
+
 #include "tnb_simt.h"
 
 namespace tnb {
@@ -66,7 +68,7 @@ struct Params {
   int hyp_off;              // byte offset of the hyper row from the node's index-set row (= 4*Ws)
   const uint16_t* hcount0;  // [Ws*32] initial hyper count of every index: holders - 1 (+1 if output), ctree.py:138-156
   int16_t* par;    // [n_chains][Npad]
-  // Per internal node a 16-byte header {+0 u32 child0 | child1 << 16, +4 unused, +8 f64 contraction cost} and
+  // Per internal node a 16-byte header {+0 u32 child0 | child1 << 16, +4 see cost_hi, +8 f64 contraction cost} and
   // an index set u32[Ws].  INTERLEAVED layout (state fits L2): one record {header, index set} of
   // stride = 16 + 4*Ws bytes per node, so everything the walk needs of a node sits in 1-2 adjacent sectors.
   // SPLIT layout (HBM-resident state): headers [n_int] x 16 B and index sets [n_int] x 4*Ws B apart, so the
@@ -74,6 +76,10 @@ struct Params {
   char* hdr;       // header of node i of chain c at hdr + (c*n_int + i) * hstride
   char* bitsb;     // index set                 at bitsb + (c*n_int + i) * bstride
   int hstride, bstride;
+  // 2^popcount kernels (DIM2; production RNG only): a contraction cost is an exact power of two (or +inf), so only the
+  // HIGH word of the double is kept -- at header +4, right behind the children word, and +8 is unused: the walk
+  // reads and writes a node as ONE 8-byte access and carries one register per cost instead of two.
+  int cost_hi;
   double* pc;      // [n_chains][n_int]   partial costs (kept by the parity modes only)
   int16_t* bpar;   // best tree (reference min_ctree)
   uint32_t* bch;
@@ -166,73 +172,124 @@ TNB_D TNB_INLINE unsigned lane_in_tile_here(int tl) {
 template <int TILE>
 struct RngPhilox {
   static constexpr bool kFast = true;  // log-domain fp32 acceptance test (see chain_sweeps)
-  uint32_t k0, k1, g0, g1;
-  // Lane tl holds the vector of event base + tl; pos = events consumed since `base`.  pos == TILE means "the held
-  // vectors are used up (or were never generated)": one compare per event decides whether to refill.
-  unsigned long long base;
-  uint32_t pos;
-  uint32_t r0, r1, r2;
-  uint32_t rc;   // this lane's vector as the sweep's levels use it: float bits of -log2(u), D/E coin in the last bit
+  // Registers held across the sweep loop: ONE cursor and the current event's word.  The key (run seed), the global
+  // chain id and the 64-bit event index of the held batch are only needed when a batch is generated (once per TILE
+  // events), so they stay in memory / are re-derived there; the batch itself (per vector: word 0 for a leaf draw,
+  // and the level word) sits in 256 bytes of shared memory per warp, where an event is ONE broadcast load at the
+  // cursor -- against a shuffle out of two loop-carried registers (which the finite-width kernel, at its register
+  // cap, spilled: it read the level word back from local memory at every level) plus the convergence check the
+  // compiler brackets every shuffle with.
+  // Vector k of the batch belongs to event base + k, base = P.rng_ctr[chain] while a generator is live.  `at` is the
+  // shared-memory byte address of the next vector's level word (its word 0 sits 128 bytes below); the tile's TILE
+  // slots are aligned, so "batch used up" is (at & (4*TILE-1)) == 0 right after an event was consumed, and the next
+  // batch is generated then (event e always uses vector e: results do not depend on when that happens).
+  // Outside the sweep loop (constructors) a generator is not `live`: no batch, rng_ctr is the next event itself.
+  const Params* Pp;
+  int chain;
+  uint32_t at;
   uint32_t e0;   // current event: word 0 (leaf draw) / the level word (coin | -log2(u))
-  TNB_D void set_counter(unsigned long long v) {
-    base = v - (unsigned long long)TILE;  // (wraps for v < TILE; base + pos == v either way)
-    pos = TILE;
+  uint32_t n_local;  // draws taken by local_next() since the last sync_from0() (zero outside the slicers)
+  bool live;
+#if defined(TNB_EMU)
+  uint32_t batch_[2][TILE];
+  TNB_D uint32_t slot0() { return 0u; }
+  TNB_D uint32_t& word(uint32_t a, int which) { return batch_[which][(a >> 2) & uint32_t(TILE - 1)]; }
+  TNB_D uint32_t get(uint32_t a, int which) { return word(a, which); }
+#else
+  // (sweep kernels run one warp per block -- kSweepBlock -- so the lane id indexes the block's only batch; a tile's
+  //  vectors sit at its own lanes' slots)
+  TNB_D TNB_INLINE uint32_t slot0() {
+    __shared__ __align__(128) uint32_t sm[2][32];
+    return uint32_t(__cvta_generic_to_shared(&sm[1][0])) + 4u * ((threadIdx.x & 31u) & ~uint32_t(TILE - 1));
   }
-  TNB_D unsigned long long counter() const { return base + pos; }
-  TNB_D void load(const Params& P, int chain) {
-    const unsigned long long s = P.seeds[chain], g = P.chain_id0 + (unsigned long long)chain;
-    k0 = uint32_t(s); k1 = uint32_t(s >> 32); g0 = uint32_t(g); g1 = uint32_t(g >> 32);
-    r0 = r1 = r2 = rc = e0 = 0;
-    set_counter(P.rng_ctr[chain]);
+  TNB_D TNB_INLINE uint32_t get(uint32_t a, int which) {
+    uint32_t v;
+    if (which) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    else asm volatile("ld.shared.u32 %0, [%1+-128];" : "=r"(v) : "r"(a));
+    return v;
   }
-  TNB_D void store(const Params& P, int chain) const { P.rng_ctr[chain] = counter(); }
+#endif
+  TNB_D TNB_INLINE uint32_t pos() const { return live ? (at >> 2) & uint32_t(TILE - 1) : 0u; }
+  TNB_D TNB_INLINE unsigned long long base() const { return Pp->rng_ctr[chain]; }
+  TNB_D TNB_INLINE void set_base(unsigned long long b) const { Pp->rng_ctr[chain] = b; }
+  TNB_D unsigned long long counter() const { return base() + pos(); }
+  TNB_D void load(const Params& P, int chain_) {
+    Pp = &P;
+    chain = chain_;
+    e0 = 0;
+    at = 0;
+    n_local = 0;
+    live = false;
+  }
+  TNB_D void begin_stream(const Tile<TILE>& t) {  // sweep kernels: generate the batch of events base ...
+    live = true;
+    at = slot0();
+    generate(t, base());
+  }
+  TNB_D void store(const Params&, int) {
+    set_base(counter());
+    live = false;
+  }
   TNB_D bool can_start(const Params&) const { return true; }
-  TNB_D void generate(const Tile<TILE>& t) {
+  TNB_D TNB_INLINE void philox(unsigned long long idx, uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) const {
+    const unsigned long long s = Pp->seeds[chain], g = Pp->chain_id0 + (unsigned long long)chain;
+    philox4x32_10(uint32_t(idx), uint32_t(idx >> 32), uint32_t(g), uint32_t(g >> 32), uint32_t(s), uint32_t(s >> 32),
+                  o0, o1, o2, o3);
+  }
+  // the batch of events b .. b + TILE - 1 into the tile's slots (`at` points at slot 0)
+  TNB_D void generate(const Tile<TILE>& t, unsigned long long b) {
     // (lane id read here, opaquely: otherwise the compiler hoists the special-register read and its masking out of
     //  this rarely taken branch into every iteration of the sweep loop)
-    const unsigned long long idx = base + (unsigned long long)lane_in_tile_here<TILE>(t.tl);
-    uint32_t r3;
-    philox4x32_10(uint32_t(idx), uint32_t(idx >> 32), g0, g1, k0, k1, r0, r1, r2, r3);
+    const unsigned tl = lane_in_tile_here<TILE>(t.tl);
+    const unsigned long long idx = b + (unsigned long long)tl;
+    uint32_t r0, r1, r2, r3;
+    philox(idx, r0, r1, r2, r3);
     // u = (r1 + 0.5) / 2^32 in (0,1);  -log2(u) = 32 - log2(r1 + 0.5), computed once per vector.  The D/E coin of
-    // the level (last bit of word 0) rides in the last mantissa bit of that float -- one shuffle per level instead
+    // the level (last bit of word 0) rides in the last mantissa bit of that float -- one load per level instead
     // of two; the bit moves the acceptance threshold by one fp32 ulp, far inside the 3e-6 of ex2.approx.
 #if defined(TNB_EMU)
     const float rf = 32.f - log2f(float(r1) + 0.5f);
     uint32_t fb;
     std::memcpy(&fb, &rf, 4);
+    word(at + 4u * tl, 0) = r0;
+    word(at + 4u * tl, 1) = (fb & ~1u) | (r0 & 1u);
 #else
     const uint32_t fb = __float_as_uint(32.f - __log2f(float(r1) + 0.5f));
+    t.sync();  // (everybody is done with the previous batch)
+    asm volatile("st.shared.u32 [%0+-128], %1;" ::"r"(at + 4u * tl), "r"(r0) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(at + 4u * tl), "r"((fb & ~1u) | (r0 & 1u)) : "memory");
+    t.sync();
 #endif
-    rc = (fb & ~1u) | (r0 & 1u);
   }
-  // Sub-warp tiles: every TILE iterations of the sweep loop ALL tiles of the warp refill together (an iteration
-  // consumes at most one event, so nobody runs dry in between).  Refilling lazily, tile by tile, made the 70
+  // Sub-warp tiles: every TILE iterations of the sweep loop ALL tiles of the warp start a fresh batch together (an
+  // iteration consumes at most one event, so nobody runs dry in between).  Refilling tile by tile made the 70
   // instructions of a refill run with 1/8 of the lanes active several times per iteration (C1: 13.5 of 32 lanes
-  // active on average).  Event e always uses vector e, so results do not depend on when a refill happens.
+  // active on average).
   TNB_D TNB_INLINE void tick(const Tile<TILE>& t, uint32_t iteration) {
-    if (TILE < 32 && (iteration & uint32_t(TILE - 1)) == 0u && pos != 0u) {  // (pos == 0: just refilled, unused)
-      base += pos;
-      pos = 0;
-      generate(t);
+    if (TILE < 32 && (iteration & uint32_t(TILE - 1)) == 0u && pos() != 0u) {  // (pos == 0: fresh batch, unused)
+      const unsigned long long b = base() + pos();
+      set_base(b);
+      at -= 4u * pos();
+      generate(t, b);
     }
   }
-  TNB_D TNB_INLINE void refill_if_used_up(const Tile<TILE>& t) {
-    if (pos == TILE) {
-      base += TILE;
-      pos = 0;
-      generate(t);
+  TNB_D TNB_INLINE void consumed(const Tile<TILE>& t) {  // one event taken: step, and start the next batch if that was the last
+    at += 4u;
+    if ((at & uint32_t(4 * TILE - 1)) == 0u) {
+      const unsigned long long b = base() + TILE;
+      set_base(b);
+      at -= 4u * TILE;
+      generate(t, b);
     }
   }
   TNB_D TNB_INLINE uint32_t leaf_word(const Tile<TILE>& t) {  // sweep start: the whole word 0
-    refill_if_used_up(t);
-    e0 = t.bcast_c(r0, int(pos));
-    ++pos;
+    e0 = get(at, 0);
+    consumed(t);
     return e0;
   }
   TNB_D TNB_INLINE void begin_level(const Tile<TILE>& t) {    // one level: coin and -log2(u) in one word
-    refill_if_used_up(t);
-    e0 = t.bcast_c(rc, int(pos));
-    ++pos;
+    e0 = get(at, 1);
+    consumed(t);
   }
   TNB_D TNB_INLINE uint32_t coin_word(const Tile<TILE>&) { return e0; }
   static TNB_D TNB_INLINE uint32_t float_bits(float f) {
@@ -253,19 +310,34 @@ struct RngPhilox {
     return __uint_as_float(e0);
 #endif
   }
-  TNB_D TNB_INLINE double uniform(const Tile<TILE>& t) {  // exact path (not used by the production kernels)
-    const int src = int(pos) - 1;
-    return uniform_from(t.bcast(r1, src), t.bcast(r2, src));
-  }
-  // lane-local draw (slicer, executed by lane 0 only); re-synchronise with sync_from0 afterwards
-  TNB_D uint32_t local_next() {
-    const unsigned long long v = counter();
+  TNB_D TNB_INLINE double uniform(const Tile<TILE>&) {  // exact path (not used by the production kernels)
     uint32_t a, b, c, d;
-    philox4x32_10(uint32_t(v), uint32_t(v >> 32), g0, g1, k0, k1, a, b, c, d);
-    set_counter(v + 1);
+    philox(counter() - 1ull, a, b, c, d);                // the event begin_level() just consumed
+    return uniform_from(b, c);
+  }
+  // Draws outside the level stream (the slicers): word 0 of the events after the last one consumed.  A slicer may
+  // draw on lane 0 only; sync_from0() afterwards makes every lane skip the events lane 0 used.
+  TNB_D uint32_t local_next() {
+    uint32_t a, b, c, d;
+    philox(counter() + n_local, a, b, c, d);
+    ++n_local;
     return a;
   }
-  TNB_D void sync_from0(const Tile<TILE>& t) { set_counter(t.bcast_u64(counter(), 0)); }
+  TNB_D void sync_from0(const Tile<TILE>& t) {
+    const uint32_t n = t.bcast(n_local, 0);
+    n_local = 0;
+    if (n == 0u) return;
+    if (!live) {
+      set_base(base() + n);
+    } else if (pos() + n < uint32_t(TILE)) {
+      at += 4u * n;
+    } else {  // past the held batch: a fresh one starting at the next event
+      const unsigned long long b = base() + pos() + n;
+      set_base(b);
+      at -= 4u * pos();
+      generate(t, b);
+    }
+  }
   TNB_D unsigned long long words() const { return 0; }
   TNB_D int overrun() const { return 0; }
 };
@@ -309,6 +381,55 @@ struct RngStream {
   }
   TNB_D unsigned long long words() const { return cur; }
   TNB_D int overrun() const { return over; }
+};
+
+// A node as the walk carries it: children word + contraction cost.  The 2^popcount kernels keep the pair in ONE 64-bit
+// value -- children in the low word, the high word of the cost (an exact power of two: its low word is zero) in the
+// high word -- exactly as it sits in memory: one 8-byte load brings it, a move updates its halves in place and one
+// 8-byte store writes it back.  (Loaded into two separate 32-bit variables instead, the compiler moved the cost out of
+// the destination pair right behind the load and the warp waited there for the load to land.)
+struct NodePacked {
+  unsigned long long v = 0ull;
+  // (mov.b64 packs / unpacks a register pair for free; 64-bit masks and ORs became real 64-bit additions)
+  static TNB_D TNB_INLINE unsigned long long pack(uint32_t lo, uint32_t hi) {
+#if defined(TNB_EMU)
+    return (unsigned long long)lo | ((unsigned long long)hi << 32);
+#else
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+#endif
+  }
+  TNB_D TNB_INLINE uint32_t w() const {
+#if defined(TNB_EMU)
+    return uint32_t(v);
+#else
+    uint32_t lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+    return lo;
+#endif
+  }
+  TNB_D TNB_INLINE uint32_t cost() const {
+#if defined(TNB_EMU)
+    return uint32_t(v >> 32);
+#else
+    uint32_t lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+    return hi;
+#endif
+  }
+  TNB_D TNB_INLINE void set_w(uint32_t w) { v = pack(w, cost()); }
+  TNB_D TNB_INLINE void set_cost(uint32_t c) { v = pack(w(), c); }
+  TNB_D TNB_INLINE double cost_f64() const { return bits_to_f64(pack(0u, cost())); }
+};
+struct NodeWide {  // table-cost kernels: the cost is a general double
+  uint32_t w_ = 0u;
+  double c_ = 0.0;
+  TNB_D TNB_INLINE uint32_t w() const { return w_; }
+  TNB_D TNB_INLINE void set_w(uint32_t w) { w_ = w; }
+  TNB_D TNB_INLINE double cost() const { return c_; }
+  TNB_D TNB_INLINE void set_cost(double c) { c_ = c; }
+  TNB_D TNB_INLINE double cost_f64() const { return c_; }
 };
 
 // ------------------------------------------------------------------------------------------ chain view
@@ -417,14 +538,76 @@ struct ChainView {
   }
   // header fields of internal node z
   TNB_D TNB_INLINE uint32_t& ch(int z) const { return *reinterpret_cast<uint32_t*>(rec + w64(z) * hstride); }
-  TNB_D TNB_INLINE double& cc(int z) const { return *reinterpret_cast<double*>(rec + w64(z) * hstride + 8); }
-  TNB_D TNB_INLINE void store_header(int z, uint32_t children, double cost) const {
+  // contraction cost of z, whichever form the batch keeps (P.cost_hi is kernel-uniform)
+  static TNB_D TNB_INLINE double hi_to_f64(uint32_t hi) { return bits_to_f64((unsigned long long)hi << 32); }
+  static TNB_D TNB_INLINE uint32_t f64_hi(double v) {
+#if defined(TNB_EMU)
+    unsigned long long u;
+    std::memcpy(&u, &v, 8);
+    return uint32_t(u >> 32);
+#else
+    return uint32_t(__double2hiint(v));
+#endif
+  }
+  TNB_D TNB_INLINE uint32_t& cc_hi(int z) const { return *reinterpret_cast<uint32_t*>(rec + w64(z) * hstride + 4); }
+  TNB_D TNB_INLINE double& cc_f64(int z) const { return *reinterpret_cast<double*>(rec + w64(z) * hstride + 8); }
+  TNB_D TNB_INLINE double cc_get(int z) const { return P.cost_hi ? hi_to_f64(cc_hi(z)) : cc_f64(z); }
+  TNB_D TNB_INLINE void cc_set(int z, double v) const {
+    if (P.cost_hi) cc_hi(z) = f64_hi(v);
+    else cc_f64(z) = v;
+  }
+  // one node of the walk: children word + cost.  DIM2 kernels: one 8-byte access, the cost as its high word.
+  TNB_D TNB_INLINE void load_node(int z, uint32_t& children, uint32_t& cost_hi_word) const {
+#if defined(TNB_EMU)
+    children = ch(z);
+    cost_hi_word = cc_hi(z);
+#else
+    // (one 64-bit scalar: as a uint2 the compiler splits the access into two 32-bit ones)
+    const unsigned long long v = *reinterpret_cast<const unsigned long long*>(rec + w64(z) * hstride);
+    children = uint32_t(v);
+    cost_hi_word = uint32_t(v >> 32);
+#endif
+  }
+  TNB_D TNB_INLINE void load_node(int z, NodePacked& h) const {
+#if defined(TNB_EMU)
+    h.v = (unsigned long long)ch(z) | ((unsigned long long)cc_hi(z) << 32);
+#else
+    h.v = *reinterpret_cast<const unsigned long long*>(rec + w64(z) * hstride);
+#endif
+  }
+  TNB_D TNB_INLINE void store_node(int z, const NodePacked& h) const {
+#if defined(TNB_EMU)
+    ch(z) = h.w();
+    cc_hi(z) = h.cost();
+#else
+    *reinterpret_cast<unsigned long long*>(rec + w64(z) * hstride) = h.v;
+#endif
+  }
+  TNB_D TNB_INLINE void load_node(int z, NodeWide& h) const {
+    h.w_ = ch(z);
+    h.c_ = cc_f64(z);
+  }
+  TNB_D TNB_INLINE void store_node(int z, const NodeWide& h) const { store_node(z, h.w_, h.c_); }
+  TNB_D TNB_INLINE void load_node(int z, uint32_t& children, double& cost) const {
+    children = ch(z);
+    cost = cc_f64(z);
+  }
+  TNB_D TNB_INLINE void store_node(int z, uint32_t children, double cost) const {  // table-cost production kernels
 #if defined(TNB_EMU)
     ch(z) = children;
-    cc(z) = cost;
+    cc_f64(z) = cost;
 #else
     const unsigned long long cb = (unsigned long long)__double_as_longlong(cost);
     *reinterpret_cast<uint4*>(rec + w64(z) * hstride) = make_uint4(children, 0u, uint32_t(cb), uint32_t(cb >> 32));
+#endif
+  }
+  TNB_D TNB_INLINE void store_node(int z, uint32_t children, uint32_t cost_hi_word) const {
+#if defined(TNB_EMU)
+    ch(z) = children;
+    cc_hi(z) = cost_hi_word;
+#else
+    *reinterpret_cast<unsigned long long*>(rec + w64(z) * hstride) =
+        (unsigned long long)children | ((unsigned long long)cost_hi_word << 32);
 #endif
   }
   TNB_D TNB_INLINE double pc_of(int node) const { return node < n ? 0.0 : pcv[node]; }
@@ -545,7 +728,7 @@ struct CacheSink {
   const ChainView<TILE, WPL>& c;
   TNB_D TNB_INLINE double pc(int node) const { return c.pc_of(node); }
   TNB_D TNB_INLINE void put(int z, double cost, double pcost) const {
-    c.cc(z) = cost;
+    c.cc_set(z, cost);
     c.pcv[z] = pcost;
   }
 };
@@ -879,8 +1062,11 @@ TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2
 //     before z are z's own subtree plus the left-sibling subtree of every right turn on the way to the root;
 //   * the per-index counters are NB bit planes in registers (lane-private: a lane counts the 32 indices of its
 //     own word), added with a ripple carry and saturating, so "largest count among the candidates" is NB votes.
-template <int TILE, int WPL, class Rng>
-TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2)[WPL]) {
+// draw0: the re-slice's tie-break word, drawn by the caller (passing the generator itself by reference to this
+// out-of-line function forced all of its state through local memory -- the sweep loop then read its level word back
+// from the stack at every level).
+template <int TILE, int WPL>
+TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, const uint32_t draw0, uint32_t (&S2)[WPL]) {
   const Params& P = c.P;
   const Tile<TILE>& t = c.t;
   constexpr int NB = 8;
@@ -963,7 +1149,6 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, Rng& rng,
   }
   t.sync();
   // (3) greedy selection (:60-104)
-  const uint32_t draw0 = rng.local_next();
   uint32_t n_draw = 0;
   uint32_t xnext[WPL];
   c.load_bits(word[0], xnext);
@@ -1189,8 +1374,8 @@ template <int TILE, int WPL, bool STORE>
 TNB_D double sum_shifted(const ChainView<TILE, WPL>& c, const int* dz, int shift0) {
   double acc = 0.0;
   for (int z = c.n + c.t.tl; z < c.P.N; z += TILE) {
-    const double v = scale_pow2(c.cc(z), shift0 + dz[z - c.n]);
-    if (STORE) c.cc(z) = v;
+    const double v = scale_pow2(c.cc_get(z), shift0 + dz[z - c.n]);
+    if (STORE) c.cc_set(z, v);
     acc += v;
   }
 #if !defined(TNB_EMU)
@@ -1548,7 +1733,9 @@ TNB_D void chain_init(const Params& P, int chain) {
       if constexpr (Rng::kFast) {
         if (P.kwsz) {  // production: the same greedy rule through the fast slicer
           build_kw_sz(c);
-          get_slices_fast(c, rng, S);
+          const uint32_t draw0 = rng.local_next();
+          rng.sync_from0(c.t);
+          get_slices_fast(c, draw0, S);
         } else {
           get_slices_dev(c, rng, S);
         }
@@ -1589,13 +1776,23 @@ TNB_D TNB_INLINE int exp_of(double x) {  // biased binary exponent
 template <int TILE, int WPL>
 TNB_D double sum_ccost(const ChainView<TILE, WPL>& c) {
   double acc = 0.0;
-  for (int z = c.n + c.t.tl; z < c.P.N; z += TILE) acc += c.cc(z);
+  for (int z = c.n + c.t.tl; z < c.P.N; z += TILE) acc += c.cc_get(z);
 #if !defined(TNB_EMU)
 #pragma unroll
   for (int d = TILE / 2; d > 0; d >>= 1)
     acc += TILE == 32 ? __shfl_xor_sync(0xffffffffu, acc, d, 32) : __shfl_xor_sync(c.t.mask, acc, d, TILE);
 #endif
   return acc;
+}
+
+// Children words (child slot 0 in the low half, slot 1 in the high half): the other child, and one slot replaced.
+TNB_D TNB_INLINE int other_child(uint32_t w, int x) { return int(w & 0xffffu) == x ? int(w >> 16) : int(w & 0xffffu); }
+TNB_D TNB_INLINE uint32_t put_child(uint32_t w, int v, bool slot1) {
+#if defined(TNB_EMU)
+  return slot1 ? (w & 0xffffu) | (uint32_t(v) << 16) : (w & 0xffff0000u) | uint32_t(v);
+#else
+  return __byte_perm(w, uint32_t(v), slot1 ? 0x5410u : 0x3254u);  // one SEL + one PRMT
+#endif
 }
 
 // One flat loop per tile: every iteration is either a sweep boundary (finish sweep s, start sweep s+1) or one
@@ -1663,11 +1860,20 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
   int sz0 = 0, sz1 = 0, szC = 0;
   Rng rng;
   rng.load(P, chain);
-  long long s = P.sweep_idx[chain];
-  double min_total = P.min_total[chain];
+  if constexpr (Rng::kFast) rng.begin_stream(t);
+  // Production kernels: every level consumes exactly one event of the generator and every sweep start one, so the
+  // proposals of a launch are (events consumed) - (sweeps done) - (draws of the re-slicer): no counter in the loop.
+  // P.n_prop[chain] is off by the starting values while the launch runs and is completed at its end.
+  if constexpr (Rng::kFast) P.n_prop[chain] += (unsigned long long)P.sweep_idx[chain] - rng.counter();
+  // (sweep indices fit 32 bits: tnb_run refuses until_sweep >= 2^31; min_total stays in memory -- it is looked at
+  //  once per sweep)
+  int s = int(P.sweep_idx[chain]);
+  const int until = int(P.until);
+  double* const min_total_p = P.min_total + chain;
   bool rebase = true;
-  // 32-bit counters, folded into the 64-bit ones in memory every 256 sweeps (keeps six registers free)
-  uint32_t q_prop = 0, q_acc = 0, q_wrej = 0;
+  // 16-bit counters in one register (proposals low, accepted moves high), folded into the 64-bit ones in memory
+  // before either half can overflow (a sweep has fewer than 2^15 levels: node ids are int16)
+  uint32_t q_pa = 0, q_wrej = 0;
   uint32_t S[WPL];
 #pragma unroll
   for (int k = 0; k < WPL; ++k) S[k] = 0u;
@@ -1679,27 +1885,39 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
   // (the host refuses them in Philox mode).
   const int f_dsi = Rng::kFast ? 0 : P.dsi, f_prob = Rng::kFast ? kProbMH : P.prob_kind;
   bool in_sweep = false;
-  int B = 0, A = -1, C = 0, p0 = 0, p1 = 0, a0 = 0, a1 = 0;
+  int B = 0, A = -1, C = 0;
   // one level ahead (loop-carried): An = parent(A) and its header, loaded during the previous level
   int An = -1, Ann = -1;  // Ann = parent(An): two levels ahead, so that An's successor header can be requested early
-  uint32_t awn = 0u;
-  double ccAn = 0.0;
+  // contraction costs as the walk carries them: the high word of the double in the 2^popcount kernels (the low word
+  // of a power of two is zero), the double itself otherwise
+  using CR = typename std::conditional<DIM2, uint32_t, double>::type;
+  auto f64 = [](CR v) -> double {
+    if constexpr (DIM2) return ChainView<TILE, WPL>::hi_to_f64(v);
+    else return v;
+  };
+  // B, A and An = parent(A) as the walk carries them (children word in slot order + contraction cost; a move replaces
+  // one slot of B's and of A's word)
+  using Node = typename std::conditional<DIM2, NodePacked, NodeWide>::type;
+  Node nodeB, nodeA, nodeAn;
   uint32_t b0[WPL], b1[WPL], bC[WPL];
   // HYPER: inds[A], hyper[A] (loaded per level) and hyper[B] (carried: next level's B is this level's A)
   uint32_t bA[WPL], hA[WPL], hB[WPL];
 #pragma unroll
   for (int k = 0; k < WPL; ++k) b0[k] = b1[k] = bC[k] = bA[k] = hA[k] = hB[k] = 0u;
-  double pc0 = 0.0, pc1 = 0.0, pcC = 0.0, ccA = 0.0, ccB = 0.0, total = 0.0, root_pc = 0.0, beta = 0.0;
+  double pc0 = 0.0, pc1 = 0.0, pcC = 0.0, total = 0.0, root_pc = 0.0, beta = 0.0;
   float inv_beta_f = 0.f;
-  int kmax = 0;  // largest (biased) exponent the running total had since it was last re-summed
+  // high word of the largest value the running total had since it was last re-summed (for positive doubles the
+  // high words order like the values: one integer max per accepted move)
+  int kmax_hi = 0;
+  auto hi_of = [](double x) -> int { return int(ChainView<TILE, WPL>::f64_hi(x)); };
 
   // Two copies of the loop body for the unconstrained kernels: the rotation of the loop-carried registers (a fifth
   // of a level's instructions were MOVs) then happens by renaming.  (The finite-width kernel, with the re-slicer in
   // its boundary branch, loses a third of its speed to the doubled body.)
   constexpr int kUnroll = FINITE ? 1 : 2;
-  if (!PC && s < P.until) {  // the running total starts from the exact sum of the contraction costs
+  if (!PC && s < until) {  // the running total starts from the exact sum of the contraction costs
     total = sum_ccost(c);
-    kmax = exp_of(total);
+    kmax_hi = hi_of(total);
   }
   // decision trace (tests): lane 0 of a traced chain appends 32-byte records
   const bool tracing = TRACE && chain < P.trace_chains;
@@ -1735,15 +1953,19 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
           if (t.any(anyS)) {
             uint32_t S2[WPL];
             dbl2* cp2 = P.cp2 + size_t(chain) * P.n_int;
+            if constexpr (Rng::kFast) P.n_prop[chain] += rng.counter();  // (the re-slicer's draws are not proposals)
             if constexpr (FS) {
-              get_slices_fast(c, rng, S2);
+              const uint32_t draw0 = rng.local_next();
+              rng.sync_from0(t);
+              get_slices_fast(c, draw0, S2);
+              P.n_prop[chain] -= rng.counter();
               bool diff = false;
 #pragma unroll
               for (int k = 0; k < WPL; ++k) diff |= S2[k] != S[k];
               if constexpr (TRACE) if (tracing && !t.any(diff)) trace_slices(S2, false, total, total);
               if (t.any(diff)) {  // same slices -> same costs: nothing to decide
                 total = sum_ccost(c);  // the decision compares exact sums
-                kmax = exp_of(total);
+                kmax_hi = hi_of(total);
                 if (DIM2 && !HYPER && P.n_inds <= 1000) {
                   int* dz = reinterpret_cast<int*>(P.wkey + size_t(chain) * P.Npad);
                   const int shift0 = mark_slice_diff(c, S, S2, dz, P.word + size_t(chain) * P.Npad);
@@ -1761,7 +1983,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
                   if constexpr (TRACE) if (tracing) trace_slices(S2, r2 < total, r2, total);
                   if (r2 < total) {
                     t.sync();
-                    for (int i = t.tl; i < P.n_int; i += TILE) c.cc(n + i) = cp2[i].x;
+                    for (int i = t.tl; i < P.n_int; i += TILE) c.cc_set(n + i, cp2[i].x);
                     t.sync();
 #pragma unroll
                     for (int k = 0; k < WPL; ++k) S[k] = S2[k];
@@ -1772,6 +1994,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
               }
             } else {
               get_slices_dev(c, rng, S2);
+              if constexpr (Rng::kFast) P.n_prop[chain] -= rng.counter();
               double seq;
               double maxw;
               cost_pass<TILE, WPL, false>(c, S2, ScratchSink{cp2, n}, seq, maxw);
@@ -1779,7 +2002,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
               if (r2 < (PC ? root_pc : total)) {
                 t.sync();
                 for (int i = t.tl; i < P.n_int; i += TILE) {
-                  c.cc(n + i) = cp2[i].x;
+                  c.cc_set(n + i, cp2[i].x);
                   c.pcv[n + i] = cp2[i].y;
                 }
                 t.sync();
@@ -1802,43 +2025,42 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
           // positive partial costs and has no cancellation at all.  This is the only re-summation inside the loop:
           // more inlined copies of sum_ccost in the unrolled body cost more than they save.)
           const int et = exp_of(total);
-          if (!(total > 0.0) || kmax - et > 10 || ((s + 1) & 63) == 0) {
+          if (!(total > 0.0) || (kmax_hi >> 20) - et > 10 || ((s + 1) & 63) == 0) {
             total = sum_ccost(c);
-            kmax = exp_of(total);
+            kmax_hi = hi_of(total);
           }
           root_pc = total;
         }
-        if (root_pc < min_total) {  // infinite_memory/optimizer.hpp:197-201
-          min_total = root_pc;
+        if (root_pc < *min_total_p) {  // infinite_memory/optimizer.hpp:197-201
+          *min_total_p = root_pc;
           snapshot_best(c, S, FINITE);
         }
         ++s;
         in_sweep = false;
-        if ((s & 255) == 0) {
-          P.n_prop[chain] += q_prop;
-          P.n_acc[chain] += q_acc;
+        if ((q_pa & 0x80008000u) != 0u || (FINITE && (s & 255) == 0)) {
+          P.n_prop[chain] += q_pa & 0xffffu;
+          P.n_acc[chain] += q_pa >> 16;
           if (FINITE) P.n_wrej[chain] += q_wrej;
-          q_prop = q_acc = q_wrej = 0;
+          q_pa = q_wrej = 0;
         }
         if (rng.overrun()) break;
       }
-      if (s >= P.until || !rng.can_start(P)) break;
+      if (s >= until || !rng.can_start(P)) break;
       {
-        const long long sb = s < P.n_betas ? s : P.n_betas - 1;
+        const long long sb = (long long)s < P.n_betas ? (long long)s : P.n_betas - 1;
         if (Rng::kFast) inv_beta_f = P.inv_betas[sb];  // 1/beta (host-computed) for the threshold acceptance test
         else beta = P.betas[sb];
       }
       // leaf = prng() % n_leaves (optimizer.hpp:103); the production RNG maps its word with a multiply-high instead
       const uint32_t lw = rng.leaf_word(t);
       const int leaf = Rng::kFast ? int(mulhi32(lw, uint32_t(n))) : int(lw % uint32_t(n));
-      if constexpr (TRACE) if (tracing) trace_put(0u, lw, 0u, uint32_t(leaf), total, min_total);
+      if constexpr (TRACE) if (tracing) trace_put(0u, lw, 0u, uint32_t(leaf), total, *min_total_p);
       B = c.par[leaf];
       if (PC) total = c.pcv[root];                       // :112
       rebase = false;
       root_pc = total;
-      const uint32_t cw = c.ch(B);
-      p0 = int(cw & 0xffffu);
-      p1 = int(cw >> 16);
+      c.load_node(B, nodeB);
+      const int p0 = int(nodeB.w() & 0xffffu), p1 = int(nodeB.w() >> 16);
       c.load_bits(p0, b0);
       c.load_bits(p1, b1);
       if (PC) {
@@ -1849,15 +2071,12 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
         sz0 = int(kws[p0] >> 16);
         sz1 = int(kws[p1] >> 16);
       }
-      ccB = c.cc(B);
       if (HYPER) c.load_hyp(B, hB);
       A = c.par[B];
       in_sweep = true;
       if (A >= 0) {
-        const uint32_t aw = c.ch(A);
-        a0 = int(aw & 0xffffu);
-        a1 = int(aw >> 16);
-        C = (a0 == B) ? a1 : a0;
+        c.load_node(A, nodeA);
+        C = other_child(nodeA.w(), B);
         c.load_bits(C, bC);
         if (HYPER) {
           c.load_bits(A, bA);
@@ -1865,12 +2084,10 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
         }
         if (PC) pcC = c.pc_of(C);
         if (FS) szC = int(kws[C] >> 16);
-        ccA = c.cc(A);
         An = c.par[A];
         Ann = -1;
         if (An >= 0) {
-          awn = c.ch(An);
-          ccAn = c.cc(An);
+          c.load_node(An, nodeAn);
           Ann = c.par[An];
         }
       }
@@ -1883,13 +2100,10 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
     //   the sibling of A under An (from An's header, in registers) and its index set; the header of Ann = parent(An)
     //   (Ann itself was requested a level ago: a load whose ADDRESS is still in flight stalls the warp at issue);
     //   and Annn = parent(Ann) for the level after.
+    rng.begin_level(t);  // (first: the event's word is needed right after the two votes below)
     const int Annn = Ann >= 0 ? int(c.par[Ann]) : -1;
-    uint32_t awnn = 0u;
-    double ccAnn = 0.0;
-    if (Ann >= 0) {
-      awnn = c.ch(Ann);
-      ccAnn = c.cc(Ann);
-    }
+    Node nodeAnn;
+    if (Ann >= 0) c.load_node(Ann, nodeAnn);
     int Cn = 0;
     uint32_t bCn[WPL], bAn[WPL], hAn[WPL];
 #pragma unroll
@@ -1897,8 +2111,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
     double pcCn = 0.0;
     int szCn = 0;
     if (An >= 0) {
-      const int x0 = int(awn & 0xffffu), x1 = int(awn >> 16);
-      Cn = (x0 == A) ? x1 : x0;
+      Cn = other_child(nodeAn.w(), A);
       c.load_bits(Cn, bCn);
       if (HYPER) {
         c.load_bits(An, bAn);
@@ -1907,7 +2120,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
       if (PC) pcCn = c.pc_of(Cn);
       if (FS) szCn = int(kws[Cn] >> 16);
     }
-    const bool bslot0 = (a0 == B);
+    const bool bslot0 = int(nodeA.w() & 0xffffu) == B;
     bool l0 = false, l1 = false;
 #pragma unroll
     for (int k = 0; k < WPL; ++k) {
@@ -1915,12 +2128,13 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
       l1 |= (b1[k] & bC[k]) != 0u;
     }
     const bool i0 = t.any_c(l0), i1 = t.any_c(l1);
-    rng.begin_level(t);
     bool pick0;
     if (f_dsi || (i0 && i1)) pick0 = (rng.coin_word(t) & 1u) != 0u;
     else pick0 = i0;
-    int E = pick0 ? p1 : p0;  // D = the other child
+    int E = pick0 ? int(nodeB.w() >> 16) : int(nodeB.w() & 0xffffu);  // D = the other child
     uint32_t bD[WPL], bE[WPL], nb[WPL];
+    // K10: no popcount of this kernel reaches 1024 (the host gives networks of 1024 and more indices two words per lane)
+    constexpr bool K10 = DIM2 && TILE * WPL <= 32;
     uint32_t kpack = 0, ks = 0, ku = 0;
 #pragma unroll
     for (int k = 0; k < WPL; ++k) {
@@ -1928,9 +2142,17 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
       bE[k] = pick0 ? b1[k] : b0[k];
       nb[k] = bD[k] ^ bC[k];  // new inds of B (infinite_memory/optimizer.hpp:147)
       if (HYPER) nb[k] |= hA[k] | hB[k];
-      kpack += uint32_t(popc32(nb[k] | bE[k] | S[k])) | (uint32_t(popc32(bD[k] | bC[k] | S[k])) << 16);
-      if (FINITE) ks += uint32_t(popc32(nb[k] & ~S[k]));
-      if (FS) ks += uint32_t(popc32(nb[k])) << 16;  // unsliced popcount of the new B rides in the same reduction
+      const uint32_t ka_l = uint32_t(popc32(nb[k] | bE[k] | S[k])), kb_l = uint32_t(popc32(bD[k] | bC[k] | S[k]));
+      if (FS && K10) {
+        // one reduction on the dependent path: sliced width of the new B and both cost exponents as 10-bit fields;
+        // the unsliced popcount of the new B (only stored, on accept) goes through a second one that nothing waits for
+        kpack += uint32_t(popc32(nb[k] & ~S[k])) | (ka_l << 10) | (kb_l << 20);
+        ku += uint32_t(popc32(nb[k]));
+      } else {
+        kpack += ka_l | (kb_l << 16);
+        if (FINITE) ks += uint32_t(popc32(nb[k] & ~S[k]));
+        if (FS) ks += uint32_t(popc32(nb[k])) << 16;  // unsliced popcount of the new B rides in the same reduction
+      }
     }
     // sparse-index cost model (table-cost kernels only): the sparse parts of the same three sets
     const bool sparse = !DIM2 && P.sparse != nullptr;
@@ -1954,14 +2176,20 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
     double pcE = pick0 ? pc1 : pc0;
     const int szD = pick0 ? sz0 : sz1;
     int szE = pick0 ? sz1 : sz0;
-    ++q_prop;
+    if (!Rng::kFast) ++q_pa;
     bool gate = true;
     float swB = 0.f;  // new_sliced_width_B
     if (FINITE) {  // finite_width/greedy/optimizer.hpp:176-188
-      ks = t.sum_c(ks);
-      if (FS) {
-        ku = ks >> 16;
-        ks &= 0xffffu;
+      if (FS && K10) {
+        kpack = t.sum_c(kpack);
+        ku = t.sum_c(ku);
+        ks = kpack & 0x3ffu;
+      } else {
+        ks = t.sum_c(ks);
+        if (FS) {
+          ku = ks >> 16;
+          ks &= 0xffffu;
+        }
       }
       if (gen) {
         uint32_t xs[WPL];
@@ -1977,13 +2205,22 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
       if (!gate) ++q_wrej;
     }
     bool acc = false;
-    double nA = 0.0, nB = 0.0, delta = 0.0;
+    CR nA{}, nB{};
+    double delta = 0.0;
     if (gate) {
-      kpack = t.sum_c(kpack);
-      if (DIM2) {  // dim == 2: the exact power of two built from its exponent (+inf past 2^1023, like pow)
-        const uint32_t ka = kpack & 0xffffu, kb = kpack >> 16;
-        nA = bits_to_f64((unsigned long long)(1023u + (ka > 1024u ? 1024u : ka)) << 52);
-        nB = bits_to_f64((unsigned long long)(1023u + (kb > 1024u ? 1024u : kb)) << 52);
+      if (!(FS && K10)) kpack = t.sum_c(kpack);
+      if constexpr (DIM2) {  // dim == 2: the exact power of two built from its exponent (+inf past 2^1023, like pow)
+        if constexpr (FS && K10) {  // the high words straight from the fields
+          nA = ((kpack << 10) & 0x3ff00000u) + 0x3ff00000u;
+          nB = (kpack & 0xfff00000u) + 0x3ff00000u;
+        } else if constexpr (K10) {
+          nA = (kpack << 20) + 0x3ff00000u;
+          nB = ((kpack >> 16) << 20) + 0x3ff00000u;
+        } else {
+          const uint32_t ka = kpack & 0xffffu, kb = kpack >> 16;
+          nA = (1023u + (ka > 1024u ? 1024u : ka)) << 20;
+          nB = (1023u + (kb > 1024u ? 1024u : kb)) << 20;
+        }
       } else if (gen) {
         uint32_t uA[WPL], uB[WPL];
 #pragma unroll
@@ -2000,7 +2237,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
         nA = c.cost_of(int(kpack & 0xffffu));  // cost(new_B | E [| slices])
         nB = c.cost_of(int(kpack >> 16));      // cost(D | C [| slices])
       }
-      delta = (nB - ccB) + (nA - ccA);       // :158, this association order
+      delta = (f64(nB) - nodeB.cost_f64()) + (f64(nA) - nodeA.cost_f64());  // :158, this association order
 
       if (Rng::kFast && f_prob == kProbMH) {
         // same rule as prob/mh.hpp:45-59, solved for the move: u <= (1 + delta/total)^-beta
@@ -2085,10 +2322,8 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
             for (int k = 0; k < WPL; ++k) S2[k] |= span_mask(idx, g, t.tl + k * TILE);
           }
           // tentative swap_with_nn(E) in memory: the cost pass walks the tree as stored
-          const int na0 = bslot0 ? a0 : E, na1 = bslot0 ? E : a1;
-          const int np0 = pick0 ? p0 : C, np1 = pick0 ? C : p1;
-          c.ch(A) = uint32_t(na0) | (uint32_t(na1) << 16);
-          c.ch(B) = uint32_t(np0) | (uint32_t(np1) << 16);
+          c.ch(A) = put_child(nodeA.w(), E, bslot0);
+          c.ch(B) = put_child(nodeB.w(), C, pick0);
           c.par[C] = int16_t(B);
           c.par[E] = int16_t(A);
           c.store_bits(B, nb);
@@ -2107,7 +2342,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
           if (u2 <= p2) {  // :290-312 (pos_C / pos_E keep their names in this branch)
             t.sync();
             for (int i = t.tl; i < P.n_int; i += TILE) {
-              c.cc(n + i) = cp2[i].x;
+              c.cc_set(n + i, cp2[i].x);
               c.pcv[n + i] = cp2[i].y;
             }
             t.sync();
@@ -2125,11 +2360,11 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
             store_slices(c, S);
             total = r2;
             root_pc = r2;
-            ++q_acc;
+            q_pa += 0x10000u;
             ns_taken = true;
           } else {  // swap back (swap_with_nn(pos_C), :314-317)
-            c.ch(A) = uint32_t(a0) | (uint32_t(a1) << 16);
-            c.ch(B) = uint32_t(p0) | (uint32_t(p1) << 16);
+            c.ch(A) = nodeA.w();
+            c.ch(B) = nodeB.w();
             c.par[C] = int16_t(A);
             c.par[E] = int16_t(B);
             uint32_t ob[WPL];
@@ -2146,33 +2381,27 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
       // above is valid any more.  Re-enter the walk at B <- A from memory, like a sweep start does.
       if constexpr (FINITE && !Rng::kFast) {
         B = A;
-        const uint32_t cw = c.ch(B);
-        p0 = int(cw & 0xffffu);
-        p1 = int(cw >> 16);
+        c.load_node(B, nodeB);
+        const int p0 = int(nodeB.w() & 0xffffu), p1 = int(nodeB.w() >> 16);
         c.load_bits(p0, b0);
         c.load_bits(p1, b1);
         pc0 = c.pc_of(p0);
         pc1 = c.pc_of(p1);
-        ccB = c.cc(B);
         if (HYPER) c.load_hyp(B, hB);
         A = c.par[B];
         if (A >= 0) {
-          const uint32_t aw = c.ch(A);
-          a0 = int(aw & 0xffffu);
-          a1 = int(aw >> 16);
-          C = (a0 == B) ? a1 : a0;
+          c.load_node(A, nodeA);
+          C = other_child(nodeA.w(), B);
           c.load_bits(C, bC);
           if (HYPER) {
             c.load_bits(A, bA);
             c.load_hyp(A, hA);
           }
           pcC = c.pc_of(C);
-          ccA = c.cc(A);
           An = c.par[A];
           Ann = -1;
           if (An >= 0) {
-            awn = c.ch(An);
-            ccAn = c.cc(An);
+            c.load_node(An, nodeAn);
             Ann = c.par[An];
           }
         }
@@ -2181,14 +2410,16 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
     uint32_t bB[WPL];
     if (acc) {
       // Tree::swap_with_nn(E): E <-> C, child slots preserved (tree.hpp:141-192)
-      if (bslot0) a1 = E; else a0 = E;
-      if (pick0) p1 = C; else p0 = C;
+      nodeA.set_w(put_child(nodeA.w(), E, bslot0));
+      nodeB.set_w(put_child(nodeB.w(), C, pick0));
+      nodeA.set_cost(nA);
+      nodeB.set_cost(nB);
       if (PC) {
-        c.ch(A) = uint32_t(a0) | (uint32_t(a1) << 16);
-        c.ch(B) = uint32_t(p0) | (uint32_t(p1) << 16);
-      } else {  // production: children word and new contraction cost of a node leave as ONE 16-byte header store
-        c.store_header(A, uint32_t(a0) | (uint32_t(a1) << 16), nA);
-        c.store_header(B, uint32_t(p0) | (uint32_t(p1) << 16), nB);
+        c.ch(A) = nodeA.w();
+        c.ch(B) = nodeB.w();
+      } else {  // production: children word and new contraction cost of a node leave as ONE header store
+        c.store_node(A, nodeA);
+        c.store_node(B, nodeB);
       }
       c.par[C] = int16_t(B);
       c.par[E] = int16_t(A);
@@ -2202,14 +2433,12 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
         c.store_hyp(A, hA);
         c.store_hyp(B, hB);
       }
-      ccB = nB;
-      ccA = nA;
       total += delta;
-      if (!PC) {  // largest exponent of the running total since it was last re-summed (see the sweep boundary)
-        const int e_now = exp_of(total);
-        kmax = e_now > kmax ? e_now : kmax;
+      if (!PC) {  // largest value of the running total since it was last re-summed (see the sweep boundary)
+        const int h_now = hi_of(total);
+        kmax_hi = h_now > kmax_hi ? h_now : kmax_hi;
       }
-      ++q_acc;
+      q_pa += 0x10000u;
       if (FS) {
         kws[B] = ku | (uint32_t(szD + szC) << 16);
       }
@@ -2230,17 +2459,18 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
     // propagate partial costs (:185-188), post-swap names
     double pcB = 0.0;
     if (PC) {
-      pcB = pcD + pcE + ccB;
-      const double pcA = pcB + pcC + ccA;
-      c.cc(B) = ccB;
+      pcB = pcD + pcE + nodeB.cost_f64();
+      const double pcA = pcB + pcC + nodeA.cost_f64();
+      if constexpr (!DIM2) {  // (PC kernels are table-cost kernels)
+        c.cc_f64(B) = nodeB.cost_f64();
+        c.cc_f64(A) = nodeA.cost_f64();
+      }
       c.pcv[B] = pcB;
-      c.cc(A) = ccA;
       c.pcv[A] = pcA;
       root_pc = pcA;
     }
-    // next level: B <- A, whose children are (a0, a1) = {B, C} in slot order
-    p0 = a0;
-    p1 = a1;
+    // next level: B <- A, whose children are {B, C} in slot order
+    nodeB = nodeA;
 #pragma unroll
     for (int k = 0; k < WPL; ++k) {
       b0[k] = bslot0 ? bB[k] : bC[k];
@@ -2255,13 +2485,11 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
       sz0 = bslot0 ? szB : szC;
       sz1 = bslot0 ? szC : szB;
     }
-    ccB = ccA;
     B = A;
     A = An;
     {  // rotate the pipeline: what was loaded for the next level becomes current.  (Unconditional: at the root,
        // An < 0, the next iteration is a sweep boundary that reloads every one of these -- two branches less.)
-      a0 = int(awn & 0xffffu);
-      a1 = int(awn >> 16);
+      nodeA = nodeAn;
       C = Cn;
 #pragma unroll
       for (int k = 0; k < WPL; ++k) bC[k] = bCn[k];
@@ -2275,12 +2503,10 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
       }
       if (PC) pcC = pcCn;
       if (FS) szC = szCn;
-      ccA = ccAn;
     }
     An = Ann;
     Ann = Annn;
-    awn = awnn;
-    ccAn = ccAnn;
+    nodeAn = nodeAnn;
     }  // (no new-slice move taken)
     }  // level
   }
@@ -2300,12 +2526,12 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
     for (int i = t.tl; i < words; i += TILE) gr[i] = sr[i];
 #endif
   }
+  if constexpr (Rng::kFast) P.n_prop[chain] += rng.counter() - (unsigned long long)s;
   rng.store(P, chain);
   P.sweep_idx[chain] = s;
-  P.min_total[chain] = min_total;
   P.total[chain] = PC ? c.pcv[root] : (rebase ? P.total[chain] : total);
-  P.n_prop[chain] += q_prop;
-  P.n_acc[chain] += q_acc;
+  if constexpr (!Rng::kFast) P.n_prop[chain] += q_pa & 0xffffu;
+  P.n_acc[chain] += q_pa >> 16;
   P.n_wrej[chain] += q_wrej;
 }
 
