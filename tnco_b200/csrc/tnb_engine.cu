@@ -328,7 +328,9 @@ static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_be
   if (e->layout == TNB_LAYOUT_INTERLEAVED || e->layout == TNB_LAYOUT_SMEM) split = false;
   if (e->layout == TNB_LAYOUT_SPLIT) split = true;
   cs.hstride = split ? 16 : e->stride;
-  cs.bstride = split ? 4 * e->Ws * (e->hyper ? 2 : 1) : e->stride;
+  // (split rows start on 32-byte sector boundaries: a 188-byte row then costs 6 sectors, not 6 or 7, and one
+  //  prefetch per 128-byte line covers it)
+  cs.bstride = split ? (4 * e->Ws * (e->hyper ? 2 : 1) + 31) / 32 * 32 : e->stride;
   // (+ tail: load_bits reads whole tiles of words and masks the ones beyond the row)
   bool ok = alloc_to(rt, cs.par, nc * e->Npad) && alloc_to(rt, cs.rec, nc * ni * size_t(cs.hstride) + 4 * kTailWords) &&
             (!split || alloc_to(rt, cs.bits_alloc, nc * ni * size_t(cs.bstride) + 4 * kTailWords)) &&

@@ -195,12 +195,52 @@ struct RngPhilox {
   TNB_D uint32_t slot0() { return 0u; }
   TNB_D uint32_t& word(uint32_t a, int which) { return batch_[which][(a >> 2) & uint32_t(TILE - 1)]; }
   TNB_D uint32_t get(uint32_t a, int which) { return word(a, which); }
+  TNB_D void ring_put(int) {}
+  TNB_D void sweep_mark() {}
+  TNB_D void note_refill() {}
+  TNB_D uint32_t sweep_events(uint32_t& s0) const { s0 = 0; return 0; }
+  TNB_D uint32_t ring_get(uint32_t) const { return 0; }
+  TNB_D void set_flag(uint32_t) {}
+  TNB_D uint32_t flag() const { return 0; }
 #else
   // (sweep kernels run one warp per block -- kSweepBlock -- so the lane id indexes the block's only batch; a tile's
   //  vectors sit at its own lanes' slots)
+  // shared memory of the warp: [0] word 0 of the 32 vectors, [1] their level words, [2] the ring of the walk (the
+  // node B of the level that consumed each vector, see ring_put), [3] bookkeeping of the current sweep
   TNB_D TNB_INLINE uint32_t slot0() {
-    __shared__ __align__(128) uint32_t sm[2][32];
+    __shared__ __align__(128) uint32_t sm[4][32];
     return uint32_t(__cvta_generic_to_shared(&sm[1][0])) + 4u * ((threadIdx.x & 31u) & ~uint32_t(TILE - 1));
+  }
+  // ---- full-warp tiles: which nodes did the current sweep walk?  Every level leaves its node B next to the vector
+  // it consumed (ONE shared-memory store per level, addressed off the cursor), so a sweep of up to 31 levels can be
+  // listed afterwards -- what the incremental best-tree snapshot needs (snapshot_walk).
+  TNB_D TNB_INLINE void ring_put(int B) { asm volatile("st.shared.u32 [%0+128], %1;" ::"r"(at), "r"(B) : "memory"); }
+  TNB_D TNB_INLINE uint32_t meta_addr() const { return (at & ~127u) + 256u; }
+  TNB_D TNB_INLINE void sweep_mark() {  // sweep start, before its leaf event: remember the cursor, no refill yet
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(meta_addr()), "r"(at), "r"(0u) : "memory");
+  }
+  TNB_D TNB_INLINE void note_refill() {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(r) : "r"(meta_addr()));
+    asm volatile("st.shared.u32 [%0+4], %1;" ::"r"(meta_addr()), "r"(r + 1u) : "memory");
+  }
+  // events consumed since sweep_mark() (the leaf event + one per level); slot_start = ring slot of the leaf event
+  TNB_D TNB_INLINE uint32_t sweep_events(uint32_t& slot_start) const {
+    uint32_t a0, r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a0), "=r"(r) : "r"(meta_addr()));
+    slot_start = (a0 >> 2) & 31u;
+    return r * 32u + ((at >> 2) & 31u) - slot_start;
+  }
+  TNB_D TNB_INLINE uint32_t ring_get(uint32_t slot) const {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((at & ~127u) + 128u + 4u * (slot & 31u)));
+    return v;
+  }
+  TNB_D TNB_INLINE void set_flag(uint32_t f) { asm volatile("st.shared.u32 [%0+8], %1;" ::"r"(meta_addr()), "r"(f) : "memory"); }
+  TNB_D TNB_INLINE uint32_t flag() const {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(v) : "r"(meta_addr()));
+    return v;
   }
   TNB_D TNB_INLINE uint32_t get(uint32_t a, int which) {
     uint32_t v;
@@ -279,6 +319,7 @@ struct RngPhilox {
       const unsigned long long b = base() + TILE;
       set_base(b);
       at -= 4u * TILE;
+      if (TILE == 32) note_refill();
       generate(t, b);
     }
   }
@@ -287,8 +328,9 @@ struct RngPhilox {
     consumed(t);
     return e0;
   }
-  TNB_D TNB_INLINE void begin_level(const Tile<TILE>& t) {    // one level: coin and -log2(u) in one word
+  TNB_D TNB_INLINE void begin_level(const Tile<TILE>& t, int B) {  // one level: coin and -log2(u) in one word
     e0 = get(at, 1);
+    if (TILE == 32) ring_put(B);
     consumed(t);
   }
   TNB_D TNB_INLINE uint32_t coin_word(const Tile<TILE>&) { return e0; }
@@ -336,7 +378,7 @@ struct RngPhilox {
       set_base(b);
       at -= 4u * pos();
       generate(t, b);
-    }
+    }  // (slicer draws come after the walk of their sweep was counted: sweep_events() is taken before)
   }
   TNB_D unsigned long long words() const { return 0; }
   TNB_D int overrun() const { return 0; }
@@ -367,7 +409,7 @@ struct RngStream {
   }
   TNB_D TNB_INLINE uint32_t leaf_word(const Tile<TILE>&) { return next(); }
   TNB_D TNB_INLINE void tick(const Tile<TILE>&, uint32_t) {}
-  TNB_D TNB_INLINE void begin_level(const Tile<TILE>&) {}
+  TNB_D TNB_INLINE void begin_level(const Tile<TILE>&, int) {}
   TNB_D TNB_INLINE uint32_t coin_word(const Tile<TILE>&) { return next(); }
   TNB_D TNB_INLINE double uniform(const Tile<TILE>&) {
     const uint32_t lo = next();
@@ -1412,12 +1454,43 @@ TNB_D void snapshot_best(const ChainView<TILE, WPL>& c, const uint32_t (&S)[WPL]
   const Params& P = c.P;
   const uint32_t* src = reinterpret_cast<const uint32_t*>(c.par);
   uint32_t* dst = reinterpret_cast<uint32_t*>(P.bpar + size_t(c.chain) * P.Npad);
+  c.t.sync();  // (see snapshot_walk)
   // (unrolled: the copies are independent, several loads in flight instead of one load-store round trip at a time)
 #pragma unroll 8
   for (int i = c.t.tl; i < P.Npad / 2; i += TILE) dst[i] = src[i];
   uint32_t* dch = P.bch + size_t(c.chain) * P.n_int;
 #pragma unroll 8
   for (int i = c.t.tl; i < P.n_int; i += TILE) dch[i] = c.ch(P.n + i);
+  if (finite) {
+    uint32_t* ds = P.bslices + size_t(c.chain) * P.Ws;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      const int w = c.t.tl + k * TILE;
+      if (w < P.W) ds[w] = S[k];
+    }
+  }
+}
+
+// Incremental form of snapshot_best for a sweep that STARTED from the best tree (the previous sweep ended with a
+// snapshot): the sweep changed the children words of the nodes it walked (the B of every level, and the root) and
+// re-parented children of those nodes only -- a node's final parent is the last walked node that adopted it.  So the
+// snapshot is brought up to date by one pass over the walked nodes, one per lane: its children word, and itself as the
+// parent of both children.  (C5: 2 x 1999 words copied per snapshot, at almost every sweep of the descent phase --
+// half of all stall samples of a short anneal -- against ~22 nodes here.)
+template <int TILE, int WPL, class Rng>
+TNB_D void snapshot_walk(const ChainView<TILE, WPL>& c, const Rng& rng, uint32_t slot_start, int levels,
+                         const uint32_t (&S)[WPL], bool finite) {
+  const Params& P = c.P;
+  int16_t* bpar = P.bpar + size_t(c.chain) * P.Npad;
+  uint32_t* dch = P.bch + size_t(c.chain) * P.n_int;
+  c.t.sync();  // (the two snapshot forms write the same words from different lanes: keep them ordered)
+  if (c.t.tl <= levels) {
+    const int X = c.t.tl < levels ? int(rng.ring_get(slot_start + 1u + uint32_t(c.t.tl))) : P.N - 1;
+    const uint32_t w = c.ch(X);
+    dch[X - P.n] = w;
+    bpar[w & 0xffffu] = int16_t(X);
+    bpar[w >> 16] = int16_t(X);
+  }
   if (finite) {
     uint32_t* ds = P.bslices + size_t(c.chain) * P.Ws;
 #pragma unroll
@@ -1849,6 +1922,8 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
   // needs no partial costs of D/E/C, no two 16-byte stores per level and half the fp64 adds; its total is a
   // running sum re-based on sum_ccost() every 64 sweeps.
   constexpr bool PC = !Rng::kFast;
+  // INC: incremental best-tree snapshots (snapshot_walk) -- production generator, full-warp tiles
+  constexpr bool INC = Rng::kFast && TILE == 32;
   // FS: production re-slicer (get_slices_fast); the walk then also maintains kw[] and sz[].  Only where a cost is
   // 2^popcount (DIM2): the table-cost kernels -- other dimensions, sparse indices -- re-slice with the reference's
   // slicer verbatim (get_slices_dev + a full cost pass), which knows every width model.
@@ -1857,13 +1932,15 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
   // kernel parameters it cost ten instructions per 2-byte access)
   uint32_t* kws = FS ? P.kwsz + size_t(chain) * P.Npad : nullptr;
   if constexpr (FS) keep_in_register(kws);
-  int sz0 = 0, sz1 = 0, szC = 0;
   Rng rng;
   rng.load(P, chain);
   if constexpr (Rng::kFast) rng.begin_stream(t);
+  if constexpr (INC) rng.set_flag(0u);
   // Production kernels: every level consumes exactly one event of the generator and every sweep start one, so the
   // proposals of a launch are (events consumed) - (sweeps done) - (draws of the re-slicer): no counter in the loop.
   // P.n_prop[chain] is off by the starting values while the launch runs and is completed at its end.
+  // Likewise width-gate rejections = proposals - proposals that passed the gate (counted where the gate is passed).
+  if constexpr (Rng::kFast && FINITE) P.n_wrej[chain] -= P.n_prop[chain];
   if constexpr (Rng::kFast) P.n_prop[chain] += (unsigned long long)P.sweep_idx[chain] - rng.counter();
   // (sweep indices fit 32 bits: tnb_run refuses until_sweep >= 2^31; min_total stays in memory -- it is looked at
   //  once per sweep)
@@ -1873,7 +1950,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
   bool rebase = true;
   // 16-bit counters in one register (proposals low, accepted moves high), folded into the 64-bit ones in memory
   // before either half can overflow (a sweep has fewer than 2^15 levels: node ids are int16)
-  uint32_t q_pa = 0, q_wrej = 0;
+  uint32_t q_pa = 0, q_wrej = 0;  // (production finite-width kernels: q_wrej counts the proposals that PASSED the width gate)
   uint32_t S[WPL];
 #pragma unroll
   for (int k = 0; k < WPL; ++k) S[k] = 0u;
@@ -1946,6 +2023,9 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
     if (A < 0) {
       // ------------------------------------------------------------------ sweep boundary
       if (in_sweep) {
+        // INC: what did this sweep walk (taken before the re-slicer moves the generator's cursor)
+        uint32_t n_ev = 0, slot_start = 0;
+        if constexpr (INC) n_ev = rng.sweep_events(slot_start);
         if (FINITE && P.every > 0 && (s % P.every) == 0) {  // finite_width/greedy/optimizer.hpp:360-376
           bool anyS = false;
 #pragma unroll
@@ -2033,14 +2113,27 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
         }
         if (root_pc < *min_total_p) {  // infinite_memory/optimizer.hpp:197-201
           *min_total_p = root_pc;
-          snapshot_best(c, S, FINITE);
+          bool done = false;
+          if constexpr (INC) {
+            if (rng.flag() != 0u && n_ev <= 32u) {  // started from the best tree, and the ring still holds the walk
+              snapshot_walk(c, rng, slot_start, int(n_ev) - 1, S, FINITE);
+              done = true;
+            }
+            rng.set_flag(1u);
+          }
+          if (!done) snapshot_best(c, S, FINITE);
+        } else {
+          if constexpr (INC) rng.set_flag(0u);
         }
         ++s;
         in_sweep = false;
         if ((q_pa & 0x80008000u) != 0u || (FINITE && (s & 255) == 0)) {
           P.n_prop[chain] += q_pa & 0xffffu;
           P.n_acc[chain] += q_pa >> 16;
-          if (FINITE) P.n_wrej[chain] += q_wrej;
+          if (FINITE) {
+            if (Rng::kFast) P.n_wrej[chain] -= q_wrej;
+            else P.n_wrej[chain] += q_wrej;
+          }
           q_pa = q_wrej = 0;
         }
         if (rng.overrun()) break;
@@ -2051,6 +2144,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
         if (Rng::kFast) inv_beta_f = P.inv_betas[sb];  // 1/beta (host-computed) for the threshold acceptance test
         else beta = P.betas[sb];
       }
+      if constexpr (INC) rng.sweep_mark();
       // leaf = prng() % n_leaves (optimizer.hpp:103); the production RNG maps its word with a multiply-high instead
       const uint32_t lw = rng.leaf_word(t);
       const int leaf = Rng::kFast ? int(mulhi32(lw, uint32_t(n))) : int(lw % uint32_t(n));
@@ -2067,10 +2161,6 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
         pc0 = c.pc_of(p0);
         pc1 = c.pc_of(p1);
       }
-      if (FS) {
-        sz0 = int(kws[p0] >> 16);
-        sz1 = int(kws[p1] >> 16);
-      }
       if (HYPER) c.load_hyp(B, hB);
       A = c.par[B];
       in_sweep = true;
@@ -2083,7 +2173,6 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
           c.load_hyp(A, hA);
         }
         if (PC) pcC = c.pc_of(C);
-        if (FS) szC = int(kws[C] >> 16);
         An = c.par[A];
         Ann = -1;
         if (An >= 0) {
@@ -2100,7 +2189,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
     //   the sibling of A under An (from An's header, in registers) and its index set; the header of Ann = parent(An)
     //   (Ann itself was requested a level ago: a load whose ADDRESS is still in flight stalls the warp at issue);
     //   and Annn = parent(Ann) for the level after.
-    rng.begin_level(t);  // (first: the event's word is needed right after the two votes below)
+    rng.begin_level(t, B);  // (first: the event's word is needed right after the two votes below)
     const int Annn = Ann >= 0 ? int(c.par[Ann]) : -1;
     Node nodeAnn;
     if (Ann >= 0) c.load_node(Ann, nodeAnn);
@@ -2109,7 +2198,6 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
 #pragma unroll
     for (int k = 0; k < WPL; ++k) bCn[k] = bAn[k] = hAn[k] = 0u;
     double pcCn = 0.0;
-    int szCn = 0;
     if (An >= 0) {
       Cn = other_child(nodeAn.w(), A);
       c.load_bits(Cn, bCn);
@@ -2118,7 +2206,6 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
         c.load_hyp(An, hAn);
       }
       if (PC) pcCn = c.pc_of(Cn);
-      if (FS) szCn = int(kws[Cn] >> 16);
     }
     const bool bslot0 = int(nodeA.w() & 0xffffu) == B;
     bool l0 = false, l1 = false;
@@ -2174,8 +2261,6 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
     }
     const double pcD = pick0 ? pc0 : pc1;
     double pcE = pick0 ? pc1 : pc0;
-    const int szD = pick0 ? sz0 : sz1;
-    int szE = pick0 ? sz1 : sz0;
     if (!Rng::kFast) ++q_pa;
     bool gate = true;
     float swB = 0.f;  // new_sliced_width_B
@@ -2202,12 +2287,13 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
       // (2^popcount kernels: width = log2(d) * popcount is monotone in the popcount, and kthr is the largest popcount
       //  whose float32 width still fits -- the same decision without the fp64 product on the dependent path)
       gate = FS ? int(ks) <= P.kthr : swB <= P.max_width;
-      if (!gate) ++q_wrej;
+      if (!Rng::kFast && !gate) ++q_wrej;
     }
     bool acc = false;
     CR nA{}, nB{};
     double delta = 0.0;
     if (gate) {
+      if (Rng::kFast && FINITE) ++q_wrej;
       if (!(FS && K10)) kpack = t.sum_c(kpack);
       if constexpr (DIM2) {  // dim == 2: the exact power of two built from its exponent (+inf past 2^1023, like pow)
         if constexpr (FS && K10) {  // the high words straight from the fields
@@ -2410,6 +2496,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
     uint32_t bB[WPL];
     if (acc) {
       // Tree::swap_with_nn(E): E <-> C, child slots preserved (tree.hpp:141-192)
+      const uint32_t oldB_w = nodeB.w();
       nodeA.set_w(put_child(nodeA.w(), E, bslot0));
       nodeB.set_w(put_child(nodeB.w(), C, pick0));
       nodeA.set_cost(nA);
@@ -2440,12 +2527,16 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
       }
       q_pa += 0x10000u;
       if (FS) {
-        kws[B] = ku | (uint32_t(szD + szC) << 16);
+        // popcount and leaf count of the new B for the re-slicer.  The leaf counts of its children (D and the old C)
+        // are fetched here, where only this store waits for them, instead of being carried through the walk (four
+        // registers and a load per level less); a lane reads back its own earlier stores, so D's count is current
+        // even when D was the B of the level below.
+        const int D = pick0 ? int(oldB_w & 0xffffu) : int(oldB_w >> 16);
+        kws[B] = ku + (kws[D] & 0xffff0000u) + (kws[C] & 0xffff0000u);
       }
       {
         const int ti = C; C = E; E = ti;
         const double td = pcC; pcC = pcE; pcE = td;
-        const int ts = szC; szC = szE; szE = ts;
       }
 #pragma unroll
       for (int k = 0; k < WPL; ++k) {
@@ -2480,11 +2571,6 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
       pc0 = bslot0 ? pcB : pcC;
       pc1 = bslot0 ? pcC : pcB;
     }
-    if (FS) {
-      const int szB = szD + szE;  // post-swap names
-      sz0 = bslot0 ? szB : szC;
-      sz1 = bslot0 ? szC : szB;
-    }
     B = A;
     A = An;
     {  // rotate the pipeline: what was loaded for the next level becomes current.  (Unconditional: at the root,
@@ -2502,7 +2588,6 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
         }
       }
       if (PC) pcC = pcCn;
-      if (FS) szC = szCn;
     }
     An = Ann;
     Ann = Annn;
@@ -2532,7 +2617,8 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
   P.total[chain] = PC ? c.pcv[root] : (rebase ? P.total[chain] : total);
   if constexpr (!Rng::kFast) P.n_prop[chain] += q_pa & 0xffffu;
   P.n_acc[chain] += q_pa >> 16;
-  P.n_wrej[chain] += q_wrej;
+  if constexpr (Rng::kFast && FINITE) P.n_wrej[chain] += P.n_prop[chain] - q_wrej;  // (n_prop is complete here)
+  else P.n_wrej[chain] += q_wrej;
 }
 
 }  // namespace tnb
