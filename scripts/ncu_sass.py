@@ -17,6 +17,7 @@ def main(path, per):
             hdr = r
             ia, isrc = hdr.index('Address'), hdr.index('Source')
             ie, isamp = hdr.index('Instructions Executed'), hdr.index('# Samples')
+            reasons = [(i, h) for i, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h]
             continue
         if hdr is None or len(r) <= max(ie, isamp):
             continue
@@ -24,7 +25,14 @@ def main(path, per):
             v, s = int(r[ie]), int(r[isamp])
         except ValueError:
             continue
-        print(f'{r[ia][-5:]} {v / per:7.3f} {s:7d}  {r[isrc][:100]}')
+        top = ''
+        try:
+            i, h = max(reasons, key=lambda ih: int(r[ih[0]] or 0))
+            if int(r[i] or 0) > 0:
+                top = f'{h[6:]}={r[i]}'
+        except (ValueError, IndexError):
+            pass
+        print(f'{r[ia][-5:]} {v / per:7.3f} {s:7d}  {r[isrc][:90]:90s} {top}')
 
 
 if __name__ == '__main__':
