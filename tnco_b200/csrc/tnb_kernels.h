@@ -1932,6 +1932,9 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
   // kernel parameters it cost ten instructions per 2-byte access)
   uint32_t* kws = FS ? P.kwsz + size_t(chain) * P.Npad : nullptr;
   if constexpr (FS) keep_in_register(kws);
+  // FS: leaves below the children of B (slot order) and below C -- carried like the index sets, the sibling's count
+  // loaded a level ahead (fetching them when a move is accepted stalled the warp on that load at every accept)
+  int sz0 = 0, sz1 = 0, szC = 0;
   Rng rng;
   rng.load(P, chain);
   if constexpr (Rng::kFast) rng.begin_stream(t);
@@ -2161,6 +2164,10 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
         pc0 = c.pc_of(p0);
         pc1 = c.pc_of(p1);
       }
+      if (FS) {
+        sz0 = int(kws[p0] >> 16);
+        sz1 = int(kws[p1] >> 16);
+      }
       if (HYPER) c.load_hyp(B, hB);
       A = c.par[B];
       in_sweep = true;
@@ -2173,6 +2180,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
           c.load_hyp(A, hA);
         }
         if (PC) pcC = c.pc_of(C);
+        if (FS) szC = int(kws[C] >> 16);
         An = c.par[A];
         Ann = -1;
         if (An >= 0) {
@@ -2198,6 +2206,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
 #pragma unroll
     for (int k = 0; k < WPL; ++k) bCn[k] = bAn[k] = hAn[k] = 0u;
     double pcCn = 0.0;
+    int szCn = 0;
     if (An >= 0) {
       Cn = other_child(nodeAn.w(), A);
       c.load_bits(Cn, bCn);
@@ -2206,6 +2215,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
         c.load_hyp(An, hAn);
       }
       if (PC) pcCn = c.pc_of(Cn);
+      if (FS) szCn = int(kws[Cn] >> 16);
     }
     const bool bslot0 = int(nodeA.w() & 0xffffu) == B;
     bool l0 = false, l1 = false;
@@ -2216,8 +2226,13 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
     }
     const bool i0 = t.any_c(l0), i1 = t.any_c(l1);
     bool pick0;
-    if (f_dsi || (i0 && i1)) pick0 = (rng.coin_word(t) & 1u) != 0u;
-    else pick0 = i0;
+    if constexpr (Rng::kFast) {  // (no disable_shared_inds here; plain predicate logic: coin when both intersect, else i0)
+      const bool coin = (rng.coin_word(t) & 1u) != 0u;
+      pick0 = i0 && (coin || !i1);
+    } else {
+      if (f_dsi || (i0 && i1)) pick0 = (rng.coin_word(t) & 1u) != 0u;
+      else pick0 = i0;
+    }
     int E = pick0 ? int(nodeB.w() >> 16) : int(nodeB.w() & 0xffffu);  // D = the other child
     uint32_t bD[WPL], bE[WPL], nb[WPL];
     // K10: no popcount of this kernel reaches 1024 (the host gives networks of 1024 and more indices two words per lane)
@@ -2261,6 +2276,8 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
     }
     const double pcD = pick0 ? pc0 : pc1;
     double pcE = pick0 ? pc1 : pc0;
+    const int szD = pick0 ? sz0 : sz1;
+    int szE = pick0 ? sz1 : sz0;
     if (!Rng::kFast) ++q_pa;
     bool gate = true;
     float swB = 0.f;  // new_sliced_width_B
@@ -2496,7 +2513,6 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
     uint32_t bB[WPL];
     if (acc) {
       // Tree::swap_with_nn(E): E <-> C, child slots preserved (tree.hpp:141-192)
-      const uint32_t oldB_w = nodeB.w();
       nodeA.set_w(put_child(nodeA.w(), E, bslot0));
       nodeB.set_w(put_child(nodeB.w(), C, pick0));
       nodeA.set_cost(nA);
@@ -2526,17 +2542,11 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
         kmax_hi = h_now > kmax_hi ? h_now : kmax_hi;
       }
       q_pa += 0x10000u;
-      if (FS) {
-        // popcount and leaf count of the new B for the re-slicer.  The leaf counts of its children (D and the old C)
-        // are fetched here, where only this store waits for them, instead of being carried through the walk (four
-        // registers and a load per level less); a lane reads back its own earlier stores, so D's count is current
-        // even when D was the B of the level below.
-        const int D = pick0 ? int(oldB_w & 0xffffu) : int(oldB_w >> 16);
-        kws[B] = ku + (kws[D] & 0xffff0000u) + (kws[C] & 0xffff0000u);
-      }
+      if (FS) kws[B] = ku | (uint32_t(szD + szC) << 16);  // popcount and leaf count of the new B for the re-slicer
       {
         const int ti = C; C = E; E = ti;
         const double td = pcC; pcC = pcE; pcE = td;
+        const int ts = szC; szC = szE; szE = ts;
       }
 #pragma unroll
       for (int k = 0; k < WPL; ++k) {
@@ -2571,6 +2581,11 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
       pc0 = bslot0 ? pcB : pcC;
       pc1 = bslot0 ? pcC : pcB;
     }
+    if (FS) {
+      const int szB = szD + szE;  // post-swap names
+      sz0 = bslot0 ? szB : szC;
+      sz1 = bslot0 ? szC : szB;
+    }
     B = A;
     A = An;
     {  // rotate the pipeline: what was loaded for the next level becomes current.  (Unconditional: at the root,
@@ -2588,6 +2603,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
         }
       }
       if (PC) pcC = pcCn;
+      if (FS) szC = szCn;
     }
     An = Ann;
     Ann = Annn;
