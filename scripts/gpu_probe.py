@@ -9,6 +9,9 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tnco_b200 import networks  # noqa: E402
+if os.environ.get('TNB_LIB'):   # A/B builds of the library (dev tool only)
+    from tnco_b200 import _lib as _l
+    _l.LIB_PATH = os.path.abspath(os.environ['TNB_LIB'])
 from tnco_b200.engine import Engine, pack_leaf_bits, random_trees  # noqa: E402
 
 

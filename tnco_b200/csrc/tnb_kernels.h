@@ -172,29 +172,41 @@ TNB_D TNB_INLINE unsigned lane_in_tile_here(int tl) {
 template <int TILE>
 struct RngPhilox {
   static constexpr bool kFast = true;  // log-domain fp32 acceptance test (see chain_sweeps)
+  // Event e of a chain (one per sweep start, one per level, one per slicer draw) takes half (e & 1) of the Philox
+  // vector with counter e >> 1: words (0,1) or (2,3) -- word A for a leaf draw / the D/E coin, word B for the uniform.
+  // That mapping does not depend on the tile shape, so neither do results.
+  //
   // Registers held across the sweep loop: ONE cursor and the current event's word.  The key (run seed), the global
-  // chain id and the 64-bit event index of the held batch are only needed when a batch is generated (once per TILE
-  // events), so they stay in memory / are re-derived there; the batch itself (per vector: word 0 for a leaf draw,
-  // and the level word) sits in 256 bytes of shared memory per warp, where an event is ONE broadcast load at the
-  // cursor -- against a shuffle out of two loop-carried registers (which the finite-width kernel, at its register
+  // chain id and the 64-bit event index of the held batch are only needed when a batch is generated, so they stay in
+  // memory / are re-derived there; the batch itself -- kEB events per tile: their words A, and their level words
+  // (-log2(u) as a float with the coin in its last bit) -- sits in shared memory, where an event is ONE broadcast load
+  // at the cursor: against a shuffle out of two loop-carried registers (which the finite-width kernel, at its register
   // cap, spilled: it read the level word back from local memory at every level) plus the convergence check the
-  // compiler brackets every shuffle with.
-  // Vector k of the batch belongs to event base + k, base = P.rng_ctr[chain] while a generator is live.  `at` is the
-  // shared-memory byte address of the next vector's level word (its word 0 sits 128 bytes below); the tile's TILE
-  // slots are aligned, so "batch used up" is (at & (4*TILE-1)) == 0 right after an event was consumed, and the next
-  // batch is generated then (event e always uses vector e: results do not depend on when that happens).
+  // compiler brackets every shuffle with.  A full-warp tile holds 64 events (one Philox call per lane); sub-warp
+  // tiles hold 32 each (32 / (2 TILE) calls per lane), so that the fixed cost of a refill -- key and event index from
+  // memory, two warp syncs -- is paid once per 32 events whatever the tile shape (with TILE events per batch C1 at
+  // TILE = 4 paid it every fourth iteration and lost 8 %).
+  // Slot k of the batch belongs to event base + k, base = P.rng_ctr[chain] (even) while a generator is live.  `at`
+  // is the shared-memory byte address of the next event's level word; the tile's kEB slots are aligned, so "batch
+  // used up" is (at & (4 kEB - 1)) == 0 right after an event was consumed, and the next batch is generated then.
   // Outside the sweep loop (constructors) a generator is not `live`: no batch, rng_ctr is the next event itself.
+  static constexpr int kEB = TILE == 32 ? 64 : (TILE == 1 ? 2 : 32);  // events per batch (TILE == 1: emulation build)
+  static constexpr int kCalls = kEB / (2 * TILE);                      // Philox calls per lane and batch
+  static constexpr int kSlotsW = kEB * (32 / (TILE == 1 ? 32 : TILE));  // slots of all tiles of a warp
   const Params* Pp;
   int chain;
   uint32_t at;
-  uint32_t e0;   // current event: word 0 (leaf draw) / the level word (coin | -log2(u))
+  uint32_t e0;   // current event: word A (leaf draw) / the level word (coin | -log2(u))
   uint32_t n_local;  // draws taken by local_next() since the last sync_from0() (zero outside the slicers)
+  uint32_t cd;   // sub-warp tiles: iterations until all tiles of the warp start a fresh batch together (tick)
   bool live;
+  bool ool = false;  // generate batches out of line (set by the kernels whose loop is instruction-cache bound)
 #if defined(TNB_EMU)
-  uint32_t batch_[2][TILE];
+  uint32_t batch_[2][kEB];
   TNB_D uint32_t slot0() { return 0u; }
-  TNB_D uint32_t& word(uint32_t a, int which) { return batch_[which][(a >> 2) & uint32_t(TILE - 1)]; }
+  TNB_D uint32_t& word(uint32_t a, int which) { return batch_[which][(a >> 2) & uint32_t(kEB - 1)]; }
   TNB_D uint32_t get(uint32_t a, int which) { return word(a, which); }
+  TNB_D void put2(uint32_t a, int which, uint32_t x, uint32_t y) { word(a, which) = x; word(a + 4u, which) = y; }
   TNB_D void ring_put(int) {}
   TNB_D void sweep_mark() {}
   TNB_D void note_refill() {}
@@ -203,19 +215,30 @@ struct RngPhilox {
   TNB_D void set_flag(uint32_t) {}
   TNB_D uint32_t flag() const { return 0; }
 #else
-  // (sweep kernels run one warp per block -- kSweepBlock -- so the lane id indexes the block's only batch; a tile's
-  //  vectors sit at its own lanes' slots)
-  // shared memory of the warp: [0] word 0 of the 32 vectors, [1] their level words, [2] the ring of the walk (the
-  // node B of the level that consumed each vector, see ring_put), [3] bookkeeping of the current sweep
+  // Shared memory of the warp (sweep kernels run one warp per block -- kSweepBlock): [0] words A of all slots,
+  // [1] their level words, and for full-warp tiles [2] the ring of the walk (the node B of the level that consumed
+  // each event, see ring_put) and [3] bookkeeping of the current sweep.  A tile's slots start at its first lane's.
   TNB_D TNB_INLINE uint32_t slot0() {
-    __shared__ __align__(128) uint32_t sm[4][32];
-    return uint32_t(__cvta_generic_to_shared(&sm[1][0])) + 4u * ((threadIdx.x & 31u) & ~uint32_t(TILE - 1));
+    __shared__ __align__(256) uint32_t sm[TILE == 32 ? 4 : 2][kSlotsW];
+    return uint32_t(__cvta_generic_to_shared(&sm[1][0])) + 4u * uint32_t(kEB) * ((threadIdx.x & 31u) / uint32_t(TILE));
   }
-  // ---- full-warp tiles: which nodes did the current sweep walk?  Every level leaves its node B next to the vector
-  // it consumed (ONE shared-memory store per level, addressed off the cursor), so a sweep of up to 31 levels can be
-  // listed afterwards -- what the incremental best-tree snapshot needs (snapshot_walk).
-  TNB_D TNB_INLINE void ring_put(int B) { asm volatile("st.shared.u32 [%0+128], %1;" ::"r"(at), "r"(B) : "memory"); }
-  TNB_D TNB_INLINE uint32_t meta_addr() const { return (at & ~127u) + 256u; }
+  TNB_D TNB_INLINE uint32_t get(uint32_t a, int which) {
+    uint32_t v;
+    if (which) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    else asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(-4 * kSlotsW));
+    return v;
+  }
+  TNB_D TNB_INLINE void put2(uint32_t a, int which, uint32_t x, uint32_t y) {
+    if (which) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+    else asm volatile("st.shared.v2.u32 [%0+%3], {%1, %2};" ::"r"(a), "r"(x), "r"(y), "n"(-4 * kSlotsW) : "memory");
+  }
+  // ---- full-warp tiles: which nodes did the current sweep walk?  Every level leaves its node B next to the event
+  // it consumed (ONE shared-memory store per level, addressed off the cursor), so a sweep of up to kEB - 1 levels can
+  // be listed afterwards -- what the incremental best-tree snapshot needs (snapshot_walk).
+  TNB_D TNB_INLINE void ring_put(int B) {
+    asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(at), "r"(B), "n"(4 * kSlotsW) : "memory");
+  }
+  TNB_D TNB_INLINE uint32_t meta_addr() const { return (at & ~uint32_t(4 * kEB - 1)) + 8u * uint32_t(kSlotsW); }
   TNB_D TNB_INLINE void sweep_mark() {  // sweep start, before its leaf event: remember the cursor, no refill yet
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(meta_addr()), "r"(at), "r"(0u) : "memory");
   }
@@ -228,12 +251,14 @@ struct RngPhilox {
   TNB_D TNB_INLINE uint32_t sweep_events(uint32_t& slot_start) const {
     uint32_t a0, r;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a0), "=r"(r) : "r"(meta_addr()));
-    slot_start = (a0 >> 2) & 31u;
-    return r * 32u + ((at >> 2) & 31u) - slot_start;
+    slot_start = (a0 >> 2) & uint32_t(kEB - 1);
+    return r * uint32_t(kEB) + ((at >> 2) & uint32_t(kEB - 1)) - slot_start;
   }
   TNB_D TNB_INLINE uint32_t ring_get(uint32_t slot) const {
     uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((at & ~127u) + 128u + 4u * (slot & 31u)));
+    asm volatile("ld.shared.u32 %0, [%1];"
+                 : "=r"(v)
+                 : "r"((at & ~uint32_t(4 * kEB - 1)) + 4u * uint32_t(kSlotsW) + 4u * (slot & uint32_t(kEB - 1))));
     return v;
   }
   TNB_D TNB_INLINE void set_flag(uint32_t f) { asm volatile("st.shared.u32 [%0+8], %1;" ::"r"(meta_addr()), "r"(f) : "memory"); }
@@ -242,14 +267,8 @@ struct RngPhilox {
     asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(v) : "r"(meta_addr()));
     return v;
   }
-  TNB_D TNB_INLINE uint32_t get(uint32_t a, int which) {
-    uint32_t v;
-    if (which) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    else asm volatile("ld.shared.u32 %0, [%1+-128];" : "=r"(v) : "r"(a));
-    return v;
-  }
 #endif
-  TNB_D TNB_INLINE uint32_t pos() const { return live ? (at >> 2) & uint32_t(TILE - 1) : 0u; }
+  TNB_D TNB_INLINE uint32_t pos() const { return live ? (at >> 2) & uint32_t(kEB - 1) : 0u; }
   TNB_D TNB_INLINE unsigned long long base() const { return Pp->rng_ctr[chain]; }
   TNB_D TNB_INLINE void set_base(unsigned long long b) const { Pp->rng_ctr[chain] = b; }
   TNB_D unsigned long long counter() const { return base() + pos(); }
@@ -259,71 +278,124 @@ struct RngPhilox {
     e0 = 0;
     at = 0;
     n_local = 0;
+    cd = uint32_t(kEB - 1);
     live = false;
   }
-  TNB_D void begin_stream(const Tile<TILE>& t) {  // sweep kernels: generate the batch of events base ...
+  // a fresh batch whose next event is b (batches start at even events: an odd b skips the first slot)
+  TNB_D TNB_INLINE void restart(const Tile<TILE>& t, unsigned long long b) {
+    at -= 4u * pos();
+    set_base(b & ~1ull);
+    generate(t, b & ~1ull);
+    at += 4u * uint32_t(b & 1ull);
+  }
+  TNB_D void begin_stream(const Tile<TILE>& t) {  // sweep kernels: the batch that holds the next event
+    const unsigned long long b = base();
     live = true;
     at = slot0();
-    generate(t, base());
+    restart(t, b);
   }
   TNB_D void store(const Params&, int) {
     set_base(counter());
     live = false;
   }
   TNB_D bool can_start(const Params&) const { return true; }
-  TNB_D TNB_INLINE void philox(unsigned long long idx, uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) const {
+  TNB_D TNB_INLINE void philox(unsigned long long ctr, uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) const {
     const unsigned long long s = Pp->seeds[chain], g = Pp->chain_id0 + (unsigned long long)chain;
-    philox4x32_10(uint32_t(idx), uint32_t(idx >> 32), uint32_t(g), uint32_t(g >> 32), uint32_t(s), uint32_t(s >> 32),
+    philox4x32_10(uint32_t(ctr), uint32_t(ctr >> 32), uint32_t(g), uint32_t(g >> 32), uint32_t(s), uint32_t(s >> 32),
                   o0, o1, o2, o3);
   }
-  // the batch of events b .. b + TILE - 1 into the tile's slots (`at` points at slot 0)
-  TNB_D void generate(const Tile<TILE>& t, unsigned long long b) {
-    // (lane id read here, opaquely: otherwise the compiler hoists the special-register read and its masking out of
-    //  this rarely taken branch into every iteration of the sweep loop)
-    const unsigned tl = lane_in_tile_here<TILE>(t.tl);
-    const unsigned long long idx = b + (unsigned long long)tl;
+  // word A of one event (leaf draw, slicer draw), whatever batch is held
+  TNB_D TNB_INLINE uint32_t word_a(unsigned long long e) const {
     uint32_t r0, r1, r2, r3;
-    philox(idx, r0, r1, r2, r3);
-    // u = (r1 + 0.5) / 2^32 in (0,1);  -log2(u) = 32 - log2(r1 + 0.5), computed once per vector.  The D/E coin of
-    // the level (last bit of word 0) rides in the last mantissa bit of that float -- one load per level instead
-    // of two; the bit moves the acceptance threshold by one fp32 ulp, far inside the 3e-6 of ex2.approx.
+    philox(e >> 1, r0, r1, r2, r3);
+    return (e & 1ull) ? r2 : r0;
+  }
+  // u = (x + 0.5) / 2^32 in (0,1);  -log2(u) = 32 - log2(x + 0.5), computed once per event.  The D/E coin of the
+  // level (last bit of word A) rides in the last mantissa bit of that float -- one load per level instead of two;
+  // the bit moves the acceptance threshold by one fp32 ulp, far inside the 3e-6 of ex2.approx.
+  static TNB_D TNB_INLINE uint32_t level_word(uint32_t a, uint32_t x) {
 #if defined(TNB_EMU)
-    const float rf = 32.f - log2f(float(r1) + 0.5f);
+    const float rf = 32.f - log2f(float(x) + 0.5f);
     uint32_t fb;
     std::memcpy(&fb, &rf, 4);
-    word(at + 4u * tl, 0) = r0;
-    word(at + 4u * tl, 1) = (fb & ~1u) | (r0 & 1u);
 #else
-    const uint32_t fb = __float_as_uint(32.f - __log2f(float(r1) + 0.5f));
-    t.sync();  // (everybody is done with the previous batch)
-    asm volatile("st.shared.u32 [%0+-128], %1;" ::"r"(at + 4u * tl), "r"(r0) : "memory");
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(at + 4u * tl), "r"((fb & ~1u) | (r0 & 1u)) : "memory");
-    t.sync();
+    const uint32_t fb = __float_as_uint(32.f - __log2f(float(x) + 0.5f));
 #endif
+    return (fb & ~1u) | (a & 1u);
   }
-  // Sub-warp tiles: every TILE iterations of the sweep loop ALL tiles of the warp start a fresh batch together (an
-  // iteration consumes at most one event, so nobody runs dry in between).  Refilling tile by tile made the 70
-  // instructions of a refill run with 1/8 of the lanes active several times per iteration (C1: 13.5 of 32 lanes
-  // active on average).
-  TNB_D TNB_INLINE void tick(const Tile<TILE>& t, uint32_t iteration) {
-    if (TILE < 32 && (iteration & uint32_t(TILE - 1)) == 0u && pos() != 0u) {  // (pos == 0: fresh batch, unused)
-      const unsigned long long b = base() + pos();
-      set_base(b);
-      at -= 4u * pos();
-      generate(t, b);
+  // The batch of events bb .. bb + kEB - 1 (bb even) into the tile's slots (at0 = address of slot 0).  Out of line
+  // and by value: ONE copy of the ~100 instructions instead of one at each of the five places a batch can start (the
+  // sweep loop of the finite-width kernel is close to the instruction cache's size: with the copies inlined 22 % of
+  // its stall samples were instruction fetches), and no generator state is forced into local memory by the call.
+#if !defined(TNB_EMU)
+  static TNB_D TNB_NOINLINE void generate_batch(const Params* P, int chain, uint32_t at0, unsigned long long bb) {
+    Tile<TILE> t;
+    RngPhilox g;
+    g.Pp = P;
+    g.chain = chain;
+    const unsigned tl = lane_in_tile_here<TILE>(t.tl);
+    t.sync();  // (everybody is done with the previous batch)
+#pragma unroll 1
+    for (int j = 0; j < kCalls; ++j) {
+      const unsigned q = tl + unsigned(j * TILE);  // events bb + 2q and bb + 2q + 1
+      uint32_t r0, r1, r2, r3;
+      g.philox((bb >> 1) + (unsigned long long)q, r0, r1, r2, r3);
+      g.put2(at0 + 8u * q, 0, r0, r2);
+      g.put2(at0 + 8u * q, 1, level_word(r0, r1), level_word(r2, r3));
+    }
+    t.sync();
+  }
+#endif
+#if defined(TNB_EMU)
+  TNB_D void generate(const Tile<TILE>&, unsigned long long bb) {  // (the emulation build keeps the batch in the object)
+    uint32_t r0, r1, r2, r3;
+    philox(bb >> 1, r0, r1, r2, r3);
+    put2(at, 0, r0, r2);
+    put2(at, 1, level_word(r0, r1), level_word(r2, r3));
+  }
+#else
+  // (the small unconstrained kernels inline it -- 2 % faster there; see `ool`)
+  TNB_D TNB_INLINE void generate(const Tile<TILE>& t, unsigned long long bb) {
+    if (ool) {
+      generate_batch(Pp, chain, at, bb);
+    } else {
+      const unsigned tl = lane_in_tile_here<TILE>(t.tl);
+      t.sync();
+#pragma unroll 1
+      for (int j = 0; j < kCalls; ++j) {
+        const unsigned q = tl + unsigned(j * TILE);
+        uint32_t r0, r1, r2, r3;
+        philox((bb >> 1) + (unsigned long long)q, r0, r1, r2, r3);
+        put2(at + 8u * q, 0, r0, r2);
+        put2(at + 8u * q, 1, level_word(r0, r1), level_word(r2, r3));
+      }
+      t.sync();
+    }
+  }
+#endif
+  // Sub-warp tiles: every kEB - 1 iterations of the sweep loop ALL tiles of the warp start a fresh batch together
+  // (an iteration consumes at most one event and a batch holds at least kEB - 1, so nobody runs dry in between).
+  // Refilling tile by tile made the instructions of a refill run with 1/8 of the lanes active several times per
+  // iteration (C1: 13.5 of 32 lanes active on average).
+  TNB_D TNB_INLINE void tick(const Tile<TILE>& t, uint32_t) {
+    if (TILE < 32) {
+      if (--cd == 0u) {
+        cd = uint32_t(kEB - 1);
+        if (pos() != 0u) restart(t, base() + pos());  // (pos == 0: fresh batch, unused)
+      }
     }
   }
   TNB_D TNB_INLINE void consumed(const Tile<TILE>& t) {  // one event taken: step, and start the next batch if that was the last
     at += 4u;
-    if ((at & uint32_t(4 * TILE - 1)) == 0u) {
-      const unsigned long long b = base() + TILE;
-      set_base(b);
-      at -= 4u * TILE;
+    if ((at & uint32_t(4 * kEB - 1)) == 0u) {
+      const unsigned long long bb = base() + uint32_t(kEB);
+      set_base(bb);
+      at -= 4u * uint32_t(kEB);
       if (TILE == 32) note_refill();
-      generate(t, b);
+      generate(t, bb);
     }
   }
-  TNB_D TNB_INLINE uint32_t leaf_word(const Tile<TILE>& t) {  // sweep start: the whole word 0
+  TNB_D TNB_INLINE uint32_t leaf_word(const Tile<TILE>& t) {  // sweep start: the whole word A
     e0 = get(at, 0);
     consumed(t);
     return e0;
@@ -353,15 +425,15 @@ struct RngPhilox {
 #endif
   }
   TNB_D TNB_INLINE double uniform(const Tile<TILE>&) {  // exact path (not used by the production kernels)
-    uint32_t a, b, c, d;
-    philox(counter() - 1ull, a, b, c, d);                // the event begin_level() just consumed
-    return uniform_from(b, c);
+    const unsigned long long e = counter() - 1ull;       // the event begin_level() just consumed
+    uint32_t r0, r1, r2, r3;
+    philox(e >> 1, r0, r1, r2, r3);
+    return (e & 1ull) ? uniform_from(r3, r2) : uniform_from(r1, r0);
   }
-  // Draws outside the level stream (the slicers): word 0 of the events after the last one consumed.  A slicer may
+  // Draws outside the level stream (the slicers): word A of the events after the last one consumed.  A slicer may
   // draw on lane 0 only; sync_from0() afterwards makes every lane skip the events lane 0 used.
   TNB_D uint32_t local_next() {
-    uint32_t a, b, c, d;
-    philox(counter() + n_local, a, b, c, d);
+    const uint32_t a = word_a(counter() + n_local);
     ++n_local;
     return a;
   }
@@ -371,13 +443,10 @@ struct RngPhilox {
     if (n == 0u) return;
     if (!live) {
       set_base(base() + n);
-    } else if (pos() + n < uint32_t(TILE)) {
+    } else if (pos() + n < uint32_t(kEB)) {
       at += 4u * n;
-    } else {  // past the held batch: a fresh one starting at the next event
-      const unsigned long long b = base() + pos() + n;
-      set_base(b);
-      at -= 4u * pos();
-      generate(t, b);
+    } else {  // past the held batch: a fresh one holding the next event
+      restart(t, base() + pos() + n);
     }  // (slicer draws come after the walk of their sweep was counted: sweep_events() is taken before)
   }
   TNB_D unsigned long long words() const { return 0; }
@@ -1484,8 +1553,8 @@ TNB_D void snapshot_walk(const ChainView<TILE, WPL>& c, const Rng& rng, uint32_t
   int16_t* bpar = P.bpar + size_t(c.chain) * P.Npad;
   uint32_t* dch = P.bch + size_t(c.chain) * P.n_int;
   c.t.sync();  // (the two snapshot forms write the same words from different lanes: keep them ordered)
-  if (c.t.tl <= levels) {
-    const int X = c.t.tl < levels ? int(rng.ring_get(slot_start + 1u + uint32_t(c.t.tl))) : P.N - 1;
+  for (int i = c.t.tl; i <= levels; i += TILE) {
+    const int X = i < levels ? int(rng.ring_get(slot_start + 1u + uint32_t(i))) : P.N - 1;
     const uint32_t w = c.ch(X);
     dch[X - P.n] = w;
     bpar[w & 0xffffu] = int16_t(X);
@@ -1937,7 +2006,10 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
   int sz0 = 0, sz1 = 0, szC = 0;
   Rng rng;
   rng.load(P, chain);
-  if constexpr (Rng::kFast) rng.begin_stream(t);
+  if constexpr (Rng::kFast) {
+    rng.ool = FINITE || TILE < 32;  // (measured per kernel: C4 +15 %, C1 at TILE 4 +4 %, C2 -2 % when out of line)
+    rng.begin_stream(t);
+  }
   if constexpr (INC) rng.set_flag(0u);
   // Production kernels: every level consumes exactly one event of the generator and every sweep start one, so the
   // proposals of a launch are (events consumed) - (sweeps done) - (draws of the re-slicer): no counter in the loop.
@@ -2118,7 +2190,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
           *min_total_p = root_pc;
           bool done = false;
           if constexpr (INC) {
-            if (rng.flag() != 0u && n_ev <= 32u) {  // started from the best tree, and the ring still holds the walk
+            if (rng.flag() != 0u && n_ev <= uint32_t(Rng::kEB)) {  // started from the best tree, and the ring still holds the walk
               snapshot_walk(c, rng, slot_start, int(n_ev) - 1, S, FINITE);
               done = true;
             }
