@@ -18,5 +18,6 @@ probe($ARGS)" > /tmp/pl_$cfg.log 2>&1
   echo "-- by stall samples" >> $OUT
   python scripts/ncu_lines.py /tmp/pl_$cfg.ncu-rep $PROPS 50 stall >> $OUT
   python scripts/ncu_sass.py /tmp/pl_$cfg.ncu-rep $PROPS > gpurun_out/sass_${TAG:-x}_$cfg.txt
+  python scripts/ncu_lines.py /tmp/pl_$cfg.ncu-rep $PROPS 2000 > gpurun_out/alllines_${TAG:-x}_$cfg.txt
   head -30 $OUT
 done

@@ -330,3 +330,20 @@ def test_per_index_dims_through_the_app(backend, max_width):
             total += math.prod(tn.dims[i] for i in tx | ty)
             work.append(tx ^ ty)
         assert abs(math.log2(total) - math.log2(float(r.cost))) < 1e-4
+
+
+def test_verbose_progress_surface(backend, capsys):
+    """verbose >= 2: the reference shows per-run status / log2_total_cost while runs are active
+    (tnco/parallel.py:229-317, infinite_memory/sa.py:208-209); here every twentieth of the anneal reports the batch's
+    status and best cost to stderr, and the result does not depend on being watched."""
+    from tnco_b200.app import Optimizer
+    ts, ni = regular_network(30, 5)
+    rows = index_rows(ts, ni)
+    kw = dict(betas=(0, 100), fuse=False, decompose_hyper_inds=False, n_steps=100, n_runs=4)
+    _, quiet = Optimizer(seed=7).optimize(rows, **kw)
+    capsys.readouterr()
+    _, loud = Optimizer(seed=7, verbose=2).optimize(rows, **kw)
+    err = capsys.readouterr().err
+    lines = [l for l in err.splitlines() if l.startswith('[tnco_b200 rank 0]')]
+    assert len(lines) == 20 and 'sweep 100/100' in lines[-1] and 'best log2 cost' in lines[0]
+    assert [r.path for r in quiet] == [r.path for r in loud] and [r.cost for r in quiet] == [r.cost for r in loud]

@@ -778,3 +778,80 @@ def test_minima_stay_exact_when_chains_wander_at_small_beta():
         assert np.allclose(np.log2(bseq), np.log2(m), atol=1e-9)
     assert peak > 70          # the scenario really occurred: totals far above what fp64 sums exactly
     e.close()
+
+
+def _ring_network(n):
+    """n tensors in a ring: tensor t holds indices t and (t + 1) % n -- n indices, all of dimension 2."""
+    return [[t, (t + 1) % n] for t in range(n)], n
+
+
+def _caterpillar(n, n_chains):
+    """The deepest tree: ((((0,1),2),3),...) -- a sweep from leaf 0 walks n - 2 levels."""
+    N = 2 * n - 1
+    P, A, B = (np.full((n_chains, N), -1, np.int32) for _ in range(3))
+    for k in range(n - 1):
+        z = n + k
+        a, b = (0, 1) if k == 0 else (z - 1, k + 1)
+        A[:, z], B[:, z] = a, b
+        P[:, a], P[:, b] = z, z
+    return P, A, B
+
+
+def test_networks_of_1024_indices_take_two_words_per_lane():
+    """The one-word-per-lane production kernels pack popcounts into 10-bit fields (no popcount reaches 1024 there):
+    a network of exactly 1024 indices fits 32 words but must run with two words per lane."""
+    from helpers import leaf_bits
+    from tnco_b200.engine import Engine
+    for n in (1023, 1024):
+        ts, ni = _ring_network(n)
+        lb = leaf_bits(ts, ni)
+        seeds = np.arange(16, dtype=np.uint64) + 3
+        for mw in (None, 3.0):
+            e = Engine()
+            e.set_network(lb, ni).set_mode(max_width=mw)
+            e.generate_chains(seeds)
+            assert e.config()['words_per_lane'] == (2 if n == 1024 else 1)
+            e.set_betas(np.linspace(0, 50, 100, endpoint=False))
+            e.run(100)
+            t, m = e.costs()
+            P, A, B = e.trees()
+            bP, bA, bB = e.trees(True)
+            S = e.slices() if mw is not None else None
+            bS = e.slices(True) if mw is not None else None
+            _, pc, w = e.eval_cost(P, A, B, slices=S)
+            _, bpc, bw = e.eval_cost(bP, bA, bB, slices=bS)
+            assert np.allclose(np.log2(pc), np.log2(t), atol=1e-9) and np.allclose(np.log2(bpc), np.log2(m), atol=1e-9)
+            if mw is not None:
+                assert (bw <= mw).all() and (w <= mw).all()
+            e.close()
+
+
+@pytest.mark.parametrize('max_width', [None, 3.0])
+def test_best_tree_snapshots_on_very_deep_trees(max_width):
+    """The incremental best-tree snapshot lists the nodes a sweep walked from a 64-entry ring; sweeps with more
+    levels (here up to 198, from caterpillar trees) must fall back to the full copy, and either way the recorded
+    best tree has to cost exactly min_total."""
+    from helpers import leaf_bits
+    from tnco_b200.engine import Engine
+    ts, ni = _ring_network(200)
+    lb = leaf_bits(ts, ni)
+    seeds = np.arange(32, dtype=np.uint64) + 5
+    P0, A0, B0 = _caterpillar(200, 32)
+    e = Engine()
+    e.set_network(lb, ni).set_mode(max_width=max_width)
+    e.set_chains(P0, A0, B0, seeds)
+    e.set_betas(np.linspace(0.5, 100, 300, endpoint=False))
+    levels = []
+    for until in (5, 20, 100, 300):
+        c0 = e.counters()
+        e.run(until)
+        c1 = e.counters()
+        levels.append((c1['proposals'] - c0['proposals']) / max(c1['sweeps'] - c0['sweeps'], 1))
+        t, m = e.costs()
+        bP, bA, bB = e.trees(True)
+        _, bpc, bw = e.eval_cost(bP, bA, bB, slices=e.slices(True) if max_width is not None else None)
+        assert np.allclose(np.log2(bpc), np.log2(m), atol=1e-9)
+        assert (m <= t * (1 + 1e-12)).all()
+    assert levels[0] > 64     # the first sweeps are longer than the ring ...
+    assert levels[-1] < 64    # ... the later ones are not
+    e.close()

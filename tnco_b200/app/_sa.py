@@ -109,6 +109,28 @@ def run_component(opt, comp, tn, imap, seeds, betas, *, finite, update_slices, d
                 if eng is not None:
                     eng.run(done)
                 stats.setdefault('global_best_history', []).append((done, _exchange_best(eng, lo, finite, n_int, W32)[0]))
+        elif eng is not None and opt.verbose >= 2:
+            # Progress surface (reference: per-run `status` and `log2_total_cost` buffers shown by a progress bar when
+            # verbose >= 2, tnco/parallel.py:229-317, infinite_memory/sa.py:208-209): the anneal runs in 20 pieces and
+            # every piece reports the batch's status and best / mean log2 cost to stderr; the same records are kept
+            # in stats['progress'].
+            import sys
+            t_run = time.perf_counter()
+            for piece in range(1, 21):
+                target = n_steps * piece // 20
+                if target == 0:
+                    continue
+                eng.run(target, timeout_s=None if deadline is None else max(deadline - time.perf_counter(), 0.0))
+                _, m_now = eng.costs()
+                rec = dict(status=eng.reached / n_steps, sweeps=eng.reached, elapsed_s=time.perf_counter() - t_run,
+                           log2_min_total_cost=float(np.log2(m_now.min())) if m_now.size and m_now.min() > 0 else float('nan'),
+                           mean_log2_min_total_cost=float(np.mean(np.log2(np.maximum(m_now, 1e-300)))))
+                stats.setdefault('progress', []).append(rec)
+                print('[tnco_b200 rank %d] %5.1f %%  sweep %d/%d  best log2 cost %.4f  mean %.4f  %.1f s' % (
+                    dist.world()[0], 100 * rec['status'], rec['sweeps'], n_steps, rec['log2_min_total_cost'],
+                    rec['mean_log2_min_total_cost'], rec['elapsed_s']), file=sys.stderr, flush=True)
+                if eng.reached < target:   # timed out
+                    break
         elif eng is not None:
             # timeout: the reference polls a stop flag every sweep (sa.py:201); here the engine checks the wall clock
             # between internal launches (tnb_run_timed)
