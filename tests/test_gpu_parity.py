@@ -842,7 +842,7 @@ def test_best_tree_snapshots_on_very_deep_trees(max_width):
     e.set_chains(P0, A0, B0, seeds)
     e.set_betas(np.linspace(0.5, 100, 300, endpoint=False))
     levels = []
-    for until in (5, 20, 100, 300):
+    for until in (1, 20, 100, 300):
         c0 = e.counters()
         e.run(until)
         c1 = e.counters()
