@@ -855,37 +855,3 @@ def test_best_tree_snapshots_on_very_deep_trees(max_width):
     assert levels[0] > 64     # the first sweeps are longer than the ring ...
     assert levels[-1] < 64    # ... the later ones are not
     e.close()
-
-
-@pytest.mark.parametrize('name', ['c3_sycamore14_inf', 'c4_sycamore20_fw32'])
-def test_two_chains_per_warp_with_two_words_per_lane_matches_golden(name):
-    """Index sets of 17 .. 32 words can also run two chains per warp (16 lanes x 2 words), the shape large batches of
-    such networks get: bit-exact against the reference goldens of the benchmarked Sycamore networks."""
-    from tnco_b200.engine import RNG_MT19937
-    g = np.load(os.path.join(GOLDEN, name + '.npz'))
-    e, mw = _engine(g, RNG_MT19937, tile=16)
-    assert e.config()['tile'] == 16 and e.config()['words_per_lane'] == 2
-    _check_against_golden(g, e, mw)
-
-
-@pytest.mark.parametrize('max_width', [None, 26.0])
-def test_results_do_not_depend_on_the_lane_layout_of_wide_index_sets(max_width):
-    """32 lanes x 1 word and 16 lanes x 2 words give identical production (Philox) results on Sycamore m=14."""
-    from tnco_b200 import networks
-    from tnco_b200.engine import Engine, pack_leaf_bits
-    ts, ni = networks.sycamore(14)
-    lb = pack_leaf_bits(ts, ni)
-    seeds = np.arange(10, dtype=np.uint64) + 21
-    outs = {}
-    for tile in (32, 16):
-        os.environ['TNB_TILE'] = str(tile)
-        e = Engine()
-        e.set_network(lb, ni).set_mode(max_width=max_width)
-        e.generate_chains(seeds)
-        os.environ.pop('TNB_TILE', None)
-        assert e.config()['tile'] == tile and e.config()['words_per_lane'] == 32 // tile
-        e.set_betas(np.linspace(0, 100, 150, endpoint=False))
-        e.run(150)
-        outs[tile] = (e.costs()[1].copy(), e.trees_packed(best=True).copy(), e.counters())
-        e.close()
-    assert (outs[16][0] == outs[32][0]).all() and (outs[16][1] == outs[32][1]).all() and outs[16][2] == outs[32][2]

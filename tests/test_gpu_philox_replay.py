@@ -178,12 +178,6 @@ def test_production_kernel_replay_finite_width_sub_warp(tile):
     run_and_replay('regular_graph(150, 5)', 12.0, 500, chains=5, tile=tile)
 
 
-@pytest.mark.parametrize('name,n_sweeps', [('C3', 400), ('C4', 300)])
-def test_production_kernel_replay_two_chains_per_warp_two_words_per_lane(name, n_sweeps):
-    net, mw = NETS[name]
-    run_and_replay(net, mw, n_sweeps, chains=6, tile=16)
-
-
 def test_production_kernel_replay_low_beta_and_every_sweep_reslice():
     # slow ramp: many uphill acceptances, totals wander (running-total guard), re-slice after every sweep
     run_and_replay('grid_rqc(5, 5, 10)', 14.0, 700, chains=4, every=1, beta1=8.0)

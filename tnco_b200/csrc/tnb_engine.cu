@@ -29,7 +29,6 @@ namespace tnb {
 TNB_EXTERN_SHAPE(4, 1)
 TNB_EXTERN_SHAPE(8, 1)
 TNB_EXTERN_SHAPE(16, 1)
-TNB_EXTERN_SHAPE(16, 2)
 TNB_EXTERN_SHAPE(32, 1)
 TNB_EXTERN_SHAPE(32, 2)
 TNB_EXTERN_SHAPE(32, 3)
@@ -63,7 +62,6 @@ static bool launch(Rt& rt, const Params& P, int tile, int wpl, bool init, bool f
     case 4 * 16 + 1: return launch_tw<4, 1>(rt, P, init, finite, stream_rng);
     case 8 * 16 + 1: return launch_tw<8, 1>(rt, P, init, finite, stream_rng);
     case 16 * 16 + 1: return launch_tw<16, 1>(rt, P, init, finite, stream_rng);
-    case 16 * 16 + 2: return launch_tw<16, 2>(rt, P, init, finite, stream_rng);
     case 32 * 16 + 1: return launch_tw<32, 1>(rt, P, init, finite, stream_rng);
     case 32 * 16 + 2: return launch_tw<32, 2>(rt, P, init, finite, stream_rng);
     case 32 * 16 + 3: return launch_tw<32, 3>(rt, P, init, finite, stream_rng);
@@ -104,7 +102,6 @@ static bool launch_treegen(Rt& rt, const Params& P, int tile, int wpl) {
     case 4 * 16 + 1: return launch_treegen_t<4, 1>(rt, P);
     case 8 * 16 + 1: return launch_treegen_t<8, 1>(rt, P);
     case 16 * 16 + 1: return launch_treegen_t<16, 1>(rt, P);
-    case 16 * 16 + 2: return launch_treegen_t<16, 2>(rt, P);
     case 32 * 16 + 1: return launch_treegen_t<32, 1>(rt, P);
     case 32 * 16 + 2: return launch_treegen_t<32, 2>(rt, P);
     case 32 * 16 + 3: return launch_treegen_t<32, 3>(rt, P);
@@ -255,12 +252,9 @@ static int pick_tile(int W, int n_inds, int& wpl, bool hyper, long long n_chains
   tile = narrowest;
   for (int t = 32; t >= narrowest; t >>= 1)
     if ((n_chains * t + 31) / 32 <= capacity) { tile = t; break; }
-  // 17 .. 32 words: a batch larger than one wave of full-warp tiles runs two chains per warp, two words per lane
-  if (narrowest == 32 && n_chains > capacity) { wpl = 2; tile = 16; }
   if (const char* f = std::getenv("TNB_TILE")) {
     const int t = std::atoi(f);
-    if ((t == 4 || t == 8 || t == 16 || t == 32) && t * 1 >= (W <= 32 ? W : 32)) { tile = t; wpl = 1; }
-    if (t == 16 && W > 16 && W <= 32) { tile = 16; wpl = 2; }
+    if ((t == 4 || t == 8 || t == 16 || t == 32) && t * 1 >= (W <= 32 ? W : 32)) tile = t;
   }
   return tile;
 }
