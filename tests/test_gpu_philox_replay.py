@@ -83,12 +83,17 @@ def run_and_replay(net, max_width, n_sweeps, chains=3, tile=None, every=10, beta
     gp, ga, gb = e.trees()
     bp, ba, bb = e.trees(best=True)
     stats = dict(proposals=0, gated=0, near=0, reslices=0, kept=0)
+    pr = e.progress()
     for c in range(chains):
         rec, cand = e.trace(c)
         kind = rec['w0'] & 3
         prop = rec[kind == 1]
         rs = rec[kind == 2]
         assert (kind == 0).sum() == n_sweeps
+        # the counters (proposals come from the generator's event index, width rejects from the gate passes)
+        assert pr['sweeps'][c] == n_sweeps and pr['proposals'][c] == len(prop)
+        assert pr['accepts'][c] == int(((prop['w0'] >> 4) & 1).sum())
+        assert pr['width_rejects'][c] == int((((prop['w0'] >> 3) & 1) == 0).sum())
         oc = so.Chain(P[c], A[c], B[c], init_bits[c], ni, max_width=max_width, seed=0,
                       init_slices=None if max_width is None else init_slices[c])
         words = synthesize_stream(rec)
