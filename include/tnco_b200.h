@@ -137,9 +137,10 @@ int tnb_set_skip_slices(tnb_engine* e, const uint32_t* skip_bits);
  * sweeps s with s % update_slices_every == 0 (tnco/app/finite_width/sa.py:228). */
 int tnb_set_mode(tnb_engine* e, double max_width, int update_slices_every, int disable_shared_inds,
                  int prob_kind, int rng_kind, int layout);
-/* TNB_RNG_PHILOX (production) runs what tnco.app runs: Metropolis-Hastings acceptance with shared-index moves.
- * Greedy / always acceptance and disable_shared_inds -- the core objects' options -- need TNB_RNG_MT19937 or
- * TNB_RNG_REPLAY; tnb_run and the chain constructors fail otherwise. */
+/* TNB_RNG_PHILOX (production) runs what tnco.app runs: shared-index moves, Metropolis-Hastings acceptance -- and
+ * greedy / always acceptance as the two limits of the same threshold test (1/beta = 0 / +inf).  disable_shared_inds
+ * -- a core-object option -- needs TNB_RNG_MT19937 or TNB_RNG_REPLAY; tnb_run and the chain constructors fail
+ * otherwise. */
 
 /* Change only the acceptance rule (the reference passes a prob object to every update()); chains are kept. */
 int tnb_set_prob(tnb_engine* e, int prob_kind);

@@ -259,9 +259,23 @@ def test_mode_and_resume_argument_errors():
     seeds = np.array([1, 2], np.uint64)
     p, a, b = random_trees(lb, ni, seeds)
     e = Engine()
-    e.set_network(lb, ni).set_mode(prob=PROB_GREEDY).set_chains(p, a, b, seeds).set_betas([1.0, 2.0])
-    with pytest.raises((EngineError, ValueError), match='Metropolis'):
-        e.run(2)
+    # greedy and always acceptance are limits of the production kernel's threshold test (1/beta = 0 / +inf)
+    from tnco_b200._lib import PROB_ALWAYS
+    e.set_network(lb, ni).set_mode(prob=PROB_GREEDY).set_chains(p, a, b, seeds).set_betas([1.0] * 40)
+    t0, _ = e.costs()
+    prev = t0
+    for s_ in (10, 20, 40):
+        e.run(s_)
+        t1, m1 = e.costs()
+        assert (t1 <= prev).all() and (m1 == t1).all()   # never uphill: the current tree is always the best one
+        prev = t1
+    assert (prev < t0).any()
+    e.set_mode(prob=PROB_ALWAYS).set_chains(p, a, b, seeds).set_betas([50.0] * 20)
+    e.run(20)
+    c_ = e.counters()
+    assert c_['accepts'] == c_['proposals'] > 0
+    e.set_prob(0)                                          # back to Metropolis-Hastings on the same chains
+    e.run(20)
     e.set_mode(disable_shared_inds=True).set_chains(p, a, b, seeds)
     with pytest.raises((EngineError, ValueError), match='Metropolis'):
         e.costs()

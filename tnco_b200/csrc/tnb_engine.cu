@@ -162,6 +162,8 @@ struct tnb_engine {
   uint64_t dim = 2;
   double log2d = 1.0;
   uint32_t* d_leaf_bits = nullptr;
+  std::vector<double> h_betas;  // the schedule as given (tnb_set_betas)
+  int inv_kind = 0;             // acceptance rule d_inv_betas was computed for
   double* d_pow_tab = nullptr;
   int16_t* d_net_own = nullptr;  // [2][n_inds] the leaves holding each index (device tree construction)
   uint16_t* d_hcount0 = nullptr;  // [Ws*32] initial hyper counts
@@ -476,9 +478,11 @@ static bool mt_refill(tnb_engine* e, bool first) {
 
 // Philox kernels are compiled for the app's mode (Metropolis-Hastings, shared-index moves)
 static bool mode_ok(tnb_engine* e) {
-  if (e->rng_kind == TNB_RNG_PHILOX && (e->dsi || e->prob_kind != TNB_PROB_MH))
-    return e->fail("TNB_RNG_PHILOX runs Metropolis-Hastings with shared-index moves only: greedy / always acceptance "
-                   "and disable_shared_inds need TNB_RNG_MT19937 or TNB_RNG_REPLAY (invalid mode)");
+  // (greedy / always acceptance are limits of the production kernel's threshold test -- 1/beta = 0 / +inf, see
+  //  upload_inv_betas -- so only disable_shared_inds is out of its reach)
+  if (e->rng_kind == TNB_RNG_PHILOX && e->dsi)
+    return e->fail("TNB_RNG_PHILOX runs Metropolis-Hastings / greedy / always acceptance with shared-index moves only: "
+                   "disable_shared_inds needs TNB_RNG_MT19937 or TNB_RNG_REPLAY (invalid mode)");
   if (e->rng_kind == TNB_RNG_PHILOX && e->finite && e->max_new > 0)
     return e->fail("max_number_new_slices > 0 is a core-object option: use TNB_RNG_MT19937 or TNB_RNG_REPLAY "
                    "(invalid mode)");
@@ -993,18 +997,31 @@ int tnb_set_stream(tnb_engine* e, const uint32_t* words, uint64_t len) {
   return 0;
 }
 
+// 1/beta per sweep for the production kernel's acceptance test  delta <= (2^(-log2(u)/beta) - 1) * total.  The other
+// two rules of the reference are its limits: greedy (prob/greedy.hpp:38-42: accept iff delta <= 0) is beta = +inf,
+// i.e. 1/beta = 0 and a threshold of exactly 0; always (prob/base.hpp:43-47) is beta = 0, a threshold of +inf.
+static bool upload_inv_betas(tnb_engine* e) {
+  const size_t n = e->h_betas.size();
+  std::vector<float> inv(n);
+  for (size_t i = 0; i < n; ++i) {
+    if (e->prob_kind == TNB_PROB_GREEDY) inv[i] = 0.f;
+    else if (e->prob_kind == TNB_PROB_ALWAYS) inv[i] = 3.0e38f;
+    else inv[i] = e->h_betas[i] > 0.0 ? 1.f / float(e->h_betas[i]) : 3.0e38f;
+  }
+  if (!e->rt.h2d(e->d_inv_betas, inv.data(), n * sizeof(float)) || !e->rt.sync()) return e->rtfail();
+  e->inv_kind = e->prob_kind;
+  return true;
+}
+
 int tnb_set_betas(tnb_engine* e, const double* betas, int64_t n) {
   if (!e) return -1;
   if (!betas || n < 1) return e->fail("tnb_set_betas: invalid arguments"), -1;
   e->rt.free_(e->d_betas);
   e->rt.free_(e->d_inv_betas);
   e->d_betas = nullptr; e->d_inv_betas = nullptr;
-  std::vector<float> inv(static_cast<size_t>(n));
-  for (int64_t i = 0; i < n; ++i) inv[size_t(i)] = betas[i] > 0.0 ? 1.f / float(betas[i]) : 3.0e38f;
+  e->h_betas.assign(betas, betas + n);
   if (!alloc_to(e->rt, e->d_betas, size_t(n)) || !alloc_to(e->rt, e->d_inv_betas, size_t(n))) return e->rtfail(), -3;
-  if (!e->rt.h2d(e->d_betas, betas, size_t(n) * sizeof(double)) ||
-      !e->rt.h2d(e->d_inv_betas, inv.data(), size_t(n) * sizeof(float)) || !e->rt.sync())
-    return e->rtfail(), -3;
+  if (!e->rt.h2d(e->d_betas, betas, size_t(n) * sizeof(double)) || !upload_inv_betas(e)) return e->rtfail(), -3;
   e->n_betas = n;
   return 0;
 }
@@ -1015,6 +1032,7 @@ int tnb_run(tnb_engine* e, int64_t until_sweep) {
   if (!ensure_init(e)) return -2;
   if (!mode_ok(e)) return -1;  // tnb_set_prob may have changed the rule since the chains were built
   if (until_sweep >= (int64_t(1) << 31)) return e->fail("tnb_run: until_sweep must be below 2^31"), -1;
+  if (e->inv_kind != e->prob_kind && !upload_inv_betas(e)) return -3;  // tnb_set_prob since the schedule was uploaded
   Params P;
   for (int guard = 0;; ++guard) {
     fill_params(e, e->cs, P);
