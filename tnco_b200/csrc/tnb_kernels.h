@@ -3,13 +3,14 @@
 //   chain_init    builds a chain's caches from its tree, like the reference constructors
 //                 (infinite_memory/optimizer.hpp:61-88, finite_width/greedy/optimizer.hpp:72-115)
 //   chain_sweeps  runs leaf->root sweeps == Optimizer::update() (infinite_memory/optimizer.hpp:90-201,
-//                 finite_width/greedy/optimizer.hpp:117-390 with max_number_new_slices == 0)
+//                 finite_width/greedy/optimizer.hpp:117-390, incl. the random-new-slice move :226-321)
 //
 // Data mapping: lane `tl` of the tile owns words tl, tl+TILE, ... of every index bitset, so all bitset
 // traffic is lane-private (no cross-lane memory hand-off); tile-uniform scalars (topology, costs) are
 // stored redundantly by all lanes with the same value (one coalesced transaction), so a lane only ever
-// reads back its own stores.  Cross-lane reads exist only in the slicer scratch and are fenced by
-// Tile::sync().  Networks must be free of hyper-indices, hence inds(z) = inds(c0) ^ inds(c1).
+// reads back its own stores.  Cross-lane reads exist only in the slicer scratch, the best-tree snapshots and the
+// generator's shared-memory batch, and are fenced by Tile::sync().  Without hyper-indices inds(z) = inds(c0) ^
+// inds(c1); the HYPER kernels carry the reference's hyper cache next to every index set.
 #pragma once
 #include <type_traits>
 
@@ -166,9 +167,9 @@ TNB_D TNB_INLINE unsigned lane_in_tile_here(int tl) {
 #endif
 }
 
-// Counter-based production RNG.  Vector index v counts "events" of the chain: one per sweep start (word 0
-// -> leaf) and one per level (word 0 -> D/E coin, words 1,2 -> uniform).  A tile generates TILE vectors at
-// a time, one per lane, and fetches them by shuffle, so the 10-round Philox costs 1/TILE per event.
+// Counter-based production RNG (Philox4x32-10; key = run seed, counter = (event index / 2, global chain id)).  An
+// "event" of a chain is a sweep start (one word -> leaf), a level (one word -> D/E coin, one -> uniform) or a slicer
+// draw; a Philox vector serves two events, and a tile generates a whole batch of them at once into shared memory.
 template <int TILE>
 struct RngPhilox {
   static constexpr bool kFast = true;  // log-domain fp32 acceptance test (see chain_sweeps)
