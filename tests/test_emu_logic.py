@@ -53,6 +53,11 @@ def test_emu_philox_finite(emu, n, max_width):
     G.test_philox_finite_width_chains_are_valid(n, max_width, None)
 
 
+@pytest.mark.parametrize('dim', [3])
+def test_emu_philox_uniform_dim3_finite_width(emu, dim):
+    G.test_philox_uniform_dimension_other_than_two_with_max_width(dim)
+
+
 @pytest.mark.parametrize('n,method', [(2, 0), (3, 1), (64, 0), (64, 1), (180, 0)])
 def test_emu_generated_trees(emu, n, method):
     G.test_device_generated_trees_are_valid(n, method)

@@ -869,3 +869,40 @@ def test_best_tree_snapshots_on_very_deep_trees(max_width):
     assert levels[0] > 64     # the first sweeps are longer than the ring ...
     assert levels[-1] < 64    # ... the later ones are not
     e.close()
+
+
+@pytest.mark.parametrize('dim', [3, 5])
+def test_philox_uniform_dimension_other_than_two_with_max_width(dim):
+    """A uniform dimension d != 2 keeps widths proportional to popcounts, so the table-cost production kernel takes
+    the production re-slicer too (costs from the d^k table, full re-cost instead of the incremental one): every
+    sliced width <= max_width for the current and the best tree, cached totals equal an independent evaluation,
+    results are deterministic, and the anneal improves on the initial trees."""
+    from helpers import leaf_bits
+    from tnco_b200.engine import Engine, random_trees
+    ts, ni = regular_network(120, 77)
+    lb = leaf_bits(ts, ni)
+    seeds = np.arange(40, dtype=np.uint64) + 9
+    p, a, b = random_trees(lb, ni, seeds)
+    max_width = 14 * float(np.log2(dim))
+    outs = []
+    for rep in range(2):
+        e = Engine()
+        e.set_network(lb, ni, dim=dim).set_mode(max_width=max_width, update_slices_every=5)
+        e.set_chains(p, a, b, seeds)
+        e.set_betas(np.linspace(0, 60, 300, endpoint=False))
+        t0, _ = e.costs()
+        e.run(150)
+        e.run(300)
+        t, m = e.costs()
+        P, A, B = e.trees()
+        seq, pc, mw = e.eval_cost(P, A, B, slices=e.slices())
+        assert np.allclose(np.log2(seq), np.log2(t), atol=1e-9) and (mw <= np.float32(max_width) + 1e-5).all()
+        bP, bA, bB = e.trees(True)
+        bseq, _, bmw = e.eval_cost(bP, bA, bB, slices=e.slices(True))
+        assert np.allclose(np.log2(bseq), np.log2(m), atol=1e-9) and (bmw <= np.float32(max_width) + 1e-5).all()
+        assert (m <= t * (1 + 1e-12)).all() and np.log2(m).mean() < np.log2(t0).mean()
+        pr = e.progress()
+        assert pr['width_rejects'].sum() > 0 and (pr['sweeps'] == 300).all()
+        outs.append((t.copy(), m.copy(), P.copy(), e.slices().copy()))
+        e.close()
+    assert all((x == y).all() for x, y in zip(outs[0], outs[1]))

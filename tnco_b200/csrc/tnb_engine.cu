@@ -188,6 +188,8 @@ struct tnb_engine {
   double* d_glog2 = nullptr;     // [Ws*32]
   // costs are 2^popcount (uniform dimension 2 or power-of-two groups, simple cost model): DIM2 kernels, fast re-slicer
   bool pow2_costs() const { return dim == 2 && !d_sparse && !generic; }
+  // widths are popcounts times a constant (any uniform dimension, power-of-two groups): the production re-slicer applies
+  bool popcount_widths() const { return !d_sparse && !generic; }
   uint8_t* d_gw = nullptr;       // [Ws*32] log2(dim) at the leader positions
 
   // caller's index space <-> virtual index space (rows of Wu / W words)
@@ -349,10 +351,11 @@ static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_be
          alloc_to(rt, cs.cp2, nc * ni);
   else if (ok && e->hyper)
     ok = alloc_to(rt, cs.nbig, nc * e->Ws * 32);  // hyper counters of build_sets
-  // per-node popcounts / leaf counts for the production re-slicer: the kernels built for 2^popcount costs only
-  // (uniform dimension 2 or power-of-two groups, no sparse indices); the table-cost kernels re-slice with the
-  // reference's slicer verbatim
-  if (ok && with_slicer && e->finite && e->pow2_costs())
+  // per-node popcounts / leaf counts for the production re-slicer: wherever a width is a popcount times a constant
+  // (any uniform dimension, power-of-two groups; no sparse indices, no general dimensions) -- otherwise the
+  // table-cost kernels re-slice with the reference's slicer verbatim
+  // (TNB_VERBATIM_RESLICER: measurement switch, keeps the table-cost kernels on the reference's slicer)
+  if (ok && with_slicer && e->finite && e->popcount_widths() && (e->pow2_costs() || !std::getenv("TNB_VERBATIM_RESLICER")))
     ok = alloc_to(rt, cs.kwsz, nc * e->Npad) &&
          alloc_to(rt, cs.word, nc * e->Npad) && alloc_to(rt, cs.wkey, nc * e->Npad);
   if (!ok) return e->rtfail();
@@ -486,7 +489,7 @@ static bool mode_ok(tnb_engine* e) {
   if (e->rng_kind == TNB_RNG_PHILOX && e->finite && e->max_new > 0)
     return e->fail("max_number_new_slices > 0 is a core-object option: use TNB_RNG_MT19937 or TNB_RNG_REPLAY "
                    "(invalid mode)");
-  if (e->rng_kind == TNB_RNG_PHILOX && e->finite && e->d_skip && e->pow2_costs())
+  if (e->rng_kind == TNB_RNG_PHILOX && e->finite && e->d_skip && e->popcount_widths())
     return e->fail("skip_slices is not known to the production re-slicer: use TNB_RNG_MT19937 or TNB_RNG_REPLAY "
                    "(invalid mode)");
   return true;

@@ -1997,11 +1997,16 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
   // FS: production re-slicer (get_slices_fast); the walk then also maintains kw[] and sz[].  Only where a cost is
   // 2^popcount (DIM2): the table-cost kernels -- other dimensions, sparse indices -- re-slice with the reference's
   // slicer verbatim (get_slices_dev + a full cost pass), which knows every width model.
-  constexpr bool FS = FINITE && Rng::kFast && DIM2;
+  // FSC: known at compile time (the 2^popcount kernels).  The table-cost production kernels take the same re-slicer
+  // when widths are still plain popcounts -- a uniform dimension other than 2, no sparse indices, no general
+  // dimensions (the host allocates kwsz[] exactly then) -- and re-cost with recost_all; otherwise the reference's
+  // slicer verbatim.
+  constexpr bool FSC = FINITE && Rng::kFast && DIM2;
+  const bool FS = FSC || (FINITE && Rng::kFast && !DIM2 && P.kwsz != nullptr);
   // popcount | leaf count << 16 of every node; the per-chain base is pinned like the others (re-derived from the
   // kernel parameters it cost ten instructions per 2-byte access)
   uint32_t* kws = FS ? P.kwsz + size_t(chain) * P.Npad : nullptr;
-  if constexpr (FS) keep_in_register(kws);
+  if constexpr (FSC) keep_in_register(kws);
   // FS: leaves below the children of B (slot order) and below C -- carried like the index sets, the sibling's count
   // loaded a level ahead (fetching them when a move is accepted stalled the warp on that load at every accept)
   int sz0 = 0, sz1 = 0, szC = 0;
@@ -2110,7 +2115,9 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
             uint32_t S2[WPL];
             dbl2* cp2 = P.cp2 + size_t(chain) * P.n_int;
             if constexpr (Rng::kFast) P.n_prop[chain] += rng.counter();  // (the re-slicer's draws are not proposals)
-            if constexpr (FS) {
+            bool fast_done = false;
+            if constexpr (FINITE && Rng::kFast) if (FS) {
+              fast_done = true;
               const uint32_t draw0 = rng.local_next();
               rng.sync_from0(t);
               get_slices_fast(c, draw0, S2);
@@ -2148,7 +2155,8 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
                   }
                 }
               }
-            } else {
+            }
+            if (!fast_done) {
               get_slices_dev(c, rng, S2);
               if constexpr (Rng::kFast) P.n_prop[chain] -= rng.counter();
               double seq;
@@ -2318,7 +2326,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
       nb[k] = bD[k] ^ bC[k];  // new inds of B (infinite_memory/optimizer.hpp:147)
       if (HYPER) nb[k] |= hA[k] | hB[k];
       const uint32_t ka_l = uint32_t(popc32(nb[k] | bE[k] | S[k])), kb_l = uint32_t(popc32(bD[k] | bC[k] | S[k]));
-      if (FS && K10) {
+      if (FSC && K10) {
         // one reduction on the dependent path: sliced width of the new B and both cost exponents as 10-bit fields;
         // the unsliced popcount of the new B (only stored, on accept) goes through a second one that nothing waits for
         kpack += uint32_t(popc32(nb[k] & ~S[k])) | (ka_l << 10) | (kb_l << 20);
@@ -2355,7 +2363,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
     bool gate = true;
     float swB = 0.f;  // new_sliced_width_B
     if (FINITE) {  // finite_width/greedy/optimizer.hpp:176-188
-      if (FS && K10) {
+      if (FSC && K10) {
         kpack = t.sum_c(kpack);
         ku = t.sum_c(ku);
         ks = kpack & 0x3ffu;
@@ -2384,9 +2392,9 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
     double delta = 0.0;
     if (gate) {
       if (Rng::kFast && FINITE) ++q_wrej;
-      if (!(FS && K10)) kpack = t.sum_c(kpack);
+      if (!(FSC && K10)) kpack = t.sum_c(kpack);
       if constexpr (DIM2) {  // dim == 2: the exact power of two built from its exponent (+inf past 2^1023, like pow)
-        if constexpr (FS && K10) {  // the high words straight from the fields
+        if constexpr (FSC && K10) {  // the high words straight from the fields
           nA = ((kpack << 10) & 0x3ff00000u) + 0x3ff00000u;
           nB = (kpack & 0xfff00000u) + 0x3ff00000u;
         } else if constexpr (K10) {
