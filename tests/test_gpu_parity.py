@@ -228,12 +228,14 @@ def test_philox_sparse_index_chains_are_valid(dim):
         outs.append((t.copy(), P.copy()))
         e.close()
     assert (outs[0][0] == outs[1][0]).all() and (outs[0][1] == outs[1][1]).all()
-    # with max_width: the table-cost kernels re-slice with the reference's slicer, which knows the sparse width model
-    # (production RNG and MT19937 mode alike)
+    # with max_width: MT19937 mode re-slices with the reference's slicer verbatim; the production generator with the
+    # production re-slicer in its sparse form (two popcounts per node, the capped width model of
+    # finite_width/cost_model/simple_sparse_inds.hpp:39-77) -- either way every sliced width fits, for the current and
+    # the best tree, and the cached totals equal an independent evaluation
     for rng in (RNG_PHILOX, RNG_MT19937):
         e = Engine()
         e.set_network(lb, ni, dim=dim, sparse_bits=sp, n_projs=8).set_mode(max_width=12 * np.log2(dim), rng=rng)
-        e.generate_chains(seeds[:6]).set_betas(np.linspace(0, 100, 200, endpoint=False))
+        e.generate_chains(seeds[:6] if rng == RNG_MT19937 else seeds).set_betas(np.linspace(0, 100, 200, endpoint=False))
         t0, _ = e.costs()
         e.run(200)
         t, m = e.costs()
@@ -244,6 +246,9 @@ def test_philox_sparse_index_chains_are_valid(dim):
         bseq, _, bmw = e.eval_cost(bP, bA, bB, slices=e.slices(True))
         assert np.allclose(np.log2(bseq), np.log2(m), atol=1e-9) and (bmw <= np.float32(12 * np.log2(dim)) + 1e-6).all()
         assert (m <= t).all() and np.log2(m).mean() < np.log2(t0).mean()
+        if rng == RNG_PHILOX:
+            sl = e.slices(True)
+            assert (sl != 0).any() and e.progress()['width_rejects'].sum() > 0
         e.close()
     with pytest.raises((EngineError, ValueError), match='n_projs'):
         Engine().set_network(lb, ni, sparse_bits=sp, n_projs=0)

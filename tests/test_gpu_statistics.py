@@ -92,3 +92,47 @@ def test_equal_sweep_distribution_on_the_benchmarked_networks(case, chains):
           f'min {ref.min():.4f} | p(ours worse) {p_worse:.3g} | se {se:.4f}')
     assert p_worse > 1e-3, (ours.mean(), ref.mean(), p_worse)
     assert ours.mean() <= ref.mean() + 4 * se, (ours.mean(), ref.mean(), se)
+
+
+# ---- the production re-slicer on the table-cost kernels (uniform dimension 3; the sparse-index width model) against
+# the reference's slicer, which the same kernels run verbatim when TNB_VERBATIM_RESLICER is set (bit-exact against
+# the reference in MT19937 mode): same generator, same initial trees, equal sweep counts.
+@pytest.mark.parametrize('case', ['d3', 'd2_sparse', 'd3_sparse'])
+def test_production_reslicer_is_no_worse_than_the_reference_slicer(case):
+    import os
+
+    from tnco_b200 import networks
+    from tnco_b200.engine import Engine, pack_index_set, pack_leaf_bits, random_trees
+    ts, ni = networks.regular_graph(200, 0)
+    lb = pack_leaf_bits(ts, ni)
+    seeds = np.arange(1536, dtype=np.uint64) + 1
+    P, A, B = random_trees(lb, ni, seeds)
+    dim = 3 if case.startswith('d3') else 2
+    sparse = case.endswith('sparse')
+    kw = dict(sparse_bits=pack_index_set(np.random.default_rng(3).choice(ni, size=40, replace=False).tolist(), ni),
+              n_projs=16) if sparse else {}
+    max_width = (18.0 if sparse else 20.0) * float(np.log2(dim))
+    out = {}
+    for verbatim in (False, True):
+        if verbatim:
+            os.environ['TNB_VERBATIM_RESLICER'] = '1'
+        try:
+            e = Engine()
+            e.set_network(lb, ni, dim=dim, **kw).set_mode(max_width=max_width, update_slices_every=10)
+            e.set_chains(P, A, B, seeds)
+        finally:
+            os.environ.pop('TNB_VERBATIM_RESLICER', None)
+        e.set_betas(np.linspace(0, 100, 2000, endpoint=False))
+        e.run(2000)
+        t, m = e.costs()
+        bp, ba, bb = e.trees(best=True)
+        _, pc, mw = e.eval_cost(bp, ba, bb, slices=e.slices(best=True))
+        assert np.allclose(np.log2(pc), np.log2(m), atol=1e-9) and (mw <= np.float32(max_width) + 1e-5).all()
+        out[verbatim] = np.log2(m)
+        e.close()
+    ours, ref = out[False], out[True]
+    p_worse = stats.mannwhitneyu(ours, ref, alternative='greater').pvalue
+    se = np.sqrt(ours.var() / len(ours) + ref.var() / len(ref))
+    print(f'{case}: production re-slicer mean {ours.mean():.4f} | reference slicer mean {ref.mean():.4f} | '
+          f'p(ours worse) {p_worse:.3g} | se {se:.4f}')
+    assert p_worse > 1e-3 and ours.mean() <= ref.mean() + 4 * se, (ours.mean(), ref.mean(), p_worse, se)

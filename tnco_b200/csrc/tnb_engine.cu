@@ -130,6 +130,7 @@ struct ChainSet {
   uint16_t* nbig = nullptr;
   int16_t *posbuf = nullptr, *kpop = nullptr, *word = nullptr;
   uint32_t *wkey = nullptr, *kwsz = nullptr;
+  int16_t* ksp = nullptr;
   int* tree_fail = nullptr;
   double* escore = nullptr;
   uint32_t* stream = nullptr;
@@ -141,7 +142,7 @@ struct ChainSet {
   int trace_chains = 0;
 
   void release(Rt& rt) {
-    void* ps[] = {par, bpar, rec, bits_alloc, bch, pc, slices, bslices, cp2, total, min_total, out_seq, out_maxw, seeds,
+    void* ps[] = {ksp, par, bpar, rec, bits_alloc, bch, pc, slices, bslices, cp2, total, min_total, out_seq, out_maxw, seeds,
                   rng_ctr, n_prop, n_acc, n_wrej, cursor, sweep_idx, overrun, nbig, posbuf, kpop, tree_fail, escore, stream, kwsz, word, wkey,
                   trace, trace_n, trace_S, trace_sn};
     for (void* p : ps) rt.free_(p);
@@ -188,8 +189,9 @@ struct tnb_engine {
   double* d_glog2 = nullptr;     // [Ws*32]
   // costs are 2^popcount (uniform dimension 2 or power-of-two groups, simple cost model): DIM2 kernels, fast re-slicer
   bool pow2_costs() const { return dim == 2 && !d_sparse && !generic; }
-  // widths are popcounts times a constant (any uniform dimension, power-of-two groups): the production re-slicer applies
-  bool popcount_widths() const { return !d_sparse && !generic; }
+  // The production re-slicer applies where a width is made of popcounts: any uniform dimension or power-of-two groups,
+  // and the sparse-index model (two popcounts per node) unless it comes with groups; not general dimensions.
+  bool popcount_widths() const { return !generic && !(d_sparse && grouped); }
   uint8_t* d_gw = nullptr;       // [Ws*32] log2(dim) at the leader positions
 
   // caller's index space <-> virtual index space (rows of Wu / W words)
@@ -296,7 +298,7 @@ static void fill_params(const tnb_engine* e, const ChainSet& cs, Params& P) {
   P.betas = e->d_betas; P.inv_betas = e->d_inv_betas; P.n_betas = e->n_betas; P.until = 0;
   P.nbig = cs.nbig; P.posbuf = cs.posbuf; P.cp2 = cs.cp2;
   P.slices_given = 0; P.out_seq = cs.out_seq; P.out_maxw = cs.out_maxw;
-  P.kwsz = cs.kwsz; P.word = cs.word; P.wkey = cs.wkey;
+  P.kwsz = cs.kwsz; P.ksp = cs.ksp; P.word = cs.word; P.wkey = cs.wkey;
   P.kthr = 0;
   if (e->finite)
     for (int k = 0; k <= e->n_inds; ++k)
@@ -356,7 +358,7 @@ static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_be
   // table-cost kernels re-slice with the reference's slicer verbatim
   // (TNB_VERBATIM_RESLICER: measurement switch, keeps the table-cost kernels on the reference's slicer)
   if (ok && with_slicer && e->finite && e->popcount_widths() && (e->pow2_costs() || !std::getenv("TNB_VERBATIM_RESLICER")))
-    ok = alloc_to(rt, cs.kwsz, nc * e->Npad) &&
+    ok = alloc_to(rt, cs.kwsz, nc * e->Npad) && (!e->d_sparse || alloc_to(rt, cs.ksp, nc * e->Npad)) &&
          alloc_to(rt, cs.word, nc * e->Npad) && alloc_to(rt, cs.wkey, nc * e->Npad);
   if (!ok) return e->rtfail();
   return true;

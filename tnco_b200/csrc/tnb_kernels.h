@@ -111,6 +111,8 @@ struct Params {
   // production re-slicer (finite width, Philox): per-node popcount / leaf count kept in step with the tree
   uint32_t* kwsz;   // [n_chains][Npad] per node: popcount of its index set (unsliced width / log2 d) in the low half,
                     //                   leaves below it in the high half -- one word, one load / store for both
+  int16_t* ksp;     // [n_chains][Npad] popcount of the SPARSE part of every node's index set (sparse-index model under
+                    //                   the production re-slicer; nullptr otherwise)
   uint32_t* wkey;   // [n_chains][Npad] scratch: (post-order rank << 16 | node) of the wide nodes
   int16_t* word;    // [n_chains][Npad] scratch: wide nodes, then wide nodes in post-order
   int kthr;         // largest popcount whose width still fits max_width
@@ -1177,12 +1179,21 @@ TNB_D void get_slices_dev(const ChainView<TILE, WPL>& c, Rng& rng, uint32_t (&S2
 // draw0: the re-slice's tie-break word, drawn by the caller (passing the generator itself by reference to this
 // out-of-line function forced all of its state through local memory -- the sweep loop then read its level word back
 // from the stack at every level).
-template <int TILE, int WPL>
+// SPARSE: the sparse-index width model (finite_width/cost_model/simple_sparse_inds.hpp:39-77): width = w(dense part) +
+// min(w(sparse part), log2 n_projs), so a node is described by two popcounts, slicing a sparse index above the cap
+// does not narrow the node (the reference slices it all the same: candidates are taken in count order until the node
+// fits), and candidates go one at a time.  A separate instantiation: the 2^popcount kernels keep the code they had.
+template <int TILE, int WPL, bool SPARSE>
 TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, const uint32_t draw0, uint32_t (&S2)[WPL]) {
   const Params& P = c.P;
   const Tile<TILE>& t = c.t;
   constexpr int NB = 8;
   const uint32_t* kwsz = P.kwsz + size_t(c.chain) * P.Npad;
+  const int16_t* ksp = SPARSE ? P.ksp + size_t(c.chain) * P.Npad : nullptr;
+  uint32_t SP[WPL];
+#pragma unroll
+  for (int k = 0; k < WPL; ++k) SP[k] = 0u;
+  if (SPARSE) c.load_sparse(SP);
   uint32_t* wkey = P.wkey + size_t(c.chain) * P.Npad;
   int16_t* word = P.word + size_t(c.chain) * P.Npad;
   uint32_t cnt[WPL][NB];
@@ -1200,10 +1211,11 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, const uin
     for (int u = 0; u < 4; ++u) {
       const int z = base + u * TILE + t.tl;
       kv[u] = z < P.N ? int(kwsz[z] & 0xffffu) : -1;
+      if (SPARSE && z < P.N) kv[u] |= int(ksp[z]) << 16;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const bool wide = kv[u] > P.kthr;
+      const bool wide = SPARSE ? (kv[u] >= 0 && c.width_sp(kv[u] & 0xffff, kv[u] >> 16) > P.max_width) : kv[u] > P.kthr;
       const uint32_t m = t.ballot(wide);
       if (wide) word[nw + popc32(m & ((1u << t.tl) - 1u))] = int16_t(base + u * TILE + t.tl);
       nw += popc32(m);
@@ -1274,9 +1286,12 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, const uin
     for (int k = 0; k < WPL; ++k) {
       x[k] &= ~S2[k];
       ks += uint32_t(popc32(x[k]));
+      if (SPARSE) ks += uint32_t(popc32(x[k] & SP[k])) << 16;
     }
     ks = t.sum(ks);
-    for (int m = int(ks) - P.kthr; m > 0;) {  // m = binary indices still to be removed from this node
+    int k_all = int(ks & 0xffffu), k_sp = int(ks >> 16);  // SPARSE: all / sparse indices left on this node
+    // m = binary indices still to be removed from this node (SPARSE: 1 while it is too wide, one candidate at a time)
+    for (int m = SPARSE ? (c.width_sp(k_all, k_sp) > P.max_width ? 1 : 0) : int(ks) - P.kthr; m > 0;) {
       uint32_t cand[WPL];
 #pragma unroll
       for (int k = 0; k < WPL; ++k) {
@@ -1321,7 +1336,7 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, const uin
         // Every candidate of the most frequent class goes anyway when the class is not larger than what is still
         // to be removed (the order inside a class is only the random tie-break): take the class in one step.
         const uint32_t all = t.sum(mine);
-        if (all != 0u && int(all) <= m) {
+        if (!SPARSE && all != 0u && int(all) <= m) {
 #pragma unroll
           for (int k = 0; k < WPL; ++k) {
             S2[k] |= cand[k];
@@ -1330,6 +1345,7 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, const uin
           m -= int(all);
           continue;
         }
+        if (SPARSE && all == 0u) break;  // (nothing left to slice on this node)
       }
       uint32_t tot;
       const uint32_t off = t.excl_scan_sum(mine, tot);
@@ -1348,6 +1364,7 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, const uin
           } else {
             S2[k] |= 1u << bpos;
             x[k] &= ~(1u << bpos);
+            if (SPARSE) picked = 1u + ((SP[k] >> bpos) & 1u);  // 2: the sliced index is a sparse one
           }
           done = true;
         }
@@ -1364,6 +1381,10 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, const uin
           x[k] &= ~msk;
         }
         m -= g;
+      } else if (SPARSE) {
+        --k_all;
+        if (t.max_u32(picked) == 2u) --k_sp;
+        m = c.width_sp(k_all, k_sp) > P.max_width ? 1 : 0;
       } else {
         --m;
       }
@@ -1378,6 +1399,11 @@ TNB_D TNB_NOINLINE double recost_all(const ChainView<TILE, WPL>& c, const uint32
   const Params& P = c.P;
   const Tile<TILE>& t = c.t;
   double acc = 0.0;
+  const bool sparse = !DIM2 && P.sparse != nullptr;
+  uint32_t SP[WPL];
+#pragma unroll
+  for (int i = 0; i < WPL; ++i) SP[i] = 0u;
+  if (sparse) c.load_sparse(SP);
   for (int base = P.n; base < P.N; base += TILE) {
     const int zz = base + t.tl;
     const uint32_t mych = zz < P.N ? c.ch(zz) : 0u;
@@ -1387,9 +1413,14 @@ TNB_D TNB_NOINLINE double recost_all(const ChainView<TILE, WPL>& c, const uint32
       uint32_t xa[WPL], xb[WPL];
       c.load_bits(int(w & 0xffffu), xa);
       c.load_bits(int(w >> 16), xb);
-      const uint32_t k = t.sum(popc_or3<WPL>(xa, xb, S2));
+      uint32_t k = popc_or3<WPL>(xa, xb, S2);
+      if (sparse) {  // (kernel-uniform) the sparse part of the same union rides in the high half
+#pragma unroll
+        for (int i = 0; i < WPL; ++i) k += uint32_t(popc32((xa[i] | xb[i] | S2[i]) & SP[i])) << 16;
+      }
+      k = t.sum(k);
       const double cost = DIM2 ? bits_to_f64((unsigned long long)(1023u + (k > 1024u ? 1024u : k)) << 52)
-                               : c.cost_of(int(k));
+                          : sparse ? c.cost_sp(int(k & 0xffffu), int(k >> 16)) : c.cost_of(int(k));
       dst[base - P.n + q].x = cost;
       acc += cost;
     }
@@ -1503,13 +1534,25 @@ template <int TILE, int WPL>
 TNB_D void build_kw_sz(const ChainView<TILE, WPL>& c) {
   const Params& P = c.P;
   uint32_t* kwsz = P.kwsz + size_t(c.chain) * P.Npad;
+  uint32_t SP[WPL];
+#pragma unroll
+  for (int i = 0; i < WPL; ++i) SP[i] = 0u;
+  if (P.ksp) c.load_sparse(SP);
   for (int z = c.po_first(); z >= 0; z = c.po_next(z)) {
     uint32_t x[WPL];
     c.load_bits(z, x);
     uint32_t k = 0;
 #pragma unroll
     for (int i = 0; i < WPL; ++i) k += uint32_t(popc32(x[i]));
+    if (P.ksp) {
+#pragma unroll
+      for (int i = 0; i < WPL; ++i) k += uint32_t(popc32(x[i] & SP[i])) << 16;
+    }
     k = c.t.sum(k);
+    if (P.ksp) {
+      P.ksp[size_t(c.chain) * P.Npad + z] = int16_t(k >> 16);
+      k &= 0xffffu;
+    }
     if (z < P.n) {
       kwsz[z] = k | (1u << 16);
     } else {
@@ -1878,7 +1921,8 @@ TNB_D void chain_init(const Params& P, int chain) {
           build_kw_sz(c);
           const uint32_t draw0 = rng.local_next();
           rng.sync_from0(c.t);
-          get_slices_fast(c, draw0, S);
+          if (P.ksp) get_slices_fast<TILE, WPL, true>(c, draw0, S);
+          else get_slices_fast<TILE, WPL, false>(c, draw0, S);
         } else {
           get_slices_dev(c, rng, S);
         }
@@ -2120,7 +2164,12 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
               fast_done = true;
               const uint32_t draw0 = rng.local_next();
               rng.sync_from0(t);
-              get_slices_fast(c, draw0, S2);
+              if constexpr (DIM2) {
+                get_slices_fast<TILE, WPL, false>(c, draw0, S2);
+              } else {
+                if (P.ksp) get_slices_fast<TILE, WPL, true>(c, draw0, S2);
+                else get_slices_fast<TILE, WPL, false>(c, draw0, S2);
+              }
               P.n_prop[chain] -= rng.counter();
               bool diff = false;
 #pragma unroll
@@ -2340,7 +2389,7 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
     // sparse-index cost model (table-cost kernels only): the sparse parts of the same three sets
     const bool sparse = !DIM2 && P.sparse != nullptr;
     const bool gen = !DIM2 && P.gdims != nullptr;  // general per-index dimensions: sequential products / sums
-    uint32_t kspack = 0, kss = 0;
+    uint32_t kspack = 0, kss = 0, kus = 0;
     uint32_t SP[WPL];
 #pragma unroll
     for (int k = 0; k < WPL; ++k) SP[k] = 0u;
@@ -2351,9 +2400,14 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
         kspack += uint32_t(popc32((nb[k] | bE[k] | S[k]) & SP[k])) |
                   (uint32_t(popc32((bD[k] | bC[k] | S[k]) & SP[k])) << 16);
         if (FINITE) kss += uint32_t(popc32(nb[k] & ~S[k] & SP[k]));
+        if (FS) kss += uint32_t(popc32(nb[k] & SP[k])) << 16;  // sparse popcount of the new B, for the re-slicer
       }
       kspack = t.sum_c(kspack);
       if (FINITE) kss = t.sum_c(kss);
+      if (FS) {
+        kus = kss >> 16;
+        kss &= 0xffffu;
+      }
     }
     const double pcD = pick0 ? pc0 : pc1;
     double pcE = pick0 ? pc1 : pc0;
@@ -2379,12 +2433,12 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
 #pragma unroll
         for (int k = 0; k < WPL; ++k) xs[k] = nb[k] & ~S[k];
         swB = c.template gwidth_model<true>(xs, SP);
-      } else if (!FS) {
+      } else if (!FS || sparse) {
         swB = sparse ? c.width_sp(int(ks), int(kss)) : c.width_of(int(ks));
       }
       // (2^popcount kernels: width = log2(d) * popcount is monotone in the popcount, and kthr is the largest popcount
       //  whose float32 width still fits -- the same decision without the fp64 product on the dependent path)
-      gate = FS ? int(ks) <= P.kthr : swB <= P.max_width;
+      gate = (FS && !sparse) ? int(ks) <= P.kthr : swB <= P.max_width;
       if (!Rng::kFast && !gate) ++q_wrej;
     }
     bool acc = false;
@@ -2624,6 +2678,9 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
       }
       q_pa += 0x10000u;
       if (FS) kws[B] = ku | (uint32_t(szD + szC) << 16);  // popcount and leaf count of the new B for the re-slicer
+      if constexpr (!DIM2) {
+        if (FS && sparse) P.ksp[size_t(chain) * P.Npad + B] = int16_t(kus);
+      }
       {
         const int ti = C; C = E; E = ti;
         const double td = pcC; pcC = pcE; pcE = td;
