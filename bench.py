@@ -39,17 +39,17 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # chains / sweeps: per GPU and per step of the headline run (C4) or of the short per-config runs (the others)
     'C1': dict(text='C1: random 3-regular graph TN, 64 tensors (96 indices, d=2), unconstrained SA',
-               make=lambda nw: nw.regular_graph(64, 0), max_width=None, chains=32768, sweeps=2000),
+               make=lambda nw: nw.regular_graph(64, 0), max_width=None, chains=32768, sweeps=10000),
     'C2': dict(text='C2: 2D-grid 6x6 random circuit depth 12 TN (180 tensors, 324 indices, d=2), unconstrained SA',
                make=lambda nw: nw.grid_rqc(6, 6, 12), max_width=None, chains=4096, sweeps=10000),
     'C3': dict(text='C3: Sycamore-style 53-qubit m=14 TN (301 tensors, 549 indices, d=2), unconstrained SA',
-               make=lambda nw: nw.sycamore(14), max_width=None, chains=12288, sweeps=1000),
+               make=lambda nw: nw.sycamore(14), max_width=None, chains=12288, sweeps=4000),
     # BASELINE.json configs[3] / north_star target: Sycamore-53 m=20, memory-constrained (max width 2^32)
     'C4': dict(text='C4: Sycamore-style 53-qubit m=20 TN (430 tensors, 807 indices, d=2), memory-constrained SA, '
                     'max_width=32, update_slices=10', make=lambda nw: nw.sycamore(20), max_width=32.0, chains=4096,
                sweeps=10000),
     'C5': dict(text='C5: random 3-regular graph TN, 1000 tensors (1500 indices, d=2), unconstrained SA, HBM-resident '
-                    'chain state', make=lambda nw: nw.regular_graph(1000, 0), max_width=None, chains=4096, sweeps=500),
+                    'chain state', make=lambda nw: nw.regular_graph(1000, 0), max_width=None, chains=4096, sweeps=2000),
 }
 _SEL = {'name': 'C4'}
 
