@@ -322,3 +322,30 @@ def test_ctree_components_and_path_merging_match_the_reference():
         if sum(lens):
             cat = np.array([x for p in paths for x in p], np.int32).reshape(1, -1, 2)
             assert merge_paths(m['n'], lens, cat)[0].tolist() == m['merged']
+
+
+def test_run_refuses_sweep_indices_beyond_31_bits():
+    """The kernels keep the sweep index in 32 bits: tnb_run must refuse anything beyond (checked before any launch;
+    here on the CPU emulation of the engine, which shares tnb_engine.cu)."""
+    import ctypes
+    import subprocess
+
+    import numpy as np
+
+    from tnco_b200 import _lib
+    here = os.path.dirname(os.path.abspath(__file__))
+    subprocess.check_call(['make', '-C', os.path.join(here, 'emu')], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    L = _lib.bind(ctypes.CDLL(os.path.join(here, 'emu', 'libtnb_emu.so')))
+    e = ctypes.c_void_p()
+    assert L.tnb_create(ctypes.byref(e), 0) == 0
+    lb = np.array([[0b011], [0b101], [0b110]], np.uint32)      # a triangle: 3 tensors, 3 indices
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    assert L.tnb_set_network(e, 3, 3, lb.ctypes.data_as(u32p), 2, None) == 0
+    assert L.tnb_set_mode(e, -1.0, 0, 0, 0, 0, 0) == 0
+    seeds = np.array([1], np.uint64)
+    assert L.tnb_generate_chains(e, 1, seeds.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), 0, 0) == 0
+    betas = np.array([1.0])
+    assert L.tnb_set_betas(e, betas.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 1) == 0
+    assert L.tnb_run(e, 2**31) != 0 and b'2^31' in L.tnb_last_error(e)
+    assert L.tnb_run(e, 5) == 0
+    L.tnb_destroy(e)
