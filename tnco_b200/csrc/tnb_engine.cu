@@ -119,6 +119,11 @@ struct ChainSet {
   uint32_t *bch = nullptr, *slices = nullptr, *bslices = nullptr;
   char *rec = nullptr, *bitsb = nullptr;  // node headers / index sets, see Params::hdr (bitsb == rec + 16 when interleaved)
   char* bits_alloc = nullptr;             // SPLIT layout only: the separate index-set array
+  // SPLIT layout only: par, the node headers and kwsz are carved out of ONE block -- everything the walk's
+  // address-dependent loads touch (parent -> header -> sibling id), a tenth of the state -- so that one L2
+  // access-policy window can keep it resident while the index sets stream through (Rt::l2_window)
+  char* hot = nullptr;
+  size_t hot_bytes = 0;
   int hstride = 0, bstride = 0;
   double* pc = nullptr;
   dbl2* cp2 = nullptr;
@@ -142,7 +147,8 @@ struct ChainSet {
   int trace_chains = 0;
 
   void release(Rt& rt) {
-    void* ps[] = {ksp, par, bpar, rec, bits_alloc, bch, pc, slices, bslices, cp2, total, min_total, out_seq, out_maxw, seeds,
+    if (hot) par = nullptr, rec = nullptr, kwsz = nullptr;  // (carved out of `hot`)
+    void* ps[] = {hot, ksp, par, bpar, rec, bits_alloc, bch, pc, slices, bslices, cp2, total, min_total, out_seq, out_maxw, seeds,
                   rng_ctr, n_prop, n_acc, n_wrej, cursor, sweep_idx, overrun, nbig, posbuf, kpop, tree_fail, escore, stream, kwsz, word, wkey,
                   trace, trace_n, trace_S, trace_sn};
     for (void* p : ps) rt.free_(p);
@@ -213,6 +219,12 @@ struct tnb_engine {
   bool finite = false;
   float max_width = 0.f;
   int every = 0, dsi = 0, prob_kind = TNB_PROB_MH, rng_kind = TNB_RNG_PHILOX, layout = TNB_LAYOUT_AUTO;
+  // L2 carve-out for the hot block of a SPLIT batch in MiB (Rt::l2_window): 0 = off, < 0 = as much as the device
+  // allows.  TNB_L2_PERSIST_MB overrides it (measurement switch).
+  int l2_persist_mb = [] {
+    const char* f = std::getenv("TNB_L2_PERSIST_MB");
+    return f ? std::atoi(f) : 0;
+  }();
   int max_new = 0;  // max_number_new_slices (tnb_set_new_slices)
   // chains
   ChainSet cs;
@@ -338,8 +350,28 @@ static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_be
   //  prefetch per 128-byte line covers it)
   cs.bstride = split ? (4 * e->Ws * (e->hyper ? 2 : 1) + 31) / 32 * 32 : e->stride;
   // (+ tail: load_bits reads whole tiles of words and masks the ones beyond the row)
-  bool ok = alloc_to(rt, cs.par, nc * e->Npad) && alloc_to(rt, cs.rec, nc * ni * size_t(cs.hstride) + 4 * kTailWords) &&
-            (!split || alloc_to(rt, cs.bits_alloc, nc * ni * size_t(cs.bstride) + 4 * kTailWords)) &&
+  // per-node popcounts / leaf counts for the production re-slicer: wherever a width is a popcount times a constant
+  // (any uniform dimension, power-of-two groups; no sparse indices, no general dimensions) -- otherwise the
+  // table-cost kernels re-slice with the reference's slicer verbatim
+  // (TNB_VERBATIM_RESLICER: measurement switch, keeps the table-cost kernels on the reference's slicer)
+  const bool want_kwsz = with_slicer && e->finite && e->popcount_widths() &&
+                         (e->pow2_costs() || !std::getenv("TNB_VERBATIM_RESLICER"));
+  bool ok = true;
+  if (split) {
+    auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t par_b = up(nc * e->Npad * sizeof(int16_t)), rec_b = up(nc * ni * 16 + 16 * kTailWords),
+                 kw_b = want_kwsz ? up(nc * e->Npad * sizeof(uint32_t)) : 0;
+    cs.hot_bytes = par_b + rec_b + kw_b;
+    ok = alloc_to(rt, cs.hot, cs.hot_bytes);
+    if (ok) {
+      cs.rec = cs.hot;  // (headers first: 8-byte accesses on a 256-byte aligned base)
+      cs.par = reinterpret_cast<int16_t*>(cs.hot + rec_b);
+      if (want_kwsz) cs.kwsz = reinterpret_cast<uint32_t*>(cs.hot + rec_b + par_b);
+    }
+  } else {
+    ok = alloc_to(rt, cs.par, nc * e->Npad) && alloc_to(rt, cs.rec, nc * ni * size_t(cs.hstride) + 4 * kTailWords);
+  }
+  ok = ok && (!split || alloc_to(rt, cs.bits_alloc, nc * ni * size_t(cs.bstride) + 4 * kTailWords)) &&
             alloc_to(rt, cs.pc, nc * ni) && alloc_to(rt, cs.bch, nc * ni) &&
             alloc_to(rt, cs.slices, nc * e->Ws) && alloc_to(rt, cs.total, nc) && alloc_to(rt, cs.min_total, nc) &&
             alloc_to(rt, cs.out_seq, nc) && alloc_to(rt, cs.out_maxw, nc) && alloc_to(rt, cs.seeds, nc) &&
@@ -353,12 +385,8 @@ static bool alloc_chains(tnb_engine* e, ChainSet& cs, int n_chains, bool with_be
          alloc_to(rt, cs.cp2, nc * ni);
   else if (ok && e->hyper)
     ok = alloc_to(rt, cs.nbig, nc * e->Ws * 32);  // hyper counters of build_sets
-  // per-node popcounts / leaf counts for the production re-slicer: wherever a width is a popcount times a constant
-  // (any uniform dimension, power-of-two groups; no sparse indices, no general dimensions) -- otherwise the
-  // table-cost kernels re-slice with the reference's slicer verbatim
-  // (TNB_VERBATIM_RESLICER: measurement switch, keeps the table-cost kernels on the reference's slicer)
-  if (ok && with_slicer && e->finite && e->popcount_widths() && (e->pow2_costs() || !std::getenv("TNB_VERBATIM_RESLICER")))
-    ok = alloc_to(rt, cs.kwsz, nc * e->Npad) && (!e->d_sparse || alloc_to(rt, cs.ksp, nc * e->Npad)) &&
+  if (ok && want_kwsz)
+    ok = (cs.kwsz || alloc_to(rt, cs.kwsz, nc * e->Npad)) && (!e->d_sparse || alloc_to(rt, cs.ksp, nc * e->Npad)) &&
          alloc_to(rt, cs.word, nc * e->Npad) && alloc_to(rt, cs.wkey, nc * e->Npad);
   if (!ok) return e->rtfail();
   return true;
@@ -1039,6 +1067,13 @@ int tnb_run(tnb_engine* e, int64_t until_sweep) {
   if (until_sweep >= (int64_t(1) << 31)) return e->fail("tnb_run: until_sweep must be below 2^31"), -1;
   if (e->inv_kind != e->prob_kind && !upload_inv_betas(e)) return -3;  // tnb_set_prob since the schedule was uploaded
   Params P;
+  // HBM-resident batches of the production kernels: the hot block stays in L2 for the launches of this call
+  struct L2Guard {
+    Rt& rt;
+    ~L2Guard() { rt.l2_window_off(); }
+  } l2guard{e->rt};
+  if (e->cs.hot && e->rng_kind == TNB_RNG_PHILOX && e->l2_persist_mb != 0)
+    e->rt.l2_window(e->cs.hot, e->cs.hot_bytes, e->l2_persist_mb > 0 ? size_t(e->l2_persist_mb) << 20 : 0);
   for (int guard = 0;; ++guard) {
     fill_params(e, e->cs, P);
     P.until = until_sweep;

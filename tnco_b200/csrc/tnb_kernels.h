@@ -2080,6 +2080,19 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
 #pragma unroll
   for (int k = 0; k < WPL; ++k) S[k] = 0u;
   if (FINITE) load_slices(c, S);
+#if !defined(TNB_EMU) && !defined(TNB_NO_SFIX)
+  // The slices are loaded here and first USED inside the loop.  ptxas then guards that first use -- the top of every
+  // level, right behind the loads the level issues for the next one -- with a wait on the scoreboard of this load,
+  // which is the scoreboard nearly all global loads of the kernel share: every level waited there for its own
+  // prefetches to land (13.5 % of C4's stall samples on that one LOP3; `cuobjdump -sass` control words decoded by
+  // scripts/sass_ctrl.py).  One ALU instruction on S before the loop consumes the load here, and the level's wait
+  // moves to where the prefetched values are really taken over, at its end.
+  if (FINITE) {
+    const uint32_t z0 = uint32_t(P.n_chains) >> 31;  // zero, but not to the compiler
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) S[k] ^= z0;
+  }
+#endif
 
   // The production (Philox) kernels run what the app runs -- Metropolis-Hastings with shared-index moves -- with the
   // two mode flags folded at compile time (per level: two constant loads, two compares and the generic acceptance

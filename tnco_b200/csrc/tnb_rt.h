@@ -26,6 +26,8 @@ struct Rt {
   bool zero(void* d, size_t b) { std::memset(d, 0, b); return true; }
   bool fill_ff(void* d, size_t b) { std::memset(d, 0xff, b); return true; }
   bool sync() { return true; }
+  void l2_window(void*, size_t, size_t) {}
+  void l2_window_off() {}
   void destroy() {}
 };
 #else
@@ -52,10 +54,45 @@ struct Rt {
     }
     device = dev;
     n_sms = prop.multiProcessorCount;
+    l2_persist_max = size_t(prop.persistingL2CacheMaxSize);
+    l2_window_max = size_t(prop.accessPolicyMaxWindowSize);
     if (!ok(cudaSetDevice(dev), "cudaSetDevice")) return false;
+    if (const char* f = std::getenv("TNB_L2_FETCH")) {  // measurement switch: DRAM -> L2 fetch granularity (32 / 64 / 128)
+      if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(std::atoi(f))) != cudaSuccess) cudaGetLastError();
+    }
     if (!ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
     if (!ok(cudaEventCreate(&ev0), "cudaEventCreate") || !ok(cudaEventCreate(&ev1), "cudaEventCreate")) return false;
     return true;
+  }
+  // L2 residency of the walk's hot block (ChainSet::hot: parents, node headers, kwsz -- the address-dependent loads
+  // of the ancestor pipeline) while an HBM-resident batch streams its index sets through L2: the kernels launched
+  // into the stream between l2_window() and l2_window_off() see [p, p + bytes) as persisting lines.  With a window
+  // larger than the carve-out the hardware keeps a `hitRatio` share of its lines.
+  size_t l2_persist_max = 0, l2_window_max = 0;
+  bool l2_on = false;
+  void l2_window(void* p, size_t bytes, size_t cap_bytes) {
+    if (!p || !bytes || !l2_persist_max || !l2_window_max) return;
+    const size_t carve = std::min(l2_persist_max, cap_bytes ? cap_bytes : l2_persist_max);
+    const size_t win = std::min(bytes, l2_window_max);
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaStreamAttrValue a;
+    std::memset(&a, 0, sizeof a);
+    a.accessPolicyWindow.base_ptr = p;
+    a.accessPolicyWindow.num_bytes = win;
+    a.accessPolicyWindow.hitRatio = float(std::min(1.0, double(carve) / double(win)));
+    a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    a.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) { cudaGetLastError(); return; }
+    l2_on = true;
+  }
+  void l2_window_off() {
+    if (!l2_on) return;
+    cudaStreamAttrValue a;
+    std::memset(&a, 0, sizeof a);
+    a.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &a);
+    cudaCtxResetPersistingL2Cache();
+    l2_on = false;
   }
   // Device allocations are recycled through an exact-size free list: cudaMalloc / cudaFree synchronise the device
   // and were the most variable part (10-350 ms) of a back-to-back optimize() call that needs the same arrays again.
