@@ -49,7 +49,10 @@ WORKLOADS = {
                     'max_width=32, update_slices=10', make=lambda nw: nw.sycamore(20), max_width=32.0, chains=4096,
                sweeps=10000),
     'C5': dict(text='C5: random 3-regular graph TN, 1000 tensors (1500 indices, d=2), unconstrained SA, HBM-resident '
-                    'chain state', make=lambda nw: nw.regular_graph(1000, 0), max_width=None, chains=4096, sweeps=2000),
+                    'chain state', make=lambda nw: nw.regular_graph(1000, 0), max_width=None,
+               # (its kernel holds 64 registers: 148 SMs x 32 resident single-warp blocks = 4736 chains fill one wave;
+               #  4096 leave an eighth of the slots empty and run 6 % slower, profiles/r02_experiments.md)
+               chains=4736, sweeps=2000),
 }
 _SEL = {'name': 'C4'}
 
