@@ -2300,35 +2300,72 @@ TNB_D void chain_sweeps(const Params& P, int chain, char* smem_tile = nullptr) {
       rebase = false;
       root_pc = total;
       c.load_node(B, nodeB);
-      const int p0 = int(nodeB.w() & 0xffffu), p1 = int(nodeB.w() >> 16);
-      c.load_bits(p0, b0);
-      c.load_bits(p1, b1);
-      if (PC) {
-        pc0 = c.pc_of(p0);
-        pc1 = c.pc_of(p1);
-      }
-      if (FS) {
-        sz0 = int(kws[p0] >> 16);
-        sz1 = int(kws[p1] >> 16);
-      }
-      if (HYPER) c.load_hyp(B, hB);
-      A = c.par[B];
-      in_sweep = true;
-      if (A >= 0) {
-        c.load_node(A, nodeA);
-        C = other_child(nodeA.w(), B);
-        c.load_bits(C, bC);
-        if (HYPER) {
-          c.load_bits(A, bA);
-          c.load_hyp(A, hA);
-        }
-        if (PC) pcC = c.pc_of(C);
-        if (FS) szC = int(kws[C] >> 16);
-        An = c.par[A];
+      // The sweep start is a chain of dependent loads -- leaf -> B -> A -> An, each with its header behind it -- and
+      // the first level can only begin when its last link has landed.
+      if constexpr (!FINITE) {
+        // Chain first (C2 +2.5 %, C3 +1.8 %): every parent is asked for together with the header of its child, and
+        // the next link is issued before the index sets that merely hang off the previous one.
+        A = c.par[B];
+        in_sweep = true;
         Ann = -1;
-        if (An >= 0) {
-          c.load_node(An, nodeAn);
-          Ann = c.par[An];
+        if (A >= 0) {
+          c.load_node(A, nodeA);
+          An = c.par[A];
+        }
+        const int p0 = int(nodeB.w() & 0xffffu), p1 = int(nodeB.w() >> 16);
+        c.load_bits(p0, b0);
+        c.load_bits(p1, b1);
+        if (PC) {
+          pc0 = c.pc_of(p0);
+          pc1 = c.pc_of(p1);
+        }
+        if (HYPER) c.load_hyp(B, hB);
+        if (A >= 0) {
+          if (An >= 0) {
+            c.load_node(An, nodeAn);
+            Ann = c.par[An];
+          }
+          C = other_child(nodeA.w(), B);
+          c.load_bits(C, bC);
+          if (HYPER) {
+            c.load_bits(A, bA);
+            c.load_hyp(A, hA);
+          }
+          if (PC) pcC = c.pc_of(C);
+        }
+      } else {
+        // The finite-width kernel keeps the plain order: with header(A) issued early ptxas puts it on the scoreboard
+        // of the index-set loads and the chain waits for them (C4 -0.6 %; with only the parents moved up -1.4 %).
+        const int p0 = int(nodeB.w() & 0xffffu), p1 = int(nodeB.w() >> 16);
+        c.load_bits(p0, b0);
+        c.load_bits(p1, b1);
+        if (PC) {
+          pc0 = c.pc_of(p0);
+          pc1 = c.pc_of(p1);
+        }
+        if (FS) {
+          sz0 = int(kws[p0] >> 16);
+          sz1 = int(kws[p1] >> 16);
+        }
+        if (HYPER) c.load_hyp(B, hB);
+        A = c.par[B];
+        in_sweep = true;
+        if (A >= 0) {
+          c.load_node(A, nodeA);
+          C = other_child(nodeA.w(), B);
+          c.load_bits(C, bC);
+          if (HYPER) {
+            c.load_bits(A, bA);
+            c.load_hyp(A, hA);
+          }
+          if (PC) pcC = c.pc_of(C);
+          if (FS) szC = int(kws[C] >> 16);
+          An = c.par[A];
+          Ann = -1;
+          if (An >= 0) {
+            c.load_node(An, nodeAn);
+            Ann = c.par[An];
+          }
         }
       }
     } else {
