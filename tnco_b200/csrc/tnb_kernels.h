@@ -1228,50 +1228,24 @@ TNB_D TNB_NOINLINE void get_slices_fast(const ChainView<TILE, WPL>& c, const uin
   // HBM round trip per row.
   for (int j = t.tl; j < nw; j += TILE) c.prefetch_row(word[j]);
   {
-    // Four rows per step: their loads are in flight together, a carry-save tree turns the four bits of every index
-    // into (ones, twos, fours), and three ripple adds put those into the planes from bit 0, 1 and 2 -- 40 % fewer
-    // instructions than four single adds, one exposed round trip per four rows instead of one per row.  The counters
-    // saturate exactly as before (an overflow of any of the adds sets every plane).
-    auto add_at = [&](int k, int b0, uint32_t carry) -> uint32_t {
+    uint32_t xn[WPL];
+    c.load_bits(word[0], xn);
+    for (int j = 0; j < nw; ++j) {
+      uint32_t x[WPL];
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        if (b >= b0) {
+      for (int k = 0; k < WPL; ++k) x[k] = xn[k];
+      if (j + 1 < nw) c.load_bits(word[j + 1], xn);  // the next row is in flight while this one is counted
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) {
+        uint32_t carry = x[k];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
           const uint32_t nc = cnt[k][b] & carry;
           cnt[k][b] ^= carry;
           carry = nc;
         }
-      }
-      return carry;
-    };
-    uint32_t r0[WPL], r1[WPL], r2[WPL], r3[WPL];
-    auto load4 = [&](int j) {
-      c.load_bits(word[j < nw ? j : 0], r0);  // (rows beyond the list: a valid address, masked below)
-      c.load_bits(word[j + 1 < nw ? j + 1 : 0], r1);
-      c.load_bits(word[j + 2 < nw ? j + 2 : 0], r2);
-      c.load_bits(word[j + 3 < nw ? j + 3 : 0], r3);
-    };
-    load4(0);
-    for (int j = 0; j < nw; j += 4) {
-      uint32_t a[WPL], b[WPL], d[WPL], e[WPL];
-      const uint32_t m1 = j + 1 < nw ? ~0u : 0u, m2 = j + 2 < nw ? ~0u : 0u, m3 = j + 3 < nw ? ~0u : 0u;
 #pragma unroll
-      for (int k = 0; k < WPL; ++k) {
-        a[k] = r0[k];
-        b[k] = r1[k] & m1;
-        d[k] = r2[k] & m2;
-        e[k] = r3[k] & m3;
-      }
-      if (j + 4 < nw) load4(j + 4);  // the next four rows are in flight while these are counted
-#pragma unroll
-      for (int k = 0; k < WPL; ++k) {
-        const uint32_t s1 = a[k] ^ b[k] ^ d[k], c1 = (a[k] & b[k]) | (d[k] & (a[k] ^ b[k]));
-        const uint32_t ones = s1 ^ e[k], c2 = s1 & e[k];
-        const uint32_t twos = c1 ^ c2, fours = c1 & c2;
-        uint32_t over = add_at(k, 0, ones);
-        over |= add_at(k, 1, twos);
-        over |= add_at(k, 2, fours);
-#pragma unroll
-        for (int q = 0; q < NB; ++q) cnt[k][q] |= over;  // saturate at 2^NB - 1
+        for (int b = 0; b < NB; ++b) cnt[k][b] |= carry;  // saturate at 2^NB - 1
       }
     }
   }
