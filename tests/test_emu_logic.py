@@ -53,6 +53,10 @@ def test_emu_philox_finite(emu, n, max_width):
     G.test_philox_finite_width_chains_are_valid(n, max_width, None)
 
 
+def test_emu_philox_skip_slices(emu):
+    G.test_philox_skip_slices_are_never_sliced()
+
+
 @pytest.mark.parametrize('dim', [3])
 def test_emu_philox_uniform_dim3_finite_width(emu, dim):
     G.test_philox_uniform_dimension_other_than_two_with_max_width(dim)

@@ -284,11 +284,8 @@ def test_mode_and_resume_argument_errors():
     e.set_mode(disable_shared_inds=True).set_chains(p, a, b, seeds)
     with pytest.raises((EngineError, ValueError), match='Metropolis'):
         e.costs()
-    e.set_mode(max_width=6.0).set_skip_slices(np.ones((ni + 31) // 32, np.uint32)).set_chains(p, a, b, seeds)
-    with pytest.raises((EngineError, ValueError), match='skip_slices'):
-        e.costs()
     # greedy acceptance on the stream kernels: costs never go up
-    e.set_skip_slices(None).set_mode(prob=PROB_GREEDY, rng=RNG_MT19937).set_chains(p, a, b, seeds).set_betas([0.0] * 30)
+    e.set_mode(prob=PROB_GREEDY, rng=RNG_MT19937).set_chains(p, a, b, seeds).set_betas([0.0] * 30)
     t0, _ = e.costs()
     e.run(30)
     assert (e.costs()[0] <= t0).all()
@@ -319,6 +316,39 @@ def _check_tree_valid(P, A, B, n):
         seen[A[z]] += 1
         seen[B[z]] += 1
     assert (seen[:N - 1] == 1).all()
+
+
+def test_philox_skip_slices_are_never_sliced():
+    """skip_slices (finite_width/greedy/utils.hpp:76-79) under the production generator: the periodic re-slicer never
+    takes a skipped index, the slices it does take still bring every tensor under max_width (the skipped ones are a
+    minority here), and cached totals equal an independent evaluation with the slices."""
+    from helpers import leaf_bits
+    from tnco_b200.engine import Engine, random_trees
+    ts, ni = regular_network(100, 11)
+    lb = leaf_bits(ts, ni)
+    seeds = np.arange(32, dtype=np.uint64) + 3
+    p, a, b = random_trees(lb, ni, seeds)
+    skip = np.zeros((ni + 31) // 32, np.uint32)
+    for x in range(0, ni, 5):
+        skip[x // 32] |= np.uint32(1 << (x % 32))
+    res = []
+    for sk in (None, skip):
+        e = Engine()
+        e.set_network(lb, ni).set_mode(max_width=7.0, update_slices_every=4)
+        if sk is not None:
+            e.set_skip_slices(sk)
+        e.set_chains(p, a, b, seeds).set_betas(np.linspace(0, 40, 300, endpoint=False))
+        e.run(300)
+        t, m = e.costs()
+        P, A, B = e.trees()
+        S = e.slices()
+        seq, pc, mw = e.eval_cost(P, A, B, slices=S)
+        assert np.allclose(np.log2(seq), np.log2(t), atol=1e-9)
+        assert (mw <= 7.0).all() and S.any()
+        res.append(S.copy())
+        e.close()
+    assert (res[0] & skip).any()          # without the option those indices do get sliced ...
+    assert not (res[1] & skip).any()      # ... with it, never
 
 
 @pytest.mark.parametrize('n,max_width,tile', [(64, 10, None), (150, 22, None), (150, 22, 16), (300, 30, None)])
