@@ -127,9 +127,9 @@ int tnb_set_sparse_inds(tnb_engine* e, const uint32_t* sparse_bits, uint64_t n_p
 
 /* skip_slices of the finite-width core object (tnco/optimize/finite_width/optimizer.py:60,96-107;
  * include/tnco/optimize/finite_width/greedy/utils.hpp:76-79): indices the greedy slicer never takes.  [W32] or NULL
- * for none.  Honoured by the reference's slicer (stream kernels, table-cost kernels), not by the production
- * re-slicer of dimension-2 networks: use TNB_RNG_MT19937 / TNB_RNG_REPLAY there.  Call after tnb_set_network; drops
- * the chains. */
+ * for none.  Honoured by the reference's slicer (stream kernels, table-cost kernels); under TNB_RNG_PHILOX a batch
+ * with skip_slices is served by the table-cost kernels, which re-slice with that slicer (the production re-slicer
+ * of the 2^popcount kernels does not know the option).  Call after tnb_set_network; drops the chains. */
 int tnb_set_skip_slices(tnb_engine* e, const uint32_t* skip_bits);
 
 /* max_width < 0 or +inf: unconstrained (infinite_memory optimizer).  Otherwise the memory-constrained
